@@ -1,0 +1,735 @@
+// libsplitvae host side: model plan (layers, buffers, parameter arena), the C-ABI of
+// include/splitvae.h, and the orchestration of one train step.  All device work is issued on the
+// caller's stream with no allocation or synchronisation so a whole step can be graph-captured.
+//
+// Mirrors: vae/main.py:63-74 (model/optimizer construction), vae/model.py:100-135,158-169,189-200,
+// 237-248 (forward), vae/trainer.py:120-173 (train steps).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/splitvae.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_kernels.h"
+
+using namespace sv;
+
+namespace {
+
+constexpr int SV_FLAG_PLAN_ONLY = 1;  // build the plan without touching CUDA (inventory / sizes only)
+constexpr int SV_FLAG_NO_TC = 2;      // bf16 precision but reference kernels everywhere (A/B debugging)
+
+char g_create_error[512] = "";
+
+struct Buf { size_t off = 0, bytes = 0; };
+
+struct Layer {
+  std::string name;
+  ConvGeom g{};
+  int in = -1, out = -1, dout = -1, din = -1;  // buffer ids (-1: external input / no dgrad)
+  int in_dt = DT_F32, out_dt = DT_F32;
+  int mask_act = ACT_NONE;                    // activation of the producer of `in`
+  TcLayer tc;                                 // tensor-core plan (tc_kernels.h)
+};
+
+struct Var { std::string name; int ndim; int shape[4]; long long off, count; };
+
+struct Decoder { int d1, d2, d3, d4, d5; int D1, D2, U1, D3, U2, D4, U3, OUT; int dD1, dD2, dU1, dD3, dU2, dD4, dU3, dOUT; int dz; };
+struct ConvEnc { int e1, e2, e3, heads; int A1, A2, A3, HEADS; int dA1, dA2, dA3, dHEADS; };
+struct GmEnc {
+  int h1, h2, h3, yb0e1, yb2, ydense, yheads, zheads;
+  int A1, A2, A3, YB0E1, YH2, LOGITS, Y, YT, U, YHEADS, HSUM, HEADS;
+  int dA1, dA2, dA3, dYB0E1, dYH2, dLOGITS, dY, dYHEADS, dHSUM, dHEADS;
+};
+
+}  // namespace
+
+struct sv_handle {
+  sv_config cfg{};
+  int act_dt = DT_BF16;
+  bool round_w = true, plan_only = false, use_tc = true;
+  int B = 0, H = 0, W = 0, F = 0, K = 0;
+  std::vector<Var> vars;
+  long long arena_floats = 0;
+  std::vector<Buf> bufs;
+  size_t ws_bytes = 0;
+  std::vector<Layer> layers;
+  ConvEnc enc_x{}, enc_xh{};
+  GmEnc gm{};
+  Decoder dec_x{}, dec_xh{};
+  int ZCAT = -1, EPS_G = -1, EPS_L = -1, Z_G = -1, Z_L = -1, ZM_G = -1, ZS_G = -1, ZM_L = -1, ZS_L = -1;
+  int ZPM_OUT = -1, ZPS_OUT = -1, SCALARS = -1, PARTIALS = -1, COLSUM = -1, ADAM = -1, TCWS = -1;
+  long long seg_split = 0;  // arena offset where the decoders start
+  // bound buffers
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  char* ws = nullptr;
+  bool bound = false;
+  long long launches = 0;
+  char err[512] = "";
+  const float* last_inputs = nullptr;  // inputs of the step in flight (first-layer wgrad reads them)
+  unsigned long long seed = 0x5EEDull;
+};
+
+namespace {
+
+sv_status fail(sv_handle* h, sv_status code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(h ? h->err : g_create_error, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void same_pad(int in, int k, int s, int& before) {
+  const int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  before = total / 2;
+}
+
+int new_buf(sv_handle* h, size_t bytes) {
+  Buf b;
+  b.off = h->ws_bytes;
+  b.bytes = bytes;
+  h->ws_bytes += (bytes + 1023) / 1024 * 1024;
+  h->bufs.push_back(b);
+  return (int)h->bufs.size() - 1;
+}
+size_t esz(int dt) { return dt == DT_F32 ? 4 : 2; }
+int act_buf(sv_handle* h, long long elems) { return new_buf(h, (size_t)elems * esz(h->act_dt)); }
+int f32_buf(sv_handle* h, long long elems) { return new_buf(h, (size_t)elems * 4); }
+
+long long add_var(sv_handle* h, const std::string& name, int ndim, const int* shape) {
+  Var v;
+  v.name = name;
+  v.ndim = ndim;
+  v.count = 1;
+  for (int i = 0; i < 4; ++i) { v.shape[i] = i < ndim ? shape[i] : 0; if (i < ndim) v.count *= shape[i]; }
+  v.off = h->arena_floats;
+  h->arena_floats += (v.count + 63) / 64 * 64;  // 256-byte aligned variables
+  h->vars.push_back(v);
+  return v.off;
+}
+
+struct PartSpec { const char* name; int n; int act; };
+
+// Creates the Keras variables (kernel, bias per part, in Keras order) and the layer record.
+int add_layer(sv_handle* h, const std::string& prefix, int kh, int kw, int stride, int Hi, int Wi, int Ci,
+              std::vector<PartSpec> parts) {
+  Layer L;
+  ConvGeom& g = L.g;
+  g.B = h->B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci;
+  g.kh = kh; g.kw = kw; g.stride = stride;
+  g.Ho = (Hi + stride - 1) / stride; g.Wo = (Wi + stride - 1) / stride;
+  same_pad(Hi, kh, stride, g.pt);
+  same_pad(Wi, kw, stride, g.pl);
+  g.nparts = (int)parts.size();
+  g.Co = 0;
+  L.name = prefix + "." + parts[0].name;
+  for (int j = 0; j < g.nparts; ++j) {
+    const std::string vn = prefix + "." + parts[j].name;
+    g.part_n[j] = parts[j].n;
+    g.part_act[j] = parts[j].act;
+    if (kh == 1 && kw == 1 && Hi == 1 && Wi == 1) {
+      int shp[2] = {Ci, parts[j].n};
+      g.part_w[j] = add_var(h, vn + ".kernel", 2, shp);
+    } else {
+      int shp[4] = {kh, kw, Ci, parts[j].n};
+      g.part_w[j] = add_var(h, vn + ".kernel", 4, shp);
+    }
+    int bs[1] = {parts[j].n};
+    g.part_b[j] = add_var(h, vn + ".bias", 1, bs);
+    g.Co += parts[j].n;
+  }
+  g.in_ld = Ci; g.in_coff = 0; g.out_ld = g.Co; g.dout_ld = g.Co; g.din_ld = Ci;
+  h->layers.push_back(L);
+  return (int)h->layers.size() - 1;
+}
+
+void wire(sv_handle* h, int li, int in, int in_dt, int in_ld, int in_coff, int out, int out_dt, int out_ld, int dout,
+          int dout_ld, int din, int din_ld, int mask_act) {
+  Layer& L = h->layers[li];
+  L.in = in; L.in_dt = in_dt; L.g.in_ld = in_ld; L.g.in_coff = in_coff;
+  L.out = out; L.out_dt = out_dt; L.g.out_ld = out_ld;
+  L.dout = dout; L.g.dout_ld = dout_ld;
+  L.din = din; L.g.din_ld = din_ld;
+  L.mask_act = mask_act;
+}
+
+ConvEnc build_conv_encoder(sv_handle* h, const char* prefix, int coff) {
+  ConvEnc e{};
+  const int B = h->B, H = h->H, W = h->W, T = h->act_dt;
+  e.e1 = add_layer(h, prefix, 6, 6, 2, H, W, 3, {{"e1", 32, ACT_RELU}});
+  e.e2 = add_layer(h, prefix, 6, 6, 2, H / 2, W / 2, 32, {{"e2", 64, ACT_RELU}});
+  e.e3 = add_layer(h, prefix, 4, 4, 2, H / 4, W / 4, 64, {{"e3", 128, ACT_RELU}});
+  e.heads = add_layer(h, prefix, 1, 1, 1, 1, 1, h->F, {{"e4_mean", 128, ACT_NONE}, {"e4_sd", 128, ACT_SOFTPLUS}});
+  e.A1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 32); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 32);
+  e.A2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 64); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 64);
+  e.A3 = act_buf(h, (long long)B * h->F); e.dA3 = act_buf(h, (long long)B * h->F);
+  e.HEADS = f32_buf(h, (long long)B * 256); e.dHEADS = act_buf(h, (long long)B * 256);
+  wire(h, e.e1, -1, DT_F32, 6, coff, e.A1, T, 32, e.dA1, 32, -1, 0, ACT_NONE);
+  wire(h, e.e2, e.A1, T, 32, 0, e.A2, T, 64, e.dA2, 64, e.dA1, 32, ACT_RELU);
+  wire(h, e.e3, e.A2, T, 64, 0, e.A3, T, 128, e.dA3, 128, e.dA2, 64, ACT_RELU);
+  wire(h, e.heads, e.A3, T, h->F, 0, e.HEADS, DT_F32, 256, e.dHEADS, 256, e.dA3, h->F, ACT_RELU);
+  return e;
+}
+
+GmEnc build_gm_encoder(sv_handle* h, const char* prefix) {
+  GmEnc e{};
+  const int B = h->B, H = h->H, W = h->W, T = h->act_dt, F = h->F, K = h->K;
+  // Keras variable order = attribute order of Encoder.__init__ (vae/model.py:49-76)
+  e.h1 = add_layer(h, prefix, 6, 6, 2, H, W, 3, {{"h_block.0", 128, ACT_ELU}});
+  e.h2 = add_layer(h, prefix, 6, 6, 2, H / 2, W / 2, 128, {{"h_block.1", 128, ACT_ELU}});
+  e.h3 = add_layer(h, prefix, 4, 4, 2, H / 4, W / 4, 128, {{"h_block.2", 128, ACT_ELU}});
+  // y_block.0 and e1 share their input and are fused along the output axis, but Keras creates
+  // y_block.0, y_block.2, y_dense, h_top_dense, z_prior_mean, z_prior_sig, e1, z_mean, z_sig in
+  // that order; the variables of the fused layer are therefore declared part by part below.
+  e.yb0e1 = add_layer(h, prefix, 1, 1, 1, 1, 1, F, {{"y_block.0", 1024, ACT_ELU}});
+  e.yb2 = add_layer(h, prefix, 1, 1, 1, 1, 1, 1024, {{"y_block.2", 128, ACT_ELU}});
+  e.ydense = add_layer(h, prefix, 1, 1, 1, 1, 1, 128, {{"y_dense", K, ACT_NONE}});
+  e.yheads = add_layer(h, prefix, 1, 1, 1, 1, 1, K,
+                       {{"h_top_dense", 512, ACT_ELU}, {"z_prior_mean", 128, ACT_NONE}, {"z_prior_sig", 128, ACT_SOFTPLUS}});
+  {  // append e1 as the second part of the fused (y_block.0 | e1) layer
+    Layer& L = h->layers[e.yb0e1];
+    int shp[2] = {F, 512};
+    L.g.part_w[1] = add_var(h, std::string(prefix) + ".e1.kernel", 2, shp);
+    int bs[1] = {512};
+    L.g.part_b[1] = add_var(h, std::string(prefix) + ".e1.bias", 1, bs);
+    L.g.part_n[1] = 512; L.g.part_act[1] = ACT_ELU; L.g.nparts = 2; L.g.Co = 1536;
+  }
+  e.zheads = add_layer(h, prefix, 1, 1, 1, 1, 1, 512, {{"z_mean", 128, ACT_NONE}, {"z_sig", 128, ACT_SOFTPLUS}});
+
+  e.A1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 128); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 128);
+  e.A2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 128); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 128);
+  e.A3 = act_buf(h, (long long)B * F); e.dA3 = act_buf(h, (long long)B * F);
+  e.YB0E1 = act_buf(h, (long long)B * 1536); e.dYB0E1 = act_buf(h, (long long)B * 1536);
+  e.YH2 = act_buf(h, (long long)B * 128); e.dYH2 = act_buf(h, (long long)B * 128);
+  e.LOGITS = f32_buf(h, (long long)B * 32); e.dLOGITS = act_buf(h, (long long)B * 32);
+  e.Y = f32_buf(h, (long long)B * 32); e.YT = act_buf(h, (long long)B * 32); e.U = f32_buf(h, (long long)B * 32);
+  e.dY = act_buf(h, (long long)B * 32);
+  e.YHEADS = f32_buf(h, (long long)B * 768); e.dYHEADS = act_buf(h, (long long)B * 768);
+  e.HSUM = act_buf(h, (long long)B * 512); e.dHSUM = act_buf(h, (long long)B * 512);
+  e.HEADS = f32_buf(h, (long long)B * 256); e.dHEADS = act_buf(h, (long long)B * 256);
+
+  wire(h, e.h1, -1, DT_F32, 6, 0, e.A1, T, 128, e.dA1, 128, -1, 0, ACT_NONE);
+  wire(h, e.h2, e.A1, T, 128, 0, e.A2, T, 128, e.dA2, 128, e.dA1, 128, ACT_ELU);
+  wire(h, e.h3, e.A2, T, 128, 0, e.A3, T, 128, e.dA3, 128, e.dA2, 128, ACT_ELU);
+  wire(h, e.yb0e1, e.A3, T, F, 0, e.YB0E1, T, 1536, e.dYB0E1, 1536, e.dA3, F, ACT_ELU);
+  wire(h, e.yb2, e.YB0E1, T, 1536, 0, e.YH2, T, 128, e.dYH2, 128, e.dYB0E1, 1536, ACT_ELU);
+  wire(h, e.ydense, e.YH2, T, 128, 0, e.LOGITS, DT_F32, 32, e.dLOGITS, 32, e.dYH2, 128, ACT_ELU);
+  wire(h, e.yheads, e.YT, T, 32, 0, e.YHEADS, DT_F32, 768, e.dYHEADS, 768, e.dY, 32, ACT_NONE);
+  wire(h, e.zheads, e.HSUM, T, 512, 0, e.HEADS, DT_F32, 256, e.dHEADS, 256, e.dHSUM, 512, ACT_NONE);
+  return e;
+}
+
+Decoder build_decoder(sv_handle* h, const char* prefix, int L, int zcoff, int dz_buf, int dz_ld, int dout_ld) {
+  Decoder d{};
+  const int B = h->B, H = h->H, W = h->W, T = h->act_dt, F = h->F;
+  d.d1 = add_layer(h, prefix, 1, 1, 1, 1, 1, L, {{"d1", F, ACT_RELU}});
+  d.d2 = add_layer(h, prefix, 4, 4, 1, H / 8, W / 8, 128, {{"d2", 128, ACT_RELU}});
+  d.d3 = add_layer(h, prefix, 4, 4, 1, H / 4, W / 4, 128, {{"d3", 64, ACT_RELU}});
+  d.d4 = add_layer(h, prefix, 6, 6, 1, H / 2, W / 2, 64, {{"d4", 32, ACT_RELU}});
+  d.d5 = add_layer(h, prefix, 6, 6, 1, H, W, 32, {{"d5", 6, ACT_NONE}});
+  const long long p8 = (long long)B * (H / 8) * (W / 8), p4 = p8 * 4, p2 = p8 * 16, p1 = p8 * 64;
+  d.D1 = act_buf(h, p8 * 128); d.dD1 = act_buf(h, p8 * 128);
+  d.D2 = act_buf(h, p8 * 128); d.dD2 = act_buf(h, p8 * 128);
+  d.U1 = act_buf(h, p4 * 128); d.dU1 = act_buf(h, p4 * 128);
+  d.D3 = act_buf(h, p4 * 64); d.dD3 = act_buf(h, p4 * 64);
+  d.U2 = act_buf(h, p2 * 64); d.dU2 = act_buf(h, p2 * 64);
+  d.D4 = act_buf(h, p2 * 32); d.dD4 = act_buf(h, p2 * 32);
+  d.U3 = act_buf(h, p1 * 32); d.dU3 = act_buf(h, p1 * 32);
+  d.OUT = f32_buf(h, p1 * 6); d.dOUT = act_buf(h, p1 * dout_ld);
+  d.dz = dz_buf;
+  wire(h, d.d1, h->ZCAT, T, 256, zcoff, d.D1, T, F, d.dD1, F, dz_buf, dz_ld, ACT_NONE);
+  wire(h, d.d2, d.D1, T, 128, 0, d.D2, T, 128, d.dD2, 128, d.dD1, 128, ACT_RELU);
+  wire(h, d.d3, d.U1, T, 128, 0, d.D3, T, 64, d.dD3, 64, d.dU1, 128, ACT_NONE);
+  wire(h, d.d4, d.U2, T, 64, 0, d.D4, T, 32, d.dD4, 32, d.dU2, 64, ACT_NONE);
+  wire(h, d.d5, d.U3, T, 32, 0, d.OUT, DT_F32, 6, d.dOUT, dout_ld, d.dU3, 32, ACT_NONE);
+  return d;
+}
+
+void* bp(sv_handle* h, int id) { return id < 0 ? nullptr : (void*)(h->ws + h->bufs[id].off); }
+
+LatentBufs latent_bufs(sv_handle* h) {
+  LatentBufs L{};
+  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  L.heads_g = (const float*)bp(h, gm ? h->gm.HEADS : h->enc_x.HEADS);
+  L.heads_l = (const float*)bp(h, h->enc_xh.HEADS);
+  L.eps_g = (float*)bp(h, h->EPS_G); L.eps_l = (float*)bp(h, h->EPS_L);
+  L.z_g = (float*)bp(h, h->Z_G); L.z_l = (float*)bp(h, h->Z_L);
+  L.zm_g = (float*)bp(h, h->ZM_G); L.zs_g = (float*)bp(h, h->ZS_G);
+  L.zm_l = (float*)bp(h, h->ZM_L); L.zs_l = (float*)bp(h, h->ZS_L);
+  L.zcat = bp(h, h->ZCAT);
+  L.dzcat = bp(h, h->dec_x.dz);
+  L.dzl2 = bp(h, h->dec_xh.dz);
+  L.dheads_g = bp(h, gm ? h->gm.dHEADS : h->enc_x.dHEADS);
+  L.dheads_l = bp(h, h->enc_xh.dHEADS);
+  L.yheads = gm ? (const float*)bp(h, h->gm.YHEADS) : nullptr;
+  return L;
+}
+
+// ---- per-layer execution ------------------------------------------------------------------
+void layer_fwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
+  Layer& L = h->layers[li];
+  const void* in = L.in < 0 ? (const void*)ext_in : bp(h, L.in);
+  if (h->use_tc && L.tc.fwd_ok) {
+    tc_conv_fwd(L.tc, L.g, h->params, bp(h, L.out), L.out_dt, s);
+    h->launches += L.tc.fwd_launches;
+  } else {
+    ref_conv_fwd(L.g, in, L.in_dt, h->params, bp(h, L.out), L.out_dt, h->round_w, s);
+    h->launches += 1;
+  }
+}
+
+void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
+  Layer& L = h->layers[li];
+  const void* in = L.in < 0 ? (const void*)ext_in : bp(h, L.in);
+  const int T = h->act_dt;
+  if (h->use_tc && L.tc.wgrad_ok) {
+    tc_conv_wgrad(L.tc, L.g, h->grads, s);
+    h->launches += L.tc.wgrad_launches;
+  } else {
+    ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, s);
+    h->launches += 1;
+  }
+  bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, h->COLSUM), h->grads, s);
+  h->launches += 2;
+  if (L.din >= 0) {
+    if (h->use_tc && L.tc.dgrad_ok) {
+      tc_conv_dgrad(L.tc, L.g, in, L.mask_act, bp(h, L.din), s);
+      h->launches += L.tc.dgrad_launches;
+    } else {
+      ref_conv_dgrad(L.g, bp(h, L.dout), T, h->params, bp(h, L.din), in, L.in_dt, L.mask_act, h->round_w, s);
+      h->launches += 1;
+    }
+  }
+}
+
+void conv_encoder_fwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaStream_t s) {
+  layer_fwd(h, e.e1, inputs, s);
+  layer_fwd(h, e.e2, nullptr, s);
+  layer_fwd(h, e.e3, nullptr, s);
+  layer_fwd(h, e.heads, nullptr, s);
+}
+void conv_encoder_bwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaStream_t s) {
+  layer_bwd(h, e.heads, nullptr, s);
+  layer_bwd(h, e.e3, nullptr, s);
+  layer_bwd(h, e.e2, nullptr, s);
+  layer_bwd(h, e.e1, inputs, s);
+}
+
+void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStream_t s) {
+  const GmEnc& e = h->gm;
+  layer_fwd(h, e.h1, inputs, s);
+  layer_fwd(h, e.h2, nullptr, s);
+  layer_fwd(h, e.h3, nullptr, s);
+  layer_fwd(h, e.yb0e1, nullptr, s);
+  layer_fwd(h, e.yb2, nullptr, s);
+  layer_fwd(h, e.ydense, nullptr, s);
+  gumbel_fwd((const float*)bp(h, e.LOGITS), u, (float*)bp(h, e.U), (float*)bp(h, e.Y), bp(h, e.YT), h->act_dt, h->B,
+             h->K, h->cfg.tau, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
+  layer_fwd(h, e.yheads, nullptr, s);
+  gm_add(bp(h, e.YB0E1), (const float*)bp(h, e.YHEADS), bp(h, e.HSUM), h->act_dt, h->B, s);
+  layer_fwd(h, e.zheads, nullptr, s);
+  h->launches += 2;
+}
+
+void gm_encoder_bwd(sv_handle* h, const float* inputs, cudaStream_t s) {
+  const GmEnc& e = h->gm;
+  const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
+  layer_bwd(h, e.zheads, nullptr, s);
+  gm_glue_a(bp(h, e.dHSUM), bp(h, e.YB0E1), (const float*)bp(h, e.YHEADS), (const float*)bp(h, h->ZM_G),
+            (const float*)bp(h, h->ZS_G), bp(h, e.dYB0E1), bp(h, e.dYHEADS), h->act_dt, h->B, h->cfg.beta, inv_batch, s);
+  layer_bwd(h, e.yheads, nullptr, s);
+  gm_glue_b(bp(h, e.dY), (const float*)bp(h, e.Y), (const float*)bp(h, e.LOGITS), bp(h, e.dLOGITS), h->act_dt, h->B,
+            h->K, h->cfg.tau, h->cfg.alpha, inv_batch, s);
+  layer_bwd(h, e.ydense, nullptr, s);
+  layer_bwd(h, e.yb2, nullptr, s);   // writes columns 0..1023 of dYB0E1; glue A wrote 1024..1535
+  layer_bwd(h, e.yb0e1, nullptr, s);
+  layer_bwd(h, e.h3, nullptr, s);
+  layer_bwd(h, e.h2, nullptr, s);
+  layer_bwd(h, e.h1, inputs, s);
+  h->launches += 2;
+}
+
+void decoder_fwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
+  const int B = h->B, H = h->H, W = h->W, T = h->act_dt;
+  layer_fwd(h, d.d1, nullptr, s);
+  layer_fwd(h, d.d2, nullptr, s);
+  upsample2x_fwd(bp(h, d.D2), bp(h, d.U1), T, B, H / 8, W / 8, 128, s);
+  layer_fwd(h, d.d3, nullptr, s);
+  upsample2x_fwd(bp(h, d.D3), bp(h, d.U2), T, B, H / 4, W / 4, 64, s);
+  layer_fwd(h, d.d4, nullptr, s);
+  upsample2x_fwd(bp(h, d.D4), bp(h, d.U3), T, B, H / 2, W / 2, 32, s);
+  layer_fwd(h, d.d5, nullptr, s);
+  h->launches += 3;
+}
+
+void decoder_bwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
+  const int B = h->B, H = h->H, W = h->W, T = h->act_dt;
+  layer_bwd(h, d.d5, nullptr, s);
+  upsample2x_bwd(bp(h, d.dU3), bp(h, d.dD4), bp(h, d.D4), ACT_RELU, T, B, H / 2, W / 2, 32, s);
+  layer_bwd(h, d.d4, nullptr, s);
+  upsample2x_bwd(bp(h, d.dU2), bp(h, d.dD3), bp(h, d.D3), ACT_RELU, T, B, H / 4, W / 4, 64, s);
+  layer_bwd(h, d.d3, nullptr, s);
+  upsample2x_bwd(bp(h, d.dU1), bp(h, d.dD2), bp(h, d.D2), ACT_RELU, T, B, H / 8, W / 8, 128, s);
+  layer_bwd(h, d.d2, nullptr, s);
+  layer_bwd(h, d.d1, nullptr, s);
+  h->launches += 3;
+}
+
+__global__ void pack_z_kernel(const float* __restrict__ zg, const float* __restrict__ zl, void* zcat, int dt, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 128) return;
+  const int b = idx >> 7, d = idx & 127;
+  if (dt == DT_F32) { ((float*)zcat)[b * 256 + d] = zg[idx]; ((float*)zcat)[b * 256 + 128 + d] = zl[idx]; }
+  else { ((bf16*)zcat)[b * 256 + d] = __float2bfloat16_rn(zg[idx]); ((bf16*)zcat)[b * 256 + 128 + d] = __float2bfloat16_rn(zl[idx]); }
+}
+__global__ void pack_y_kernel(const float* __restrict__ y, void* yt, int dt, int B, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 32) return;
+  const int b = idx >> 5, k = idx & 31;
+  const float v = k < K ? y[b * K + k] : 0.f;
+  if (dt == DT_F32) ((float*)yt)[idx] = v; else ((bf16*)yt)[idx] = __float2bfloat16_rn(v);
+}
+__global__ void copy_cols_kernel(const float* __restrict__ src, int ld, int coff, float* __restrict__ dst, int B, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n) return;
+  dst[idx] = src[(idx / n) * ld + coff + idx % n];
+}
+
+sv_status check_launch(sv_handle* h, const char* what) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, SV_ERR_DEVICE, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return SV_OK;
+}
+
+#define REQUIRE_BOUND(h)                                                         \
+  do {                                                                           \
+    if (!(h)) return SV_ERR_INVALID;                                             \
+    if ((h)->plan_only) return fail((h), SV_ERR_STATE, "handle is plan-only");   \
+    if (!(h)->bound) return fail((h), SV_ERR_STATE, "sv_bind has not been called"); \
+  } while (0)
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* sv_version(void) { return "splitvae-b200 0.1 (sm_100a)"; }
+
+const char* sv_last_error(const sv_handle* h) { return h ? h->err : g_create_error; }
+
+sv_status sv_create(const sv_config* cfg, sv_handle** out) {
+  if (!cfg || !out) return fail(nullptr, SV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->model != SV_MODEL_LGVAE && cfg->model != SV_MODEL_LGGMVAE)
+    return fail(nullptr, SV_ERR_INVALID, "unknown model %d", cfg->model);
+  if (cfg->height < 16 || cfg->width < 16 || cfg->height % 16 || cfg->width % 16 || cfg->height > 256 || cfg->width > 256)
+    return fail(nullptr, SV_ERR_INVALID, "image size %dx%d unsupported (multiples of 16 in [16,256])", cfg->height, cfg->width);
+  if (cfg->batch < 1 || cfg->batch > 65536) return fail(nullptr, SV_ERR_INVALID, "batch %d unsupported", cfg->batch);
+  if (cfg->global_latent_dims != 128 || cfg->local_latent_dims != 128)
+    return fail(nullptr, SV_ERR_INVALID, "latent dims must be 128/128 (got %d/%d)", cfg->global_latent_dims, cfg->local_latent_dims);
+  if (cfg->model == SV_MODEL_LGGMVAE && (cfg->y_size < 2 || cfg->y_size > 32))
+    return fail(nullptr, SV_ERR_INVALID, "y_size %d unsupported (2..32)", cfg->y_size);
+  if (cfg->world_size < 1) return fail(nullptr, SV_ERR_INVALID, "world_size must be >= 1");
+  if (cfg->precision != SV_PRECISION_BF16_TC && cfg->precision != SV_PRECISION_FP32_REF)
+    return fail(nullptr, SV_ERR_INVALID, "unknown precision %d", cfg->precision);
+  const bool plan_only = (cfg->flags & SV_FLAG_PLAN_ONLY) != 0;
+  if (!plan_only) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(nullptr, SV_ERR_DEVICE, "no CUDA device available: libsplitvae has no CPU fallback");
+    }
+    if (prop.major != 10)
+      return fail(nullptr, SV_ERR_DEVICE, "device '%s' is sm_%d%d; libsplitvae is built for sm_100a only", prop.name, prop.major, prop.minor);
+  }
+
+  sv_handle* h = new sv_handle();
+  h->cfg = *cfg;
+  h->plan_only = plan_only;
+  h->act_dt = cfg->precision == SV_PRECISION_FP32_REF ? DT_F32 : DT_BF16;
+  h->round_w = h->act_dt == DT_BF16;
+  h->use_tc = cfg->precision == SV_PRECISION_BF16_TC && !(cfg->flags & SV_FLAG_NO_TC);
+  h->B = cfg->batch; h->H = cfg->height; h->W = cfg->width;
+  h->F = ((cfg->height / 8) * cfg->width) / 8 * 128;  // vae/model.py:152 precedence
+  h->K = cfg->model == SV_MODEL_LGGMVAE ? cfg->y_size : 0;
+  h->seed = 0x5EEDull + 0x9E3779B97F4A7C15ull * (unsigned long long)(unsigned)(cfg->flags >> 8);
+  const int B = h->B;
+  const int dout_ld = h->act_dt == DT_F32 ? 6 : 16;
+
+  // shared latent buffers first (decoders reference ZCAT)
+  h->ZCAT = act_buf(h, (long long)B * 256);
+  h->EPS_G = f32_buf(h, B * 128); h->EPS_L = f32_buf(h, B * 128);
+  h->Z_G = f32_buf(h, B * 128); h->Z_L = f32_buf(h, B * 128);
+  h->ZM_G = f32_buf(h, B * 128); h->ZS_G = f32_buf(h, B * 128);
+  h->ZM_L = f32_buf(h, B * 128); h->ZS_L = f32_buf(h, B * 128);
+  h->ZPM_OUT = f32_buf(h, B * 128); h->ZPS_OUT = f32_buf(h, B * 128);
+  h->SCALARS = f32_buf(h, 64);
+  h->PARTIALS = f32_buf(h, 2 * 148 * 8 + 64);
+  h->COLSUM = f32_buf(h, 256 * 8192);
+  h->ADAM = new_buf(h, 1024);
+  const int dzcat = act_buf(h, (long long)B * 256), dzl2 = act_buf(h, (long long)B * 128);
+
+  // Keras variable order: encoder_x, encoder_x_hat, decoder_x, decoder_x_hat (model.py:182-186, 230-234)
+  if (cfg->model == SV_MODEL_LGVAE) h->enc_x = build_conv_encoder(h, "encoder_x", 0);
+  else h->gm = build_gm_encoder(h, "encoder_x");
+  h->enc_xh = build_conv_encoder(h, "encoder_x_hat", 3);
+  h->seg_split = h->arena_floats;
+  h->dec_x = build_decoder(h, "decoder_x", 256, 0, dzcat, 256, dout_ld);
+  h->dec_xh = build_decoder(h, "decoder_x_hat", 128, 128, dzl2, 128, dout_ld);
+
+  if (h->use_tc) {
+    for (auto& L : h->layers) tc_plan_layer(L.tc, L.g, L.in_dt, L.out_dt, L.in >= 0, L.din >= 0);
+    size_t tcws = 0;
+    for (auto& L : h->layers) tcws += tc_workspace_bytes(L.tc, L.g);
+    h->TCWS = new_buf(h, tcws + 1024);
+  }
+  *out = h;
+  return SV_OK;
+}
+
+sv_status sv_destroy(sv_handle* h) {
+  delete h;
+  return SV_OK;
+}
+
+int32_t sv_param_count(const sv_handle* h) { return h ? (int32_t)h->vars.size() : 0; }
+
+sv_status sv_param_describe(const sv_handle* h, int32_t i, sv_param_desc* out) {
+  if (!h || !out || i < 0 || i >= (int32_t)h->vars.size()) return SV_ERR_INVALID;
+  const Var& v = h->vars[i];
+  memset(out, 0, sizeof(*out));
+  snprintf(out->name, sizeof(out->name), "%s", v.name.c_str());
+  out->ndim = v.ndim;
+  for (int k = 0; k < 4; ++k) out->shape[k] = v.shape[k];
+  out->offset = v.off;
+  out->count = v.count;
+  return SV_OK;
+}
+
+int64_t sv_arena_floats(const sv_handle* h) { return h ? h->arena_floats : 0; }
+int64_t sv_workspace_bytes(const sv_handle* h) { return h ? (int64_t)h->ws_bytes : 0; }
+
+sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, float* adam_v, void* ws, int64_t ws_bytes) {
+  if (!h) return SV_ERR_INVALID;
+  if (h->plan_only) return fail(h, SV_ERR_STATE, "handle is plan-only");
+  if (!params || !grads || !adam_m || !adam_v || !ws) return fail(h, SV_ERR_INVALID, "null buffer");
+  if (ws_bytes < (int64_t)h->ws_bytes) return fail(h, SV_ERR_STATE, "workspace too small: %lld < %lld", (long long)ws_bytes, (long long)h->ws_bytes);
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)adam_m | (uintptr_t)adam_v) & 255) return fail(h, SV_ERR_INVALID, "arenas must be 256-byte aligned");
+  if ((uintptr_t)ws & 1023) return fail(h, SV_ERR_INVALID, "workspace must be 1024-byte aligned");
+  h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v; h->ws = (char*)ws;
+  if (h->use_tc) {
+    char* tcws = (char*)bp(h, h->TCWS);
+    for (auto& L : h->layers) {
+      const char* err = tc_bind_layer(L.tc, L.g, L.in >= 0 ? bp(h, L.in) : nullptr, bp(h, L.out), bp(h, L.dout),
+                                      L.din >= 0 ? bp(h, L.din) : nullptr, tcws);
+      if (err) return fail(h, SV_ERR_DEVICE, "tensor-core plan for %s: %s", L.name.c_str(), err);
+      tcws += tc_workspace_bytes(L.tc, L.g);
+    }
+  }
+  h->bound = true;
+  return SV_OK;
+}
+
+sv_status sv_params_updated(sv_handle* h, void* stream) {
+  REQUIRE_BOUND(h);
+  if (h->use_tc) {
+    for (auto& L : h->layers) h->launches += tc_repack_weights(L.tc, L.g, h->params, (cudaStream_t)stream);
+  }
+  return check_launch(h, "sv_params_updated");
+}
+
+static sv_status forward_impl(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u,
+                              void* stream, bool prior_copies) {
+  REQUIRE_BOUND(h);
+  if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
+  conv_encoder_fwd(h, h->enc_xh, inputs, s);
+  reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
+  h->launches += 1;
+  decoder_fwd(h, h->dec_x, s);
+  decoder_fwd(h, h->dec_xh, s);
+  if (gm && prior_copies) {  // contiguous z_prior_mean / z_prior_sig for the reference's output tuple
+    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
+    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
+    h->launches += 2;
+  }
+  return check_launch(h, "sv_forward");
+}
+
+sv_status sv_forward(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u, void* stream) {
+  return forward_impl(h, inputs, eps_g, eps_l, u, stream, true);
+}
+
+sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  const long long npix = (long long)h->B * h->H * h->W;
+  const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
+  pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), (const float*)bp(h, h->dec_xh.OUT), bp(h, h->dec_x.dOUT),
+             bp(h, h->dec_xh.dOUT), h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
+             (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s);
+  loss_scalars(latent_bufs(h), gm ? (const float*)bp(h, h->gm.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
+               (const float*)bp(h, h->PARTIALS), pixel_loss_blocks(npix), (float*)bp(h, h->SCALARS), s);
+  h->launches += 2;
+  h->last_inputs = inputs;
+  return check_launch(h, "sv_loss_fwd_bwd");
+}
+
+int32_t sv_num_segments(const sv_handle* h) { return h ? 2 : 0; }
+
+sv_status sv_segment_range(const sv_handle* h, int32_t seg, int64_t* off, int64_t* cnt) {
+  if (!h || !off || !cnt || seg < 0 || seg > 1) return SV_ERR_INVALID;
+  if (seg == 0) { *off = h->seg_split; *cnt = h->arena_floats - h->seg_split; }
+  else { *off = 0; *cnt = h->seg_split; }
+  return SV_OK;
+}
+
+sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
+  REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* inputs = h->last_inputs;
+  if (seg == 0) {
+    decoder_bwd(h, h->dec_x, s);
+    decoder_bwd(h, h->dec_xh, s);
+  } else if (seg == 1) {
+    if (!inputs) return fail(h, SV_ERR_STATE, "sv_loss_fwd_bwd must precede sv_backward_segment");
+    const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+    const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
+    latent_bwd(latent_bufs(h), h->B, h->act_dt, gm, h->cfg.beta, inv_batch, s);
+    h->launches += 1;
+    conv_encoder_bwd(h, h->enc_xh, inputs, s);
+    if (gm) gm_encoder_bwd(h, inputs, s); else conv_encoder_bwd(h, h->enc_x, inputs, s);
+  } else {
+    return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
+  }
+  return check_launch(h, "sv_backward_segment");
+}
+
+sv_status sv_adam_step(sv_handle* h, void* stream) {
+  REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  AdamState* st = (AdamState*)bp(h, h->ADAM);
+  adam_prepare(st, h->cfg.learning_rate, h->cfg.model == SV_MODEL_LGGMVAE, s);
+  adam_apply(h->params, h->grads, h->adam_m, h->adam_v, h->arena_floats, st, 0.f, s);
+  h->launches += 2;
+  if (h->use_tc)
+    for (auto& L : h->layers) h->launches += tc_repack_weights(L.tc, L.g, h->params, s);
+  return check_launch(h, "sv_adam_step");
+}
+
+sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u, void* stream) {
+  sv_status st = forward_impl(h, inputs, eps_g, eps_l, u, stream, false);
+  if (st) return st;
+  if ((st = sv_loss_fwd_bwd(h, inputs, stream))) return st;
+  if ((st = sv_backward_segment(h, 0, stream))) return st;
+  if ((st = sv_backward_segment(h, 1, stream))) return st;
+  return sv_adam_step(h, stream);
+}
+
+sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t* count) {
+  sv_handle* h = const_cast<sv_handle*>(hc);
+  if (!h || !ptr || !count) return SV_ERR_INVALID;
+  if (!h->bound) return fail(h, SV_ERR_STATE, "sv_bind has not been called");
+  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  const long long B = h->B;
+  int id = -1;
+  long long n = 0;
+  switch (which) {
+    case SV_OUT_DEC_X: id = h->dec_x.OUT; n = B * h->H * h->W * 6; break;
+    case SV_OUT_DEC_X_HAT: id = h->dec_xh.OUT; n = B * h->H * h->W * 6; break;
+    case SV_OUT_Z_X: id = h->Z_G; n = B * 128; break;
+    case SV_OUT_Z_MEAN_X: id = h->ZM_G; n = B * 128; break;
+    case SV_OUT_Z_SIG_X: id = h->ZS_G; n = B * 128; break;
+    case SV_OUT_Z_X_HAT: id = h->Z_L; n = B * 128; break;
+    case SV_OUT_Z_MEAN_X_HAT: id = h->ZM_L; n = B * 128; break;
+    case SV_OUT_Z_SIG_X_HAT: id = h->ZS_L; n = B * 128; break;
+    case SV_OUT_Y: if (gm) { id = h->gm.Y; n = B * 32; } break;
+    case SV_OUT_Y_LOGITS: if (gm) { id = h->gm.LOGITS; n = B * 32; } break;
+    case SV_OUT_Z_PRIOR_MEAN: if (gm) { id = h->ZPM_OUT; n = B * 128; } break;
+    case SV_OUT_Z_PRIOR_SIG: if (gm) { id = h->ZPS_OUT; n = B * 128; } break;
+    case SV_OUT_SCALARS: id = h->SCALARS; n = SV_SCALAR_COUNT; break;
+    default: break;
+  }
+  if (id < 0) return fail(h, SV_ERR_INVALID, "output %d not available for this model", which);
+  *ptr = bp(h, id);
+  *count = n;
+  return SV_OK;
+}
+
+sv_status sv_decode(sv_handle* h, const float* z_x, const float* z_x_hat, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!z_x || !z_x_hat) return fail(h, SV_ERR_INVALID, "null latent");
+  cudaStream_t s = (cudaStream_t)stream;
+  pack_z_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>(z_x, z_x_hat, bp(h, h->ZCAT), h->act_dt, h->B);
+  h->launches += 1;
+  decoder_fwd(h, h->dec_x, s);
+  decoder_fwd(h, h->dec_xh, s);
+  return check_launch(h, "sv_decode");
+}
+
+sv_status sv_encode_y(sv_handle* h, const float* y, void* stream) {
+  REQUIRE_BOUND(h);
+  if (h->cfg.model != SV_MODEL_LGGMVAE) return fail(h, SV_ERR_INVALID, "encode_y needs the lggmvae model");
+  if (!y) return fail(h, SV_ERR_INVALID, "null y");
+  cudaStream_t s = (cudaStream_t)stream;
+  pack_y_kernel<<<(h->B * 32 + 255) / 256, 256, 0, s>>>(y, bp(h, h->gm.YT), h->act_dt, h->B, h->K);
+  layer_fwd(h, h->gm.yheads, nullptr, s);
+  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
+  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
+  h->launches += 3;
+  return check_launch(h, "sv_encode_y");
+}
+
+sv_status sv_get_iterations(sv_handle* h, int64_t* it) {
+  REQUIRE_BOUND(h);
+  if (!it) return SV_ERR_INVALID;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, bp(h, h->ADAM), 8, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, SV_ERR_DEVICE, "memcpy failed");
+  *it = (int64_t)v;
+  return SV_OK;
+}
+
+sv_status sv_set_iterations(sv_handle* h, int64_t it) {
+  REQUIRE_BOUND(h);
+  unsigned long long v = (unsigned long long)it;
+  if (cudaMemcpy(bp(h, h->ADAM), &v, 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail(h, SV_ERR_DEVICE, "memcpy failed");
+  return SV_OK;
+}
+
+int64_t sv_launch_count(const sv_handle* h) { return h ? h->launches : 0; }
+
+sv_status sv_discretised_logistic_loss(const float* x, const float* m, const float* ls, float* out, int64_t n, void* stream) {
+  if (!x || !m || !ls || !out || n < 0) return SV_ERR_INVALID;
+  dll_elementwise(x, m, ls, out, n, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+sv_status sv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float alpha, void* stream) {
+  if (!p || !g || !m || !v || n < 0) return SV_ERR_INVALID;
+  adam_apply(p, g, m, v, n, nullptr, alpha, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+sv_status sv_stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int32_t B, int32_t H, int32_t W, int32_t p, void* stream) {
+  if (!u8 || !perm || !inputs || B < 1 || p < 1 || H % p || W % p) return SV_ERR_INVALID;
+  stage_scramble(u8, perm, inputs, B, H, W, p, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+}  // extern "C"

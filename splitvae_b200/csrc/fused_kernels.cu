@@ -1,0 +1,530 @@
+// HBM-bound fused kernels of the train step: reparameterisation, the fused reconstruction
+// log-likelihood forward+backward, KL scalars, latent/gumbel gradient glue, multi-tensor Keras
+// Adam, and the on-device scramble staging.
+//
+// Reference semantics: Sampling (vae/model.py:9-13), gumbel-softmax (vae/model.py:122-123),
+// kl_divergence / kl_divergence_two_gauss / discretised_logistic_loss (vae/trainer.py:11-38),
+// loss assembly (vae/trainer.py:125-135, 151-164), tf.keras.optimizers.Adam (vae/main.py:65-68),
+// Augmentator.scramble (augmentation.py:43-57).  Analytic backward: SURVEY.md section 9.2.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sv {
+
+// ------------------------------------------------------------------ Philox4x32-10 counter RNG
+struct U4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ U4 philox4x32(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
+  return sqrtf(-2.f * logf(u01(a))) * cospif(2.f * u01(b));
+}
+
+template <typename T>
+__device__ __forceinline__ T ld_as(const void* p, long long i) { return ((const T*)p)[i]; }
+
+// ------------------------------------------------------------------ reparameterisation
+template <typename T>
+__global__ void reparam_kernel(LatentBufs L, int B, const float* __restrict__ ueg, const float* __restrict__ uel,
+                               unsigned long long seed, const unsigned long long* __restrict__ counter) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 128) return;
+  const int b = idx >> 7, d = idx & 127;
+  float eg, el;
+  if (ueg && uel) {
+    eg = ueg[idx];
+    el = uel[idx];
+  } else {
+    const unsigned long long step = *counter;
+    const U4 r = philox4x32(U4{(uint32_t)idx, 0x5A17u, (uint32_t)step, (uint32_t)(step >> 32)}, (uint32_t)seed,
+                            (uint32_t)(seed >> 32));
+    eg = ueg ? ueg[idx] : normal_from(r.x, r.y);
+    el = uel ? uel[idx] : normal_from(r.z, r.w);
+  }
+  const float mg = L.heads_g[b * 256 + d], sg = L.heads_g[b * 256 + 128 + d];
+  const float ml = L.heads_l[b * 256 + d], sl = L.heads_l[b * 256 + 128 + d];
+  const float zg = mg + sg * eg, zl = ml + sl * el;  // vae/model.py:13
+  L.eps_g[idx] = eg; L.eps_l[idx] = el;
+  L.z_g[idx] = zg; L.z_l[idx] = zl;
+  L.zm_g[idx] = mg; L.zs_g[idx] = sg; L.zm_l[idx] = ml; L.zs_l[idx] = sl;
+  ((T*)L.zcat)[b * 256 + d] = from_f32<T>(zg);
+  ((T*)L.zcat)[b * 256 + 128 + d] = from_f32<T>(zl);
+}
+
+void reparam(const LatentBufs& L, int B, int act_dt, const float* ueg, const float* uel, unsigned long long seed,
+             const unsigned long long* counter, cudaStream_t s) {
+  const int n = B * 128;
+  if (act_dt == DT_F32) reparam_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(L, B, ueg, uel, seed, counter);
+  else reparam_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>(L, B, ueg, uel, seed, counter);
+}
+
+// gradient w.r.t. the pre-activation encoder heads: reparam adjoint + KL gradient + softplus'
+template <typename T>
+__global__ void latent_bwd_kernel(LatentBufs L, int B, int gm, float beta, float inv_batch) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 128) return;
+  const int b = idx >> 7, d = idx & 127;
+  const float dzg = to_f32(ld_as<T>(L.dzcat, b * 256 + d));
+  const float dzl = to_f32(ld_as<T>(L.dzcat, b * 256 + 128 + d)) + to_f32(ld_as<T>(L.dzl2, idx));
+  const float mg = L.zm_g[idx], sg = L.zs_g[idx], ml = L.zm_l[idx], sl = L.zs_l[idx];
+  const float k = beta * inv_batch;
+  float dmg, dsg;
+  if (gm) {
+    const float pm = L.yheads[b * 768 + 512 + d], ps = L.yheads[b * 768 + 640 + d];
+    const float ip2 = 1.f / (ps * ps);
+    dmg = dzg + k * (mg - pm) * ip2;
+    dsg = dzg * L.eps_g[idx] + k * (sg * ip2 - 1.f / sg);
+  } else {
+    dmg = dzg + k * mg;
+    dsg = dzg * L.eps_g[idx] + k * (sg - 1.f / sg);
+  }
+  const float dml = dzl + k * ml;
+  const float dsl = dzl * L.eps_l[idx] + k * (sl - 1.f / sl);
+  ((T*)L.dheads_g)[b * 256 + d] = from_f32<T>(dmg);
+  ((T*)L.dheads_g)[b * 256 + 128 + d] = from_f32<T>(dsg * (1.f - expf(-sg)));
+  ((T*)L.dheads_l)[b * 256 + d] = from_f32<T>(dml);
+  ((T*)L.dheads_l)[b * 256 + 128 + d] = from_f32<T>(dsl * (1.f - expf(-sl)));
+}
+
+void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s) {
+  const int n = B * 128;
+  if (act_dt == DT_F32) latent_bwd_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(L, B, gm, beta, inv_batch);
+  else latent_bwd_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>(L, B, gm, beta, inv_batch);
+}
+
+// ------------------------------------------------------------------ gumbel softmax (one warp per row)
+template <typename T>
+__global__ void gumbel_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ user_u,
+                                  float* __restrict__ u_saved, float* __restrict__ y, T* __restrict__ y_act, int B,
+                                  int K, float tau, unsigned long long seed,
+                                  const unsigned long long* __restrict__ counter) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int k = threadIdx.x & 31;
+  if (row >= B) return;
+  float u = 0.5f, l = -INFINITY;
+  if (k < K) {
+    if (user_u) u = user_u[row * K + k];
+    else {
+      const unsigned long long step = *counter;
+      const U4 r = philox4x32(U4{(uint32_t)(row * 32 + k), 0x6B31u, (uint32_t)step, (uint32_t)(step >> 32)},
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+      u = u01(r.x);
+    }
+    l = (logits[row * 32 + k] - logf(-logf(u))) / tau;  // vae/model.py:123
+  }
+  float mx = l;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e = k < K ? expf(l - mx) : 0.f;
+  float sum = e;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float yv = e / sum;
+  u_saved[row * 32 + k] = u;
+  y[row * 32 + k] = yv;
+  y_act[row * 32 + k] = from_f32<T>(yv);
+}
+
+void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, int act_dt, int B,
+                int K, float tau, unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
+  const int rows_per_block = 8;
+  dim3 grid((B + rows_per_block - 1) / rows_per_block), block(32 * rows_per_block);
+  if (act_dt == DT_F32) gumbel_fwd_kernel<float><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (float*)y_act, B, K, tau, seed, counter);
+  else gumbel_fwd_kernel<bf16><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (bf16*)y_act, B, K, tau, seed, counter);
+}
+
+template <typename T>
+__global__ void gm_add_kernel(const T* __restrict__ yb0e1, const float* __restrict__ yheads, T* __restrict__ hsum, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 512) return;
+  const int b = idx >> 9, j = idx & 511;
+  hsum[idx] = from_f32<T>(to_f32(yb0e1[(long long)b * 1536 + 1024 + j]) + yheads[b * 768 + j]);  // model.py:130
+}
+void gm_add(const void* yb0e1_out, const float* yheads, void* hsum, int act_dt, int B, cudaStream_t s) {
+  const int n = B * 512;
+  if (act_dt == DT_F32) gm_add_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)yb0e1_out, yheads, (float*)hsum, B);
+  else gm_add_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)yb0e1_out, yheads, (bf16*)hsum, B);
+}
+
+template <typename T>
+__global__ void gm_glue_a_kernel(const T* __restrict__ dhsum, const T* __restrict__ yb0e1, const float* __restrict__ yheads,
+                                 const float* __restrict__ zm_g, const float* __restrict__ zs_g, T* __restrict__ d_yb0e1,
+                                 T* __restrict__ d_yheads, int B, float beta, float inv_batch) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 640) return;
+  const int b = idx / 640, j = idx % 640;
+  if (j < 512) {
+    const float dh = to_f32(dhsum[b * 512 + j]);
+    const float e1o = to_f32(yb0e1[(long long)b * 1536 + 1024 + j]);
+    const float ht = yheads[b * 768 + j];
+    d_yb0e1[(long long)b * 1536 + 1024 + j] = from_f32<T>(dh * act_grad_from_out(e1o, ACT_ELU));
+    d_yheads[b * 768 + j] = from_f32<T>(dh * act_grad_from_out(ht, ACT_ELU));
+  } else {
+    const int d = j - 512;
+    const float pm = yheads[b * 768 + 512 + d], ps = yheads[b * 768 + 640 + d];
+    const float mg = zm_g[b * 128 + d], sg = zs_g[b * 128 + d];
+    const float k = beta * inv_batch, dl = mg - pm, ip2 = 1.f / (ps * ps);
+    const float dpm = -k * dl * ip2;
+    const float dps = k * (1.f / ps - (sg * sg + dl * dl) * ip2 / ps);
+    d_yheads[b * 768 + 512 + d] = from_f32<T>(dpm);
+    d_yheads[b * 768 + 640 + d] = from_f32<T>(dps * (1.f - expf(-ps)));
+  }
+}
+void gm_glue_a(const void* dhsum, const void* yb0e1_out, const float* yheads, const float* zm_g, const float* zs_g,
+               void* d_yb0e1, void* d_yheads, int act_dt, int B, float beta, float inv_batch, cudaStream_t s) {
+  const int n = B * 640;
+  if (act_dt == DT_F32)
+    gm_glue_a_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)dhsum, (const float*)yb0e1_out, yheads, zm_g, zs_g, (float*)d_yb0e1, (float*)d_yheads, B, beta, inv_batch);
+  else
+    gm_glue_a_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)dhsum, (const bf16*)yb0e1_out, yheads, zm_g, zs_g, (bf16*)d_yb0e1, (bf16*)d_yheads, B, beta, inv_batch);
+}
+
+template <typename T>
+__global__ void gm_glue_b_kernel(const T* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ logits,
+                                 T* __restrict__ dlogits, int B, int K, float tau, float alpha, float inv_batch) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int k = threadIdx.x & 31;
+  if (row >= B) return;
+  const bool ok = k < K;
+  const float yv = ok ? y[row * 32 + k] : 0.f;
+  const float dyv = ok ? to_f32(dy[row * 32 + k]) : 0.f;
+  float t = yv * dyv;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  const float d_gs = yv * (dyv - t) / tau;
+  // categorical KL (vae/trainer.py:160-161)
+  const float l = ok ? logits[row * 32 + k] : -INFINITY;
+  float mx = l;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = ok ? expf(l - mx) : 0.f;
+  float sum = e;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float py = e / sum;
+  const float dfdp = ok ? logf(py + 1e-8f) + logf((float)K) + py / (py + 1e-8f) : 0.f;
+  float w = py * dfdp;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  const float d_kl = alpha * inv_batch * py * (dfdp - w);
+  dlogits[row * 32 + k] = from_f32<T>(ok ? d_gs + d_kl : 0.f);
+}
+void gm_glue_b(const void* dy, const float* y, const float* logits, void* dlogits, int act_dt, int B, int K, float tau,
+               float alpha, float inv_batch, cudaStream_t s) {
+  dim3 grid((B + 7) / 8), block(256);
+  if (act_dt == DT_F32) gm_glue_b_kernel<float><<<grid, block, 0, s>>>((const float*)dy, y, logits, (float*)dlogits, B, K, tau, alpha, inv_batch);
+  else gm_glue_b_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dy, y, logits, (bf16*)dlogits, B, K, tau, alpha, inv_batch);
+}
+
+// ------------------------------------------------------------------ discretised logistic likelihood
+// One element: returns the NLL (= -log_prob) and its derivatives w.r.t. mean and log_scale.
+// Branch structure follows vae/trainer.py:37 exactly; the arithmetic is arranged so that only
+// exp(-|.|) is ever exponentiated (no overflow) and a single log serves the three main branches.
+template <bool FAST>
+__device__ __forceinline__ float dll_elem(float x, float m, float ls, float& g_m, float& g_ls) {
+  const float s = FAST ? __expf(-ls) : expf(-ls);
+  const float c = x - m;
+  const float plus = s * (c + (1.f / 255.f));
+  const float mn = s * (c - (1.f / 255.f));
+  const float tp = FAST ? __expf(-fabsf(plus)) : expf(-fabsf(plus));
+  const float tm = FAST ? __expf(-fabsf(mn)) : expf(-fabsf(mn));
+  const float rp = FAST ? __fdividef(1.f, 1.f + tp) : 1.f / (1.f + tp);
+  const float rm = FAST ? __fdividef(1.f, 1.f + tm) : 1.f / (1.f + tm);
+  const float sp = plus >= 0.f ? rp : tp * rp, csp = plus >= 0.f ? tp * rp : rp;  // sigmoid(plus), 1-sigmoid(plus)
+  const float sm = mn >= 0.f ? rm : tm * rm, csm = mn >= 0.f ? tm * rm : rm;
+  const float delta = mn >= 0.f ? csm - csp : sp - sm;
+  float lp, dm, dls;
+  if (x < -0.999f) {            // log_cdf_plus = plus - softplus(plus) = log sigmoid(plus)
+    const float lg = FAST ? __logf(1.f + tp) : log1pf(tp);
+    lp = fminf(plus, 0.f) - lg;
+    dm = -s * csp;
+    dls = -plus * csp;
+  } else if (x > 0.999f) {      // log_one_minus_cdf_min = -softplus(min)
+    const float lg = FAST ? __logf(1.f + tm) : log1pf(tm);
+    lp = -fmaxf(mn, 0.f) - lg;
+    dm = s * sm;
+    dls = mn * sm;
+  } else if (delta > 1e-5f) {   // log(max(cdf_delta, 1e-12))
+    lp = FAST ? __logf(delta) : logf(delta);
+    const float dsp = sp * csp, dsm = sm * csm;
+    const float inv = FAST ? __fdividef(1.f, delta) : 1.f / delta;
+    dm = -s * (dsp - dsm) * inv;
+    dls = -(plus * dsp - mn * dsm) * inv;
+  } else {                      // log_pdf_mid - log(127.5)
+    const float mid = s * c;
+    const float tmid = expf(-fabsf(mid));
+    const float spm = fmaxf(mid, 0.f) + log1pf(tmid);
+    lp = mid - ls - 2.f * spm - 4.8481163645f;
+    const float sg = mid >= 0.f ? 1.f / (1.f + tmid) : tmid / (1.f + tmid);
+    const float q = 1.f - 2.f * sg;
+    dm = -s * q;
+    dls = -mid * q - 1.f;
+  }
+  g_m = -dm;
+  g_ls = -dls;
+  return -lp;
+}
+
+__global__ void dll_elementwise_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                       const float* __restrict__ ls, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a, b;
+    out[i] = dll_elem<false>(x[i], m[i], ls[i], a, b);
+  }
+}
+void dll_elementwise(const float* x, const float* m, const float* ls, float* out, long long n, cudaStream_t s) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  dll_elementwise_kernel<<<(int)blocks, 256, 0, s>>>(x, m, ls, out, n);
+}
+
+template <typename T, int LD>
+__device__ __forceinline__ void store_dout(T* p, const float* g) {  // g[6] -> LD channels (zero padded)
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < LD; ++i) p[i] = i < 6 ? g[i] : 0.f;
+  } else {
+    static_assert(LD % 8 == 0 || sizeof(T) == 4, "bf16 dout pitch must be a multiple of 8");
+    __nv_bfloat162 v[LD / 2];
+#pragma unroll
+    for (int i = 0; i < LD / 2; ++i)
+      v[i] = __floats2bfloat162_rn(2 * i < 6 ? g[2 * i] : 0.f, 2 * i + 1 < 6 ? g[2 * i + 1] : 0.f);
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < LD / 8; ++i) q[i] = reinterpret_cast<uint4*>(v)[i];
+  }
+}
+
+// One thread = two consecutive pixels of both streams (x | x_hat): 3 x 16-byte loads per tensor.
+// Writes d(loss)/d(decoder output) (scaled by grad_scale = 1/(B*world)) and per-block partial
+// sums of the two reconstruction losses.
+constexpr int kLossThreads = 256;
+template <typename T, int LD, bool FAST>
+__global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* __restrict__ inputs,
+                                                                  const float* __restrict__ dec_x,
+                                                                  const float* __restrict__ dec_xh,
+                                                                  T* __restrict__ dout_x, T* __restrict__ dout_xh,
+                                                                  long long npairs, float grad_scale,
+                                                                  float* __restrict__ partials) {
+  float sum_x = 0.f, sum_xh = 0.f;
+  for (long long pr = blockIdx.x * (long long)kLossThreads + threadIdx.x; pr < npairs;
+       pr += (long long)gridDim.x * kLossThreads) {
+    float in[12], ox[12], oh[12];
+    const float4* ip = reinterpret_cast<const float4*>(inputs + pr * 12);
+    const float4* xp = reinterpret_cast<const float4*>(dec_x + pr * 12);
+    const float4* hp = reinterpret_cast<const float4*>(dec_xh + pr * 12);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      reinterpret_cast<float4*>(in)[i] = __ldg(ip + i);
+      reinterpret_cast<float4*>(ox)[i] = __ldg(xp + i);
+      reinterpret_cast<float4*>(oh)[i] = __ldg(hp + i);
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      float gx[6], gh[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float gm_, gl_;
+        sum_x += dll_elem<FAST>(in[px * 6 + c], ox[px * 6 + c], ox[px * 6 + 3 + c], gm_, gl_);
+        gx[c] = gm_ * grad_scale; gx[3 + c] = gl_ * grad_scale;
+        sum_xh += dll_elem<FAST>(in[px * 6 + 3 + c], oh[px * 6 + c], oh[px * 6 + 3 + c], gm_, gl_);
+        gh[c] = gm_ * grad_scale; gh[3 + c] = gl_ * grad_scale;
+      }
+      store_dout<T, LD>(dout_x + (pr * 2 + px) * LD, gx);
+      store_dout<T, LD>(dout_xh + (pr * 2 + px) * LD, gh);
+    }
+  }
+  // deterministic block reduction
+  __shared__ float red[2][kLossThreads / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sum_x += __shfl_xor_sync(0xffffffffu, sum_x, o);
+    sum_xh += __shfl_xor_sync(0xffffffffu, sum_xh, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sum_x; red[1][threadIdx.x >> 5] = sum_xh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLossThreads / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+  }
+}
+
+int pixel_loss_blocks(long long npix) {
+  long long b = (npix / 2 + kLossThreads - 1) / kLossThreads;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, void* dout_x, void* dout_xh, int dout_dt,
+                int dout_ld, long long npix, float grad_scale, float* partials, bool fast_math, cudaStream_t s) {
+  const int blocks = pixel_loss_blocks(npix);
+  const long long npairs = npix / 2;
+#define LAUNCH(T, LD, F) pixel_loss_kernel<T, LD, F><<<blocks, kLossThreads, 0, s>>>(inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials)
+  if (dout_dt == DT_F32) {
+    if (fast_math) LAUNCH(float, 6, true); else LAUNCH(float, 6, false);
+  } else if (dout_ld == 8) {
+    if (fast_math) LAUNCH(bf16, 8, true); else LAUNCH(bf16, 8, false);
+  } else {
+    if (fast_math) LAUNCH(bf16, 16, true); else LAUNCH(bf16, 16, false);
+  }
+#undef LAUNCH
+}
+
+// KL scalars (vae/trainer.py:11-18, 130-132, 157-161) + fixed-order reduction of the pixel partials.
+__global__ void __launch_bounds__(1024) loss_scalars_kernel(LatentBufs L, const float* __restrict__ y_logits, int B, int K,
+                                                            int gm, float beta, float alpha,
+                                                            const float* __restrict__ partials, int nblocks,
+                                                            float* __restrict__ scalars) {
+  __shared__ double red[5][32];
+  double acc[5] = {0, 0, 0, 0, 0};  // kl_x, kl_x_hat, y_kl, recon_x, recon_x_hat
+  for (int idx = threadIdx.x; idx < B * 128; idx += blockDim.x) {
+    const int b = idx >> 7, d = idx & 127;
+    const float mg = L.zm_g[idx], sg = L.zs_g[idx], ml = L.zm_l[idx], sl = L.zs_l[idx];
+    if (gm) {
+      const float pm = L.yheads[b * 768 + 512 + d], ps = L.yheads[b * 768 + 640 + d];
+      acc[0] += logf(ps) - logf(sg) + (sg * sg + (mg - pm) * (mg - pm)) / (2.f * ps * ps) - 0.5f;
+      acc[1] += -logf(sl) + (sl * sl + ml * ml) * 0.5f - 0.5f;
+    } else {
+      acc[0] += -0.5f * (1.f + logf(sg * sg) - mg * mg - sg * sg);
+      acc[1] += -0.5f * (1.f + logf(sl * sl) - ml * ml - sl * sl);
+    }
+  }
+  if (gm) {
+    for (int row = threadIdx.x; row < B; row += blockDim.x) {
+      float mx = -INFINITY;
+      for (int k = 0; k < K; ++k) mx = fmaxf(mx, y_logits[row * 32 + k]);
+      float sum = 0.f;
+      for (int k = 0; k < K; ++k) sum += expf(y_logits[row * 32 + k] - mx);
+      float t = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float py = expf(y_logits[row * 32 + k] - mx) / sum;
+        t += py * (logf(py + 1e-8f) - logf(1.0f / (float)K));
+      }
+      acc[2] += t;
+    }
+  }
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { acc[3] += partials[2 * i]; acc[4] += partials[2 * i + 1]; }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[5];
+    for (int q = 0; q < 5; ++q) {
+      double v = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[q][i];
+      t[q] = v / B;
+    }
+    const double klsum = beta * (t[0] + t[1]);
+    scalars[0] = (float)t[3];
+    scalars[1] = (float)t[4];
+    scalars[2] = (float)t[0];
+    scalars[3] = (float)t[1];
+    scalars[4] = gm ? (float)t[2] : (float)klsum;
+    scalars[5] = (float)(t[3] + t[4] + klsum + (gm ? alpha * t[2] : 0.0));
+    scalars[6] = 0.f;
+    scalars[7] = 0.f;
+  }
+}
+
+void loss_scalars(const LatentBufs& L, const float* y_logits, int B, int K, int gm, float beta, float alpha,
+                  const float* partials, int nblocks, float* scalars, cudaStream_t s) {
+  loss_scalars_kernel<<<1, 1024, 0, s>>>(L, y_logits, B, K, gm, beta, alpha, partials, nblocks, scalars);
+}
+
+// ------------------------------------------------------------------ Keras Adam (ResourceApplyAdam)
+__global__ void adam_prepare_kernel(AdamState* st, float lr, int staircase) {
+  const unsigned long long it = st->iterations;
+  const double t = (double)(it + 1);
+  double lr_t = (double)lr;
+  if (staircase) lr_t *= pow(0.4, floor((double)it / 1000000.0));  // ExponentialDecay(lr,1e6,0.4,staircase) main.py:67
+  st->alpha = (float)(lr_t * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+  st->iterations = it + 1;
+}
+void adam_prepare(AdamState* st, float lr, int staircase, cudaStream_t s) { adam_prepare_kernel<<<1, 1, 0, s>>>(st, lr, staircase); }
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float alpha) {
+  // exact op order of TF's ApplyAdam functor; explicit roundings forbid FMA contraction so the
+  // result is bit-identical to the fp32 numpy oracle.
+  const float omb1 = __fsub_rn(1.0f, 0.9f), omb2 = __fsub_rn(1.0f, 0.999f);
+  m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+  v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), 1e-7f)));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, const AdamState* __restrict__ st,
+                                                   float alpha_host) {
+  const float alpha = st ? st->alpha : alpha_host;
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    adam_one(pp.x, gg.x, mm.x, vv.x, alpha);
+    adam_one(pp.y, gg.y, mm.y, vv.y, alpha);
+    adam_one(pp.z, gg.z, mm.z, vv.z, alpha);
+    adam_one(pp.w, gg.w, mm.w, vv.w, alpha);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) adam_one(p[i], g[i], m[i], v[i], alpha);
+}
+
+void adam_apply(float* p, const float* g, float* m, float* v, long long n, const AdamState* st, float alpha_host,
+                cudaStream_t s) {
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, n, st, alpha_host);
+}
+
+// ------------------------------------------------------------------ scramble staging
+__global__ void stage_scramble_kernel(const uint8_t* __restrict__ u8, const int32_t* __restrict__ perm,
+                                      float* __restrict__ inputs, int B, int H, int W, int p) {
+  const long long total = (long long)B * H * W;
+  const int G = W / p, npatch = (H / p) * G;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W), y = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
+    const int q = perm[(long long)b * npatch + (y / p) * G + (x / p)];
+    const int sy = (q / G) * p + y % p, sx = (q % G) * p + x % p;  // augmentation.py:47-54
+    const uint8_t* a = u8 + idx * 3;
+    const uint8_t* h = u8 + (((long long)b * H + sy) * W + sx) * 3;
+    float* o = inputs + idx * 6;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = (float)((double)a[c] / 255.0 * 2.0 - 1.0);      // vae/data.py:52: float64 math, then astype(float32)
+      o[3 + c] = (float)((double)h[c] / 255.0 * 2.0 - 1.0);
+    }
+  }
+}
+void stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int H, int W, int p, cudaStream_t s) {
+  const long long total = (long long)B * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_scramble_kernel<<<(int)blocks, 256, 0, s>>>(u8, perm, inputs, B, H, W, p);
+}
+
+}  // namespace sv

@@ -1,0 +1,76 @@
+// Host-callable launchers of every kernel in libsplitvae (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sv {
+
+// ---- ref_kernels.cu --------------------------------------------------------------------------
+void ref_conv_fwd(const ConvGeom& g, const void* in, int in_dt, const float* params, void* out, int out_dt,
+                  bool round_w, cudaStream_t s);
+void ref_conv_dgrad(const ConvGeom& g, const void* dout, int dt, const float* params, void* din,
+                    const void* mask_src, int mask_dt, int mask_act, bool round_w, cudaStream_t s);
+void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads,
+                    cudaStream_t s);
+int colsum_chunks(long long rows);
+void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, float* grads, cudaStream_t s);
+void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s);
+void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
+                    int C, cudaStream_t s);
+
+// ---- fused_kernels.cu -------------------------------------------------------------------------
+struct LatentBufs {
+  // forward
+  const float* heads_g;   // [B,256] (z_mean | z_sig) of encoder_x
+  const float* heads_l;   // [B,256] of encoder_x_hat
+  float* eps_g;           // [B,128] saved noise
+  float* eps_l;
+  float* z_g;             // [B,128] fp32 outputs
+  float* z_l;
+  float* zm_g; float* zs_g; float* zm_l; float* zs_l;   // contiguous copies for the output tuple
+  void* zcat;             // [B,256] activation dtype: decoder_x input (z_g | z_l)
+  // backward
+  const void* dzcat;      // [B,256] activation dtype: dgrad of decoder_x.d1
+  const void* dzl2;       // [B,128] activation dtype: dgrad of decoder_x_hat.d1
+  void* dheads_g;         // [B,256] activation dtype, gradient w.r.t. pre-activation heads
+  void* dheads_l;
+  // gm prior (NULL for lgvae)
+  const float* yheads;    // [B,768] (h_top | z_prior_mean | z_prior_sig), fp32
+};
+
+void reparam(const LatentBufs& L, int B, int act_dt, const float* user_eps_g, const float* user_eps_l,
+             unsigned long long seed, const unsigned long long* counter_dev, cudaStream_t s);
+void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s);
+
+void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, int act_dt, int B,
+                int K, float tau, unsigned long long seed, const unsigned long long* counter_dev, cudaStream_t s);
+// h = e1out + h_top  (vae/model.py:130)
+void gm_add(const void* yb0e1_out, const float* yheads, void* hsum, int act_dt, int B, cudaStream_t s);
+// glue A: gradients entering the (y_block.0|e1) and (h_top|z_prior_mean|z_prior_sig) fused layers
+void gm_glue_a(const void* dhsum, const void* yb0e1_out, const float* yheads, const float* zm_g, const float* zs_g,
+               void* d_yb0e1, void* d_yheads, int act_dt, int B, float beta, float inv_batch, cudaStream_t s);
+// glue B: gumbel-softmax backward + categorical-KL gradient -> d y_logits
+void gm_glue_b(const void* dy, const float* y, const float* logits, void* dlogits, int act_dt, int B, int K, float tau,
+               float alpha, float inv_batch, cudaStream_t s);
+
+// fused reconstruction likelihood fwd+bwd for both decoders; partial sums -> loss_partials[2*nblocks]
+int pixel_loss_blocks(long long npix);
+void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, void* dout_x, void* dout_xh, int dout_dt,
+                int dout_ld, long long npix, float grad_scale, float* loss_partials, bool fast_math, cudaStream_t s);
+// KL scalars + final reduction of the pixel partials -> scalars[8]
+void loss_scalars(const LatentBufs& L, const float* y_logits, int B, int K, int gm, float beta, float alpha,
+                  const float* loss_partials, int nblocks, float* scalars, cudaStream_t s);
+
+void dll_elementwise(const float* x, const float* m, const float* ls, float* out, long long n, cudaStream_t s);
+
+// Keras Adam.  state_dev: {iterations (u64), alpha (f32)}; adam_prepare advances it on the device.
+struct AdamState { unsigned long long iterations; float alpha; float pad; };
+void adam_prepare(AdamState* st, float lr, int staircase, cudaStream_t s);
+void adam_apply(float* p, const float* g, float* m, float* v, long long n, const AdamState* st, float alpha_host,
+                cudaStream_t s);
+
+void stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int H, int W, int p, cudaStream_t s);
+
+}  // namespace sv

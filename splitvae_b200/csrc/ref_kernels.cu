@@ -1,0 +1,297 @@
+// Reference (SIMT, fp32-accumulate) kernels: Conv2D/Dense forward, dgrad, wgrad, bias gradient,
+// bilinear 2x resize and its adjoint.  They define the arithmetic of every layer on the device
+// and are the production path for SV_PRECISION_FP32_REF and for the layers the tcgen05 path does
+// not cover yet; the tensor-core kernels in tc_kernels.cu are checked against them.
+//
+// Reference semantics: Keras Conv2D(padding='same') / Dense (vae/model.py:36-42,49-76,152-156),
+// tf.image.resize bilinear half-pixel (vae/model.py:163-167), tape.gradient (vae/trainer.py:137).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sv {
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) ref_conv_fwd_kernel(ConvGeom g, const TI* __restrict__ in,
+                                                           const float* __restrict__ params,
+                                                           TO* __restrict__ out, int round_w) {
+  const long long total = (long long)g.B * g.Ho * g.Wo * g.Co;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % g.Co);
+    long long pix = idx / g.Co;
+    const int wo = (int)(pix % g.Wo);
+    const int ho = (int)((pix / g.Wo) % g.Ho);
+    const int n = (int)(pix / ((long long)g.Wo * g.Ho));
+    int lc;
+    const int j = part_of(g, co, lc);
+    const float* w = params + g.part_w[j] + lc;
+    const int ldw = g.part_n[j];
+    float acc = 0.f;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int y = ho * g.stride + kh - g.pt;
+      if (y < 0 || y >= g.Hi) continue;
+      for (int kw = 0; kw < g.kw; ++kw) {
+        const int x = wo * g.stride + kw - g.pl;
+        if (x < 0 || x >= g.Wi) continue;
+        const TI* ip = in + (((long long)n * g.Hi + y) * g.Wi + x) * g.in_ld + g.in_coff;
+        const float* wp = w + (long long)((kh * g.kw + kw) * g.Ci) * ldw;
+        for (int ci = 0; ci < g.Ci; ++ci) {
+          float wv = wp[(long long)ci * ldw];
+          if (round_w) wv = round_bf16(wv);
+          acc = fmaf(to_f32(ip[ci]), wv, acc);
+        }
+      }
+    }
+    acc += params[g.part_b[j] + lc];
+    out[pix * g.out_ld + co] = from_f32<TO>(apply_act(acc, g.part_act[j]));
+  }
+}
+
+// dX[n,h,w,ci] = sum_{kh,kw,co} dY[n,(h+pt-kh)/s,(w+pl-kw)/s,co] * W[kh,kw,ci,co], then multiplied by
+// the derivative of the activation that produced X (taken from X itself).
+template <typename T, typename TM>
+__global__ void __launch_bounds__(256) ref_conv_dgrad_kernel(ConvGeom g, const T* __restrict__ dout,
+                                                             const float* __restrict__ params,
+                                                             T* __restrict__ din, const TM* __restrict__ mask_src,
+                                                             int mask_act, int round_w) {
+  const long long total = (long long)g.B * g.Hi * g.Wi * g.Ci;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % g.Ci);
+    long long pix = idx / g.Ci;
+    const int x = (int)(pix % g.Wi);
+    const int y = (int)((pix / g.Wi) % g.Hi);
+    const int n = (int)(pix / ((long long)g.Wi * g.Hi));
+    float acc = 0.f;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int ty = y + g.pt - kh;
+      if (ty < 0 || ty % g.stride) continue;
+      const int ho = ty / g.stride;
+      if (ho >= g.Ho) continue;
+      for (int kw = 0; kw < g.kw; ++kw) {
+        const int tx = x + g.pl - kw;
+        if (tx < 0 || tx % g.stride) continue;
+        const int wo = tx / g.stride;
+        if (wo >= g.Wo) continue;
+        const T* dp = dout + (((long long)n * g.Ho + ho) * g.Wo + wo) * g.dout_ld;
+        int co = 0;
+        for (int j = 0; j < g.nparts; ++j) {
+          const int ldw = g.part_n[j];
+          const float* wp = params + g.part_w[j] + ((long long)(kh * g.kw + kw) * g.Ci + ci) * ldw;
+          for (int lc = 0; lc < ldw; ++lc, ++co) {
+            float wv = wp[lc];
+            if (round_w) wv = round_bf16(wv);
+            acc = fmaf(to_f32(dp[co]), wv, acc);
+          }
+        }
+      }
+    }
+    if (mask_act != ACT_NONE)
+      acc *= act_grad_from_out(to_f32(mask_src[pix * g.in_ld + g.in_coff + ci]), mask_act);
+    din[pix * g.din_ld + ci] = from_f32<T>(acc);
+  }
+}
+
+// dW[kh,kw,ci,co] = sum_{n,ho,wo} X[n,s*ho+kh-pt,s*wo+kw-pl,ci] * dY[n,ho,wo,co]; one thread per
+// weight, fixed summation order (deterministic).
+template <typename TI, typename TD>
+__global__ void __launch_bounds__(256) ref_conv_wgrad_kernel(ConvGeom g, const TI* __restrict__ in,
+                                                             const TD* __restrict__ dout,
+                                                             float* __restrict__ grads) {
+  const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % g.Co);
+    const int ci = (int)((idx / g.Co) % g.Ci);
+    const int tap = (int)(idx / ((long long)g.Co * g.Ci));
+    const int kh = tap / g.kw, kw = tap % g.kw;
+    float acc = 0.f;
+    for (int n = 0; n < g.B; ++n)
+      for (int ho = 0; ho < g.Ho; ++ho) {
+        const int y = ho * g.stride + kh - g.pt;
+        if (y < 0 || y >= g.Hi) continue;
+        for (int wo = 0; wo < g.Wo; ++wo) {
+          const int x = wo * g.stride + kw - g.pl;
+          if (x < 0 || x >= g.Wi) continue;
+          const float a = to_f32(in[(((long long)n * g.Hi + y) * g.Wi + x) * g.in_ld + g.in_coff + ci]);
+          const float d = to_f32(dout[(((long long)n * g.Ho + ho) * g.Wo + wo) * g.dout_ld + co]);
+          acc = fmaf(a, d, acc);
+        }
+      }
+    int lc;
+    const int j = part_of(g, co, lc);
+    grads[g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc] = acc;
+  }
+}
+
+// Column sums of dY [rows, C] (pitch ld) -> bias gradients.  Two deterministic stages:
+// partial[chunk][c] over row chunks, then a fixed-order sum over chunks.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ d, long long rows, int C, int ld,
+                                                             int rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f32(d[r * ld + c]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    partial[(long long)blockIdx.y * C + c] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(ConvGeom g, const float* __restrict__ partial, int nchunks,
+                                    float* __restrict__ grads) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.Co) return;
+  float s = 0.f;
+  for (int k = 0; k < nchunks; ++k) s += partial[(long long)k * g.Co + c];
+  int lc;
+  const int j = part_of(g, c, lc);
+  grads[g.part_b[j] + lc] = s;
+}
+
+// tf.image.resize(x, [2H, 2W]) (bilinear, half-pixel centres):
+//   out[2i] = .25*in[max(i-1,0)] + .75*in[i];  out[2i+1] = .75*in[i] + .25*in[min(i+1,n-1)]
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                             int B, int H, int W, int C) {
+  const long long total = (long long)B * 2 * H * 2 * W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long p = idx / C;
+    const int ox = (int)(p % (2 * W));
+    const int oy = (int)((p / (2 * W)) % (2 * H));
+    const int n = (int)(p / ((long long)4 * W * H));
+    const int iy = oy >> 1, ix = ox >> 1;
+    const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, H - 1) : iy;
+    const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, W - 1) : ix;
+    const float ly = (oy & 1) ? 0.25f : 0.75f;  // weight of y1
+    const float lx = (ox & 1) ? 0.25f : 0.75f;  // weight of x1
+    const T* b = in + (long long)n * H * W * C + c;
+    const float tl = to_f32(b[((long long)y0 * W + x0) * C]), tr = to_f32(b[((long long)y0 * W + x1) * C]);
+    const float bl = to_f32(b[((long long)y1 * W + x0) * C]), br = to_f32(b[((long long)y1 * W + x1) * C]);
+    const float top = tl + (tr - tl) * lx;
+    const float bot = bl + (br - bl) * lx;
+    out[idx] = from_f32<T>(top + (bot - top) * ly);
+  }
+}
+
+// Adjoint of the above as a gather (deterministic), fused with the activation derivative of the
+// layer that produced the low-resolution tensor.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din,
+                                                             const T* __restrict__ mask_src, int mask_act,
+                                                             int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long p = idx / C;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int n = (int)(p / ((long long)W * H));
+    // 1-D adjoint taps: rows {2y-1 (or 0 at the edge), 2y, 2y+1, 2y+2 (or 2H-1 at the edge)}, weights .25,.75,.75,.25
+    int ry[4] = {y > 0 ? 2 * y - 1 : 0, 2 * y, 2 * y + 1, y < H - 1 ? 2 * y + 2 : 2 * H - 1};
+    int rx[4] = {x > 0 ? 2 * x - 1 : 0, 2 * x, 2 * x + 1, x < W - 1 ? 2 * x + 2 : 2 * W - 1};
+    const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    const T* b = dout + (long long)n * 4 * H * W * C + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float row = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) row += wt[q] * to_f32(b[((long long)ry[a] * 2 * W + rx[q]) * C]);
+      acc += wt[a] * row;
+    }
+    if (mask_act != ACT_NONE) acc *= act_grad_from_out(to_f32(mask_src[idx]), mask_act);
+    din[idx] = from_f32<T>(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long b = (total + block - 1) / block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define SV_DISPATCH2(dtA, dtB, CALL)                                   \
+  do {                                                                 \
+    if ((dtA) == DT_F32 && (dtB) == DT_F32) { CALL(float, float); }    \
+    else if ((dtA) == DT_F32 && (dtB) == DT_BF16) { CALL(float, bf16); } \
+    else if ((dtA) == DT_BF16 && (dtB) == DT_F32) { CALL(bf16, float); } \
+    else { CALL(bf16, bf16); }                                         \
+  } while (0)
+
+void ref_conv_fwd(const ConvGeom& g, const void* in, int in_dt, const float* params, void* out, int out_dt,
+                  bool round_w, cudaStream_t s) {
+  const long long total = (long long)g.B * g.Ho * g.Wo * g.Co;
+#define CALL(TI, TO) ref_conv_fwd_kernel<TI, TO><<<grid_for(total), 256, 0, s>>>(g, (const TI*)in, params, (TO*)out, round_w)
+  SV_DISPATCH2(in_dt, out_dt, CALL);
+#undef CALL
+}
+
+void ref_conv_dgrad(const ConvGeom& g, const void* dout, int dt, const float* params, void* din,
+                    const void* mask_src, int mask_dt, int mask_act, bool round_w, cudaStream_t s) {
+  const long long total = (long long)g.B * g.Hi * g.Wi * g.Ci;
+  if (mask_act == ACT_NONE) { mask_src = din; mask_dt = dt; }
+#define CALL(T, TM) ref_conv_dgrad_kernel<T, TM><<<grid_for(total), 256, 0, s>>>(g, (const T*)dout, params, (T*)din, (const TM*)mask_src, mask_act, round_w)
+  SV_DISPATCH2(dt, mask_dt, CALL);
+#undef CALL
+}
+
+void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads,
+                    cudaStream_t s) {
+  const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+#define CALL(TI, TD) ref_conv_wgrad_kernel<TI, TD><<<grid_for(total, 256, 1 << 20), 256, 0, s>>>(g, (const TI*)in, (const TD*)dout, grads)
+  SV_DISPATCH2(in_dt, dout_dt, CALL);
+#undef CALL
+}
+
+int colsum_chunks(long long rows) {
+  long long c = (rows + 511) / 512;
+  if (c > 256) c = 256;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, float* grads, cudaStream_t s) {
+  const long long rows = (long long)g.B * g.Ho * g.Wo;
+  const int nch = colsum_chunks(rows);
+  const int rpc = (int)((rows + nch - 1) / nch);
+  dim3 grid((g.Co + 31) / 32, nch), block(32, 8);
+  if (dt == DT_F32)
+    colsum_partial_kernel<float><<<grid, block, 0, s>>>((const float*)dout, rows, g.Co, g.dout_ld, rpc, partial_ws);
+  else
+    colsum_partial_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dout, rows, g.Co, g.dout_ld, rpc, partial_ws);
+  colsum_final_kernel<<<(g.Co + 127) / 128, 128, 0, s>>>(g, partial_ws, nch, grads);
+}
+
+void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s) {
+  const long long total = (long long)B * 4 * H * W * C;
+  if (dt == DT_F32)
+    upsample2x_fwd_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)in, (float*)out, B, H, W, C);
+  else
+    upsample2x_fwd_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C);
+}
+
+void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
+                    int C, cudaStream_t s) {
+  const long long total = (long long)B * H * W * C;
+  if (dt == DT_F32)
+    upsample2x_bwd_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)dout, (float*)din, (const float*)mask_src, mask_act, B, H, W, C);
+  else
+    upsample2x_bwd_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C);
+}
+
+}  // namespace sv

@@ -1,0 +1,46 @@
+"""Synthetic stand-ins for vae/data.py:get_dataset (the real SVHN / CelebA readers need the network
+and the datasets).  Shapes and value grid follow the reference:
+uint8 pixels mapped k/255*2-1 (vae/data.py:52); `svhn*` -> 32x32x3, `celeba64` -> 64x64x3."""
+from __future__ import annotations
+
+import torch
+
+IMAGE_SIZE = {"svhn": 32, "svhn_no_extra": 32, "celeba64": 64, "celeba128": 128}
+
+
+def image_shape(dataset):
+    if dataset not in IMAGE_SIZE:
+        raise NotImplementedError(dataset)  # vae/data.py:21
+    s = IMAGE_SIZE[dataset]
+    return [-1, s, s, 3]
+
+
+class SyntheticBatches:
+    """Infinite iterator of scrambled batches [B,H,W,6] built on the device from pinned uint8 host
+    images: the host->device copy and the scramble kernel are what an input pipeline must do per step."""
+
+    def __init__(self, dataset, batch_size, augmentor, seed=0, pool=8, device="cuda"):
+        self.shape = image_shape(dataset)
+        self.B, self.S = int(batch_size), self.shape[1]
+        self.aug = augmentor
+        g = torch.Generator().manual_seed(seed)
+        self.pool = [torch.randint(0, 256, (self.B, self.S, self.S, 3), dtype=torch.uint8, generator=g).pin_memory()
+                     for _ in range(pool)]
+        self.device = device
+        self.i = 0
+        self.u8 = torch.empty(self.B, self.S, self.S, 3, dtype=torch.uint8, device=device)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self.u8.copy_(self.pool[self.i % len(self.pool)], non_blocking=True)
+        self.i += 1
+        return self.aug.scramble(self.u8)
+
+
+def get_dataset(dataset, get_label=False, batch_size=64, augmentor=None, seed=0):
+    """Same return contract as vae/data.py:11-21: (train_dataset, test_dataset, image_shape)."""
+    shp = image_shape(dataset)
+    train = SyntheticBatches(dataset, batch_size, augmentor, seed=seed)
+    return train, None, shp

@@ -1,0 +1,73 @@
+"""CLI with the flags of vae/main.py:16-31 (names and defaults verbatim).  New flags have new names.
+
+    python -m splitvae_b200.main --model lgvae --beta 120 --patch_size 8 --dataset celeba64 -no_label
+"""
+from __future__ import annotations
+
+import argparse
+
+from .utils import dotdict
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('-viz', action='store_true')  # accepted; visualisation is out of scope
+    parser.add_argument('--global_latent_dims', type=int, nargs='?', default=128)
+    parser.add_argument('--local_latent_dims', type=int, nargs='?', default=128)
+    parser.add_argument('--learning_rate', type=float, nargs='?', default=1e-4)
+    parser.add_argument('--beta', type=float, nargs='?', default=40)
+    parser.add_argument('--dataset', type=str, nargs='?', default='svhn')
+    parser.add_argument('--training_steps', type=int, nargs='?', default=1000000)
+    parser.add_argument('--batch_size', type=int, nargs='?', default=64)
+    parser.add_argument('--patch_size', type=int, nargs='?', default=1)
+    parser.add_argument('--augmentation', type=str, nargs='?', default='scramble')
+    parser.add_argument('-no_label', action='store_true')
+    parser.add_argument('--model', type=str, nargs='?', default='lgvae')
+    parser.add_argument('--y_size', type=int, nargs='?', default=30)
+    parser.add_argument('--tau', type=float, nargs='?', default=0.4)
+    parser.add_argument('--alpha', type=float, nargs='?', default=40)
+    parser.add_argument('-allow_growth', action='store_true')  # TF session option; no effect here
+    # new in this build
+    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument('--report_every', type=int, default=10000)
+    parser.add_argument('--seed', type=int, default=0)
+    parser.add_argument('--no_graph', action='store_true')
+    return parser
+
+
+def make_config(argv=None):
+    args = build_parser().parse_args(argv)
+    config = dotdict(vars(args))
+    config.label = not config.no_label           # vae/main.py:49
+    config.use_graph = not config.no_graph
+    return config
+
+
+def main(argv=None):
+    config = make_config(argv)
+    print('Config:', config)
+    from . import data, trainer
+    from .augmentation import Augmentator
+    from .model import LGGMVae, LGVae
+    augmentor = Augmentator(type=config.augmentation, size=config.patch_size)
+    train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=False,
+                                                                batch_size=config.batch_size, augmentor=augmentor,
+                                                                seed=config.seed)
+    config.label = False  # synthetic data carries no labels
+    if config.model == 'lgvae':
+        model = LGVae(global_latent_dims=config.global_latent_dims, local_latent_dims=config.local_latent_dims,
+                      image_shape=input_shape, precision=config.precision)
+        optimizer = trainer.Adam(learning_rate=config.learning_rate)
+    elif config.model == 'lggmvae':
+        lr_schedule = trainer.ExponentialDecay(config.learning_rate, decay_steps=1000000, decay_rate=0.4, staircase=True)
+        optimizer = trainer.Adam(learning_rate=lr_schedule)
+        model = LGGMVae(global_latent_dims=config.global_latent_dims, local_latent_dims=config.local_latent_dims,
+                        image_shape=input_shape, y_size=config.y_size, tau=config.tau, precision=config.precision)
+    else:
+        raise NotImplementedError("--model %s is outside the hot path of this build (lgvae | lggmvae)" % config.model)
+    print('Training local-global autoencoder')
+    return trainer.train_local_global_autoencoder(model, optimizer, config.dataset, train_dataset, test_dataset, config=config)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,71 @@
+"""Data-parallel plumbing (new in this build; the reference is single-device).
+
+The train step shards by batch only (every loss term is a batch mean of per-image sums,
+vae/trainer.py:13,18,127-128,161): each rank runs the step on its contiguous shard with gradients
+pre-scaled by 1/(per_gpu_batch * world_size), and the only exchange is a SUM all-reduce of the
+flat fp32 gradient arena, issued per backward segment so it overlaps the remaining backward
+work.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) carries the collective.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialises torch.distributed from torchrun's environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def shard_range(global_batch: int, world: int, rank: int):
+    """Contiguous shard [start, stop) of the global batch owned by `rank` (equal shards required)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class BucketReducer:
+    """SUM all-reduce of contiguous ranges ("buckets") of one flat tensor, asynchronously."""
+
+    def __init__(self, flat: torch.Tensor, segments, group=None):
+        self.flat = flat
+        self.segments = [(int(o), int(c)) for o, c in segments]
+        self.group = group
+        self._work = []
+        self.enabled = dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def reduce(self, seg: int):
+        if not self.enabled:
+            return
+        off, cnt = self.segments[seg]
+        self._work.append(dist.all_reduce(self.flat[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait_all(self):
+        for w in self._work:
+            w.wait()
+        self._work = []
+
+
+def mean_scalars(values: torch.Tensor, group=None) -> torch.Tensor:
+    """Average of per-rank loss scalars = the scalar of the global batch (equal shards)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        values = values.clone()
+        dist.all_reduce(values, op=dist.ReduceOp.SUM, group=group)
+        values /= dist.get_world_size(group)
+    return values

@@ -1,0 +1,80 @@
+"""GPU parity of the stand-alone operators exported by the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import splitvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def test_discretised_logistic_loss_all_branches():
+    from splitvae_b200 import trainer
+    rng = np.random.default_rng(0)
+    n = 1 << 16
+    k = rng.integers(0, 256, n)
+    x = (k / 255.0 * 2 - 1).astype(np.float32)
+    m = rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    ls = rng.uniform(-7, 2, n).astype(np.float32)
+    nll, _, _, branch = O.dll_fwd_bwd_numpy(x, m, ls)
+    assert set(np.unique(branch)) == {0, 1, 2, 3}
+    got = trainer.discretised_logistic_loss(torch.from_numpy(x).cuda(), torch.from_numpy(m).cuda(), torch.from_numpy(ls).cuda()).cpu().numpy()
+    ref32 = O.discretised_logistic_loss(torch.from_numpy(x), torch.from_numpy(m), torch.from_numpy(ls)).numpy()
+    # against float64 truth, wherever fp32 itself resolves the value (branch decisions at the 1e-5 threshold are
+    # taken in fp32 by the reference too, so compare against the fp32 restatement as well)
+    err64 = np.abs(got - nll) / np.maximum(1.0, np.abs(nll))
+    err32 = np.abs(got - ref32) / np.maximum(1.0, np.abs(ref32))
+    assert np.quantile(err64, 0.999) < 2e-4
+    assert np.minimum(err64, err32).max() < 2e-3
+
+
+def test_pmf_normalisation_known_answer():
+    """sum over the 256 grid values of exp(-NLL) == 1 for any (m, log_scale): the likelihood is a pmf."""
+    from splitvae_b200 import trainer
+    grid = torch.tensor((np.arange(256) / 255.0 * 2 - 1).astype(np.float32)).cuda()
+    for m, ls in [(0.0, 0.0), (0.3, -1.0), (-0.9, -2.0), (0.95, 0.5), (0.1, -3.0)]:
+        nll = trainer.discretised_logistic_loss(grid, torch.full_like(grid, m), torch.full_like(grid, ls))
+        total = torch.exp(-nll.double()).sum().item()
+        assert abs(total - 1.0) < 5e-4, (m, ls, total)
+
+
+def test_adam_flat_bit_exact():
+    from splitvae_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    n = 100003
+    p = rng.standard_normal(n).astype(np.float32)
+    g = (rng.standard_normal(n) * 10 ** rng.uniform(-6, 1, n)).astype(np.float32)
+    m = (rng.standard_normal(n) * 0.01).astype(np.float32)
+    v = (rng.random(n) * 1e-3).astype(np.float32)
+    alpha = O.adam_alpha(1e-4, 7)
+    rp, rm, rv = O.keras_adam_update(p, g, m, v, alpha)
+    tp, tg, tm, tv = (torch.from_numpy(a.copy()).cuda() for a in (p, g, m, v))
+    _lib.check(lib.sv_adam_flat(C.c_void_p(tp.data_ptr()), C.c_void_p(tg.data_ptr()), C.c_void_p(tm.data_ptr()),
+                                C.c_void_p(tv.data_ptr()), n, C.c_float(float(alpha)), _stream()), None, "sv_adam_flat")
+    torch.cuda.synchronize()
+    assert np.array_equal(tm.cpu().numpy(), rm)
+    assert np.array_equal(tv.cpu().numpy(), rv)
+    assert np.array_equal(tp.cpu().numpy(), rp)
+
+
+@pytest.mark.parametrize("H,p", [(32, 1), (32, 4), (64, 8), (32, 32)])
+def test_stage_scramble_bit_exact(H, p):
+    from splitvae_b200.augmentation import Augmentator
+    B = 5
+    batch = O.synthetic_batch(B, H, p, seed_base=3)
+    aug = Augmentator("scramble", p)
+    out = aug.scramble(torch.from_numpy(batch["u8"]).cuda(), torch.from_numpy(batch["perms"]).cuda())
+    assert np.array_equal(out.cpu().numpy(), batch["inputs"])
+    # properties: x_hat is a permutation of x's pixels; p == H is the identity
+    o = out.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(np.sort(o[b, :, :, :3].reshape(-1, 3), axis=0), np.sort(o[b, :, :, 3:].reshape(-1, 3), axis=0))
+    if p == H:
+        assert np.array_equal(o[..., :3], o[..., 3:])

@@ -1,0 +1,119 @@
+"""GPU parity: libsplitvae (through the C-ABI) vs the CPU oracle on identical weights, inputs, noise.
+
+Tolerances (stated per SURVEY.md section 7 "Precision"):
+  * fp32 reference-kernel mode: scalars rel 1e-5, every gradient tensor rel-L2 2e-4 (fp32 summation order only).
+  * bf16 tensor-core mode (bf16 operands, fp32 accumulate): scalars rel 1e-3 (the north-star tolerance),
+    gradient tensors rel-L2 3e-2 (bf16 has 8 mantissa bits; activations and activation-gradients are stored in bf16).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import splitvae_oracle as O
+from helpers import compare_grads, make_case, make_engine, rel_l2, run_engine_step, to_dev
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # model, H, B, patch, beta, alpha
+    ("lgvae", 32, 4, 1, 1.0, 40.0),        # C1 shape (reduced batch)
+    ("lgvae", 64, 2, 8, 120.0, 40.0),      # C2 shape
+    ("lggmvae", 32, 4, 4, 40.0, 40.0),     # C3 shape
+    ("lggmvae", 64, 2, 8, 120.0, 40.0),    # C4 shape
+]
+
+
+def _oracle(model, params, batch, beta, alpha, dtype=torch.float32, outputs=False):
+    u = batch["u"] if model == "lggmvae" else None
+    return O.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha,
+                              dtype=dtype, want_outputs=outputs)
+
+
+@pytest.mark.parametrize("model,H,B,p,beta,alpha", CASES)
+def test_step_fp32_reference_kernels(model, H, B, p, beta, alpha):
+    params, batch = make_case(model, H, B, p)
+    e = make_engine(model, H, B, "fp32", beta, alpha)
+    e.load_params(params)
+    sc, grads = run_engine_step(e, batch, model, adam=False)
+    ref_sc, ref_g = _oracle(model, params, batch, beta, alpha, torch.float64)
+    for k, v in ref_sc.items():
+        assert abs(sc[k] - v) <= 1e-5 * max(1.0, abs(v)), (k, sc[k], v)
+    worst, bad = compare_grads(grads, ref_g, 2e-4)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("model,H,B,p,beta,alpha", CASES)
+def test_step_bf16(model, H, B, p, beta, alpha):
+    params, batch = make_case(model, H, B, p)
+    e = make_engine(model, H, B, "bf16", beta, alpha)
+    e.load_params(params)
+    sc, grads = run_engine_step(e, batch, model, adam=False)
+    ref_sc, ref_g = _oracle(model, params, batch, beta, alpha, torch.float64)
+    for k, v in ref_sc.items():
+        tol = 1e-3 * max(1.0, abs(v)) if k in ("total", "recon_x", "recon_x_hat") else 2e-2 * max(0.05, abs(v))
+        assert abs(sc[k] - v) <= tol, (k, sc[k], v)
+    worst, bad = compare_grads(grads, ref_g, 3e-2)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("model", ["lgvae", "lggmvae"])
+def test_forward_outputs_fp32(model):
+    H, B = 32, 4
+    params, batch = make_case(model, H, B, 4, seed_base=10)
+    e = make_engine(model, H, B, "fp32", 40.0)
+    e.load_params(params)
+    x = to_dev(batch["inputs"])
+    e.forward(x, to_dev(batch["eps_g"]), to_dev(batch["eps_l"]), to_dev(batch["u"]) if model == "lggmvae" else None)
+    torch.cuda.synchronize()
+    _, _, out = _oracle(model, params, batch, 40.0, 40.0, torch.float64, outputs=True)
+    dx = e.output("dec_x").cpu().numpy()
+    assert rel_l2(dx[..., :3], out["x_mean"]) < 1e-4
+    assert rel_l2(dx[..., 3:], out["x_log_scale"]) < 1e-4
+    for mine, theirs in [("z_x", "z_x"), ("z_mean_x", "z_mean_x"), ("z_sig_x", "z_sig_x"), ("z_x_hat", "z_x_hat"),
+                         ("z_mean_x_hat", "z_mean_x_hat"), ("z_sig_x_hat", "z_sig_x_hat")]:
+        assert rel_l2(e.output(mine).cpu().numpy(), out[theirs]) < 1e-4, mine
+    if model == "lggmvae":
+        for name in ("y", "y_logits", "z_prior_mean", "z_prior_sig"):
+            assert rel_l2(e.output(name).cpu().numpy(), out[name]) < 1e-4, name
+
+
+@pytest.mark.parametrize("model", ["lgvae", "lggmvae"])
+def test_multi_step_training_fp32(model):
+    """5 train steps (Keras Adam, staircase LR for the GM model): scalars and final weights track the oracle."""
+    H, B, beta = 32, 4, 10.0
+    lr = float(np.float32(1e-4))
+    params, batch = make_case(model, H, B, 4, seed_base=20)
+    e = make_engine(model, H, B, "fp32", beta, lr=lr)
+    e.load_params(params)
+    st = O.TrainState(params)
+    x, eg, el = to_dev(batch["inputs"]), to_dev(batch["eps_g"]), to_dev(batch["eps_l"])
+    u = to_dev(batch["u"]) if model == "lggmvae" else None
+    for step in range(5):
+        e.train_step(x, eg, el, u)
+        torch.cuda.synchronize()
+        sc = e.scalars()
+        ref_sc, _ = O.train_step(st, model, batch["inputs"], batch["eps_g"], batch["eps_l"], batch["u"] if model == "lggmvae" else None,
+                                 beta=beta, lr=lr)
+        assert abs(sc["total"] - ref_sc["total"]) <= 2e-4 * abs(ref_sc["total"]), (step, sc, ref_sc)
+    assert e.iterations == 5
+    mine = e.get_params()
+    # Adam normalises the step to ~lr per element: compare the parameter *displacement* from the initial weights
+    worst = 0.0
+    for k in params:
+        dm, dr = mine[k] - params[k], st.params[k] - params[k]
+        if np.linalg.norm(dr) < 1e-9:
+            continue
+        worst = max(worst, rel_l2(dm, dr))
+    assert worst < 0.05, worst
+
+
+def test_trained_like_weights_cover_all_likelihood_branches():
+    """Decoder log-scale bias -4: narrow scales make branches 3 and 4 of the likelihood fire (trainer.py:37)."""
+    model, H, B = "lgvae", 32, 4
+    params, batch = make_case(model, H, B, 4, seed_base=30, ls_bias=-4.0)
+    e = make_engine(model, H, B, "fp32", 1.0)
+    e.load_params(params)
+    sc, grads = run_engine_step(e, batch, model, adam=False)
+    ref_sc, ref_g = _oracle(model, params, batch, 1.0, 40.0, torch.float64)
+    assert abs(sc["total"] - ref_sc["total"]) <= 2e-5 * abs(ref_sc["total"])
+    worst, bad = compare_grads(grads, ref_g, 5e-4)
+    assert not bad, bad
