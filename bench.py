@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the SPLIT-VAE train step (BASELINE.json metric: train images/sec, CelebA64 shape).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|c4]
+
+One "step" = one train_step_lg_vae (vae/trainer.py:120-144): forward, fused loss fwd+bwd, backward,
+Keras Adam, captured in a CUDA graph.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, H, per-GPU batch, patch, beta, alpha, description)
+    "c1": ("lgvae", 32, 64, 1, 1.0, 40.0, "SPLIT-VAE SVHN-shape 32x32x3 --beta 1 --patch_size 1 batch 64"),
+    "c2": ("lgvae", 64, 256, 8, 120.0, 40.0, "SPLIT-VAE CelebA64-shape 64x64x3 --beta 120 --patch_size 8 -no_label batch 256/GPU"),
+    "c3": ("lggmvae", 32, 256, 4, 40.0, 40.0, "SPLIT-GMVAE SVHN-shape --beta 40 --alpha 40 --y_size 30 --patch_size 4 batch 256/GPU"),
+    "c4": ("lggmvae", 64, 256, 8, 120.0, 40.0, "SPLIT-GMVAE CelebA64-shape --beta 120 --alpha 40 --y_size 30 --patch_size 8 batch 256/GPU"),
+}
+TRAIN_GFLOP_PER_IMAGE = {"c1": 0.5623, "c2": 2.2492, "c3": 0.8011, "c4": 3.1994}
+LOSS_BYTES_PER_IMAGE = {32: 122880, 64: 491520}  # fused loss fwd+bwd, fp32 in/out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.period, self.index = period, index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(model, H, batch, patch, beta, alpha, steps, threads=None):
+    """The oracle (CPU restatement of the TF reference; TF itself is not installable) timed on the host
+    cores over a bounded sample: `steps` train steps of `batch` images of this workload's shape."""
+    import torch
+    from oracle import splitvae_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    params = O.init_params(model, H, H)
+    st = O.TrainState(params)
+    b = O.synthetic_batch(batch, H, patch)
+    u = b["u"] if model == "lggmvae" else None
+    O.train_step(st, model, b["inputs"], b["eps_g"], b["eps_l"], u, beta=beta, alpha=alpha)  # warm-up
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(st, model, b["inputs"], b["eps_g"], b["eps_l"], u, beta=beta, alpha=alpha)
+        times.append(time.perf_counter() - t0)
+    return batch * steps / sum(times), threads, times
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; TF 2.0 cannot be installed)."""
+    model, H, B, patch, beta, alpha, desc = WORKLOADS[wl]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 16 if H == 64 else 64
+    ips, threads, times = cpu_baseline(model, H, sample_batch, patch, beta, alpha, max(1, args.steps))
+    ms = 1000.0 * sum(times) / len(times)
+    line = {"impl": "reference", "metric": "train images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "per_step_sample": f"{sample_batch} images of the same shape per CPU step"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} oracle train steps of {sample_batch} images ({H}x{H}x3), torch CPU fp32"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from splitvae_b200.augmentation import Augmentator
+    from splitvae_b200.engine import Engine
+    from splitvae_b200.parallel import init_from_env
+    from splitvae_b200.trainer import StepRunner
+
+    model, H, B, patch, beta, alpha, desc = WORKLOADS[wl]
+    rank, world, local_rank = init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    K, Wm = args.steps, max(3, args.warmup)
+
+    e = Engine(model=model, height=H, width=H, batch=B, beta=beta, alpha=alpha, learning_rate=1e-4, world_size=world,
+               precision=args.precision, rng_stream=rank)
+    e.init_params(seed=5)  # same seed on every rank: replicated weights
+    runner = StepRunner(e, use_graph=not args.no_graph)
+    aug = Augmentator("scramble", patch)
+
+    # synthetic data: a pool of pinned uint8 batches (distinct per rank) + per-image patch permutations
+    g = torch.Generator().manual_seed(1000 + rank)
+    pool = 4
+    host_u8 = [torch.randint(0, 256, (B, H, H, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(pool)]
+    n_patch = (H // patch) ** 2
+    host_perm = [torch.stack([torch.randperm(n_patch, generator=g) for _ in range(B)]).to(torch.int32).pin_memory() for _ in range(pool)]
+    dev_u8 = torch.empty(B, H, H, 3, dtype=torch.uint8, device=dev)
+    dev_perm = torch.empty(B, n_patch, dtype=torch.int32, device=dev)
+    host_scalars = torch.empty(8, dtype=torch.float32).pin_memory()
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def stage(i):
+        dev_u8.copy_(host_u8[i % pool], non_blocking=True)
+        dev_perm.copy_(host_perm[i % pool], non_blocking=True)
+        aug.scramble(dev_u8, dev_perm, out=runner.inputs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- launches per step (eager, un-captured) + warm-up ------------------------------------
+    stage(0)
+    l0 = e.launch_count
+    runner._issue()
+    torch.cuda.synchronize()
+    launches_per_step = e.launch_count - l0
+    if not args.no_graph:
+        runner.capture(warmup=1)
+    for i in range(Wm):
+        runner.step()
+    barrier()
+
+    # ---- (A) device-resident throughput: K graph replays, inputs already in HBM -----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        runner.step()
+    ev1.record()
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1000.0
+
+    # ---- (B) end to end: pinned host uint8 -> H2D -> scramble -> step -> D2H scalars, every step ---
+    for i in range(2):
+        stage(i); runner.step(); host_scalars.copy_(e.output("scalars"), non_blocking=True)
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for i in range(K):
+        stage(i)
+        runner.step()
+        host_scalars.copy_(e.output("scalars"), non_blocking=True)
+    ev3.record()
+    barrier()
+    t_e2e = ev2.elapsed_time(ev3) / 1000.0
+    clocks = sampler.stop()
+    final_total = float(host_scalars[5])
+
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = t.tolist()
+
+    # ---- roofline of the dominant kernel class, timed alone with an L2 flush between launches ------
+    peaks = measured_peaks()
+    roof = None
+    if rank == 0:
+        reps = 10
+        times = []
+        for i in range(reps):
+            l2_flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            e.loss_fwd_bwd(runner.inputs)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b) / 1000.0)
+        t_loss = sorted(times)[len(times) // 2]
+        loss_bytes = B * LOSS_BYTES_PER_IMAGE[H]
+        ach = loss_bytes / t_loss / 1e9
+        roof = {"kernel": "pixel_loss_kernel (fused likelihood fwd+bwd, both decoders)", "bound": "hbm", "achieved": ach,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": loss_bytes, "us_per_launch": t_loss * 1e6}
+        step_flops = B * TRAIN_GFLOP_PER_IMAGE[wl] * 1e9
+        roof["step_tensor"] = {"achieved_tflops": step_flops / (t_dev / K) / 1e12, "peak_tflops": peaks["tensor_sustained"],
+                               "frac": step_flops / (t_dev / K) / 1e12 / peaks["tensor_sustained"],
+                               "note": "whole train step, algorithmic FLOPs (BASELINE.md section 3) / step time, vs sustained bf16 peak"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            sb = 16 if H == 64 else 64
+            ips, threads, times = cpu_baseline(model, H, sb, patch, beta, alpha, 2)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"2 oracle train steps of {sb} images ({H}x{H}x3) after 1 warm-up, torch CPU fp32 (TF 2.0 not installable)"}
+        total_images = world * B * K
+        line = {
+            "metric": "train images/sec", "value": total_images / t_dev, "unit": "images/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": 1000.0 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": desc, "model": model, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "cuda_graph": not args.no_graph, "l2": "per-step working set (activations + weights + Adam state) exceeds the 126 MB L2; no flush between steps",
+                       "noise": "in-kernel Philox"},
+            "e2e": {"value": total_images / t_e2e, "unit": "images/s", "h2d_bytes_per_step": int(dev_u8.numel() + dev_perm.numel() * 4),
+                    "d2h_bytes_per_step": 32, "ms_per_step": 1000.0 * t_e2e / K},
+            "gpu_launches": int(launches_per_step * K),
+            "launches_per_step": int(launches_per_step),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_total_loss": final_total,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

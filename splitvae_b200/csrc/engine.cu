@@ -294,7 +294,7 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
     tc_conv_wgrad(L.tc, L.g, h->grads, s);
     h->launches += L.tc.wgrad_launches;
   } else {
-    ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, s);
+    ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, h->round_w, s);
     h->launches += 1;
   }
   bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, h->COLSUM), h->grads, s);

@@ -12,7 +12,7 @@ void ref_conv_fwd(const ConvGeom& g, const void* in, int in_dt, const float* par
                   bool round_w, cudaStream_t s);
 void ref_conv_dgrad(const ConvGeom& g, const void* dout, int dt, const float* params, void* din,
                     const void* mask_src, int mask_dt, int mask_act, bool round_w, cudaStream_t s);
-void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads,
+void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads, bool round_in,
                     cudaStream_t s);
 int colsum_chunks(long long rows);
 void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, float* grads, cudaStream_t s);

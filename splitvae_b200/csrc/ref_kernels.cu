@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(256) ref_conv_fwd_kernel(ConvGeom g, const TI*
         for (int ci = 0; ci < g.Ci; ++ci) {
           float wv = wp[(long long)ci * ldw];
           if (round_w) wv = round_bf16(wv);
-          acc = fmaf(to_f32(ip[ci]), wv, acc);
+          float iv = to_f32(ip[ci]);
+          if (round_w && sizeof(TI) == 4) iv = round_bf16(iv);  // bf16 path: the image is a bf16 operand too
+          acc = fmaf(iv, wv, acc);
         }
       }
     }
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) ref_conv_dgrad_kernel(ConvGeom g, const T
 template <typename TI, typename TD>
 __global__ void __launch_bounds__(256) ref_conv_wgrad_kernel(ConvGeom g, const TI* __restrict__ in,
                                                              const TD* __restrict__ dout,
-                                                             float* __restrict__ grads) {
+                                                             float* __restrict__ grads, int round_in) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(256) ref_conv_wgrad_kernel(ConvGeom g, const T
         for (int wo = 0; wo < g.Wo; ++wo) {
           const int x = wo * g.stride + kw - g.pl;
           if (x < 0 || x >= g.Wi) continue;
-          const float a = to_f32(in[(((long long)n * g.Hi + y) * g.Wi + x) * g.in_ld + g.in_coff + ci]);
+          float a = to_f32(in[(((long long)n * g.Hi + y) * g.Wi + x) * g.in_ld + g.in_coff + ci]);
+          if (round_in && sizeof(TI) == 4) a = round_bf16(a);
           const float d = to_f32(dout[(((long long)n * g.Ho + ho) * g.Wo + wo) * g.dout_ld + co]);
           acc = fmaf(a, d, acc);
         }
@@ -250,10 +253,10 @@ void ref_conv_dgrad(const ConvGeom& g, const void* dout, int dt, const float* pa
 #undef CALL
 }
 
-void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads,
+void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* dout, int dout_dt, float* grads, bool round_in,
                     cudaStream_t s) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
-#define CALL(TI, TD) ref_conv_wgrad_kernel<TI, TD><<<grid_for(total, 256, 1 << 20), 256, 0, s>>>(g, (const TI*)in, (const TD*)dout, grads)
+#define CALL(TI, TD) ref_conv_wgrad_kernel<TI, TD><<<grid_for(total, 256, 1 << 20), 256, 0, s>>>(g, (const TI*)in, (const TD*)dout, grads, round_in)
   SV_DISPATCH2(in_dt, dout_dt, CALL);
 #undef CALL
 }

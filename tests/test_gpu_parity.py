@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import bf16_emulation as E
 from oracle import splitvae_oracle as O
 from helpers import compare_grads, make_case, make_engine, rel_l2, run_engine_step, to_dev
 
@@ -47,11 +48,22 @@ def test_step_bf16(model, H, B, p, beta, alpha):
     e = make_engine(model, H, B, "bf16", beta, alpha)
     e.load_params(params)
     sc, grads = run_engine_step(e, batch, model, adam=False)
+    # (1) against the exact (fp64) oracle: ELBO terms within the north-star tolerance; gradients within the
+    #     statistical error of 8-bit-mantissa storage compounding through the backward chain.
     ref_sc, ref_g = _oracle(model, params, batch, beta, alpha, torch.float64)
     for k, v in ref_sc.items():
         tol = 1e-3 * max(1.0, abs(v)) if k in ("total", "recon_x", "recon_x_hat") else 2e-2 * max(0.05, abs(v))
         assert abs(sc[k] - v) <= tol, (k, sc[k], v)
-    worst, bad = compare_grads(grads, ref_g, 3e-2)
+    worst, bad = compare_grads(grads, ref_g, 0.2)
+    assert not bad, bad
+    # (2) against the oracle with the device's bf16 storage roundings modelled: only summation order and
+    #     1-ulp rounding ties remain -> every gradient tensor within rel-L2 3e-2 (worst seen 2.4e-2 at batch 2,
+    #     typically 3e-3), scalars within 1e-4.
+    u = batch["u"] if model == "lggmvae" else None
+    emu_sc, emu_g = E.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha)
+    for k, v in emu_sc.items():
+        assert abs(sc[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, sc[k], v)
+    worst, bad = compare_grads(grads, emu_g, 3e-2)
     assert not bad, bad
 
 
