@@ -168,6 +168,23 @@ sv_status sv_adam_flat(float* p_dev, const float* g_dev, float* m_dev, float* v_
 sv_status sv_stage_scramble(const uint8_t* u8_dev, const int32_t* perm_dev, float* inputs_dev,
                             int32_t batch, int32_t height, int32_t width, int32_t patch, void* stream);
 
+/* ---- test hooks: run ONE layer of the plan with the reference (SIMT) or the tensor-core kernel on the
+ * handle's own buffers, so the parity tests can check each tcgen05 kernel against its reference. --------- */
+typedef struct sv_layer_info {
+  char name[64];
+  int32_t kh, kw, stride, Hi, Wi, Ci, Ho, Wo, Co;
+  int32_t in_ld, in_coff, out_ld, dout_ld, din_ld;
+  int32_t in_dt, out_dt, act_dt;          /* 0 = fp32, 1 = bf16 */
+  int32_t has_dgrad, tc_fwd, tc_dgrad, tc_wgrad;
+  void *in, *out, *dout, *din;            /* device pointers; in == NULL: the layer reads the caller's inputs */
+  int64_t in_elems, out_elems, dout_elems, din_elems;
+} sv_layer_info;
+enum { SV_PASS_FWD = 0, SV_PASS_DGRAD = 1, SV_PASS_WGRAD = 2 };
+enum { SV_IMPL_REF = 0, SV_IMPL_TC = 1 };
+int32_t sv_debug_layer_count(const sv_handle* h);
+sv_status sv_debug_layer_info(const sv_handle* h, int32_t index, sv_layer_info* out);
+sv_status sv_debug_run_layer(sv_handle* h, int32_t index, int32_t pass, int32_t impl, const float* inputs_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

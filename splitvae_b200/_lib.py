@@ -24,7 +24,8 @@ SYMBOLS = ["sv_create", "sv_destroy", "sv_last_error", "sv_version", "sv_param_c
            "sv_arena_floats", "sv_workspace_bytes", "sv_bind", "sv_params_updated", "sv_forward", "sv_loss_fwd_bwd",
            "sv_num_segments", "sv_segment_range", "sv_backward_segment", "sv_adam_step", "sv_train_step",
            "sv_output_ptr", "sv_decode", "sv_encode_y", "sv_get_iterations", "sv_set_iterations", "sv_launch_count",
-           "sv_discretised_logistic_loss", "sv_adam_flat", "sv_stage_scramble"]
+           "sv_discretised_logistic_loss", "sv_adam_flat", "sv_stage_scramble", "sv_debug_layer_count",
+           "sv_debug_layer_info", "sv_debug_run_layer"]
 
 
 class SvConfig(C.Structure):
@@ -37,6 +38,14 @@ class SvConfig(C.Structure):
 class SvParamDesc(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("ndim", C.c_int32), ("shape", C.c_int32 * 4),
                 ("offset", C.c_int64), ("count", C.c_int64)]
+
+
+class SvLayerInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64)] + [(n, C.c_int32) for n in
+                ("kh", "kw", "stride", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "in_ld", "in_coff", "out_ld", "dout_ld", "din_ld",
+                 "in_dt", "out_dt", "act_dt", "has_dgrad", "tc_fwd", "tc_dgrad", "tc_wgrad")] + \
+               [(n, C.c_void_p) for n in ("in_", "out", "dout", "din")] + \
+               [(n, C.c_int64) for n in ("in_elems", "out_elems", "dout_elems", "din_elems")]
 
 
 class SplitVaeError(RuntimeError):
@@ -87,6 +96,9 @@ def load():
     lib.sv_discretised_logistic_loss.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.sv_adam_flat.argtypes = [vp, vp, vp, vp, i64, f32, vp]
     lib.sv_stage_scramble.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.sv_debug_layer_count.argtypes = [vp]
+    lib.sv_debug_layer_info.argtypes = [vp, i32, C.POINTER(SvLayerInfo)]
+    lib.sv_debug_run_layer.argtypes = [vp, i32, i32, i32, vp, vp]
     _lib = lib
     return lib
 

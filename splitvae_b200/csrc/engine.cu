@@ -73,6 +73,7 @@ struct sv_handle {
   char err[512] = "";
   const float* last_inputs = nullptr;  // inputs of the step in flight (first-layer wgrad reads them)
   unsigned long long seed = 0x5EEDull;
+  TcPackTable* pack = nullptr;
 };
 
 namespace {
@@ -278,7 +279,7 @@ void layer_fwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
   Layer& L = h->layers[li];
   const void* in = L.in < 0 ? (const void*)ext_in : bp(h, L.in);
   if (h->use_tc && L.tc.fwd_ok) {
-    tc_conv_fwd(L.tc, L.g, h->params, bp(h, L.out), L.out_dt, s);
+    tc_conv_fwd(L.tc, s);
     h->launches += L.tc.fwd_launches;
   } else {
     ref_conv_fwd(L.g, in, L.in_dt, h->params, bp(h, L.out), L.out_dt, h->round_w, s);
@@ -301,7 +302,7 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
   h->launches += 2;
   if (L.din >= 0) {
     if (h->use_tc && L.tc.dgrad_ok) {
-      tc_conv_dgrad(L.tc, L.g, in, L.mask_act, bp(h, L.din), s);
+      tc_conv_dgrad(L.tc, s);
       h->launches += L.tc.dgrad_launches;
     } else {
       ref_conv_dgrad(L.g, bp(h, L.dout), T, h->params, bp(h, L.din), in, L.in_dt, L.mask_act, h->round_w, s);
@@ -500,6 +501,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 }
 
 sv_status sv_destroy(sv_handle* h) {
+  if (h) tc_pack_table_destroy(h->pack);
   delete h;
   return SV_OK;
 }
@@ -533,10 +535,17 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     char* tcws = (char*)bp(h, h->TCWS);
     for (auto& L : h->layers) {
       const char* err = tc_bind_layer(L.tc, L.g, L.in >= 0 ? bp(h, L.in) : nullptr, bp(h, L.out), bp(h, L.dout),
-                                      L.din >= 0 ? bp(h, L.din) : nullptr, tcws);
+                                      L.din >= 0 ? bp(h, L.din) : nullptr, L.in >= 0 ? bp(h, L.in) : nullptr, L.mask_act, tcws);
       if (err) return fail(h, SV_ERR_DEVICE, "tensor-core plan for %s: %s", L.name.c_str(), err);
       tcws += tc_workspace_bytes(L.tc, L.g);
     }
+    std::vector<TcLayer*> tl;
+    std::vector<const ConvGeom*> tg;
+    for (auto& L : h->layers) { tl.push_back(&L.tc); tg.push_back(&L.g); }
+    const char* perr = nullptr;
+    tc_pack_table_destroy(h->pack);
+    h->pack = tc_pack_table_create(tl.data(), tg.data(), (int)tl.size(), &perr);
+    if (!h->pack) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
   }
   h->bound = true;
   return SV_OK;
@@ -545,7 +554,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
 sv_status sv_params_updated(sv_handle* h, void* stream) {
   REQUIRE_BOUND(h);
   if (h->use_tc) {
-    for (auto& L : h->layers) h->launches += tc_repack_weights(L.tc, L.g, h->params, (cudaStream_t)stream);
+    h->launches += tc_repack_all(h->pack, h->params, (cudaStream_t)stream);
   }
   return check_launch(h, "sv_params_updated");
 }
@@ -628,8 +637,7 @@ sv_status sv_adam_step(sv_handle* h, void* stream) {
   adam_prepare(st, h->cfg.learning_rate, h->cfg.model == SV_MODEL_LGGMVAE, s);
   adam_apply(h->params, h->grads, h->adam_m, h->adam_v, h->arena_floats, st, 0.f, s);
   h->launches += 2;
-  if (h->use_tc)
-    for (auto& L : h->layers) h->launches += tc_repack_weights(L.tc, L.g, h->params, s);
+  if (h->use_tc) h->launches += tc_repack_all(h->pack, h->params, s);
   return check_launch(h, "sv_adam_step");
 }
 
@@ -724,6 +732,47 @@ sv_status sv_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, 
   if (!p || !g || !m || !v || n < 0) return SV_ERR_INVALID;
   adam_apply(p, g, m, v, n, nullptr, alpha, (cudaStream_t)stream);
   return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+int32_t sv_debug_layer_count(const sv_handle* h) { return h ? (int32_t)h->layers.size() : 0; }
+
+sv_status sv_debug_layer_info(const sv_handle* hc, int32_t i, sv_layer_info* o) {
+  sv_handle* h = const_cast<sv_handle*>(hc);
+  if (!h || !o || i < 0 || i >= (int32_t)h->layers.size()) return SV_ERR_INVALID;
+  const Layer& L = h->layers[i];
+  const ConvGeom& g = L.g;
+  memset(o, 0, sizeof(*o));
+  snprintf(o->name, sizeof(o->name), "%s", L.name.c_str());
+  o->kh = g.kh; o->kw = g.kw; o->stride = g.stride; o->Hi = g.Hi; o->Wi = g.Wi; o->Ci = g.Ci; o->Ho = g.Ho; o->Wo = g.Wo; o->Co = g.Co;
+  o->in_ld = g.in_ld; o->in_coff = g.in_coff; o->out_ld = g.out_ld; o->dout_ld = g.dout_ld; o->din_ld = g.din_ld;
+  o->in_dt = L.in_dt; o->out_dt = L.out_dt; o->act_dt = h->act_dt;
+  o->has_dgrad = L.din >= 0; o->tc_fwd = L.tc.fwd_ok; o->tc_dgrad = L.tc.dgrad_ok; o->tc_wgrad = L.tc.wgrad_ok;
+  if (h->bound) { o->in = bp(h, L.in); o->out = bp(h, L.out); o->dout = bp(h, L.dout); o->din = bp(h, L.din); }
+  o->in_elems = (int64_t)g.B * g.Hi * g.Wi * g.in_ld; o->out_elems = (int64_t)g.B * g.Ho * g.Wo * g.out_ld;
+  o->dout_elems = (int64_t)g.B * g.Ho * g.Wo * g.dout_ld; o->din_elems = (int64_t)g.B * g.Hi * g.Wi * g.din_ld;
+  return SV_OK;
+}
+
+sv_status sv_debug_run_layer(sv_handle* h, int32_t i, int32_t pass, int32_t impl, const float* inputs, void* stream) {
+  REQUIRE_BOUND(h);
+  if (i < 0 || i >= (int32_t)h->layers.size()) return fail(h, SV_ERR_INVALID, "layer %d out of range", i);
+  Layer& L = h->layers[i];
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* in = L.in < 0 ? (const void*)inputs : bp(h, L.in);
+  if (L.in < 0 && !inputs && pass != SV_PASS_DGRAD) return fail(h, SV_ERR_INVALID, "layer %d reads the external inputs", i);
+  const int T = h->act_dt;
+  if (impl == SV_IMPL_TC) {
+    if (pass == SV_PASS_FWD) { if (!L.tc.fwd_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core fwd for %s", L.name.c_str()); tc_conv_fwd(L.tc, s); }
+    else if (pass == SV_PASS_DGRAD) { if (!L.tc.dgrad_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core dgrad for %s", L.name.c_str()); tc_conv_dgrad(L.tc, s); }
+    else { if (!L.tc.wgrad_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core wgrad for %s", L.name.c_str()); tc_conv_wgrad(L.tc, L.g, h->grads, s); }
+  } else {
+    if (pass == SV_PASS_FWD) ref_conv_fwd(L.g, in, L.in_dt, h->params, bp(h, L.out), L.out_dt, h->round_w, s);
+    else if (pass == SV_PASS_DGRAD) {
+      if (L.din < 0) return fail(h, SV_ERR_INVALID, "layer %d has no dgrad", i);
+      ref_conv_dgrad(L.g, bp(h, L.dout), T, h->params, bp(h, L.din), in, L.in_dt, L.mask_act, h->round_w, s);
+    } else ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, h->round_w, s);
+  }
+  return check_launch(h, "sv_debug_run_layer");
 }
 
 sv_status sv_stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int32_t B, int32_t H, int32_t W, int32_t p, void* stream) {

@@ -1,21 +1,537 @@
-// Tensor-core (tcgen05 + TMA) implicit-GEMM path.  Placeholder: no layer is planned onto the
-// tensor cores yet, so every layer runs the reference kernels.
+// Tensor-core implicit-GEMM convolution / dense kernels for sm_100a.
+//
+//   * operands are staged by TMA (cp.async.bulk.tensor) into 128B/64B/32B-swizzled shared memory:
+//     the A tile of a conv tap is ONE 4-D box of the NHWC activation tensor shifted by the tap offset
+//     (out-of-bounds rows/cols are zero-filled by the TMA unit = TF 'same' padding; stride-2 layers use the
+//     tensor map's element strides), the B tile is a 2-D box of the packed bf16 weights;
+//   * one elected thread issues tcgen05.mma (M=128, N=tile_cols, K=16 per instruction, bf16 x bf16 -> fp32)
+//     with the accumulator in TMEM; tcgen05.commit releases smem stages / signals the epilogue;
+//   * four epilogue warps read the accumulator with tcgen05.ld (thread = output pixel), add the bias, apply the
+//     activation (forward) or the activation derivative of the producer layer (dgrad), convert and store NHWC.
+//
+// Reference semantics: Keras Conv2D / Dense forward (vae/model.py:36-42,49-76,152-156) and their
+// input gradients under tape.gradient (vae/trainer.py:137,166).
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "tc_device.cuh"
 #include "tc_kernels.h"
 
 namespace sv {
 
-void tc_plan_layer(TcLayer& t, const ConvGeom&, int in_dt, int out_dt, bool, bool) {
-  t.in_dt = in_dt;
-  t.out_dt = out_dt;
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+char g_tc_error[256] = "";
+
+struct SmemCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
-size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom&) { return t.w_fwd_bytes + t.w_dgrad_bytes + t.partial_bytes; }
-const char* tc_bind_layer(TcLayer& t, const ConvGeom&, const void* in, void* out, void* dout, void* din, char*) {
-  t.in = in; t.out = out; t.dout = dout; t.din = din;
+
+__global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__ TcLaunch P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = 128 * P.bk * 2;
+  const int b_bytes = (P.tile_cols * P.bk * 2 + 1023) & ~1023;
+  const int stage_bytes = a_bytes + b_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)P.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int tiles_per_img = P.grid_h / P.tile_h;   // tile_w == grid_w
+  const int n0 = (m_tile / tiles_per_img) * P.tile_n_img;
+  const int y0 = (m_tile % tiles_per_img) * P.tile_h;
+  const int num_kb = P.taps_h * P.taps_w * P.kc;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_a);
+    tc::prefetch_tmap(&P.map_b);
+    for (int i = 0; i < P.stages; ++i) { tc::mbar_init(&ctl->full[i], 1); tc::mbar_init(&ctl->empty[i], 1); }
+    tc::mbar_init(&ctl->tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)P.tile_cols) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % P.stages, phase = (kb / P.stages) & 1;
+        tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+        const int tap = kb / P.kc, chunk = kb - tap * P.kc;
+        const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        tc::mbar_expect_tx(&ctl->full[stage], a_bytes + P.tile_cols * P.bk * 2);
+        tc::tma_load_4d(sa, &P.map_a, &ctl->full[stage], chunk * P.bk, tb - P.pad_l, y0 * P.a_stride + ta - P.pad_t, n0);
+        tc::tma_load_2d(sa + a_bytes, &P.map_b, &ctl->full[stage], kb * P.bk, n_tile * P.tile_cols);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
+      const uint32_t lt = tc::layout_type_for(P.swizzle);
+      const uint32_t sbo = 16u * P.bk;  // 8 rows x (bk*2) bytes
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % P.stages, phase = (kb / P.stages) & 1;
+        tc::mbar_wait(&ctl->full[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        for (int k = 0; k < P.bk / 16; ++k) {
+          const uint64_t da = tc::make_smem_desc(sa + k * 32, 16, sbo, lt);
+          const uint64_t db = tc::make_smem_desc(sb + k * 32, 16, sbo, lt);
+          tc::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        tc::umma_commit(&ctl->empty[stage]);   // frees this smem stage once the MMAs above have read it
+      }
+      tc::umma_commit(&ctl->tmem_full);        // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global -----------------------------------------
+    tc::mbar_wait(&ctl->tmem_full, 0);
+    tc::tc_fence_after();
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const int per_img = P.tile_h * P.tile_w;
+    const int nn = row / per_img, rem = row - nn * per_img;
+    const int hh = rem / P.tile_w, ww = rem - hh * P.tile_w;
+    const int n = n0 + nn, y = y0 + hh, x = ww;
+    const bool valid = n < P.n_img;
+    const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
+    const int col_base = n_tile * P.tile_cols;
+    int act = ACT_NONE;
+    {
+      int c = col_base, j = 0;
+      while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
+      act = P.part_act[j];
+    }
+    const int esz = P.out_f32 ? 4 : 2;
+    const bool vec_ok = ((P.out_ld * esz) % 16) == 0;
+    for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      const int ncol = min(32, P.tile_cols - c0);
+      if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
+      tc::tmem_ld_wait();
+      if (valid) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = col_base + c0 + i;
+          float a = __uint_as_float(v[i]);
+          if (i < ncol && col < P.n_valid) {
+            if (P.bias) a += P.bias[col];
+            a = apply_act(a, act);
+            if (P.mask_act != ACT_NONE) {
+              const float m = __bfloat162float(((const bf16*)P.mask_src)[opix * P.mask_ld + P.mask_coff + col]);
+              a *= act_grad_from_out(m, P.mask_act);
+            }
+          } else {
+            a = 0.f;
+          }
+          f[i] = a;
+        }
+        const int cfirst = col_base + c0;
+        if (P.out_f32) {
+          float* o = (float*)P.out + opix * P.out_ld + cfirst;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (i >= ncol) break;
+            if (vec_ok && cfirst + i + 4 <= P.n_valid) {
+              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (cfirst + i + q < P.n_valid) o[i + q] = f[i + q];
+            }
+          }
+        } else {
+          bf16* o = (bf16*)P.out + opix * P.out_ld + cfirst;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (i >= ncol) break;
+            if (vec_ok && cfirst + i + 8 <= P.n_valid) {
+              uint4 pk;
+              pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
+              pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
+              *reinterpret_cast<uint4*>(o + i) = pk;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (cfirst + i + q < P.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: one multi-tensor kernel refreshes every bf16 operand copy from the fp32 masters
+// ------------------------------------------------------------------------------------------------
+struct PackJob {
+  int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias
+  int KH, KW, Ci, Co;       // layer geometry (logical)
+  int nparts, part_n[3];
+  long long part_w[3], part_b[3];
+  int rows_pad, taps_h, taps_w, k_pad;   // dst = [rows_pad][taps_h*taps_w][k_pad]
+  int stride, rh, rw;       // dgrad: kh = stride*(taps_h-1-a) + rh  (stride 1: rh = 0)
+  void* dst;
+  long long count;
+  int block_start;
+};
+
+__device__ __forceinline__ float master_w(const PackJob& J, const float* params, int kh, int kw, int ci, int co) {
+  int j = 0, lc = co;
+  while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+  return params[J.part_w[j] + ((long long)(kh * J.KW + kw) * J.Ci + ci) * J.part_n[j] + lc];
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* __restrict__ params) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {  // last job whose block_start <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob& J = jobs[lo];
+  const long long base = (long long)(blockIdx.x - J.block_start) * 2048;
+  for (int t = threadIdx.x; t < 2048; t += 256) {
+    const long long idx = base + t;
+    if (idx >= J.count) return;
+    if (J.kind == 2) {
+      int j = 0, lc = (int)idx;
+      float v = 0.f;
+      if (idx < J.Co) {
+        while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+        v = params[J.part_b[j] + lc];
+      }
+      ((float*)J.dst)[idx] = v;
+      continue;
+    }
+    const int kk = (int)(idx % J.k_pad);
+    const int tap = (int)((idx / J.k_pad) % (J.taps_h * J.taps_w));
+    const int r = (int)(idx / ((long long)J.k_pad * J.taps_h * J.taps_w));
+    const int a = tap / J.taps_w, b = tap % J.taps_w;
+    float v = 0.f;
+    if (J.kind == 0) {           // fwd: rows = co, k = ci
+      if (r < J.Co && kk < J.Ci) v = master_w(J, params, a, b, kk, r);
+    } else {                     // dgrad: rows = ci, k = co, flipped (sub-)kernel
+      const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
+      if (r < J.Ci && kk < J.Co) v = master_w(J, params, kh, kw, r, kk);
+    }
+    ((bf16*)J.dst)[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: TMA descriptors
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+CUtensorMapSwizzle swz(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                                                                            : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// activation tensor [N][H][W][ld] (bf16), channels [coff, coff+C): box = {bk, tw*s, th*s, tn}, element strides {1,s,s,1}
+const char* make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int ld, int coff, int C, int bk, int tw, int th, int tn,
+                         int s, int swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+  if (s > 1) { box[1] -= (s - 1); box[2] -= (s - 1); }  // ceil(box/stride) elements are loaded
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)((const bf16*)base + coff), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(act) failed: %d (dims %d,%d,%d,%d ld %d box %u,%u,%u,%u s %d)", (int)r,
+             C, W, H, N, ld, box[0], box[1], box[2], box[3], s);
+    return g_tc_error;
+  }
   return nullptr;
 }
-int tc_repack_weights(TcLayer&, const ConvGeom&, const float*, cudaStream_t) { return 0; }
-void tc_conv_fwd(TcLayer&, const ConvGeom&, const float*, void*, int, cudaStream_t) {}
-void tc_conv_dgrad(TcLayer&, const ConvGeom&, const void*, int, void*, cudaStream_t) {}
+
+// packed weights [rows][k_total] bf16: box = {bk, tile_rows}
+const char* make_w_map(CUtensorMap* m, const void* base, int rows, long long k_total, int bk, int tile_rows, int swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)tile_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(weights) failed: %d (rows %d k %lld bk %d tile %d)", (int)r, rows,
+             k_total, bk, tile_rows);
+    return g_tc_error;
+  }
+  return nullptr;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// K chunking for a channel count: returns bk (64/32/16) and the padded channel count
+void choose_bk(int C, int& bk, int& c_pad) {
+  if (C >= 64) { bk = 64; c_pad = round_up(C, 64); }
+  else if (C > 16) { bk = 32; c_pad = 32; }
+  else { bk = 16; c_pad = 16; }
+}
+
+int pad_cols(int n) { return n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : round_up(n, 128); }
+
+// fills the geometry part of a launch for an output grid GH x GW (per image)
+bool tile_grid(TcLaunch& L, int GH, int GW, int n_img) {
+  if (!is_pow2(GW) || !is_pow2(GH) || GW > 128) return false;
+  L.tile_w = GW;
+  L.tile_h = GH < 128 / GW ? GH : 128 / GW;
+  L.tile_n_img = 128 / (L.tile_w * L.tile_h);
+  L.grid_h = GH; L.grid_w = GW; L.n_img = n_img;
+  return true;
+}
+
+void finish_launch(TcLaunch& L, int n_cols_pad) {
+  L.tile_cols = n_cols_pad < 128 ? n_cols_pad : 128;
+  L.n_tiles = n_cols_pad / L.tile_cols;
+  const int a_bytes = 128 * L.bk * 2, b_bytes = round_up(L.tile_cols * L.bk * 2, 1024);
+  int stages = (100 * 1024) / (a_bytes + b_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  const int num_kb = L.taps_h * L.taps_w * L.kc;
+  if (stages > num_kb) stages = num_kb < 1 ? 1 : num_kb;
+  L.stages = stages;
+  L.smem_bytes = (size_t)stages * (a_bytes + b_bytes) + sizeof(SmemCtl) + 1024;
+}
+
+}  // namespace
+
+const char* tc_last_error() { return g_tc_error; }
+
+void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad) {
+  t.in_dt = in_dt;
+  t.out_dt = out_dt;
+  size_t off = 0;
+  // ---- forward: A = layer input (must be an internal bf16 tensor) ----
+  if (has_internal_input && in_dt == DT_BF16 && (g.in_ld % 8) == 0 && (g.in_coff % 8) == 0) {
+    TcLaunch& L = t.fwd;
+    int bk, cpad;
+    choose_bk(g.Ci, bk, cpad);
+    if (cpad <= g.in_ld - g.in_coff || cpad == round_up(g.Ci, 8)) {
+      if (tile_grid(L, g.Ho, g.Wo, g.B)) {
+        L.taps_h = g.kh; L.taps_w = g.kw; L.pad_t = g.pt; L.pad_l = g.pl; L.a_stride = g.stride;
+        L.bk = bk; L.swizzle = bk * 2; L.kc = cpad / bk;
+        t.ci_pad = cpad;
+        t.n_pad_fwd = pad_cols(g.Co);
+        L.n_valid = g.Co;
+        L.OH = g.Ho; L.OW = g.Wo; L.osy = 1; L.ooy = 0; L.osx = 1; L.oox = 0;
+        L.out_ld = g.out_ld; L.out_f32 = out_dt == DT_F32;
+        L.nparts = g.nparts;
+        for (int j = 0; j < 3; ++j) { L.part_n[j] = g.part_n[j]; L.part_act[j] = g.part_act[j]; }
+        L.mask_act = ACT_NONE;
+        finish_launch(L, t.n_pad_fwd);
+        t.fwd_ok = true;
+        t.fwd_launches = 1;
+        t.w_fwd_off = off;
+        off += round_up((int)((size_t)t.n_pad_fwd * g.kh * g.kw * cpad * 2), 1024);
+        t.bias_off = off;
+        off += round_up(t.n_pad_fwd * 4, 1024);
+      }
+    }
+  }
+  // ---- dgrad: A = dY (bf16, pitch dout_ld), output = dX ----
+  if (has_dgrad && (g.dout_ld % 8) == 0 && (g.stride == 1 || g.stride == 2)) {
+    int bk, copad;
+    choose_bk(g.Co, bk, copad);
+    const int s = g.stride;
+    const int GH = g.Hi / s, GW = g.Wi / s;
+    bool ok = copad <= g.dout_ld && (g.kh % s) == 0 && (g.kw % s) == 0 && (g.Hi % s) == 0 && (g.Wi % s) == 0;
+    t.n_dgrad = s * s;
+    t.dg_taps_h = g.kh / s; t.dg_taps_w = g.kw / s;
+    t.co_pad = copad;
+    t.n_pad_dg = pad_cols(g.Ci);
+    for (int cls = 0; ok && cls < s * s; ++cls) {
+      TcLaunch& L = t.dgrad[cls];
+      const int ph = cls / s, pw = cls % s;
+      if (!tile_grid(L, GH, GW, g.B)) { ok = false; break; }
+      const int rh = (ph + g.pt) % s, rw = (pw + g.pl) % s;
+      const int qh = (ph + g.pt - rh) / s, qw = (pw + g.pl - rw) / s;
+      L.taps_h = t.dg_taps_h; L.taps_w = t.dg_taps_w;
+      L.pad_t = t.dg_taps_h - 1 - qh; L.pad_l = t.dg_taps_w - 1 - qw;
+      L.a_stride = 1;
+      L.bk = bk; L.swizzle = bk * 2; L.kc = copad / bk;
+      L.n_valid = g.Ci;
+      L.OH = g.Hi; L.OW = g.Wi; L.osy = s; L.ooy = ph; L.osx = s; L.oox = pw;
+      L.out_ld = g.din_ld; L.out_f32 = 0;
+      L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
+      finish_launch(L, t.n_pad_dg);
+    }
+    if (ok) {
+      t.dgrad_ok = true;
+      t.dgrad_launches = s * s;
+      t.w_dgrad_off = off;
+      off += (size_t)s * s * round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * copad * 2), 1024);
+    }
+  }
+  t.bytes = off;
+}
+
+size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom&) { return t.bytes; }
+
+const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din, const void* mask_src,
+                          int mask_act, char* ws) {
+  t.ws = ws;
+  if (t.fwd_ok) {
+    TcLaunch& L = t.fwd;
+    const char* e = make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci,
+                                 L.bk, L.tile_w, L.tile_h, L.tile_n_img, g.stride, L.swizzle);
+    if (e) return e;
+    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)g.kh * g.kw * t.ci_pad, L.bk, L.tile_cols, L.swizzle);
+    if (e) return e;
+    L.bias = (const float*)(ws + t.bias_off);
+    L.out = out;
+    L.mask_src = nullptr;
+    if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  }
+  if (t.dgrad_ok) {
+    const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
+    for (int cls = 0; cls < t.n_dgrad; ++cls) {
+      TcLaunch& L = t.dgrad[cls];
+      const char* e = make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.tile_w, L.tile_h, L.tile_n_img, 1,
+                                   L.swizzle);
+      if (e) return e;
+      e = make_w_map(&L.map_b, ws + t.w_dgrad_off + cls * per_class, t.n_pad_dg, (long long)t.dg_taps_h * t.dg_taps_w * t.co_pad, L.bk,
+                     L.tile_cols, L.swizzle);
+      if (e) return e;
+      L.bias = nullptr;
+      L.out = din;
+      L.mask_src = mask_src;
+      L.mask_act = mask_act;
+      L.mask_ld = g.in_ld;
+      L.mask_coff = g.in_coff;
+    }
+    if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  }
+  return nullptr;
+}
+
+struct TcPackTable {
+  PackJob* dev = nullptr;
+  int njobs = 0, nblocks = 0;
+};
+
+TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const* geoms, int n, const char** err) {
+  std::vector<PackJob> jobs;
+  int blocks = 0;
+  auto push = [&](PackJob J) {
+    J.block_start = blocks;
+    blocks += (int)((J.count + 2047) / 2048);
+    jobs.push_back(J);
+  };
+  for (int i = 0; i < n; ++i) {
+    const TcLayer& t = *layers[i];
+    const ConvGeom& g = *geoms[i];
+    PackJob B{};
+    B.KH = g.kh; B.KW = g.kw; B.Ci = g.Ci; B.Co = g.Co; B.nparts = g.nparts;
+    for (int j = 0; j < 3; ++j) { B.part_n[j] = g.part_n[j]; B.part_w[j] = g.part_w[j]; B.part_b[j] = g.part_b[j]; }
+    if (t.fwd_ok) {
+      PackJob J = B;
+      J.kind = 0; J.rows_pad = t.n_pad_fwd; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = t.ci_pad;
+      J.dst = t.ws + t.w_fwd_off;
+      J.count = (long long)t.n_pad_fwd * g.kh * g.kw * t.ci_pad;
+      push(J);
+      PackJob Jb = B;
+      Jb.kind = 2; Jb.dst = t.ws + t.bias_off; Jb.count = t.n_pad_fwd;
+      push(Jb);
+    }
+    if (t.dgrad_ok) {
+      const int s = g.stride;
+      const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
+      for (int cls = 0; cls < t.n_dgrad; ++cls) {
+        PackJob J = B;
+        J.kind = 1; J.rows_pad = t.n_pad_dg; J.taps_h = t.dg_taps_h; J.taps_w = t.dg_taps_w; J.k_pad = t.co_pad;
+        J.stride = s; J.rh = (cls / s + g.pt) % s; J.rw = (cls % s + g.pl) % s;
+        J.dst = t.ws + t.w_dgrad_off + cls * per_class;
+        J.count = (long long)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad;
+        push(J);
+      }
+    }
+  }
+  TcPackTable* T = new TcPackTable();
+  T->njobs = (int)jobs.size();
+  T->nblocks = blocks;
+  if (T->njobs) {
+    if (cudaMalloc(&T->dev, jobs.size() * sizeof(PackJob)) != cudaSuccess ||
+        cudaMemcpy(T->dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = "pack table upload failed";
+      delete T;
+      return nullptr;
+    }
+  }
+  return T;
+}
+
+void tc_pack_table_destroy(TcPackTable* t) {
+  if (!t) return;
+  if (t->dev) cudaFree(t->dev);
+  delete t;
+}
+
+int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
+  if (!t || !t->njobs) return 0;
+  pack_kernel<<<t->nblocks, 256, 0, s>>>(t->dev, t->njobs, params);
+  return 1;
+}
+
+static void launch(const TcLaunch& L, cudaStream_t s) {
+  const int tiles_per_img = L.grid_h / L.tile_h;
+  const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
+  dim3 grid(m_tiles, L.n_tiles);
+  igemm_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+}
+
+void tc_conv_fwd(TcLayer& t, cudaStream_t s) { launch(t.fwd, s); }
+void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
+  for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
+}
 void tc_conv_wgrad(TcLayer&, const ConvGeom&, float*, cudaStream_t) {}
 
 }  // namespace sv

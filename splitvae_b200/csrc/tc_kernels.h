@@ -8,44 +8,58 @@
 
 namespace sv {
 
-constexpr int kTcMaxMaps = 8;
-
-struct TcGemmPlan {          // one implicit-GEMM launch configuration
-  bool ok = false;
-  int tile_n = 0, tile_h = 0, tile_w = 0;   // M tile = tile_n images x tile_h rows x tile_w cols = 128 pixels
-  int bk = 0;                // K elements per pipeline stage (channels per TMA box)
-  int swizzle = 0;           // bytes: 128 / 64 / 32
-  int n_pad = 0;             // UMMA N (Cout padded)
-  int n_tiles = 1;           // CTAs along N (Cout split)
-  int stages = 0;
-  int ci_pad = 0;            // packed input channels per tap
-  int taps_h = 0, taps_w = 0, pad_t = 0, pad_l = 0;  // effective stride-1 conv on the A tensor
-  int splits = 1;            // split-K
-  CUtensorMap map_a[4];      // A operand maps (dgrad stride-2: one per output parity class)
-  CUtensorMap map_b[4];
+// One launch of the implicit-GEMM kernel  D[pixels, N] = A[pixels, taps*C] * B[N, taps*C]^T.
+//   A = an NHWC bf16 activation tensor read through a 4-D TMA map (C, W, H, N) with a per-tap shift,
+//   B = a packed bf16 weight matrix [n_pad][taps*c_pad] read through a 2-D TMA map.
+struct TcLaunch {
+  CUtensorMap map_a, map_b;
+  int taps_h, taps_w, pad_t, pad_l, a_stride;   // A coordinate of (out y, tap a) = y*a_stride + a - pad_t
+  int kc;                                       // channel chunks per tap (c_pad / bk)
+  int bk, swizzle;                              // K elements per stage, swizzle bytes (= 2*bk)
+  int tile_n_img, tile_h, tile_w;               // M tile = tile_n_img x tile_h x tile_w = 128 output pixels
+  int grid_h, grid_w, n_img;                    // output grid per image (before scatter) and image count
+  int tile_cols;                                // UMMA N of one CTA
+  int n_tiles;                                  // CTAs along N
+  int n_valid;                                  // valid output columns in total
+  int stages;
+  // epilogue: out pixel (n,y,x) -> ((n*OH + y*osy + ooy)*OW + x*osx + oox)*out_ld + col
+  int OH, OW, osy, ooy, osx, oox, out_ld, out_f32;
+  int nparts, part_n[3], part_act[3];
+  int mask_act, mask_ld, mask_coff;
+  const float* bias;                            // packed fp32 bias [n_pad] or NULL
+  void* out;
+  const void* mask_src;
+  size_t smem_bytes;
 };
 
 struct TcLayer {
   bool fwd_ok = false, dgrad_ok = false, wgrad_ok = false;
   int fwd_launches = 0, dgrad_launches = 0, wgrad_launches = 0;
-  TcGemmPlan fwd, dgrad, wgrad;
-  // packed bf16 weights inside the tensor-core workspace
-  void* w_fwd = nullptr;     // [n_pad][taps][ci_pad]
-  void* w_dgrad = nullptr;   // [classes][ci_pad_out][taps'][co_pad]
-  size_t w_fwd_bytes = 0, w_dgrad_bytes = 0, partial_bytes = 0;
-  float* partial = nullptr;  // split-K partial sums
-  const void* in = nullptr; void* out = nullptr; void* dout = nullptr; void* din = nullptr;
+  int n_dgrad = 0;
+  TcLaunch fwd{}, dgrad[4]{};
+  // geometry of the packed operands
+  int n_pad_fwd = 0, ci_pad = 0;      // fwd : B = [n_pad_fwd][taps][ci_pad]
+  int n_pad_dg = 0, co_pad = 0;       // dgrad: B = [classes][n_pad_dg][taps'][co_pad]
+  int dg_taps_h = 0, dg_taps_w = 0;
+  size_t w_fwd_off = 0, w_dgrad_off = 0, bias_off = 0, bytes = 0;   // offsets inside this layer's workspace slice
+  char* ws = nullptr;
   int in_dt = 0, out_dt = 0;
 };
 
 // plan (no CUDA calls), workspace size, bind (creates TMA descriptors; returns NULL or an error text)
 void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad);
 size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom& g);
-const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din, char* ws);
-int tc_repack_weights(TcLayer& t, const ConvGeom& g, const float* params, cudaStream_t s);  // returns #launches
+const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din,
+                          const void* mask_src, int mask_act, char* ws);
+// One multi-tensor launch that refreshes every packed operand from the fp32 master weights.
+struct TcPackTable;
+TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const* geoms, int n, const char** err);
+void tc_pack_table_destroy(TcPackTable* t);
+int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s);  // returns #launches
 
-void tc_conv_fwd(TcLayer& t, const ConvGeom& g, const float* params, void* out, int out_dt, cudaStream_t s);
-void tc_conv_dgrad(TcLayer& t, const ConvGeom& g, const void* mask_src, int mask_act, void* din, cudaStream_t s);
+void tc_conv_fwd(TcLayer& t, cudaStream_t s);
+void tc_conv_dgrad(TcLayer& t, cudaStream_t s);
 void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s);
+const char* tc_last_error();
 
 }  // namespace sv

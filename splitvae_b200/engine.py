@@ -189,3 +189,21 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.sv_launch_count(self.h))
+
+    # ---- test hooks (sv_debug_*) ---------------------------------------------------------------
+    def debug_layers(self):
+        infos = []
+        for i in range(self.lib.sv_debug_layer_count(self.h)):
+            info = _lib.SvLayerInfo()
+            check(self.lib.sv_debug_layer_info(self.h, i, C.byref(info)), self.h, "sv_debug_layer_info")
+            infos.append(info)
+        return infos
+
+    def debug_view(self, ptr, elems, dt):
+        """torch view of `elems` elements of a workspace buffer (dt: 0 fp32, 1 bf16)."""
+        off = ptr - self._ws.data_ptr()
+        nbytes = elems * (4 if dt == 0 else 2)
+        return self._ws[off:off + nbytes].view(torch.float32 if dt == 0 else torch.bfloat16)
+
+    def debug_run_layer(self, index, pass_, impl, inputs=None):
+        check(self.lib.sv_debug_run_layer(self.h, index, pass_, impl, _ptr(inputs), _stream()), self.h, "sv_debug_run_layer")
