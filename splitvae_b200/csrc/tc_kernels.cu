@@ -189,6 +189,160 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[(tap,ci), co] = sum over pixels; K axis = pixels (64 per stage), both operands MN-major.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgMaxA = 6, kWgMaxB = 2;
+struct WgCtl {
+  uint64_t a_full[kWgMaxA], a_empty[kWgMaxA], b_full[kWgMaxB], b_empty[kWgMaxB], tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ TcWgradLaunch P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kPix = 64;
+  const int a_box = kPix * P.cb * 2;             // one (tap, channel-block) box
+  const int a_stage = 128 * kPix * 2;            // nsub boxes = 128 rows of the M axis
+  const int b_box = kPix * P.cbn * 2;
+  const int b_stage = P.tile_cols * kPix * 2;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + (size_t)P.a_stages * a_stage;
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(b_ring + (size_t)P.b_stages * b_stage);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g0 = blockIdx.x * P.groups_per_cta;
+  const int ng = min(P.groups_per_cta, P.groups - g0);
+  const int n_tile = blockIdx.y;
+  const int c_begin = blockIdx.z * P.chunks_per_split;
+  const int c_end = min(P.nchunks, c_begin + P.chunks_per_split);
+  const int chunks_per_img = P.grid_h / P.tile_h;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_a);
+    tc::prefetch_tmap(&P.map_b);
+    for (int i = 0; i < P.a_stages; ++i) { tc::mbar_init(&ctl->a_full[i], 1); tc::mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < P.b_stages; ++i) { tc::mbar_init(&ctl->b_full[i], 1); tc::mbar_init(&ctl->b_empty[i], 1); }
+    tc::mbar_init(&ctl->tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(P.groups_per_cta * P.tile_cols)) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int ia = 0;  // running A-stage counter
+      for (int c = c_begin; c < c_end; ++c) {
+        const int ib = c - c_begin;
+        const int bs = ib % P.b_stages, bph = (ib / P.b_stages) & 1;
+        const int n0 = P.tile_n_img > 1 ? c * P.tile_n_img : c / chunks_per_img;
+        const int y0 = P.tile_n_img > 1 ? 0 : (c % chunks_per_img) * P.tile_h;
+        tc::mbar_wait(&ctl->b_empty[bs], bph ^ 1);
+        tc::mbar_expect_tx(&ctl->b_full[bs], b_stage);
+        for (int j = 0; j < P.tile_cols / P.cbn; ++j)
+          tc::tma_load_4d(b_ring + (size_t)bs * b_stage + (size_t)j * b_box, &P.map_b, &ctl->b_full[bs],
+                          n_tile * P.tile_cols + j * P.cbn, 0, y0, n0);
+        for (int g = 0; g < ng; ++g, ++ia) {
+          const int as = ia % P.a_stages, aph = (ia / P.a_stages) & 1;
+          tc::mbar_wait(&ctl->a_empty[as], aph ^ 1);
+          const int sb0 = (g0 + g) * P.nsub;
+          const int nv = min(P.nsub, P.total_sb - sb0);
+          tc::mbar_expect_tx(&ctl->a_full[as], nv * a_box);
+          for (int j = 0; j < nv; ++j) {
+            const int sb = sb0 + j;
+            const int tap = sb / P.ncb, cblk = sb - tap * P.ncb;
+            const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
+            tc::tma_load_4d(a_ring + (size_t)as * a_stage + (size_t)j * a_box, &P.map_a, &ctl->a_full[as], cblk * P.cb,
+                            tb - P.pad_l, y0 * P.a_stride + ta - P.pad_t, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 1, 1);
+      const uint32_t lta = tc::layout_type_for(P.a_swizzle), ltb = tc::layout_type_for(P.b_swizzle);
+      const uint32_t a_row = P.cb * 2, b_row = P.cbn * 2;  // bytes per pixel row inside a box
+      int ia = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int ib = c - c_begin;
+        const int bs = ib % P.b_stages, bph = (ib / P.b_stages) & 1;
+        tc::mbar_wait(&ctl->b_full[bs], bph);
+        const uint32_t sb_addr = tc::smem_u32(b_ring + (size_t)bs * b_stage);
+        for (int g = 0; g < ng; ++g, ++ia) {
+          const int as = ia % P.a_stages, aph = (ia / P.a_stages) & 1;
+          tc::mbar_wait(&ctl->a_full[as], aph);
+          tc::tc_fence_after();
+          const uint32_t sa_addr = tc::smem_u32(a_ring + (size_t)as * a_stage);
+#pragma unroll
+          for (int k = 0; k < kPix / 16; ++k) {
+            // MN-major: LBO = distance between channel blocks (one box), SBO = 8 pixel rows
+            const uint64_t da = tc::make_smem_desc(sa_addr + k * 16 * a_row, a_box, 8 * a_row, lta);
+            const uint64_t db = tc::make_smem_desc(sb_addr + k * 16 * b_row, b_box, 8 * b_row, ltb);
+            tc::umma_bf16(tmem_base + (uint32_t)(g * P.tile_cols), da, db, idesc, (c > c_begin) || (k > 0));
+          }
+          tc::umma_commit(&ctl->a_empty[as]);
+        }
+        tc::umma_commit(&ctl->b_empty[bs]);
+      }
+      tc::umma_commit(&ctl->tmem_full);
+    }
+  } else {
+    tc::mbar_wait(&ctl->tmem_full, 0);
+    tc::tc_fence_after();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    for (int g = 0; g < ng; ++g) {
+      float* dst = P.partial + ((size_t)blockIdx.z * P.m_pad + (size_t)(g0 + g) * 128 + row) * P.n_pad + (size_t)n_tile * P.tile_cols;
+      for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * P.tile_cols + c0);
+        const int ncol = min(32, P.tile_cols - c0);
+        if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
+        tc::tmem_ld_wait();
+        if (c_end > c_begin) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (i < ncol) *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (i < ncol) *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
+                                                           int ci_pad, float* __restrict__ grads) {
+  const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % g.Co);
+    const int ci = (int)((idx / g.Co) % g.Ci);
+    const int tap = (int)(idx / ((long long)g.Co * g.Ci));
+    const size_t row = (size_t)tap * ci_pad + ci;
+    float s = 0.f;
+    for (int k = 0; k < k_splits; ++k) s += partial[((size_t)k * m_pad + row) * n_pad + co];
+    int lc;
+    const int j = part_of(g, co, lc);
+    grads[g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing: one multi-tensor kernel refreshes every bf16 operand copy from the fp32 masters
 // ------------------------------------------------------------------------------------------------
@@ -411,6 +565,46 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       off += (size_t)s * s * round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * copad * 2), 1024);
     }
   }
+  // ---- wgrad: A = layer input, B = dY, K axis = pixels ----
+  if (has_internal_input && in_dt == DT_BF16 && (g.in_ld % 8) == 0 && (g.in_coff % 8) == 0 && (g.dout_ld % 8) == 0 &&
+      is_pow2(g.Ho) && is_pow2(g.Wo) && g.Wo <= 64) {
+    TcWgradLaunch& L = t.wg;
+    int cb, cipad, cbn, copad;
+    choose_bk(g.Ci, cb, cipad);
+    choose_bk(g.Co, cbn, copad);
+    const bool a_fits = cipad <= g.in_ld - g.in_coff, b_fits = copad <= g.dout_ld;
+    if (a_fits && b_fits) {
+      L.taps_h = g.kh; L.taps_w = g.kw; L.pad_t = g.pt; L.pad_l = g.pl; L.a_stride = g.stride;
+      L.cb = cb; L.ncb = cipad / cb; L.a_swizzle = cb * 2;
+      L.cbn = cbn; L.b_swizzle = cbn * 2;
+      L.nsub = 128 / cb;
+      L.total_sb = g.kh * g.kw * L.ncb;
+      L.groups = (L.total_sb + L.nsub - 1) / L.nsub;
+      L.n_pad = copad;
+      L.tile_cols = copad < 256 ? copad : 256;
+      if (copad % L.tile_cols) L.tile_cols = 128;
+      L.n_tiles = copad / L.tile_cols;
+      L.groups_per_cta = 512 / L.tile_cols;
+      if (L.groups_per_cta > L.groups) L.groups_per_cta = L.groups;
+      if (L.groups_per_cta > 8) L.groups_per_cta = 8;
+      L.m_pad = L.groups * 128;
+      L.tile_w = g.Wo; L.tile_h = g.Ho < 64 / g.Wo ? g.Ho : 64 / g.Wo; L.tile_n_img = 64 / (L.tile_w * L.tile_h);
+      L.grid_h = g.Ho; L.n_img = g.B;
+      L.nchunks = L.tile_n_img > 1 ? (g.B + L.tile_n_img - 1) / L.tile_n_img : g.B * (g.Ho / L.tile_h);
+      const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
+      int ks = (296 + m_splits * L.n_tiles - 1) / (m_splits * L.n_tiles);
+      if (ks > L.nchunks) ks = L.nchunks;
+      if (ks < 1) ks = 1;
+      L.chunks_per_split = (L.nchunks + ks - 1) / ks;
+      L.k_splits = (L.nchunks + L.chunks_per_split - 1) / L.chunks_per_split;
+      L.a_stages = 4; L.b_stages = 2;
+      L.smem_bytes = (size_t)L.a_stages * 128 * 64 * 2 + (size_t)L.b_stages * L.tile_cols * 64 * 2 + sizeof(WgCtl) + 1024;
+      t.wgrad_ok = true;
+      t.wgrad_launches = 2;
+      t.wg_partial_off = off;
+      off += ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024;
+    }
+  }
   t.bytes = off;
 }
 
@@ -449,6 +643,16 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       L.mask_coff = g.in_coff;
     }
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  }
+  if (t.wgrad_ok) {
+    TcWgradLaunch& L = t.wg;
+    const char* e = make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, L.ncb * L.cb, L.cb, L.tile_w, L.tile_h, L.tile_n_img,
+                                 g.stride, L.a_swizzle);
+    if (e) return e;
+    e = make_act_map(&L.map_b, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, L.n_pad, L.cbn, L.tile_w, L.tile_h, L.tile_n_img, 1, L.b_swizzle);
+    if (e) return e;
+    L.partial = (float*)(ws + t.wg_partial_off);
+    if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   return nullptr;
 }
@@ -532,6 +736,15 @@ void tc_conv_fwd(TcLayer& t, cudaStream_t s) { launch(t.fwd, s); }
 void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
 }
-void tc_conv_wgrad(TcLayer&, const ConvGeom&, float*, cudaStream_t) {}
+void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) {
+  const TcWgradLaunch& L = t.wg;
+  const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
+  dim3 grid(m_splits, L.n_tiles, L.k_splits);
+  wgrad_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+  const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, grads);
+}
 
 }  // namespace sv

@@ -32,11 +32,33 @@ struct TcLaunch {
   size_t smem_bytes;
 };
 
+// Weight gradient  dW[(tap,ci), co] = sum_pixels X[pixel+tap, ci] * dY[pixel, co]  as a GEMM whose K axis is the
+// pixel axis: both operands are "MN-major" (channels contiguous) 64-pixel TMA boxes of NHWC tensors.
+struct TcWgradLaunch {
+  CUtensorMap map_a, map_b;       // A = layer input (box: cb channels x 64 pixels), B = dY (box: cbn channels x 64 pixels)
+  int taps_h, taps_w, pad_t, pad_l, a_stride;
+  int cb, ncb, a_swizzle;         // A channel block (64/32/16), blocks per tap, swizzle bytes
+  int cbn, b_swizzle;             // B channel block
+  int nsub;                       // A sub-boxes per 128-row group (128 / cb)
+  int total_sb;                   // taps * ncb
+  int groups, groups_per_cta;     // 128-row groups in total / per CTA
+  int tile_cols, n_tiles;         // UMMA N per CTA, CTAs along N
+  int tile_n_img, tile_h, tile_w; // 64-pixel chunk decomposition
+  int grid_h, n_img;
+  int nchunks, chunks_per_split, k_splits;
+  int a_stages, b_stages;
+  int m_pad, n_pad;               // partial buffer dims
+  float* partial;
+  size_t smem_bytes;
+};
+
 struct TcLayer {
   bool fwd_ok = false, dgrad_ok = false, wgrad_ok = false;
   int fwd_launches = 0, dgrad_launches = 0, wgrad_launches = 0;
   int n_dgrad = 0;
   TcLaunch fwd{}, dgrad[4]{};
+  TcWgradLaunch wg{};
+  size_t wg_partial_off = 0;
   // geometry of the packed operands
   int n_pad_fwd = 0, ci_pad = 0;      // fwd : B = [n_pad_fwd][taps][ci_pad]
   int n_pad_dg = 0, co_pad = 0;       // dgrad: B = [classes][n_pad_dg][taps'][co_pad]

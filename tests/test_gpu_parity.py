@@ -42,28 +42,32 @@ def test_step_fp32_reference_kernels(model, H, B, p, beta, alpha):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("no_tc", [True, False], ids=["bf16-reference-kernels", "bf16-tcgen05"])
 @pytest.mark.parametrize("model,H,B,p,beta,alpha", CASES)
-def test_step_bf16(model, H, B, p, beta, alpha):
+def test_step_bf16(model, H, B, p, beta, alpha, no_tc):
     params, batch = make_case(model, H, B, p)
-    e = make_engine(model, H, B, "bf16", beta, alpha)
+    e = make_engine(model, H, B, "bf16", beta, alpha, no_tc=no_tc)
     e.load_params(params)
     sc, grads = run_engine_step(e, batch, model, adam=False)
-    # (1) against the exact (fp64) oracle: ELBO terms within the north-star tolerance; gradients within the
-    #     statistical error of 8-bit-mantissa storage compounding through the backward chain.
+    # (1) against the exact (fp64) oracle: ELBO terms within the north-star tolerance (rel 1e-3); gradients within
+    #     the statistical error of 8-bit-mantissa storage, which this network amplifies ~3x per decoder layer on the
+    #     way back (measured: the bf16-storage model below sits 6-9% from fp64 on the deepest tensors).
     ref_sc, ref_g = _oracle(model, params, batch, beta, alpha, torch.float64)
     for k, v in ref_sc.items():
         tol = 1e-3 * max(1.0, abs(v)) if k in ("total", "recon_x", "recon_x_hat") else 2e-2 * max(0.05, abs(v))
         assert abs(sc[k] - v) <= tol, (k, sc[k], v)
     worst, bad = compare_grads(grads, ref_g, 0.2)
     assert not bad, bad
-    # (2) against the oracle with the device's bf16 storage roundings modelled: only summation order and
-    #     1-ulp rounding ties remain -> every gradient tensor within rel-L2 3e-2 (worst seen 2.4e-2 at batch 2,
-    #     typically 3e-3), scalars within 1e-4.
+    # (2) against the oracle with the device's bf16 storage roundings modelled.
+    #     reference kernels (exact fp32 FMA chains): only summation order differs -> rel-L2 <= 3e-2 (typ. 3e-3).
+    #     tcgen05 kernels: the tensor core's internal accumulation differs from an fp32 FMA chain at the 1e-5 level,
+    #     which flips ~1e-3 of the bf16 roundings per layer; the same 3x-per-layer amplification turns that into
+    #     up to 4e-2 on decoder d1 (it stays ~7x below the bf16 storage noise itself) -> rel-L2 <= 8e-2.
     u = batch["u"] if model == "lggmvae" else None
     emu_sc, emu_g = E.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha)
     for k, v in emu_sc.items():
-        assert abs(sc[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, sc[k], v)
-    worst, bad = compare_grads(grads, emu_g, 3e-2)
+        assert abs(sc[k] - v) <= (1e-4 if no_tc else 1e-3) * max(1.0, abs(v)), (k, sc[k], v)
+    worst, bad = compare_grads(grads, emu_g, 3e-2 if no_tc else 8e-2)
     assert not bad, bad
 
 

@@ -66,4 +66,19 @@ def test_tc_layers_match_reference(model, H, B):
             torch.cuda.synchronize()
             _close(vdin, ref, f"{name} dgrad")
             n_checked += 1
+        if L.tc_wgrad:
+            _fill(e.debug_view(L.in_, L.in_elems, L.in_dt), 1.0, valid_cols=None)
+            if L.in_ld - L.in_coff > L.Ci and L.Ci < 32:   # zero the channel padding of narrow inputs (y: 30 of 32)
+                e.debug_view(L.in_, L.in_elems, L.in_dt).view(-1, L.in_ld)[:, L.in_coff + L.Ci:] = 0
+            _fill(e.debug_view(L.dout, L.dout_elems, 1), 1.0, valid_cols=L.Co, ld=L.dout_ld)
+            e.grads.zero_()
+            e.debug_run_layer(i, WGRAD, REF, inputs)
+            ref = e.grads.clone()
+            e.grads.zero_()
+            e.debug_run_layer(i, WGRAD, TC, inputs)
+            torch.cuda.synchronize()
+            assert ref.abs().sum().item() > 0
+            _close(e.grads, ref, f"{name} wgrad")
+            n_checked += 1
     assert n_checked > 0
+    print(f"{model} H={H} B={B}: {n_checked} tensor-core kernels checked")
