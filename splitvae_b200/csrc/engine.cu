@@ -34,6 +34,7 @@ struct Layer {
   int in = -1, out = -1, dout = -1, din = -1;  // buffer ids (-1: external input / no dgrad)
   int in_dt = DT_F32, out_dt = DT_F32;
   int mask_act = ACT_NONE;                    // activation of the producer of `in`
+  int xp = -1;                                // first conv of an encoder: staged padded bf16 image (tensor-core path)
   TcLayer tc;                                 // tensor-core plan (tc_kernels.h)
 };
 
@@ -64,6 +65,7 @@ struct sv_handle {
   Decoder dec_x{}, dec_xh{};
   int ZCAT = -1, EPS_G = -1, EPS_L = -1, Z_G = -1, Z_L = -1, ZM_G = -1, ZS_G = -1, ZM_L = -1, ZS_L = -1;
   int ZPM_OUT = -1, ZPS_OUT = -1, SCALARS = -1, PARTIALS = -1, COLSUM = -1, ADAM = -1, TCWS = -1;
+  int XP[2] = {-1, -1};     // staged first-layer images (x, x_hat) for the tensor-core path
   long long seg_split = 0;  // arena offset where the decoders start
   // bound buffers
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
@@ -404,6 +406,15 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ld, int coff
   dst[idx] = src[(idx / n) * ld + coff + idx % n];
 }
 
+void stage_first_inputs(sv_handle* h, const float* inputs, cudaStream_t s) {
+  if (!h->use_tc) return;
+  for (int i = 0; i < 2; ++i)
+    if (h->XP[i] >= 0) {
+      tc_stage_first(inputs, bp(h, h->XP[i]), i ? 3 : 0, h->B, h->H, h->W, s);
+      h->launches += 1;
+    }
+}
+
 sv_status check_launch(sv_handle* h, const char* what) {
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -491,7 +502,14 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->dec_xh = build_decoder(h, "decoder_x_hat", 128, 128, dzl2, 128, dout_ld);
 
   if (h->use_tc) {
-    for (auto& L : h->layers) tc_plan_layer(L.tc, L.g, L.in_dt, L.out_dt, L.in >= 0, L.din >= 0);
+    for (auto& L : h->layers) {
+      const bool first = L.in < 0;
+      tc_plan_layer(L.tc, L.g, L.in_dt, L.out_dt, L.in >= 0, L.din >= 0, first);
+      if (first && (L.tc.fwd_ok || L.tc.wgrad_ok)) {
+        if (h->XP[L.g.in_coff ? 1 : 0] < 0) h->XP[L.g.in_coff ? 1 : 0] = new_buf(h, tc_first_stage_bytes(h->B, h->H, h->W));
+        L.xp = h->XP[L.g.in_coff ? 1 : 0];
+      }
+    }
     size_t tcws = 0;
     for (auto& L : h->layers) tcws += tc_workspace_bytes(L.tc, L.g);
     h->TCWS = new_buf(h, tcws + 1024);
@@ -534,7 +552,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (h->use_tc) {
     char* tcws = (char*)bp(h, h->TCWS);
     for (auto& L : h->layers) {
-      const char* err = tc_bind_layer(L.tc, L.g, L.in >= 0 ? bp(h, L.in) : nullptr, bp(h, L.out), bp(h, L.dout),
+      const char* err = tc_bind_layer(L.tc, L.g, L.in >= 0 ? bp(h, L.in) : bp(h, L.xp), bp(h, L.out), bp(h, L.dout),
                                       L.din >= 0 ? bp(h, L.din) : nullptr, L.in >= 0 ? bp(h, L.in) : nullptr, L.mask_act, tcws);
       if (err) return fail(h, SV_ERR_DEVICE, "tensor-core plan for %s: %s", L.name.c_str(), err);
       tcws += tc_workspace_bytes(L.tc, L.g);
@@ -565,6 +583,7 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
   cudaStream_t s = (cudaStream_t)stream;
   const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  stage_first_inputs(h, inputs, s);
   if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
   conv_encoder_fwd(h, h->enc_xh, inputs, s);
   reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
@@ -762,6 +781,7 @@ sv_status sv_debug_run_layer(sv_handle* h, int32_t i, int32_t pass, int32_t impl
   if (L.in < 0 && !inputs && pass != SV_PASS_DGRAD) return fail(h, SV_ERR_INVALID, "layer %d reads the external inputs", i);
   const int T = h->act_dt;
   if (impl == SV_IMPL_TC) {
+    if (L.in < 0 && inputs) stage_first_inputs(h, inputs, s);
     if (pass == SV_PASS_FWD) { if (!L.tc.fwd_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core fwd for %s", L.name.c_str()); tc_conv_fwd(L.tc, s); }
     else if (pass == SV_PASS_DGRAD) { if (!L.tc.dgrad_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core dgrad for %s", L.name.c_str()); tc_conv_dgrad(L.tc, s); }
     else { if (!L.tc.wgrad_ok) return fail(h, SV_ERR_NOT_IMPLEMENTED, "no tensor-core wgrad for %s", L.name.c_str()); tc_conv_wgrad(L.tc, L.g, h->grads, s); }

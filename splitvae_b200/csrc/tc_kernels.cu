@@ -328,13 +328,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
 
 // sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
-                                                           int ci_pad, float* __restrict__ grads) {
+                                                           int ci_pad, int first, float* __restrict__ grads) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(idx % g.Co);
     const int ci = (int)((idx / g.Co) % g.Ci);
     const int tap = (int)(idx / ((long long)g.Co * g.Ci));
-    const size_t row = (size_t)tap * ci_pad + ci;
+    const size_t row = first ? (size_t)(tap / g.kw) * 64 + (tap % g.kw) * 8 + ci : (size_t)tap * ci_pad + ci;
     float s = 0.f;
     for (int k = 0; k < k_splits; ++k) s += partial[((size_t)k * m_pad + row) * n_pad + co];
     int lc;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const flo
 // weight packing: one multi-tensor kernel refreshes every bf16 operand copy from the fp32 masters
 // ------------------------------------------------------------------------------------------------
 struct PackJob {
-  int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias
+  int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias, 3: first-layer fwd weights
   int KH, KW, Ci, Co;       // layer geometry (logical)
   int nparts, part_n[3];
   long long part_w[3], part_b[3];
@@ -392,6 +392,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     float v = 0.f;
     if (J.kind == 0) {           // fwd: rows = co, k = ci
       if (r < J.Co && kk < J.Ci) v = master_w(J, params, a, b, kk, r);
+    } else if (J.kind == 3) {    // first layer: one K block per kernel row, k = (kw, c) with 8 pixels x 8 channels
+      const int kw = kk >> 3, c = kk & 7;
+      if (r < J.Co && kw < J.KW && c < J.Ci) v = master_w(J, params, tap, kw, c, r);
     } else {                     // dgrad: rows = ci, k = co, flipped (sub-)kernel
       const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
       if (r < J.Ci && kk < J.Co) v = master_w(J, params, kh, kw, r, kk);
@@ -461,6 +464,39 @@ const char* make_w_map(CUtensorMap* m, const void* base, int rows, long long k_t
   return nullptr;
 }
 
+// first-layer input as overlapping 8-pixel windows: element (k, wo, y, n) = xp[n][y][2*wo + k/8][k%8]
+const char* make_window_map(CUtensorMap* m, const void* xp, int N, int H, int W, int Wo, int tw, int th, int tn) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  const cuuint64_t row_pitch = (cuuint64_t)(W + 8) * 16;
+  cuuint64_t dims[4] = {64, (cuuint64_t)Wo, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {32, row_pitch, row_pitch * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)(th * 2 - 1), (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 2, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)xp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(window) failed: %d (H %d W %d Wo %d box %u,%u,%u)", (int)r, H, W, Wo, box[1],
+             box[2], box[3]);
+    return g_tc_error;
+  }
+  return nullptr;
+}
+
+__global__ void __launch_bounds__(256) stage_first_kernel(const float* __restrict__ inputs, bf16* __restrict__ xp, int coff, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const long long row = idx / W;  // n*H + y
+    const float* ip = inputs + idx * 6 + coff;
+    uint4 pk;
+    pk.x = pack_bf16x2(ip[0], ip[1]);
+    pk.y = pack_bf16x2(ip[2], 0.f);
+    pk.z = 0u; pk.w = 0u;
+    *reinterpret_cast<uint4*>(xp + (row * (W + 8) + x + 2) * 8) = pk;
+  }
+}
+
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -500,10 +536,85 @@ void finish_launch(TcLaunch& L, int n_cols_pad) {
 
 const char* tc_last_error() { return g_tc_error; }
 
-void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad) {
+size_t tc_first_stage_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 16; }
+
+void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, cudaStream_t s) {
+  const long long total = (long long)B * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_first_kernel<<<(int)blocks, 256, 0, s>>>(inputs, (bf16*)xp, coff, B, H, W);
+}
+
+// First conv of an encoder (6x6, stride 2, 3 input channels): the staged image is read as overlapping
+// 8-pixel x 8-channel windows, one K block of 64 per kernel row (48 of the 64 K entries carry weights).
+static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& off) {
+  if (!(g.Ci == 3 && g.kh == 6 && g.kw == 6 && g.stride == 2 && g.pl == 2 && is_pow2(g.Ho) && is_pow2(g.Wo) && g.Wo <= 64 &&
+        g.Wi == 2 * g.Wo && g.Hi == 2 * g.Ho && (g.dout_ld % 8) == 0))
+    return;
+  t.first = true;
+  {
+    TcLaunch& L = t.fwd;
+    if (!tile_grid(L, g.Ho, g.Wo, g.B)) return;
+    L.taps_h = 6; L.taps_w = 1; L.pad_t = g.pt; L.pad_l = 0; L.a_stride = 2;
+    L.bk = 64; L.swizzle = 128; L.kc = 1;
+    t.ci_pad = 64;
+    t.n_pad_fwd = pad_cols(g.Co);
+    L.n_valid = g.Co;
+    L.OH = g.Ho; L.OW = g.Wo; L.osy = 1; L.ooy = 0; L.osx = 1; L.oox = 0;
+    L.out_ld = g.out_ld; L.out_f32 = out_dt == DT_F32;
+    L.nparts = g.nparts;
+    for (int j = 0; j < 3; ++j) { L.part_n[j] = g.part_n[j]; L.part_act[j] = g.part_act[j]; }
+    L.mask_act = ACT_NONE;
+    finish_launch(L, t.n_pad_fwd);
+    t.fwd_ok = true;
+    t.fwd_launches = 1;
+    t.w_fwd_off = off;
+    off += round_up(t.n_pad_fwd * 6 * 64 * 2, 1024);
+    t.bias_off = off;
+    off += round_up(t.n_pad_fwd * 4, 1024);
+  }
+  {
+    TcWgradLaunch& L = t.wg;
+    int cbn, copad;
+    choose_bk(g.Co, cbn, copad);
+    if (copad > g.dout_ld) return;
+    L.first = 1;
+    L.taps_h = 6; L.taps_w = 1; L.pad_t = g.pt; L.pad_l = 0; L.a_stride = 2;
+    L.cb = 64; L.ncb = 1; L.a_swizzle = 128;
+    L.cbn = cbn; L.b_swizzle = cbn * 2;
+    L.nsub = 2; L.total_sb = 6; L.groups = 3;
+    L.n_pad = copad;
+    L.tile_cols = copad < 256 ? copad : 256;
+    L.n_tiles = copad / L.tile_cols;
+    L.groups_per_cta = 512 / L.tile_cols < 3 ? 512 / L.tile_cols : 3;
+    L.m_pad = L.groups * 128;
+    L.tile_w = g.Wo; L.tile_h = g.Ho < 64 / g.Wo ? g.Ho : 64 / g.Wo; L.tile_n_img = 64 / (L.tile_w * L.tile_h);
+    L.grid_h = g.Ho; L.n_img = g.B;
+    L.nchunks = L.tile_n_img > 1 ? (g.B + L.tile_n_img - 1) / L.tile_n_img : g.B * (g.Ho / L.tile_h);
+    const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
+    int ks = (296 + m_splits * L.n_tiles - 1) / (m_splits * L.n_tiles);
+    if (ks > L.nchunks) ks = L.nchunks;
+    if (ks < 1) ks = 1;
+    L.chunks_per_split = (L.nchunks + ks - 1) / ks;
+    L.k_splits = (L.nchunks + L.chunks_per_split - 1) / L.chunks_per_split;
+    L.a_stages = 4; L.b_stages = 2;
+    L.smem_bytes = (size_t)L.a_stages * 128 * 64 * 2 + (size_t)L.b_stages * L.tile_cols * 64 * 2 + sizeof(WgCtl) + 1024;
+    t.wgrad_ok = true;
+    t.wgrad_launches = 2;
+    t.wg_partial_off = off;
+    off += ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024;
+  }
+}
+
+void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer) {
   t.in_dt = in_dt;
   t.out_dt = out_dt;
   size_t off = 0;
+  if (first_layer) {
+    plan_first_layer(t, g, out_dt, off);
+    t.bytes = off;
+    return;
+  }
   // ---- forward: A = layer input (must be an internal bf16 tensor) ----
   if (has_internal_input && in_dt == DT_BF16 && (g.in_ld % 8) == 0 && (g.in_coff % 8) == 0) {
     TcLaunch& L = t.fwd;
@@ -615,10 +726,12 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
   t.ws = ws;
   if (t.fwd_ok) {
     TcLaunch& L = t.fwd;
-    const char* e = make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci,
-                                 L.bk, L.tile_w, L.tile_h, L.tile_n_img, g.stride, L.swizzle);
+    const char* e = t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
+                            : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff,
+                                           t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk, L.tile_w, L.tile_h, L.tile_n_img,
+                                           g.stride, L.swizzle);
     if (e) return e;
-    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)g.kh * g.kw * t.ci_pad, L.bk, L.tile_cols, L.swizzle);
+    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * t.ci_pad, L.bk, L.tile_cols, L.swizzle);
     if (e) return e;
     L.bias = (const float*)(ws + t.bias_off);
     L.out = out;
@@ -646,8 +759,9 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
   }
   if (t.wgrad_ok) {
     TcWgradLaunch& L = t.wg;
-    const char* e = make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, L.ncb * L.cb, L.cb, L.tile_w, L.tile_h, L.tile_n_img,
-                                 g.stride, L.a_swizzle);
+    const char* e = t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
+                            : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, L.ncb * L.cb, L.cb, L.tile_w, L.tile_h,
+                                           L.tile_n_img, g.stride, L.a_swizzle);
     if (e) return e;
     e = make_act_map(&L.map_b, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, L.n_pad, L.cbn, L.tile_w, L.tile_h, L.tile_n_img, 1, L.b_swizzle);
     if (e) return e;
@@ -678,9 +792,9 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     for (int j = 0; j < 3; ++j) { B.part_n[j] = g.part_n[j]; B.part_w[j] = g.part_w[j]; B.part_b[j] = g.part_b[j]; }
     if (t.fwd_ok) {
       PackJob J = B;
-      J.kind = 0; J.rows_pad = t.n_pad_fwd; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = t.ci_pad;
+      J.kind = t.first ? 3 : 0; J.rows_pad = t.n_pad_fwd; J.taps_h = t.fwd.taps_h; J.taps_w = t.fwd.taps_w; J.k_pad = t.ci_pad;
       J.dst = t.ws + t.w_fwd_off;
-      J.count = (long long)t.n_pad_fwd * g.kh * g.kw * t.ci_pad;
+      J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * t.ci_pad;
       push(J);
       PackJob Jb = B;
       Jb.kind = 2; Jb.dst = t.ws + t.bias_off; Jb.count = t.n_pad_fwd;
@@ -744,7 +858,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, grads);
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
 }
 
 }  // namespace sv

@@ -49,11 +49,13 @@ struct TcWgradLaunch {
   int a_stages, b_stages;
   int m_pad, n_pad;               // partial buffer dims
   float* partial;
+  int first;                      // first-layer row mapping: row = kh*64 + kw*8 + ci
   size_t smem_bytes;
 };
 
 struct TcLayer {
   bool fwd_ok = false, dgrad_ok = false, wgrad_ok = false;
+  bool first = false;                 // first conv of an encoder: reads the staged, padded bf16 image (tc_stage_first)
   int fwd_launches = 0, dgrad_launches = 0, wgrad_launches = 0;
   int n_dgrad = 0;
   TcLaunch fwd{}, dgrad[4]{};
@@ -69,7 +71,10 @@ struct TcLayer {
 };
 
 // plan (no CUDA calls), workspace size, bind (creates TMA descriptors; returns NULL or an error text)
-void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad);
+void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer);
+// staged first-layer input: [B][H][W+8][8] bf16, real pixel x at column x+2, channels 3..7 and the borders zero
+size_t tc_first_stage_bytes(int B, int H, int W);
+void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, cudaStream_t s);
 size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom& g);
 const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din,
                           const void* mask_src, int mask_act, char* ws);

@@ -41,9 +41,9 @@ def test_tc_layers_match_reference(model, H, B):
     for i, L in enumerate(e.debug_layers()):
         name = L.name.decode()
         if L.tc_fwd:
-            vin = e.debug_view(L.in_, L.in_elems, L.in_dt)
             vout = e.debug_view(L.out, L.out_elems, L.out_dt)
-            _fill(vin, 1.0)
+            if L.in_:   # first convs (in_ == NULL) read the caller's image batch
+                _fill(e.debug_view(L.in_, L.in_elems, L.in_dt), 1.0)
             vout.zero_()
             e.debug_run_layer(i, FWD, REF, inputs)
             ref = vout.clone()
@@ -67,8 +67,9 @@ def test_tc_layers_match_reference(model, H, B):
             _close(vdin, ref, f"{name} dgrad")
             n_checked += 1
         if L.tc_wgrad:
-            _fill(e.debug_view(L.in_, L.in_elems, L.in_dt), 1.0, valid_cols=None)
-            if L.in_ld - L.in_coff > L.Ci and L.Ci < 32:   # zero the channel padding of narrow inputs (y: 30 of 32)
+            if L.in_:
+                _fill(e.debug_view(L.in_, L.in_elems, L.in_dt), 1.0, valid_cols=None)
+            if L.in_ and L.in_ld - L.in_coff > L.Ci and L.Ci < 32:   # zero the channel padding of narrow inputs (y: 30 of 32)
                 e.debug_view(L.in_, L.in_elems, L.in_dt).view(-1, L.in_ld)[:, L.in_coff + L.Ci:] = 0
             _fill(e.debug_view(L.dout, L.dout_elems, 1), 1.0, valid_cols=L.Co, ld=L.dout_ld)
             e.grads.zero_()
