@@ -1,0 +1,98 @@
+"""Host-side logic on CPU: CLI surface (vae/main.py:16-31), optimizer objects, sharding, and the data-parallel
+gradient exchange over gloo with world_size 2 (the N>1 path; NCCL carries the same calls on the GPU box)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import splitvae_oracle as O
+from splitvae_b200 import main as cli
+from splitvae_b200 import parallel, trainer
+from splitvae_b200.utils import dotdict
+
+
+def test_cli_defaults_match_reference_flags():
+    c = cli.make_config([])
+    # vae/main.py:16-31 defaults, verbatim
+    assert (c.global_latent_dims, c.local_latent_dims, c.learning_rate, c.beta, c.dataset) == (128, 128, 1e-4, 40, "svhn")
+    assert (c.training_steps, c.batch_size, c.patch_size, c.augmentation, c.model) == (1000000, 64, 1, "scramble", "lgvae")
+    assert (c.y_size, c.tau, c.alpha, c.viz, c.no_label, c.allow_growth) == (30, 0.4, 40, False, False, False)
+    assert c.label is True and c.nonexistent_key is None                   # dotdict: missing keys read as None (vae/utils.py:3-7)
+    c = cli.make_config("--model lggmvae --beta 120 --alpha 40 --y_size 30 --patch_size 8 --dataset celeba64 -no_label".split())
+    assert c.model == "lggmvae" and c.beta == 120 and c.patch_size == 8 and c.dataset == "celeba64" and c.label is False
+
+
+def test_dataset_shapes_and_errors():
+    from splitvae_b200 import data
+    assert data.image_shape("svhn") == [-1, 32, 32, 3] and data.image_shape("celeba64") == [-1, 64, 64, 3]
+    with pytest.raises(NotImplementedError):
+        data.image_shape("mnist")                                            # vae/data.py:21
+
+
+def test_optimizer_objects():
+    opt = trainer.Adam(learning_rate=3e-4)
+    assert opt.learning_rate == 3e-4 and opt.schedule is None
+    sched = trainer.ExponentialDecay(1e-4, decay_steps=1000000, decay_rate=0.4, staircase=True)     # vae/main.py:67
+    assert trainer.Adam(learning_rate=sched).learning_rate == 1e-4
+    with pytest.raises(NotImplementedError):
+        trainer.ExponentialDecay(1e-4, decay_steps=10, decay_rate=0.5, staircase=False)
+
+
+def test_shard_range():
+    assert [parallel.shard_range(2048, 8, r) for r in (0, 7)] == [(0, 256), (1792, 2048)]
+    with pytest.raises(ValueError):
+        parallel.shard_range(10, 4, 0)
+
+
+def test_loss_functions_match_oracle_on_cpu_tensors():
+    rng = np.random.default_rng(0)
+    mu, sg = torch.tensor(rng.standard_normal((4, 128))), torch.tensor(rng.uniform(0.3, 2, (4, 128)))
+    assert abs(float(trainer.kl_divergence(mu, sg)) - float(O.kl_divergence(mu, sg))) < 1e-12
+    assert abs(float(trainer.kl_divergence_two_gauss(mu, sg, 0., 1.)) - float(O.kl_divergence_two_gauss(mu, sg, 0., 1.))) < 1e-12
+
+
+def _dp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = parallel.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    torch.set_num_threads(1)
+    model, H, Bg, beta = "lgvae", 16, 4, 3.0
+    params = O.init_params(model, H, H, seed=7)
+    b = O.synthetic_batch(Bg, H, 2, seed_base=60)
+    lo, hi = parallel.shard_range(Bg, world, rank)
+    # per-rank step on its contiguous shard (the engine scales gradients by 1/(b*world); the oracle's batch mean is 1/b)
+    sc, grads = O.forward_backward(params, model, b["inputs"][lo:hi], b["eps_g"][lo:hi], b["eps_l"][lo:hi], None, beta=beta,
+                                   dtype=torch.float64)
+    names = list(grads.keys())
+    flat = torch.cat([torch.tensor(grads[k]).reshape(-1) for k in names]) / world
+    split = flat.numel() // 3
+    red = parallel.BucketReducer(flat, [(split, flat.numel() - split), (0, split)])      # two buckets, backward order
+    assert red.enabled
+    red.reduce(0)
+    red.reduce(1)
+    red.wait_all()
+    scal = parallel.mean_scalars(torch.tensor([sc["total"], sc["recon_x"]], dtype=torch.float64))
+    if rank == 0:
+        ret["flat"] = flat.numpy().copy()
+        ret["scal"] = scal.numpy().copy()
+        ret["names"] = names
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_world_size_2_equals_global_batch():
+    """N ranks x batch b with SUM all-reduce of pre-scaled gradients == one step at batch N*b."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_dp_worker, args=(2, port, ret), nprocs=2, join=True)
+    model, H, Bg, beta = "lgvae", 16, 4, 3.0
+    params = O.init_params(model, H, H, seed=7)
+    b = O.synthetic_batch(Bg, H, 2, seed_base=60)
+    sc, grads = O.forward_backward(params, model, b["inputs"], b["eps_g"], b["eps_l"], None, beta=beta, dtype=torch.float64)
+    full = np.concatenate([grads[k].reshape(-1) for k in ret["names"]])
+    assert np.allclose(ret["flat"], full, rtol=1e-9, atol=1e-12)
+    assert np.allclose(ret["scal"], [sc["total"], sc["recon_x"]], rtol=1e-12)

@@ -1,0 +1,201 @@
+"""CPU tests of the oracle itself (no GPU): analytic known answers, fp64 finite differences, the second
+(hand-derived numpy) restatement of the loss backward, and the committed golden vectors."""
+import glob
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import splitvae_oracle as O
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+
+
+# ---- analytic known answers -------------------------------------------------------------------
+def test_kl_known_answers():
+    rng = np.random.default_rng(0)
+    mu, sg = T(rng.standard_normal((5, 128))), T(rng.uniform(0.2, 2.0, (5, 128)))
+    assert float(O.kl_divergence(torch.zeros(3, 128, dtype=torch.float64), torch.ones(3, 128, dtype=torch.float64))) == 0.0
+    assert abs(float(O.kl_divergence_two_gauss(mu, sg, mu, sg))) < 1e-12
+    # KL(q || N(0,1)) through both formulas (trainer.py:11-15 vs 17-18 with python scalars 0., 1.)
+    assert abs(float(O.kl_divergence_two_gauss(mu, sg, 0., 1.)) - float(O.kl_divergence(mu, sg))) < 1e-10
+    # total_kl == beta * (kl_x + kl_x_hat)   (trainer.py:130-132)
+    mu2, sg2 = T(rng.standard_normal((5, 128))), T(rng.uniform(0.2, 2.0, (5, 128)))
+    cat = O.kl_divergence(torch.cat([mu, mu2], 1), torch.cat([sg, sg2], 1))
+    assert abs(float(cat) - float(O.kl_divergence(mu, sg)) - float(O.kl_divergence(mu2, sg2))) < 1e-10
+
+
+def test_y_kl_known_answers():
+    K = 30
+    out = O.latent_fwd_bwd_numpy("lggmvae", np.zeros((2, 128)), np.ones((2, 128)), np.zeros((2, 128)), np.ones((2, 128)), 1.0,
+                                 y_logits=np.zeros((2, K)), zpm=np.zeros((2, 128)), zps=np.ones((2, 128)))
+    assert abs(out["y_kl"] - math.log(1 + K * 1e-8)) < 1e-12       # not exactly 0: the +1e-8 of trainer.py:161
+    onehot = np.full((1, K), -80.0); onehot[0, 3] = 80.0
+    out = O.latent_fwd_bwd_numpy("lggmvae", np.zeros((1, 128)), np.ones((1, 128)), np.zeros((1, 128)), np.ones((1, 128)), 1.0,
+                                 y_logits=onehot, zpm=np.zeros((1, 128)), zps=np.ones((1, 128)))
+    assert abs(out["y_kl"] - math.log(K)) < 1e-6
+
+
+@pytest.mark.parametrize("m,ls", [(0.0, 0.0), (0.3, -1.0), (-0.9, -2.0), (0.95, 0.5), (0.1, -3.0), (-0.9, -4.0)])
+def test_discretised_logistic_is_a_pmf(m, ls):
+    grid = torch.tensor(np.arange(256) / 255.0 * 2 - 1, dtype=torch.float64)     # vae/data.py:52
+    nll = O.discretised_logistic_loss(grid, torch.full_like(grid, m), torch.full_like(grid, ls))
+    assert abs(float(torch.exp(-nll).sum()) - 1.0) < 3e-7
+
+
+def test_discretised_logistic_branches_and_numpy_twin():
+    rng = np.random.default_rng(1)
+    n = 20000
+    x = rng.integers(0, 256, n) / 255.0 * 2 - 1
+    m, ls = rng.uniform(-1.5, 1.5, n), rng.uniform(-7, 2, n)
+    nll, dm, dls, branch = O.dll_fwd_bwd_numpy(x, m, ls)
+    assert set(np.unique(branch)) == {0, 1, 2, 3}
+    tm, tls = T(m).requires_grad_(), T(ls).requires_grad_()
+    ref = O.discretised_logistic_loss(T(x), tm, tls)
+    ref.sum().backward()
+    assert np.allclose(ref.detach().numpy(), nll, rtol=1e-8, atol=1e-9)   # two softplus formulations
+    # autograd (tf.where-style: gradient of the selected branch) vs the hand-derived backward of SURVEY.md 9.2
+    assert np.allclose(tm.grad.numpy(), dm, rtol=1e-6, atol=1e-8)
+    assert np.allclose(tls.grad.numpy(), dls, rtol=1e-6, atol=1e-8)
+
+
+def test_latent_numpy_twin_matches_autograd():
+    rng = np.random.default_rng(2)
+    B, K, beta, alpha = 3, 30, 7.0, 3.0
+    v = {k: T(rng.standard_normal((B, 128))).requires_grad_() for k in ("zm_g", "zm_l", "zpm")}
+    s = {k: T(rng.uniform(0.3, 2.0, (B, 128))).requires_grad_() for k in ("zs_g", "zs_l", "zps")}
+    yl = T(rng.standard_normal((B, K)) * 2).requires_grad_()
+    kl_x = O.kl_divergence_two_gauss(v["zm_g"], s["zs_g"], v["zpm"], s["zps"])
+    kl_l = O.kl_divergence_two_gauss(v["zm_l"], s["zs_l"], 0., 1.)
+    py = torch.softmax(yl, 1)
+    y_kl = torch.mean(torch.sum(py * (torch.log(py + 1e-8) - math.log(1.0 / K)), 1))
+    (beta * (kl_x + kl_l) + alpha * y_kl).backward()
+    out = O.latent_fwd_bwd_numpy("lggmvae", v["zm_g"].detach(), s["zs_g"].detach(), v["zm_l"].detach(), s["zs_l"].detach(), beta, alpha,
+                                 y_logits=yl.detach(), zpm=v["zpm"].detach(), zps=s["zps"].detach())
+    for name, t in [("d_zm_g", v["zm_g"]), ("d_zs_g", s["zs_g"]), ("d_zm_l", v["zm_l"]), ("d_zs_l", s["zs_l"]), ("d_zpm", v["zpm"]),
+                    ("d_zps", s["zps"]), ("d_y_logits", yl)]:
+        assert np.allclose(out[name], t.grad.numpy(), rtol=1e-9, atol=1e-12), name
+    assert abs(out["kl_x"] - float(kl_x)) < 1e-10 and abs(out["y_kl"] - float(y_kl)) < 1e-12
+
+
+# ---- TF / Keras op semantics ------------------------------------------------------------------
+def test_same_padding_table():
+    # s1 k4: 1/2; s1 k6: 2/3; s2 k6: 2/2; s2 k4: 1/1
+    assert O.same_pad(32, 4, 1) == (1, 2) and O.same_pad(32, 6, 1) == (2, 3)
+    assert O.same_pad(32, 6, 2) == (2, 2) and O.same_pad(32, 4, 2) == (1, 1)
+    x = torch.arange(16.).reshape(1, 4, 4, 1)
+    y = O.conv2d_same(x, torch.ones(4, 4, 1, 1), torch.zeros(1), 1)
+    assert y.shape == (1, 4, 4, 1)
+    assert float(y[0, 0, 0, 0]) == float(x[0, :3, :3, 0].sum())          # 1 row/col of padding before, 2 after
+    assert float(y[0, 3, 3, 0]) == float(x[0, 2:, 2:, 0].sum())
+
+
+def test_bilinear_half_pixel_weights():
+    x = torch.tensor([[0., 4.], [8., 12.]]).reshape(1, 2, 2, 1)
+    y = O.resize2x(x)[0, :, :, 0]
+    assert torch.allclose(y[0], torch.tensor([0., 1., 3., 4.]))           # .75/.25 interior, clamped edges
+    assert torch.allclose(y[:, 0], torch.tensor([0., 2., 6., 8.]))
+
+
+def test_keras_adam_and_schedule_known_answers():
+    f = np.float32
+    p, g = np.array([1.0, -2.0], f), np.array([0.5, -0.25], f)
+    a = O.adam_alpha(1e-3, 1)
+    assert abs(float(a) - 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)) < 1e-10
+    p1, m1, v1 = O.keras_adam_update(p, g, np.zeros(2, f), np.zeros(2, f), a)
+    # first step: m = 0.1 g, v = 0.001 g^2 -> update = alpha * 0.1 g / (sqrt(0.001) |g| + 1e-7) ~= lr * sign(g)
+    assert np.allclose(m1, 0.1 * g, rtol=1e-6) and np.allclose(v1, 0.001 * g * g, rtol=1e-5)
+    assert np.allclose(p - p1, 1e-3 * np.sign(g), rtol=1e-4)
+    assert O.lr_at("lgvae", 1e-4, 2_500_000) == 1e-4
+    assert O.lr_at("lggmvae", 1e-4, 999_999) == 1e-4
+    assert abs(O.lr_at("lggmvae", 1e-4, 1_000_000) - 0.4e-4) < 1e-12       # staircase on the 0-based count
+    assert abs(O.lr_at("lggmvae", 1e-4, 2_000_001) - 0.16e-4) < 1e-12
+
+
+@pytest.mark.parametrize("H,p", [(32, 1), (32, 4), (64, 8), (16, 16)])
+def test_scramble_index_map(H, p):
+    """x_hat[g*p+i, t*p+j] = x[pr(pi[g*G+t])*p+i, pc(pi[g*G+t])*p+j]  (augmentation.py:43-57)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((H, H, 3)).astype(np.float32)
+    G = H // p
+    perm = rng.permutation(G * G)
+    out = O.scramble(x, p, perm)
+    assert out.shape == (H, H, 6) and np.array_equal(out[..., :3], x)
+    for q in rng.integers(0, G * G, 8):
+        g, t = divmod(int(q), G)
+        pr, pc = divmod(int(perm[q]), G)
+        assert np.array_equal(out[g * p:(g + 1) * p, t * p:(t + 1) * p, 3:], x[pr * p:(pr + 1) * p, pc * p:(pc + 1) * p])
+    if p == H:
+        assert np.array_equal(out[..., 3:], x)
+
+
+def test_variable_inventory_counts():
+    # tensors / parameters per model
+    for model, H, n_t, n_p in [("lgvae", 32, 40, 3_204_748), ("lgvae", 64, 40, 8_722_060), ("lggmvae", 32, 54, 6_775_370),
+                               ("lggmvae", 64, 54, 20_157_002)]:
+        P = O.init_params(model, H, H)
+        assert len(P) == n_t and sum(v.size for v in P.values()) == n_p
+    P = O.init_params("lggmvae", 32, 32)
+    assert np.all(P["encoder_x.z_prior_sig.bias"] == 1) and np.all(P["encoder_x.z_sig.bias"] == 1)   # model.py:68,76
+    assert np.all(P["encoder_x.z_mean.bias"] == 0)
+
+
+# ---- fp64 finite differences of the whole step ---------------------------------------------------
+@pytest.mark.parametrize("model", ["lgvae", "lggmvae"])
+def test_autograd_matches_finite_differences(model):
+    H, B, beta, alpha = 16, 2, 3.0, 2.0
+    params = O.init_params(model, H, H, seed=11)
+    params = {k: v.astype(np.float64) for k, v in params.items()}
+    b = O.synthetic_batch(B, H, 4, seed_base=50)
+    u = b["u"] if model == "lggmvae" else None
+    kw = dict(beta=beta, alpha=alpha, dtype=torch.float64)
+    _, grads = O.forward_backward(params, model, b["inputs"], b["eps_g"], b["eps_l"], u, **kw)
+    rng = np.random.default_rng(4)
+    names = ["encoder_x_hat.e1.kernel", "encoder_x_hat.e4_sd.bias", "decoder_x.d1.kernel", "decoder_x.d3.kernel", "decoder_x_hat.d5.bias",
+             "decoder_x_hat.d4.kernel"]
+    names += ["encoder_x.e2.kernel", "encoder_x.e4_mean.kernel"] if model == "lgvae" else \
+        ["encoder_x.h_block.1.kernel", "encoder_x.y_dense.kernel", "encoder_x.z_prior_sig.kernel", "encoder_x.h_top_dense.bias", "encoder_x.z_sig.kernel"]
+    for name in names:
+        idx = tuple(int(rng.integers(0, s)) for s in params[name].shape)
+        h = 1e-6
+        vals = []
+        for sgn in (+1, -1):
+            q = dict(params)
+            q[name] = params[name].copy()
+            q[name][idx] += sgn * h
+            P = O.to_torch(q, torch.float64, requires_grad=False)
+            tin = T(b["inputs"])
+            out = O.model_forward(P, model, tin, T(b["eps_g"]), T(b["eps_l"]), None if u is None else T(u))
+            vals.append(float(O.step_losses(out, tin, model, beta, alpha)["total"]))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        an = grads[name][idx]
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)) + 1e-6, (name, idx, fd, an)
+
+
+# ---- committed golden vectors -----------------------------------------------------------------------
+def test_golden_files_exist():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "h64" not in p], ids=lambda p: os.path.basename(p)[:-5])
+def test_oracle_reproduces_golden(path):
+    """The oracle, re-run from seeds, reproduces the committed vectors (the H=64 cases are re-checked on the GPU box)."""
+    with open(path) as f:
+        G = json.load(f)
+    c = G["case"]
+    params = O.init_params(c["model"], c["H"], c["H"], seed=5 + c["seed_base"])
+    b = O.synthetic_batch(c["B"], c["H"], c["patch"], seed_base=c["seed_base"])
+    assert abs(float(np.asarray(b["inputs"], np.float64).sum()) - G["inputs_sum"]) < 1e-9
+    assert abs(float(sum(np.asarray(v, np.float64).sum() for v in params.values())) - G["params_sum"]) < 1e-9
+    u = b["u"] if c["model"] == "lggmvae" else None
+    sc, grads = O.forward_backward(params, c["model"], b["inputs"], b["eps_g"], b["eps_l"], u, beta=c["beta"], alpha=c["alpha"],
+                                   dtype=torch.float64)
+    for k, v in G["scalars_fp64"].items():
+        assert abs(sc[k] - v) <= 1e-9 * max(1.0, abs(v)), k
+    for k, s in G["grads_fp64"].items():
+        assert abs(float(np.linalg.norm(grads[k])) - s["l2"]) <= 1e-8 * max(1e-6, s["l2"]), k
+        assert np.allclose(np.asarray(grads[k]).ravel()[:4], s["head"], rtol=1e-7, atol=1e-12), k
