@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -76,6 +77,12 @@ struct sv_handle {
   const float* last_inputs = nullptr;  // inputs of the step in flight (first-layer wgrad reads them)
   unsigned long long seed = 0x5EEDull;
   TcPackTable* pack = nullptr;
+  // the x / x_hat encoders and the two decoders are independent: they run on two streams (fork/join with events, which
+  // CUDA-graph capture turns into parallel branches)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int COLSUM2 = -1;
+  bool two_streams = true;
 };
 
 namespace {
@@ -300,7 +307,7 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
     ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, h->round_w, s);
     h->launches += 1;
   }
-  bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, h->COLSUM), h->grads, s);
+  bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, s == h->side ? h->COLSUM2 : h->COLSUM), h->grads, s);
   h->launches += 2;
   if (L.din >= 0) {
     if (h->use_tc && L.tc.dgrad_ok) {
@@ -415,6 +422,19 @@ void stage_first_inputs(sv_handle* h, const float* inputs, cudaStream_t s) {
     }
 }
 
+// side-stream branch: returns the stream the second branch should use (the main stream if two-stream mode is off)
+cudaStream_t fork_side(sv_handle* h, cudaStream_t s) {
+  if (!h->two_streams || !h->side) return s;
+  cudaEventRecord(h->ev_fork, s);
+  cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+  return h->side;
+}
+void join_side(sv_handle* h, cudaStream_t s) {
+  if (!h->two_streams || !h->side) return;
+  cudaEventRecord(h->ev_join, h->side);
+  cudaStreamWaitEvent(s, h->ev_join, 0);
+}
+
 sv_status check_launch(sv_handle* h, const char* what) {
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -490,6 +510,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->SCALARS = f32_buf(h, 64);
   h->PARTIALS = f32_buf(h, 2 * 148 * 8 + 64);
   h->COLSUM = f32_buf(h, 256 * 8192);
+  h->COLSUM2 = f32_buf(h, 256 * 8192);
   h->ADAM = new_buf(h, 1024);
   const int dzcat = act_buf(h, (long long)B * 256), dzl2 = act_buf(h, (long long)B * 128);
 
@@ -519,7 +540,12 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 }
 
 sv_status sv_destroy(sv_handle* h) {
-  if (h) tc_pack_table_destroy(h->pack);
+  if (h) {
+    tc_pack_table_destroy(h->pack);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
+  }
   delete h;
   return SV_OK;
 }
@@ -565,6 +591,15 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     h->pack = tc_pack_table_create(tl.data(), tg.data(), (int)tl.size(), &perr);
     if (!h->pack) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
   }
+  if (!h->side) {
+    const char* one = getenv("SV_ONE_STREAM");
+    h->two_streams = !(one && *one == '1');
+    if (h->two_streams &&
+        (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
+      return fail(h, SV_ERR_DEVICE, "side stream / event creation failed");
+  }
   h->bound = true;
   return SV_OK;
 }
@@ -584,12 +619,16 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   cudaStream_t s = (cudaStream_t)stream;
   const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
   stage_first_inputs(h, inputs, s);
+  cudaStream_t s2 = fork_side(h, s);
   if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
-  conv_encoder_fwd(h, h->enc_xh, inputs, s);
+  conv_encoder_fwd(h, h->enc_xh, inputs, s2);
+  join_side(h, s);
   reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
   h->launches += 1;
+  s2 = fork_side(h, s);
   decoder_fwd(h, h->dec_x, s);
-  decoder_fwd(h, h->dec_xh, s);
+  decoder_fwd(h, h->dec_xh, s2);
+  join_side(h, s);
   if (gm && prior_copies) {  // contiguous z_prior_mean / z_prior_sig for the reference's output tuple
     copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
     copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
@@ -633,16 +672,20 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const float* inputs = h->last_inputs;
   if (seg == 0) {
+    cudaStream_t s2 = fork_side(h, s);
     decoder_bwd(h, h->dec_x, s);
-    decoder_bwd(h, h->dec_xh, s);
+    decoder_bwd(h, h->dec_xh, s2);
+    join_side(h, s);
   } else if (seg == 1) {
     if (!inputs) return fail(h, SV_ERR_STATE, "sv_loss_fwd_bwd must precede sv_backward_segment");
     const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
     const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
     latent_bwd(latent_bufs(h), h->B, h->act_dt, gm, h->cfg.beta, inv_batch, s);
     h->launches += 1;
-    conv_encoder_bwd(h, h->enc_xh, inputs, s);
+    cudaStream_t s2 = fork_side(h, s);
+    conv_encoder_bwd(h, h->enc_xh, inputs, s2);
     if (gm) gm_encoder_bwd(h, inputs, s); else conv_encoder_bwd(h, h->enc_x, inputs, s);
+    join_side(h, s);
   } else {
     return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
   }
@@ -705,8 +748,10 @@ sv_status sv_decode(sv_handle* h, const float* z_x, const float* z_x_hat, void* 
   cudaStream_t s = (cudaStream_t)stream;
   pack_z_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>(z_x, z_x_hat, bp(h, h->ZCAT), h->act_dt, h->B);
   h->launches += 1;
+  cudaStream_t s2 = fork_side(h, s);
   decoder_fwd(h, h->dec_x, s);
-  decoder_fwd(h, h->dec_xh, s);
+  decoder_fwd(h, h->dec_xh, s2);
+  join_side(h, s);
   return check_launch(h, "sv_decode");
 }
 

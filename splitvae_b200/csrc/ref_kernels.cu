@@ -150,15 +150,24 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   }
 }
 
-__global__ void colsum_final_kernel(ConvGeom g, const float* __restrict__ partial, int nchunks,
-                                    float* __restrict__ grads) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.Co) return;
+// block = 32 columns x 8 chunk lanes; fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) colsum_final_kernel(ConvGeom g, const float* __restrict__ partial, int nchunks,
+                                                           float* __restrict__ grads) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int k = 0; k < nchunks; ++k) s += partial[(long long)k * g.Co + c];
-  int lc;
-  const int j = part_of(g, c, lc);
-  grads[g.part_b[j] + lc] = s;
+  if (c < g.Co)
+    for (int k = threadIdx.y; k < nchunks; k += 8) s += partial[(long long)k * g.Co + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < g.Co) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    int lc;
+    const int j = part_of(g, c, lc);
+    grads[g.part_b[j] + lc] = t;
+  }
 }
 
 // tf.image.resize(x, [2H, 2W]) (bilinear, half-pixel centres):
@@ -355,6 +364,34 @@ void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* do
 #undef CALL
 }
 
+// bf16, ld % 8 == 0: each thread sums 8 adjacent columns (one 128-bit load per row); block = (ld/8 column groups) x row lanes
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const bf16* __restrict__ d, long long rows, int C, int ld,
+                                                                 int rows_per_chunk, float* __restrict__ partial) {
+  extern __shared__ float red_v[];   // [blockDim.y][ld]
+  const int groups = ld >> 3;
+  const int gi = threadIdx.x;        // column group
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (gi < groups)
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const F8 v = ld_bf16x8(d + r * ld + gi * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v.v[i];
+    }
+  if (gi < groups) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red_v[threadIdx.y * ld + gi * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+    float s = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y) s += red_v[y * ld + c];
+    partial[(long long)blockIdx.x * C + c] = s;
+  }
+}
+
 int colsum_chunks(long long rows) {
   long long c = (rows + 511) / 512;
   if (c > 256) c = 256;
@@ -366,12 +403,22 @@ void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, f
   const long long rows = (long long)g.B * g.Ho * g.Wo;
   const int nch = colsum_chunks(rows);
   const int rpc = (int)((rows + nch - 1) / nch);
+  if (dt == DT_BF16 && (g.dout_ld % 8) == 0 && g.dout_ld <= 2048) {
+    const int groups = g.dout_ld / 8;
+    int bx = 1;
+    while (bx < groups && bx < 256) bx <<= 1;
+    const int by = 256 / bx > 0 ? 256 / bx : 1;
+    colsum_partial_vec_kernel<<<nch, dim3(bx, by), (size_t)by * g.dout_ld * sizeof(float), s>>>((const bf16*)dout, rows, g.Co, g.dout_ld, rpc,
+                                                                                               partial_ws);
+    colsum_final_kernel<<<(g.Co + 31) / 32, dim3(32, 8), 0, s>>>(g, partial_ws, nch, grads);
+    return;
+  }
   dim3 grid((g.Co + 31) / 32, nch), block(32, 8);
   if (dt == DT_F32)
     colsum_partial_kernel<float><<<grid, block, 0, s>>>((const float*)dout, rows, g.Co, g.dout_ld, rpc, partial_ws);
   else
     colsum_partial_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dout, rows, g.Co, g.dout_ld, rpc, partial_ws);
-  colsum_final_kernel<<<(g.Co + 127) / 128, 128, 0, s>>>(g, partial_ws, nch, grads);
+  colsum_final_kernel<<<(g.Co + 31) / 32, dim3(32, 8), 0, s>>>(g, partial_ws, nch, grads);
 }
 
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s) {

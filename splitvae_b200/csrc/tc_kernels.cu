@@ -12,6 +12,7 @@
 // Reference semantics: Keras Conv2D / Dense forward (vae/model.py:36-42,49-76,152-156) and their
 // input gradients under tape.gradient (vae/trainer.py:137,166).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -38,6 +39,170 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+
+// One epilogue thread = one accumulator row (TMEM lane) = one output pixel: reads tile_cols fp32 columns, adds the bias,
+// applies the activation (forward) or multiplies by the activation derivative of the producer layer (dgrad), stores NHWC.
+// The activation / mask kind / output type are compile-time so each instantiation is a short straight-line loop
+// (a single generic body with every activation inlined was ~6000 instructions and I-cache bound).
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_ELU) return x > 0.f ? x : expm1f(x);
+  if (ACT == ACT_SOFTPLUS) return softplus_f(x);
+  return x;
+}
+template <int MASK>
+__device__ __forceinline__ float mask_t(float y) {
+  if (MASK == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (MASK == ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+  if (MASK == ACT_SOFTPLUS) return 1.f - expf(-y);
+  return 1.f;
+}
+
+template <int ACT, int MASK, bool OUT_F32>
+__device__ __forceinline__ void epilogue_rows_t(const TcLaunch& P, uint32_t tmem_acc, int quarter, bool valid, long long opix, int n_tile) {
+  const int col_base = n_tile * P.tile_cols;
+  const int esz = OUT_F32 ? 4 : 2;
+  const bool vec_ok = ((P.out_ld * esz) % 16) == 0;
+  const bool mask_vec = MASK != ACT_NONE && (P.mask_ld % 8) == 0 && (P.mask_coff % 8) == 0;
+  const bf16* mrow = MASK != ACT_NONE ? (const bf16*)P.mask_src + opix * P.mask_ld + P.mask_coff : nullptr;
+  for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+    const int ncol = min(32, P.tile_cols - c0);
+    if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
+    tc::tmem_ld_wait();
+    if (!valid) continue;
+    const int cfirst = col_base + c0;
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    if (P.bias) {   // packed bias is padded to n_pad (zeros beyond n_valid), 16-byte aligned
+      const float4* bp = reinterpret_cast<const float4*>(P.bias + cfirst);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i * 4 < ncol) {
+          const float4 b = __ldg(bp + i);
+          f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+        }
+      }
+    }
+    if (ACT != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = act_t<ACT>(f[i]);
+    }
+    if (MASK != ACT_NONE) {
+      if (mask_vec && cfirst + ncol <= P.n_valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          if (i < ncol) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow + cfirst + i));
+            f[i + 0] *= mask_t<MASK>(__uint_as_float(q.x << 16)); f[i + 1] *= mask_t<MASK>(__uint_as_float(q.x & 0xffff0000u));
+            f[i + 2] *= mask_t<MASK>(__uint_as_float(q.y << 16)); f[i + 3] *= mask_t<MASK>(__uint_as_float(q.y & 0xffff0000u));
+            f[i + 4] *= mask_t<MASK>(__uint_as_float(q.z << 16)); f[i + 5] *= mask_t<MASK>(__uint_as_float(q.z & 0xffff0000u));
+            f[i + 6] *= mask_t<MASK>(__uint_as_float(q.w << 16)); f[i + 7] *= mask_t<MASK>(__uint_as_float(q.w & 0xffff0000u));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncol && cfirst + i < P.n_valid) f[i] *= mask_t<MASK>(__bfloat162float(mrow[cfirst + i]));
+      }
+    }
+    if (OUT_F32) {
+      float* o = (float*)P.out + opix * P.out_ld + cfirst;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (i < ncol) {
+          if (vec_ok && cfirst + i + 4 <= P.n_valid) {
+            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (cfirst + i + q < P.n_valid) o[i + q] = f[i + q];
+          }
+        }
+      }
+    } else {
+      bf16* o = (bf16*)P.out + opix * P.out_ld + cfirst;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < ncol) {
+          if (vec_ok && cfirst + i + 8 <= P.n_valid) {
+            uint4 pk;
+            pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
+            pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            *reinterpret_cast<uint4*>(o + i) = pk;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (cfirst + i + q < P.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// warp-uniform dispatch on (activation of this column tile, mask kind, output type)
+struct EpiSel { int act, mask, f32; };
+__device__ __forceinline__ EpiSel epilogue_select(const TcLaunch& P, int n_tile) {
+  int c = n_tile * P.tile_cols, j = 0;
+  while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
+  return EpiSel{P.part_act[j], P.mask_act, P.out_f32};
+}
+#define SV_EPI_CALL(A, M, F) epilogue_rows_t<A, M, F>(P, tmem_acc, quarter, valid, opix, n_tile)
+__device__ __forceinline__ void epilogue_rows(const TcLaunch& P, EpiSel e, uint32_t tmem_acc, int quarter, bool valid, long long opix, int n_tile) {
+  if (e.mask != ACT_NONE) {            // dgrad: linear, bf16 out
+    if (e.mask == ACT_RELU) SV_EPI_CALL(ACT_NONE, ACT_RELU, false);
+    else if (e.mask == ACT_ELU) SV_EPI_CALL(ACT_NONE, ACT_ELU, false);
+    else SV_EPI_CALL(ACT_NONE, ACT_SOFTPLUS, false);
+  } else if (e.f32) {
+    if (e.act == ACT_NONE) SV_EPI_CALL(ACT_NONE, ACT_NONE, true);
+    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, true);
+    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, true);
+    else SV_EPI_CALL(ACT_RELU, ACT_NONE, true);
+  } else {
+    if (e.act == ACT_RELU) SV_EPI_CALL(ACT_RELU, ACT_NONE, false);
+    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, false);
+    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, false);
+    else SV_EPI_CALL(ACT_NONE, ACT_NONE, false);
+  }
+}
+#undef SV_EPI_CALL
+
+// halo kernel: the loop over the CTA's accumulators lives INSIDE each instantiation (one dispatch per thread)
+template <int ACT, int MASK, bool OUT_F32>
+__device__ __noinline__ void halo_epilogue_t(const TcLaunch& P, uint32_t tmem_base, int quarter, int lane, int n, int y0, int x0, int n_tile) {
+  const int row = quarter * 32 + lane;
+  const int g = row >> 3, i = row & 7;
+  for (int ty = 0; ty < P.mty; ++ty)
+    for (int tx = 0; tx < P.mtx; ++tx) {
+      const int y = y0 + ty * 16 + g, x = x0 + tx * 8 + i;
+      const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
+      epilogue_rows_t<ACT, MASK, OUT_F32>(P, tmem_base + (uint32_t)((ty * P.mtx + tx) * P.tile_cols), quarter, true, opix, n_tile);
+    }
+}
+#define SV_EPI_CALL(A, M, F) halo_epilogue_t<A, M, F>(P, tmem_base, quarter, lane, n, y0, x0, n_tile)
+__device__ __forceinline__ void halo_epilogue(const TcLaunch& P, EpiSel e, uint32_t tmem_base, int quarter, int lane, int n, int y0, int x0, int n_tile) {
+  if (e.mask != ACT_NONE) {
+    if (e.mask == ACT_RELU) SV_EPI_CALL(ACT_NONE, ACT_RELU, false);
+    else if (e.mask == ACT_ELU) SV_EPI_CALL(ACT_NONE, ACT_ELU, false);
+    else SV_EPI_CALL(ACT_NONE, ACT_SOFTPLUS, false);
+  } else if (e.f32) {
+    if (e.act == ACT_NONE) SV_EPI_CALL(ACT_NONE, ACT_NONE, true);
+    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, true);
+    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, true);
+    else SV_EPI_CALL(ACT_RELU, ACT_NONE, true);
+  } else {
+    if (e.act == ACT_RELU) SV_EPI_CALL(ACT_RELU, ACT_NONE, false);
+    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, false);
+    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, false);
+    else SV_EPI_CALL(ACT_NONE, ACT_NONE, false);
+  }
+}
+#undef SV_EPI_CALL
 
 __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__ TcLaunch P) {
   extern __shared__ uint8_t smem_raw[];
@@ -87,17 +252,17 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
       const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
       const uint32_t lt = tc::layout_type_for(P.swizzle);
       const uint32_t sbo = 16u * P.bk;  // 8 rows x (bk*2) bytes
+      const uint64_t tmpl = tc::make_smem_desc(0, 16, sbo, lt);   // + start address >> 4 in bits 0-13
+      const int ksteps = P.bk / 16;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % P.stages, phase = (kb / P.stages) & 1;
         tc::mbar_wait(&ctl->full[stage], phase);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
-        for (int k = 0; k < P.bk / 16; ++k) {
-          const uint64_t da = tc::make_smem_desc(sa + k * 32, 16, sbo, lt);
-          const uint64_t db = tc::make_smem_desc(sb + k * 32, 16, sbo, lt);
-          tc::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
-        }
+        const uint64_t da = tmpl + (sa >> 4), db = tmpl + ((sa + a_bytes) >> 4);
+        tc::umma_bf16(tmem_base, da, db, idesc, kb != 0);
+        if (ksteps > 1) tc::umma_bf16(tmem_base, da + 2, db + 2, idesc, 1u);
+        if (ksteps > 2) { tc::umma_bf16(tmem_base, da + 4, db + 4, idesc, 1u); tc::umma_bf16(tmem_base, da + 6, db + 6, idesc, 1u); }
         tc::umma_commit(&ctl->empty[stage]);   // frees this smem stage once the MMAs above have read it
       }
       tc::umma_commit(&ctl->tmem_full);        // accumulator complete
@@ -114,72 +279,7 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
     const int n = n0 + nn, y = y0 + hh, x = ww;
     const bool valid = n < P.n_img;
     const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
-    const int col_base = n_tile * P.tile_cols;
-    int act = ACT_NONE;
-    {
-      int c = col_base, j = 0;
-      while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
-      act = P.part_act[j];
-    }
-    const int esz = P.out_f32 ? 4 : 2;
-    const bool vec_ok = ((P.out_ld * esz) % 16) == 0;
-    for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      const int ncol = min(32, P.tile_cols - c0);
-      if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
-      tc::tmem_ld_wait();
-      if (valid) {
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = col_base + c0 + i;
-          float a = __uint_as_float(v[i]);
-          if (i < ncol && col < P.n_valid) {
-            if (P.bias) a += P.bias[col];
-            a = apply_act(a, act);
-            if (P.mask_act != ACT_NONE) {
-              const float m = __bfloat162float(((const bf16*)P.mask_src)[opix * P.mask_ld + P.mask_coff + col]);
-              a *= act_grad_from_out(m, P.mask_act);
-            }
-          } else {
-            a = 0.f;
-          }
-          f[i] = a;
-        }
-        const int cfirst = col_base + c0;
-        if (P.out_f32) {
-          float* o = (float*)P.out + opix * P.out_ld + cfirst;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if (i >= ncol) break;
-            if (vec_ok && cfirst + i + 4 <= P.n_valid) {
-              *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (cfirst + i + q < P.n_valid) o[i + q] = f[i + q];
-            }
-          }
-        } else {
-          bf16* o = (bf16*)P.out + opix * P.out_ld + cfirst;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            if (i >= ncol) break;
-            if (vec_ok && cfirst + i + 8 <= P.n_valid) {
-              uint4 pk;
-              pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
-              pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
-              *reinterpret_cast<uint4*>(o + i) = pk;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (cfirst + i + q < P.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
-            }
-          }
-        }
-      }
-    }
+    epilogue_rows(P, epilogue_select(P, n_tile), tmem_base, quarter, valid, opix, n_tile);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -189,6 +289,139 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// Halo-resident implicit GEMM (stride-1 convolutions: decoder forward layers, every dgrad).
+//   * warp 0 loads the (TH+taps_h-1) x (TW+taps_w-1) input halo of a TW x TH output tile ONCE (one 4-D TMA box per
+//     64/32/16-channel chunk; OOB zero fill = TF 'same' padding) and then streams the packed weights through a ring
+//     (kb_per_stage 2-D TMA boxes of [tile_cols][chunk] K-major per stage, one mbarrier);
+//   * the A operand of filter tap (a,b) for accumulator (tx,ty) is the SAME shared-memory halo addressed through a
+//     shifted UMMA descriptor: start = halo + ((ty*16+a)*TWp + tx*8 + b) * pixel_bytes, SBO = TWp * pixel_bytes
+//     (an M row group = 8 horizontally adjacent pixels, 16 groups = 16 image rows); the 128B/64B/32B swizzle is a
+//     function of absolute shared-memory address bits for TMA and UMMA alike, so shifted views stay consistent;
+//   * (TW/8)*(TH/16) accumulators of 128 x tile_cols live in TMEM; the epilogue drains them as in igemm_kernel.
+// L2->SMEM traffic per output tile drops from taps*(A+B) to halo + weights (10-16x for the 6x6 layers).
+// ------------------------------------------------------------------------------------------------
+struct HaloCtl {
+  uint64_t halo_full;
+  uint64_t w_full[kMaxStages];
+  uint64_t w_empty[kMaxStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_constant__ TcLaunch P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nchunks = P.kc;
+  uint8_t* halo = smem;
+  uint8_t* wring = smem + (size_t)nchunks * P.chunk_bytes;
+  HaloCtl* ctl = reinterpret_cast<HaloCtl*>(wring + (size_t)P.w_stages * P.w_stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  int t = blockIdx.x;
+  const int tile_x = t % P.tiles_x; t /= P.tiles_x;
+  const int tile_y = t % P.tiles_y;
+  const int n = t / P.tiles_y;
+  const int x0 = tile_x * P.TW, y0 = tile_y * P.TH;
+  const int num_kb = P.taps_h * P.taps_w * nchunks;
+  const int num_stages_total = (num_kb + P.kb_per_stage - 1) / P.kb_per_stage;
+  const int MT = P.mtx * P.mty;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_a);
+    tc::prefetch_tmap(&P.map_b);
+    tc::mbar_init(&ctl->halo_full, 1);
+    for (int i = 0; i < P.w_stages; ++i) { tc::mbar_init(&ctl->w_full[i], 1); tc::mbar_init(&ctl->w_empty[i], 1); }
+    tc::mbar_init(&ctl->tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(MT * P.tile_cols)) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int kb_bytes = P.tile_cols * P.bk * 2;   // one k-block of weights
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&ctl->halo_full, (uint32_t)(nchunks * P.THp * P.TWp * P.bk * 2));
+      for (int c = 0; c < nchunks; ++c)
+        tc::tma_load_4d(halo + (size_t)c * P.chunk_bytes, &P.map_a, &ctl->halo_full, c * P.bk, x0 - P.pad_l, y0 - P.pad_t, n);
+      for (int st = 0; st < num_stages_total; ++st) {
+        const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
+        tc::mbar_wait(&ctl->w_empty[slot], phase ^ 1);
+        const int kb0 = st * P.kb_per_stage;
+        const int nkb = min(P.kb_per_stage, num_kb - kb0);
+        tc::mbar_expect_tx(&ctl->w_full[slot], (uint32_t)(nkb * kb_bytes));
+        for (int j = 0; j < nkb; ++j)
+          tc::tma_load_2d(wring + (size_t)slot * P.w_stage_bytes + (size_t)j * kb_bytes, &P.map_b, &ctl->w_full[slot], (kb0 + j) * P.bk,
+                          n_tile * P.tile_cols);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
+      const uint32_t lt = tc::layout_type_for(P.swizzle);
+      const uint32_t pix = (uint32_t)P.bk * 2u;              // bytes per pixel inside a chunk
+      const uint32_t a_sbo = (uint32_t)P.TWp * pix;          // next row group = next image row
+      const uint32_t b_sbo = 8u * pix;                       // weights: dense [tile_cols][bk]
+      const uint32_t halo_addr = tc::smem_u32(halo);
+      tc::mbar_wait(&ctl->halo_full, 0);
+      tc::tc_fence_after();
+      // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 B): build one template per
+      // operand and add offsets, so the single issuing thread spends a handful of instructions per MMA.
+      const uint64_t a_tmpl = tc::make_smem_desc(0, 16, a_sbo, lt), b_tmpl = tc::make_smem_desc(0, 16, b_sbo, lt);
+      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)P.TWp * pix) >> 4;
+      const uint32_t tile_cols = (uint32_t)P.tile_cols;
+      const int ksteps = P.bk / 16;
+      int kb = 0;
+      for (int st = 0; st < num_stages_total; ++st) {
+        const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
+        tc::mbar_wait(&ctl->w_full[slot], phase);
+        tc::tc_fence_after();
+        const uint32_t wbase = tc::smem_u32(wring + (size_t)slot * P.w_stage_bytes);
+        const int kb_end = min(num_kb, kb + P.kb_per_stage);
+        uint32_t b_addr = wbase >> 4;
+        int tap = kb / nchunks, chunk = kb - tap * nchunks;
+        int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
+        for (; kb < kb_end; ++kb, b_addr += (uint32_t)kb_bytes >> 4) {
+          const uint32_t a_tap = (halo_addr + (uint32_t)chunk * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4;
+          const uint64_t db = b_tmpl + b_addr;
+          const uint32_t first = kb != 0;
+          // k-step outermost: consecutive MMAs target DIFFERENT accumulators, so the dependent (same-accumulator) MMAs
+          // are MT instructions apart and the tensor pipe's accumulate latency is hidden (small-N MMAs are only N/2 cycles long)
+          for (int k = 0; k < ksteps; ++k) {
+            uint32_t a_row = a_tap + 2u * k, acc = tmem_base;
+            const uint64_t dbk = db + 2u * k;
+            const uint32_t accum = k ? 1u : first;
+            for (int ty = 0; ty < P.mty; ++ty, a_row += ty_step) {
+              uint64_t da = a_tmpl + a_row;
+              for (int tx = 0; tx < P.mtx; ++tx, da += tx_step, acc += tile_cols) tc::umma_bf16(acc, da, dbk, idesc, accum);
+            }
+          }
+          if (++chunk == nchunks) { chunk = 0; if (++tb == P.taps_w) { tb = 0; ++ta; } }
+        }
+        tc::umma_commit(&ctl->w_empty[slot]);
+      }
+      tc::umma_commit(&ctl->tmem_full);
+    }
+  } else {
+    tc::mbar_wait(&ctl->tmem_full, 0);
+    tc::tc_fence_after();
+    halo_epilogue(P, epilogue_select(P, n_tile), tmem_base, warp & 3, lane, n, y0, x0, n_tile);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci), co] = sum over pixels; K axis = pixels (64 per stage), both operands MN-major.
@@ -269,6 +502,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 1, 1);
       const uint32_t lta = tc::layout_type_for(P.a_swizzle), ltb = tc::layout_type_for(P.b_swizzle);
       const uint32_t a_row = P.cb * 2, b_row = P.cbn * 2;  // bytes per pixel row inside a box
+      const uint64_t a_tmpl = tc::make_smem_desc(0, a_box, 8 * a_row, lta), b_tmpl = tc::make_smem_desc(0, b_box, 8 * b_row, ltb);
       int ia = 0;
       for (int c = c_begin; c < c_end; ++c) {
         const int ib = c - c_begin;
@@ -280,13 +514,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
           tc::mbar_wait(&ctl->a_full[as], aph);
           tc::tc_fence_after();
           const uint32_t sa_addr = tc::smem_u32(a_ring + (size_t)as * a_stage);
-#pragma unroll
-          for (int k = 0; k < kPix / 16; ++k) {
-            // MN-major: LBO = distance between channel blocks (one box), SBO = 8 pixel rows
-            const uint64_t da = tc::make_smem_desc(sa_addr + k * 16 * a_row, a_box, 8 * a_row, lta);
-            const uint64_t db = tc::make_smem_desc(sb_addr + k * 16 * b_row, b_box, 8 * b_row, ltb);
-            tc::umma_bf16(tmem_base + (uint32_t)(g * P.tile_cols), da, db, idesc, (c > c_begin) || (k > 0));
-          }
+          // MN-major: LBO = distance between channel blocks (one box), SBO = 8 pixel rows; a K step of 16 pixels advances
+          // the start address by 16 pixel rows (a_row / b_row in units of 16 B)
+          const uint64_t da = a_tmpl + (sa_addr >> 4), db = b_tmpl + (sb_addr >> 4);
+          const uint32_t acc = tmem_base + (uint32_t)(g * P.tile_cols);
+          tc::umma_bf16(acc, da, db, idesc, c > c_begin);
+          tc::umma_bf16(acc, da + a_row, db + b_row, idesc, 1u);
+          tc::umma_bf16(acc, da + 2 * a_row, db + 2 * b_row, idesc, 1u);
+          tc::umma_bf16(acc, da + 3 * a_row, db + 3 * b_row, idesc, 1u);
           tc::umma_commit(&ctl->a_empty[as]);
         }
         tc::umma_commit(&ctl->b_empty[bs]);
@@ -326,20 +561,50 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   }
 }
 
-// sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena
+// sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena.
+// block = 32 consecutive output columns x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), then the
+// 8 partial sums are combined in a fixed order through shared memory -> deterministic, no atomics.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                            int ci_pad, int first, float* __restrict__ grads) {
+  __shared__ float red[8][33];
+  const int rows = g.kh * g.kw * g.Ci;
+  const int cblocks = (g.Co + 31) / 32;
+  const int r = blockIdx.x / cblocks, cb = blockIdx.x - r * cblocks;
+  const int co = cb * 32 + threadIdx.x;
+  const int ci = r % g.Ci, tap = r / g.Ci;
+  const size_t row = first ? (size_t)(tap / g.kw) * 64 + (tap % g.kw) * 8 + ci : (size_t)tap * ci_pad + ci;
+  float s = 0.f;
+  if (co < g.Co && r < rows)
+    for (int k = threadIdx.y; k < k_splits; k += 8) s += partial[((size_t)k * m_pad + row) * n_pad + co];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && co < g.Co && r < rows) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    int lc;
+    const int j = part_of(g, co, lc);
+    grads[g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
+                                                               int ci_pad, int first, float* __restrict__ grads) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(idx % g.Co);
-    const int ci = (int)((idx / g.Co) % g.Ci);
-    const int tap = (int)(idx / ((long long)g.Co * g.Ci));
+    const int r = (int)(idx / g.Co);
+    const int ci = r % g.Ci, tap = r / g.Ci;
     const size_t row = first ? (size_t)(tap / g.kw) * 64 + (tap % g.kw) * 8 + ci : (size_t)tap * ci_pad + ci;
-    float s = 0.f;
-    for (int k = 0; k < k_splits; ++k) s += partial[((size_t)k * m_pad + row) * n_pad + co];
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < k_splits ? partial[((size_t)k * m_pad + row) * n_pad + co] : 0.f;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += v[k];
     int lc;
     const int j = part_of(g, co, lc);
-    grads[g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc] = s;
+    grads[g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc] = t;
   }
 }
 
@@ -532,6 +797,71 @@ void finish_launch(TcLaunch& L, int n_cols_pad) {
   L.smem_bytes = (size_t)stages * (a_bytes + b_bytes) + sizeof(SmemCtl) + 1024;
 }
 
+
+// Converts an igemm launch (stride-1 A addressing) into a halo-resident launch when the output grid allows 8x16 row
+// groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
+// for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
+  L.halo = 0;
+  if (env_int("SV_NO_HALO", 0)) return;
+  if (L.a_stride != 1 || (GH % 16) || (GW % 8) || L.taps_h * L.taps_w < 2) return;
+  // measured on B200 (scripts/bench_layers.py): the halo kernel wins where the per-tap kernel is L2-bound with little
+  // tensor work per byte (<= 32 channels per pixel: d5 forward 166 vs 221 us, d5 dgrad 102 vs 234 us); with 64+ channel
+  // chunks the per-tap kernel (2 CTAs/SM, deep ring) is as fast or faster (d4 forward 97 vs 130 us) -> keep it there.
+  if (L.bk > 32 && !env_int("SV_HALO_ALL", 0)) return;
+  const int pix = L.bk * 2, nch = L.kc;
+  const int kb_bytes = L.tile_cols * L.bk * 2;
+  const int num_kb = L.taps_h * L.taps_w * nch;
+  const double w_total = (double)num_kb * kb_bytes;
+  int KB = 8192 / kb_bytes;
+  if (KB < 1) KB = 1;
+  if (KB > num_kb) KB = num_kb;
+  int best_tw = 0, best_th = 0, best_stages = 0;
+  double best_cost = 1e30;
+  const int force_tw = env_int("SV_HALO_TW", 0), force_th = env_int("SV_HALO_TH", 0);
+  for (int TH = 16; TH <= 32 && TH <= GH; TH += 16) {
+    if (GH % TH) continue;
+    for (int TW = 8; TW <= 64 && TW <= GW; TW += 8) {
+      if (GW % TW) continue;
+      if (force_tw && TW != force_tw) continue;
+      if (force_th && TH != force_th) continue;
+      const int MT = (TW / 8) * (TH / 16);
+      if (MT * L.tile_cols > 512) continue;
+      const int TWp = TW + L.taps_w - 1, THp = TH + L.taps_h - 1;
+      if (TWp > 256 || THp > 256) continue;
+      const size_t chunk = ((size_t)THp * TWp * pix + 1023) / 1024 * 1024;
+      for (int stages = 3; stages >= 2; --stages) {
+        const size_t smem = chunk * nch + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
+        if (smem > 200 * 1024) continue;
+        int tmem_cols = 32;
+        while (tmem_cols < MT * L.tile_cols) tmem_cols <<= 1;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+        if (per_sm < 1) continue;
+        const double traffic = ((double)chunk * nch + w_total) / (TW * TH);
+        double cost = traffic * (per_sm == 1 ? 1.6 : 1.0);
+        if (TW == 32 && TH == 16) cost *= 0.5;   // measured best shape for the 64x64 layers
+        if (cost < best_cost) { best_cost = cost; best_tw = TW; best_th = TH; best_stages = stages; }
+        break;
+      }
+    }
+  }
+  if (!best_tw) return;
+  L.halo = 1;
+  L.TW = best_tw; L.TH = best_th; L.TWp = best_tw + L.taps_w - 1; L.THp = best_th + L.taps_h - 1;
+  L.mtx = best_tw / 8; L.mty = best_th / 16;
+  L.chunk_bytes = (int)(((size_t)L.THp * L.TWp * pix + 1023) / 1024 * 1024);
+  L.kb_per_stage = KB; L.w_stages = best_stages; L.w_stage_bytes = KB * kb_bytes;
+  L.tiles_x = GW / best_tw; L.tiles_y = GH / best_th;
+  L.n_img = n_img;
+  L.smem_bytes = (size_t)L.chunk_bytes * nch + (size_t)L.w_stages * L.w_stage_bytes + sizeof(HaloCtl) + 1024;
+}
+
 }  // namespace
 
 const char* tc_last_error() { return g_tc_error; }
@@ -633,6 +963,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         for (int j = 0; j < 3; ++j) { L.part_n[j] = g.part_n[j]; L.part_act[j] = g.part_act[j]; }
         L.mask_act = ACT_NONE;
         finish_launch(L, t.n_pad_fwd);
+        if (cpad <= g.in_ld - g.in_coff) try_halo(L, g.Ho, g.Wo, g.B);
         t.fwd_ok = true;
         t.fwd_launches = 1;
         t.w_fwd_off = off;
@@ -668,6 +999,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.out_ld = g.din_ld; L.out_f32 = 0;
       L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
       finish_launch(L, t.n_pad_dg);
+      try_halo(L, GH, GW, g.B);
     }
     if (ok) {
       t.dgrad_ok = true;
@@ -727,6 +1059,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
   if (t.fwd_ok) {
     TcLaunch& L = t.fwd;
     const char* e = t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
+                    : L.halo ? make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, 1, 1, L.swizzle)
                             : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff,
                                            t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk, L.tile_w, L.tile_h, L.tile_n_img,
                                            g.stride, L.swizzle);
@@ -742,8 +1075,9 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
     for (int cls = 0; cls < t.n_dgrad; ++cls) {
       TcLaunch& L = t.dgrad[cls];
-      const char* e = make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.tile_w, L.tile_h, L.tile_n_img, 1,
-                                   L.swizzle);
+      const char* e = L.halo ? make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.TWp, L.THp, 1, 1, L.swizzle)
+                             : make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.tile_w, L.tile_h, L.tile_n_img, 1,
+                                            L.swizzle);
       if (e) return e;
       e = make_w_map(&L.map_b, ws + t.w_dgrad_off + cls * per_class, t.n_pad_dg, (long long)t.dg_taps_h * t.dg_taps_w * t.co_pad, L.bk,
                      L.tile_cols, L.swizzle);
@@ -756,6 +1090,20 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       L.mask_coff = g.in_coff;
     }
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  }
+  if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  if (env_int("SV_TC_VERBOSE", 0)) {
+    auto show = [&](const char* what, const TcLaunch& L) {
+      if (L.halo)
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: HALO tile %dx%d halo %dx%d chunks %d x %d B, N %d x%d, w ring %d x %d B (%d kb/stage), smem %zu\n",
+                g.kh, g.kw, g.stride, g.Ci, g.Co, what, L.TW, L.TH, L.TWp, L.THp, L.kc, L.chunk_bytes, L.tile_cols, L.n_tiles, L.w_stages,
+                L.w_stage_bytes, L.kb_per_stage, L.smem_bytes);
+      else
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: per-tap tile %dx%dx%d bk %d N %d x%d stages %d smem %zu\n", g.kh, g.kw, g.stride, g.Ci, g.Co,
+                what, L.tile_n_img, L.tile_h, L.tile_w, L.bk, L.tile_cols, L.n_tiles, L.stages, L.smem_bytes);
+    };
+    if (t.fwd_ok) show("fwd", t.fwd);
+    if (t.dgrad_ok) for (int c = 0; c < t.n_dgrad; ++c) show("dgrad", t.dgrad[c]);
   }
   if (t.wgrad_ok) {
     TcWgradLaunch& L = t.wg;
@@ -840,6 +1188,11 @@ int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
 }
 
 static void launch(const TcLaunch& L, cudaStream_t s) {
+  if (L.halo) {
+    dim3 grid(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles);
+    halo_conv_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+    return;
+  }
   const int tiles_per_img = L.grid_h / L.tile_h;
   const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
   dim3 grid(m_tiles, L.n_tiles);
@@ -855,10 +1208,15 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
   const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
   dim3 grid(m_splits, L.n_tiles, L.k_splits);
   wgrad_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
-  const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
+  if (L.k_splits <= 8) {   // few splits, many outputs (dense layers): one thread per output, all splits in flight at once
+    const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
+  } else {
+    const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
+    wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
+  }
 }
 
 }  // namespace sv

@@ -30,6 +30,14 @@ struct TcLaunch {
   void* out;
   const void* mask_src;
   size_t smem_bytes;
+  // halo-resident variant (halo_conv_kernel): the (TH+taps_h-1) x (TW+taps_w-1) input halo of a TW x TH output tile is
+  // loaded ONCE into shared memory; every tap's A operand is a shifted UMMA view of it; only weights stream.
+  int halo;                                     // 1: use halo_conv_kernel
+  int TW, TH, TWp, THp;                         // output tile and halo extents (pixels)
+  int mtx, mty;                                 // 128-row accumulators per CTA: (TW/8) x (TH/16)
+  int chunk_bytes;                              // bytes of one channel-chunk halo (1024-aligned)
+  int kb_per_stage, w_stages, w_stage_bytes;    // weight ring: k-blocks (tap, chunk) per stage
+  int tiles_x, tiles_y;
 };
 
 // Weight gradient  dW[(tap,ci), co] = sum_pixels X[pixel+tap, ci] * dY[pixel, co]  as a GEMM whose K axis is the
