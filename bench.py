@@ -134,7 +134,11 @@ def main():
     ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hang-dump", type=int, default=0, help="dump all Python stacks after this many seconds (debugging)")
     args = ap.parse_args()
+    if args.hang_dump:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.hang_dump, exit=True)
     wl = args.workload
     if args.impl == "reference":
         return run_reference(args, wl)
@@ -275,8 +279,14 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # release the captured graph (it holds NCCL kernels) before tearing the communicator down; destroy_process_group()
+        # was observed to block forever with a live captured collective, so leave the teardown to process exit
+        runner.graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
