@@ -561,18 +561,168 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Halo-resident wgrad (see TcHaloWgrad in tc_kernels.h).
+// ------------------------------------------------------------------------------------------------
+struct HwCtl {
+  uint64_t full[2], empty[2], tmem_full;
+  uint32_t tmem_base;
+  uint32_t goff[32];   // per row group: byte offset >> 4 of its first sub-block inside a stage's X halo
+};
+
+__global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_constant__ TcHaloWgrad P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  HwCtl* ctl = reinterpret_cast<HwCtl*>(smem + (size_t)P.stages * P.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g0 = blockIdx.x * P.groups_per_cta;
+  const int ng = min(P.groups_per_cta, P.groups - g0);
+  const int t_begin = blockIdx.z * P.tiles_per_split;
+  const int t_end = min(P.tiles, t_begin + P.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_x);
+    tc::prefetch_tmap(&P.map_dy);
+    for (int i = 0; i < P.stages; ++i) { tc::mbar_init(&ctl->full[i], 1); tc::mbar_init(&ctl->empty[i], 1); }
+    tc::mbar_init(&ctl->tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(P.groups_per_cta * P.n_pad)) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int x_bytes = P.nchunks * P.x_chunk_bytes;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)(P.nchunks * P.THp * P.TWp * P.cb * 2 + P.nbchunks * P.TH * P.TW * P.cbn * 2);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
+        int r = t;
+        const int tile_x = r % P.tiles_x; r /= P.tiles_x;
+        const int tile_y = r % P.tiles_y;
+        const int n = r / P.tiles_y;
+        const int x0 = tile_x * P.TW, y0 = tile_y * P.TH;
+        uint8_t* sx = smem + (size_t)st * P.stage_bytes;
+        tc::mbar_wait(&ctl->empty[st], ph ^ 1);
+        tc::mbar_expect_tx(&ctl->full[st], tx_bytes);
+        for (int c = 0; c < P.nchunks; ++c)
+          tc::tma_load_4d(sx + (size_t)c * P.x_chunk_bytes, &P.map_x, &ctl->full[st], c * P.cb, x0 - P.pad_l, y0 - P.pad_t, n);
+        for (int c = 0; c < P.nbchunks; ++c)
+          tc::tma_load_4d(sx + x_bytes + (size_t)c * P.dy_chunk_bytes, &P.map_dy, &ctl->full[st], c * P.cbn, x0, y0, n);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t pix = (uint32_t)P.cb * 2u, pixb = (uint32_t)P.cbn * 2u;
+    if (lane < ng) {   // group -> offset table (keeps integer divisions out of the issue loop)
+      const int g = g0 + lane;
+      uint32_t off;
+      if (P.mode == 0) {
+        const int a = g / P.gw, b0 = (g - a * P.gw) * P.nsub;
+        off = (uint32_t)(a * P.TWp + b0) * pix;
+      } else {
+        const int tap = g / P.gpt, c0 = (g - tap * P.gpt) * P.nsub;
+        const int a = tap / P.taps_w, b = tap - a * P.taps_w;
+        off = (uint32_t)c0 * (uint32_t)P.x_chunk_bytes + (uint32_t)(a * P.TWp + b) * pix;
+      }
+      ctl->goff[lane] = off >> 4;
+    }
+    __syncwarp();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.n_pad, 1, 1);
+      const uint32_t a_lbo = P.mode == 0 ? pix : (uint32_t)P.x_chunk_bytes;
+      const uint64_t a_tmpl = tc::make_smem_desc(0, a_lbo, 8u * pix, tc::layout_type_for(P.x_swizzle));
+      const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)P.dy_chunk_bytes, 8u * pixb, tc::layout_type_for(P.dy_swizzle));
+      const uint32_t n_pad = (uint32_t)P.n_pad;
+      const int ksx = P.TW / 16;
+      const uint32_t a_xs = (16u * pix) >> 4, b_xs = (16u * pixb) >> 4;
+      const uint32_t a_row = ((uint32_t)P.TWp * pix) >> 4, b_row = ((uint32_t)P.TW * pixb) >> 4;
+      const volatile uint32_t* goff = ctl->goff;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
+        tc::mbar_wait(&ctl->full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t sx = tc::smem_u32(smem + (size_t)st * P.stage_bytes);
+        uint64_t da_y = a_tmpl + (sx >> 4);
+        uint64_t db_y = b_tmpl + ((sx + (uint32_t)x_bytes) >> 4);
+        uint32_t accum = t > t_begin ? 1u : 0u;
+        for (int yy = 0; yy < P.TH; ++yy, da_y += a_row, db_y += b_row) {
+          uint64_t da = da_y, db = db_y;
+          for (int xs = 0; xs < ksx; ++xs, da += a_xs, db += b_xs) {
+            uint32_t acc = tmem_base;
+            int g = 0;
+            for (; g + 4 <= ng; g += 4) {
+              const uint32_t o0 = goff[g], o1 = goff[g + 1], o2 = goff[g + 2], o3 = goff[g + 3];
+              tc::umma_bf16(acc, da + o0, db, idesc, accum);
+              tc::umma_bf16(acc + n_pad, da + o1, db, idesc, accum);
+              tc::umma_bf16(acc + 2 * n_pad, da + o2, db, idesc, accum);
+              tc::umma_bf16(acc + 3 * n_pad, da + o3, db, idesc, accum);
+              acc += 4 * n_pad;
+            }
+            for (; g < ng; ++g, acc += n_pad) tc::umma_bf16(acc, da + goff[g], db, idesc, accum);
+            accum = 1u;
+          }
+        }
+        tc::umma_commit(&ctl->empty[st]);
+      }
+      tc::umma_commit(&ctl->tmem_full);
+    }
+  } else {
+    tc::mbar_wait(&ctl->tmem_full, 0);
+    tc::tc_fence_after();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    for (int g = 0; g < ng; ++g) {
+      float* dst = P.partial + ((size_t)blockIdx.z * P.m_pad + (size_t)(g0 + g) * 128 + row) * P.n_pad;
+      for (int c0 = 0; c0 < P.n_pad; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * P.n_pad + c0);
+        const int ncol = min(32, P.n_pad - c0);
+        if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
+        tc::tmem_ld_wait();
+        const bool have = t_end > t_begin;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (i < ncol)
+            *reinterpret_cast<uint4*>(dst + c0 + i) = have ? make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// row of (tap, ci) inside the split-K partial buffer for each wgrad flavour
+struct WgRowMap { int mode, kw, ci_pad, cb, nsub, gw, gpt; };   // mode 0: tap*ci_pad+ci, 1: first layer, 2: halo taps, 3: halo chunks
+__device__ __forceinline__ size_t wg_row(const WgRowMap& R, int tap, int ci) {
+  switch (R.mode) {
+    case 1: return (size_t)(tap / R.kw) * 64 + (tap % R.kw) * 8 + ci;
+    case 2: { const int a = tap / R.kw, b = tap % R.kw; return (size_t)(a * R.gw + b / R.nsub) * 128 + (b % R.nsub) * R.cb + ci; }
+    case 3: { const int c = ci / R.cb; return (size_t)(tap * R.gpt + c / R.nsub) * 128 + (c % R.nsub) * R.cb + ci % R.cb; }
+    default: return (size_t)tap * R.ci_pad + ci;
+  }
+}
+
 // sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena.
 // block = 32 consecutive output columns x 8 split lanes: lane y sums splits y, y+8, ... (coalesced 128-byte rows), then the
 // 8 partial sums are combined in a fixed order through shared memory -> deterministic, no atomics.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
-                                                           int ci_pad, int first, float* __restrict__ grads) {
+                                                           WgRowMap R, float* __restrict__ grads) {
   __shared__ float red[8][33];
   const int rows = g.kh * g.kw * g.Ci;
   const int cblocks = (g.Co + 31) / 32;
   const int r = blockIdx.x / cblocks, cb = blockIdx.x - r * cblocks;
   const int co = cb * 32 + threadIdx.x;
   const int ci = r % g.Ci, tap = r / g.Ci;
-  const size_t row = first ? (size_t)(tap / g.kw) * 64 + (tap % g.kw) * 8 + ci : (size_t)tap * ci_pad + ci;
+  const size_t row = wg_row(R, tap, ci);
   float s = 0.f;
   if (co < g.Co && r < rows)
     for (int k = threadIdx.y; k < k_splits; k += 8) s += partial[((size_t)k * m_pad + row) * n_pad + co];
@@ -589,13 +739,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const flo
 }
 
 __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
-                                                               int ci_pad, int first, float* __restrict__ grads) {
+                                                               WgRowMap R, float* __restrict__ grads) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(idx % g.Co);
     const int r = (int)(idx / g.Co);
     const int ci = r % g.Ci, tap = r / g.Ci;
-    const size_t row = first ? (size_t)(tap / g.kw) * 64 + (tap % g.kw) * 8 + ci : (size_t)tap * ci_pad + ci;
+    const size_t row = wg_row(R, tap, ci);
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = k < k_splits ? partial[((size_t)k * m_pad + row) * n_pad + co] : 0.f;
@@ -862,6 +1012,64 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
   L.smem_bytes = (size_t)L.chunk_bytes * nch + (size_t)L.w_stages * L.w_stage_bytes + sizeof(HaloCtl) + 1024;
 }
 
+
+// Plans the halo-resident wgrad for a stride-1 convolution; returns false when the layer is not eligible.
+bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int cbn, int copad) {
+  if (env_int("SV_NO_HALO_WGRAD", 0)) return false;
+  if (g.stride != 1 || (g.Wo % 16) || g.Wo != g.Wi || g.Ho != g.Hi || copad > 256 || g.kh * g.kw < 2) return false;
+  H.taps_h = g.kh; H.taps_w = g.kw; H.pad_t = g.pt; H.pad_l = g.pl;
+  H.cb = cb; H.nchunks = cipad / cb; H.x_swizzle = cb * 2;
+  H.cbn = cbn; H.nbchunks = copad / cbn; H.dy_swizzle = cbn * 2;
+  H.n_pad = copad;
+  H.nsub = 128 / cb;
+  if (H.nchunks == 1) {
+    H.mode = 0;
+    H.gw = (g.kw + H.nsub - 1) / H.nsub;
+    H.gpt = 0;
+    H.groups = g.kh * H.gw;
+  } else {
+    if (H.nchunks % H.nsub) return false;
+    H.mode = 1;
+    H.gpt = H.nchunks / H.nsub;
+    H.gw = 0;
+    H.groups = g.kh * g.kw * H.gpt;
+  }
+  H.m_pad = H.groups * 128;
+  int gpc = 512 / H.n_pad;
+  if (gpc > H.groups) gpc = H.groups;
+  H.m_splits = (H.groups + gpc - 1) / gpc;
+  H.groups_per_cta = (H.groups + H.m_splits - 1) / H.m_splits;   // balanced
+  // tile: TW = 32 when it divides the width (16 otherwise); TH = largest divisor of the height whose two stages fit
+  const int force_th = env_int("SV_HWG_TH", 0), force_tw = env_int("SV_HWG_TW", 0);
+  H.TW = force_tw ? force_tw : ((g.Wo % 32) == 0 ? 32 : 16);
+  if (g.Wo % H.TW) return false;
+  H.stages = 2;
+  int best_th = 0;
+  for (int th = 1; th <= g.Ho && th <= 32; ++th) {
+    if (g.Ho % th) continue;
+    if (force_th && th != force_th) continue;
+    const int twp = H.TW + g.kw - 1, thp = th + g.kh - 1;
+    const size_t xc = ((size_t)thp * twp * cb * 2 + 1023) / 1024 * 1024, dc = ((size_t)th * H.TW * cbn * 2 + 1023) / 1024 * 1024;
+    const size_t smem = (size_t)H.stages * (xc * H.nchunks + dc * H.nbchunks) + sizeof(HwCtl) + 1024;
+    if (smem <= 190 * 1024) best_th = th;
+  }
+  if (!best_th) return false;
+  H.TH = best_th;
+  H.TWp = H.TW + g.kw - 1; H.THp = H.TH + g.kh - 1;
+  H.x_chunk_bytes = (int)(((size_t)H.THp * H.TWp * cb * 2 + 1023) / 1024 * 1024);
+  H.dy_chunk_bytes = (int)(((size_t)H.TH * H.TW * cbn * 2 + 1023) / 1024 * 1024);
+  H.stage_bytes = H.x_chunk_bytes * H.nchunks + H.dy_chunk_bytes * H.nbchunks;
+  H.smem_bytes = (size_t)H.stages * H.stage_bytes + sizeof(HwCtl) + 1024;
+  H.tiles_x = g.Wo / H.TW; H.tiles_y = g.Ho / H.TH; H.n_img = g.B;
+  H.tiles = H.tiles_x * H.tiles_y * g.B;
+  int ks = env_int("SV_HWG_SPLITS", 148) / H.m_splits;
+  if (ks < 1) ks = 1;
+  if (ks > H.tiles) ks = H.tiles;
+  H.tiles_per_split = (H.tiles + ks - 1) / ks;
+  H.k_splits = (H.tiles + H.tiles_per_split - 1) / H.tiles_per_split;
+  return true;
+}
+
 }  // namespace
 
 const char* tc_last_error() { return g_tc_error; }
@@ -1044,8 +1252,14 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.smem_bytes = (size_t)L.a_stages * 128 * 64 * 2 + (size_t)L.b_stages * L.tile_cols * 64 * 2 + sizeof(WgCtl) + 1024;
       t.wgrad_ok = true;
       t.wgrad_launches = 2;
+      size_t partial_bytes = (size_t)L.k_splits * L.m_pad * L.n_pad * 4;
+      if (plan_halo_wgrad(t.hw, g, cb, cipad, cbn, copad)) {
+        t.wg_halo = true;
+        const size_t hb = (size_t)t.hw.k_splits * t.hw.m_pad * t.hw.n_pad * 4;
+        if (hb > partial_bytes) partial_bytes = hb;
+      }
       t.wg_partial_off = off;
-      off += ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024;
+      off += (partial_bytes + 1023) / 1024 * 1024;
     }
   }
   t.bytes = off;
@@ -1115,6 +1329,18 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (e) return e;
     L.partial = (float*)(ws + t.wg_partial_off);
     if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+    if (t.wg_halo) {
+      TcHaloWgrad& H = t.hw;
+      e = make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, H.nchunks * H.cb, H.cb, H.TWp, H.THp, 1, 1, H.x_swizzle);
+      if (e) return e;
+      e = make_act_map(&H.map_dy, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, H.n_pad, H.cbn, H.TW, H.TH, 1, 1, H.dy_swizzle);
+      if (e) return e;
+      H.partial = (float*)(ws + t.wg_partial_off);
+      if (cudaFuncSetAttribute(halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+      if (env_int("SV_TC_VERBOSE", 0))
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d wgrad: HALO mode %d tile %dx%d groups %d (%d/CTA, m_splits %d) N %d tiles %d k_splits %d smem %zu\n", g.kh,
+                g.kw, g.stride, g.Ci, g.Co, H.mode, H.TW, H.TH, H.groups, H.groups_per_cta, H.m_splits, H.n_pad, H.tiles, H.k_splits, H.smem_bytes);
+    }
   }
   return nullptr;
 }
@@ -1203,20 +1429,34 @@ void tc_conv_fwd(TcLayer& t, cudaStream_t s) { launch(t.fwd, s); }
 void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
 }
+static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_splits, int m_pad, int n_pad, const WgRowMap& R, float* grads,
+                                cudaStream_t s) {
+  if (k_splits <= 8) {   // few splits, many outputs (dense layers): one thread per output, all splits in flight at once
+    const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+  } else {
+    const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
+    wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+  }
+}
+
 void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) {
+  if (t.wg_halo) {
+    const TcHaloWgrad& H = t.hw;
+    dim3 grid(H.m_splits, 1, H.k_splits);
+    halo_wgrad_kernel<<<grid, kThreads, H.smem_bytes, s>>>(H);
+    const WgRowMap R{H.mode == 0 ? 2 : 3, g.kw, 0, H.cb, H.nsub, H.gw, H.gpt};
+    launch_wgrad_reduce(g, H.partial, H.k_splits, H.m_pad, H.n_pad, R, grads, s);
+    return;
+  }
   const TcWgradLaunch& L = t.wg;
   const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
   dim3 grid(m_splits, L.n_tiles, L.k_splits);
   wgrad_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
-  if (L.k_splits <= 8) {   // few splits, many outputs (dense layers): one thread per output, all splits in flight at once
-    const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
-  } else {
-    const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
-    wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, L.partial, L.k_splits, L.m_pad, L.n_pad, L.ncb * L.cb, L.first, grads);
-  }
+  const WgRowMap R{L.first ? 1 : 0, g.kw, L.ncb * L.cb, 0, 0, 0, 0};
+  launch_wgrad_reduce(g, L.partial, L.k_splits, L.m_pad, L.n_pad, R, grads, s);
 }
 
 }  // namespace sv

@@ -61,6 +61,26 @@ struct TcWgradLaunch {
   size_t smem_bytes;
 };
 
+// Halo-resident weight gradient (stride-1 convolutions with W % 16 == 0): per pixel tile the X halo and the dY tile are loaded
+// once; every (filter tap, channel block) A operand is a shifted MN-major view of the same shared-memory halo.
+// An M = 128 row group stacks `nsub` sub-blocks of `cb` channels: horizontally adjacent taps (mode 0, LBO = one pixel) or
+// channel chunks of one tap (mode 1, LBO = one chunk).  K steps are 16 horizontally adjacent pixels.
+struct TcHaloWgrad {
+  CUtensorMap map_x, map_dy;
+  int taps_h, taps_w, pad_t, pad_l;
+  int cb, nchunks, x_swizzle;       // X channel chunk (elements), chunks per pixel
+  int cbn, nbchunks, dy_swizzle;    // dY channel chunk, chunks
+  int n_pad;                        // UMMA N
+  int TW, TH, TWp, THp;
+  int x_chunk_bytes, dy_chunk_bytes, stage_bytes, stages;
+  int mode, nsub, gw, gpt;          // grouping (see above): gw = groups per filter row (mode 0), gpt = groups per tap (mode 1)
+  int groups, groups_per_cta, m_splits;
+  int tiles_x, tiles_y, n_img, tiles, tiles_per_split, k_splits;
+  int m_pad;
+  float* partial;
+  size_t smem_bytes;
+};
+
 struct TcLayer {
   bool fwd_ok = false, dgrad_ok = false, wgrad_ok = false;
   bool first = false;                 // first conv of an encoder: reads the staged, padded bf16 image (tc_stage_first)
@@ -68,6 +88,8 @@ struct TcLayer {
   int n_dgrad = 0;
   TcLaunch fwd{}, dgrad[4]{};
   TcWgradLaunch wg{};
+  bool wg_halo = false;
+  TcHaloWgrad hw{};
   size_t wg_partial_off = 0;
   // geometry of the packed operands
   int n_pad_fwd = 0, ci_pad = 0;      // fwd : B = [n_pad_fwd][taps][ci_pad]
