@@ -303,6 +303,23 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
 //   * (TW/8)*(TH/16) accumulators of 128 x tile_cols live in TMEM; the epilogue drains them as in igemm_kernel.
 // L2->SMEM traffic per output tile drops from taps*(A+B) to halo + weights (10-16x for the 6x6 layers).
 // ------------------------------------------------------------------------------------------------
+// MMAs of one k-block (tap, channel chunk) for MTX (compile-time) x mty accumulators: k-step outermost so that consecutive
+// MMAs target different accumulators; the tile-column loop is unrolled and everything stays in (uniform) registers.
+template <int MTX>
+__device__ __forceinline__ void halo_issue_kb(uint64_t da0, uint64_t db0, uint32_t tmem_base, uint32_t tile_cols, uint32_t idesc, int mty, int ksteps,
+                                              uint32_t ty_step, uint32_t tx_step, uint32_t accum0) {
+  for (int k = 0; k < ksteps; ++k) {
+    const uint64_t dbk = db0 + 2u * k;
+    const uint32_t accum = k ? 1u : accum0;
+    uint64_t da_row = da0 + 2u * k;
+    uint32_t acc = tmem_base;
+    for (int ty = 0; ty < mty; ++ty, da_row += ty_step, acc += MTX * tile_cols) {
+#pragma unroll
+      for (int tx = 0; tx < MTX; ++tx) tc::umma_bf16(acc + tx * tile_cols, da_row + tx * tx_step, dbk, idesc, accum);
+    }
+  }
+}
+
 struct HaloCtl {
   uint64_t halo_full;
   uint64_t w_full[kMaxStages];
@@ -393,16 +410,21 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
           const uint32_t a_tap = (halo_addr + (uint32_t)chunk * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4;
           const uint64_t db = b_tmpl + b_addr;
           const uint32_t first = kb != 0;
-          // k-step outermost: consecutive MMAs target DIFFERENT accumulators, so the dependent (same-accumulator) MMAs
-          // are MT instructions apart and the tensor pipe's accumulate latency is hidden (small-N MMAs are only N/2 cycles long)
-          for (int k = 0; k < ksteps; ++k) {
-            uint32_t a_row = a_tap + 2u * k, acc = tmem_base;
-            const uint64_t dbk = db + 2u * k;
-            const uint32_t accum = k ? 1u : first;
-            for (int ty = 0; ty < P.mty; ++ty, a_row += ty_step) {
-              uint64_t da = a_tmpl + a_row;
-              for (int tx = 0; tx < P.mtx; ++tx, da += tx_step, acc += tile_cols) tc::umma_bf16(acc, da, dbk, idesc, accum);
-            }
+          switch (P.mtx) {
+            case 1: halo_issue_kb<1>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
+            case 2: halo_issue_kb<2>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
+            case 4: halo_issue_kb<4>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
+            case 8: halo_issue_kb<8>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
+            default:
+              for (int k = 0; k < ksteps; ++k) {
+                uint32_t a_row = a_tap + 2u * k, acc = tmem_base;
+                const uint64_t dbk = db + 2u * k;
+                const uint32_t accum = k ? 1u : first;
+                for (int ty = 0; ty < P.mty; ++ty, a_row += ty_step) {
+                  uint64_t da = a_tmpl + a_row;
+                  for (int tx = 0; tx < P.mtx; ++tx, da += tx_step, acc += tile_cols) tc::umma_bf16(acc, da, dbk, idesc, accum);
+                }
+              }
           }
           if (++chunk == nchunks) { chunk = 0; if (++tb == P.taps_w) { tb = 0; ++ta; } }
         }
@@ -571,6 +593,28 @@ struct HwCtl {
   uint32_t goff[32];   // per row group: byte offset >> 4 of its first sub-block inside a stage's X halo
 };
 
+// Issues the MMAs of one pixel tile for NG (compile-time) row groups: descriptors live in registers and the group loop is
+// fully unrolled, so the single issuing thread spends only a few (uniform-datapath) instructions per tcgen05.mma.
+template <int NG>
+__device__ __forceinline__ void hw_issue_tile(uint64_t da0, uint64_t db0, const uint32_t* goff, uint32_t tmem_base, uint32_t n_pad, uint32_t idesc,
+                                              int TH, int ksx, uint32_t a_row, uint32_t b_row, uint32_t a_xs, uint32_t b_xs, uint32_t accum0) {
+  uint64_t dag[NG];
+  uint32_t acc[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) { dag[g] = da0 + goff[g]; acc[g] = tmem_base + (uint32_t)g * n_pad; }
+  uint32_t accum = accum0;
+  uint32_t ao = 0, bo = 0;
+  for (int yy = 0; yy < TH; ++yy, ao += a_row, bo += b_row) {
+    uint32_t ax = ao, bx = bo;
+    for (int xs = 0; xs < ksx; ++xs, ax += a_xs, bx += b_xs) {
+      const uint64_t db = db0 + bx;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) tc::umma_bf16(acc[g], dag[g] + ax, db, idesc, accum);
+      accum = 1u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_constant__ TcHaloWgrad P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -599,7 +643,7 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)(P.nchunks * P.THp * P.TWp * P.cb * 2 + P.nbchunks * P.TH * P.TW * P.cbn * 2);
+      const uint32_t tx_bytes = (uint32_t)(P.nchunks * P.x_th * P.x_tw * P.cb * 2 + P.nbchunks * P.dy_th * P.dy_tw * P.cbn * 2);
       for (int t = t_begin; t < t_end; ++t) {
         const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
         int r = t;
@@ -611,60 +655,60 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
         tc::mbar_wait(&ctl->empty[st], ph ^ 1);
         tc::mbar_expect_tx(&ctl->full[st], tx_bytes);
         for (int c = 0; c < P.nchunks; ++c)
-          tc::tma_load_4d(sx + (size_t)c * P.x_chunk_bytes, &P.map_x, &ctl->full[st], c * P.cb, x0 - P.pad_l, y0 - P.pad_t, n);
+          tc::tma_load_4d(sx + (size_t)c * P.x_chunk_bytes, &P.map_x, &ctl->full[st], c * P.cb, x0 + P.x_dx, y0 + P.x_dy, n);
         for (int c = 0; c < P.nbchunks; ++c)
-          tc::tma_load_4d(sx + x_bytes + (size_t)c * P.dy_chunk_bytes, &P.map_dy, &ctl->full[st], c * P.cbn, x0, y0, n);
+          tc::tma_load_4d(sx + x_bytes + (size_t)c * P.dy_chunk_bytes, &P.map_dy, &ctl->full[st], c * P.cbn, x0 + P.dy_dx, y0, n);
       }
     }
   } else if (warp == 1) {
     const uint32_t pix = (uint32_t)P.cb * 2u, pixb = (uint32_t)P.cbn * 2u;
-    if (lane < ng) {   // group -> offset table (keeps integer divisions out of the issue loop)
-      const int g = g0 + lane;
-      uint32_t off;
-      if (P.mode == 0) {
-        const int a = g / P.gw, b0 = (g - a * P.gw) * P.nsub;
-        off = (uint32_t)(a * P.TWp + b0) * pix;
-      } else {
-        const int tap = g / P.gpt, c0 = (g - tap * P.gpt) * P.nsub;
-        const int a = tap / P.taps_w, b = tap - a * P.taps_w;
-        off = (uint32_t)c0 * (uint32_t)P.x_chunk_bytes + (uint32_t)(a * P.TWp + b) * pix;
-      }
-      ctl->goff[lane] = off >> 4;
-    }
+    if (lane < ng) ctl->goff[lane] = P.goff[g0 + lane];   // host-computed group offsets
     __syncwarp();
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(128, P.n_pad, 1, 1);
-      const uint32_t a_lbo = P.mode == 0 ? pix : (uint32_t)P.x_chunk_bytes;
-      const uint64_t a_tmpl = tc::make_smem_desc(0, a_lbo, 8u * pix, tc::layout_type_for(P.x_swizzle));
-      const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)P.dy_chunk_bytes, 8u * pixb, tc::layout_type_for(P.dy_swizzle));
+      const uint64_t a_tmpl = tc::make_smem_desc(0, (uint32_t)P.a_lbo, 8u * pix, tc::layout_type_for(P.x_swizzle));
+      const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)P.b_lbo, 8u * pixb, tc::layout_type_for(P.dy_swizzle));
       const uint32_t n_pad = (uint32_t)P.n_pad;
       const int ksx = P.TW / 16;
       const uint32_t a_xs = (16u * pix) >> 4, b_xs = (16u * pixb) >> 4;
-      const uint32_t a_row = ((uint32_t)P.TWp * pix) >> 4, b_row = ((uint32_t)P.TW * pixb) >> 4;
+      const uint32_t a_row = ((uint32_t)P.x_tw * pix) >> 4, b_row = ((uint32_t)P.dy_tw * pixb) >> 4;
       const volatile uint32_t* goff = ctl->goff;
       for (int t = t_begin; t < t_end; ++t) {
         const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
         tc::mbar_wait(&ctl->full[st], ph);
         tc::tc_fence_after();
         const uint32_t sx = tc::smem_u32(smem + (size_t)st * P.stage_bytes);
-        uint64_t da_y = a_tmpl + (sx >> 4);
-        uint64_t db_y = b_tmpl + ((sx + (uint32_t)x_bytes) >> 4);
-        uint32_t accum = t > t_begin ? 1u : 0u;
-        for (int yy = 0; yy < P.TH; ++yy, da_y += a_row, db_y += b_row) {
-          uint64_t da = da_y, db = db_y;
-          for (int xs = 0; xs < ksx; ++xs, da += a_xs, db += b_xs) {
-            uint32_t acc = tmem_base;
-            int g = 0;
-            for (; g + 4 <= ng; g += 4) {
-              const uint32_t o0 = goff[g], o1 = goff[g + 1], o2 = goff[g + 2], o3 = goff[g + 3];
-              tc::umma_bf16(acc, da + o0, db, idesc, accum);
-              tc::umma_bf16(acc + n_pad, da + o1, db, idesc, accum);
-              tc::umma_bf16(acc + 2 * n_pad, da + o2, db, idesc, accum);
-              tc::umma_bf16(acc + 3 * n_pad, da + o3, db, idesc, accum);
-              acc += 4 * n_pad;
+        const uint64_t da0 = a_tmpl + (sx >> 4), db0 = b_tmpl + ((sx + (uint32_t)x_bytes) >> 4);
+        const uint32_t accum0 = t > t_begin ? 1u : 0u;
+        if (ng <= 4) {
+          uint32_t go[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) go[g] = goff[g < ng ? g : 0];
+          switch (ng) {
+            case 1: hw_issue_tile<1>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            case 2: hw_issue_tile<2>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            case 3: hw_issue_tile<3>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            default: hw_issue_tile<4>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+          }
+        } else {
+          uint64_t da_y = da0, db_y = db0;
+          uint32_t accum = accum0;
+          for (int yy = 0; yy < P.TH; ++yy, da_y += a_row, db_y += b_row) {
+            uint64_t da = da_y, db = db_y;
+            for (int xs = 0; xs < ksx; ++xs, da += a_xs, db += b_xs) {
+              uint32_t acc = tmem_base;
+              int g = 0;
+              for (; g + 4 <= ng; g += 4) {
+                const uint32_t o0 = goff[g], o1 = goff[g + 1], o2 = goff[g + 2], o3 = goff[g + 3];
+                tc::umma_bf16(acc, da + o0, db, idesc, accum);
+                tc::umma_bf16(acc + n_pad, da + o1, db, idesc, accum);
+                tc::umma_bf16(acc + 2 * n_pad, da + o2, db, idesc, accum);
+                tc::umma_bf16(acc + 3 * n_pad, da + o3, db, idesc, accum);
+                acc += 4 * n_pad;
+              }
+              for (; g < ng; ++g, acc += n_pad) tc::umma_bf16(acc, da + goff[g], db, idesc, accum);
+              accum = 1u;
             }
-            for (; g < ng; ++g, acc += n_pad) tc::umma_bf16(acc, da + goff[g], db, idesc, accum);
-            accum = 1u;
           }
         }
         tc::umma_commit(&ctl->empty[st]);
@@ -701,14 +745,22 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
 }
 
 // row of (tap, ci) inside the split-K partial buffer for each wgrad flavour
-struct WgRowMap { int mode, kw, ci_pad, cb, nsub, gw, gpt; };   // mode 0: tap*ci_pad+ci, 1: first layer, 2: halo taps, 3: halo chunks
+struct WgRowMap { int mode, kw, ci_pad, cb, nsub, gw, gpt, nb; };
+// mode 0: tap*ci_pad+ci; 1: first layer; 2: halo, taps stacked along the filter row; 3: halo, chunks of one tap;
+// 4/5: N-stacked halo (rows enumerate (filter row a, ci); columns (kw-1-b)*nb + co): 4 = vertical taps stacked, 5 = chunks stacked
 __device__ __forceinline__ size_t wg_row(const WgRowMap& R, int tap, int ci) {
+  const int a = tap / R.kw, b = tap - a * R.kw;
   switch (R.mode) {
-    case 1: return (size_t)(tap / R.kw) * 64 + (tap % R.kw) * 8 + ci;
-    case 2: { const int a = tap / R.kw, b = tap % R.kw; return (size_t)(a * R.gw + b / R.nsub) * 128 + (b % R.nsub) * R.cb + ci; }
+    case 1: return (size_t)a * 64 + b * 8 + ci;
+    case 2: return (size_t)(a * R.gw + b / R.nsub) * 128 + (b % R.nsub) * R.cb + ci;
     case 3: { const int c = ci / R.cb; return (size_t)(tap * R.gpt + c / R.nsub) * 128 + (c % R.nsub) * R.cb + ci % R.cb; }
+    case 4: return (size_t)(a / R.nsub) * 128 + (a % R.nsub) * R.cb + ci;
+    case 5: { const int c = ci / R.cb; return (size_t)(a * R.gpt + c / R.nsub) * 128 + (c % R.nsub) * R.cb + ci % R.cb; }
     default: return (size_t)tap * R.ci_pad + ci;
   }
+}
+__device__ __forceinline__ int wg_col(const WgRowMap& R, int tap, int co) {
+  return R.mode >= 4 ? (R.kw - 1 - tap % R.kw) * R.nb + co : co;
 }
 
 // sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena.
@@ -725,7 +777,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const flo
   const size_t row = wg_row(R, tap, ci);
   float s = 0.f;
   if (co < g.Co && r < rows)
-    for (int k = threadIdx.y; k < k_splits; k += 8) s += partial[((size_t)k * m_pad + row) * n_pad + co];
+    for (int k = threadIdx.y; k < k_splits; k += 8) s += partial[((size_t)k * m_pad + row) * n_pad + wg_col(R, tap, co)];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && co < g.Co && r < rows) {
@@ -748,7 +800,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const
     const size_t row = wg_row(R, tap, ci);
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = k < k_splits ? partial[((size_t)k * m_pad + row) * n_pad + co] : 0.f;
+    const int pc = wg_col(R, tap, co);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < k_splits ? partial[((size_t)k * m_pad + row) * n_pad + pc] : 0.f;
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += v[k];
@@ -961,9 +1015,9 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
   if (env_int("SV_NO_HALO", 0)) return;
   if (L.a_stride != 1 || (GH % 16) || (GW % 8) || L.taps_h * L.taps_w < 2) return;
   // measured on B200 (scripts/bench_layers.py): the halo kernel wins where the per-tap kernel is L2-bound with little
-  // tensor work per byte (<= 32 channels per pixel: d5 forward 166 vs 221 us, d5 dgrad 102 vs 234 us); with 64+ channel
+  // tensor work per byte (<= 32 channels per pixel and N <= 32: d5 forward 150 vs 221 us, d5 dgrad 103 vs 234 us); with 64+ channel
   // chunks the per-tap kernel (2 CTAs/SM, deep ring) is as fast or faster (d4 forward 97 vs 130 us) -> keep it there.
-  if (L.bk > 32 && !env_int("SV_HALO_ALL", 0)) return;
+  if ((L.bk > 32 || L.tile_cols > 32) && !env_int("SV_HALO_ALL", 0)) return;
   const int pix = L.bk * 2, nch = L.kc;
   const int kb_bytes = L.tile_cols * L.bk * 2;
   const int num_kb = L.taps_h * L.taps_w * nch;
@@ -1020,20 +1074,24 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   H.taps_h = g.kh; H.taps_w = g.kw; H.pad_t = g.pt; H.pad_l = g.pl;
   H.cb = cb; H.nchunks = cipad / cb; H.x_swizzle = cb * 2;
   H.cbn = cbn; H.nbchunks = copad / cbn; H.dy_swizzle = cbn * 2;
-  H.n_pad = copad;
   H.nsub = 128 / cb;
+  // N-stacked variant: dY must be a single swizzle atom per pixel and kw blocks must fit one MMA
+  H.nstack = (H.nbchunks == 1 && g.kw * copad <= 256 && !env_int("SV_NO_NSTACK", 0)) ? 1 : 0;
+  H.nb = copad;
+  H.n_pad = H.nstack ? g.kw * copad : copad;
   if (H.nchunks == 1) {
     H.mode = 0;
-    H.gw = (g.kw + H.nsub - 1) / H.nsub;
+    H.gw = H.nstack ? 0 : (g.kw + H.nsub - 1) / H.nsub;
     H.gpt = 0;
-    H.groups = g.kh * H.gw;
+    H.groups = H.nstack ? (g.kh + H.nsub - 1) / H.nsub : g.kh * H.gw;
   } else {
     if (H.nchunks % H.nsub) return false;
     H.mode = 1;
     H.gpt = H.nchunks / H.nsub;
     H.gw = 0;
-    H.groups = g.kh * g.kw * H.gpt;
+    H.groups = (H.nstack ? g.kh : g.kh * g.kw) * H.gpt;
   }
+  if (H.groups > 32) return false;
   H.m_pad = H.groups * 128;
   int gpc = 512 / H.n_pad;
   if (gpc > H.groups) gpc = H.groups;
@@ -1044,22 +1102,40 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   H.TW = force_tw ? force_tw : ((g.Wo % 32) == 0 ? 32 : 16);
   if (g.Wo % H.TW) return false;
   H.stages = 2;
+  const int x_tw = H.nstack ? H.TW : H.TW + g.kw - 1, dy_tw = H.nstack ? H.TW + g.kw - 1 : H.TW;
+  // garbage sub-blocks of a partially filled group read up to (nsub-1) rows (N-stack) / pixels (plain) past the X tile
+  const size_t slack = H.nstack ? (size_t)(H.nsub - 1) * x_tw * cb * 2 : (size_t)H.nsub * cb * 2;
   int best_th = 0;
   for (int th = 1; th <= g.Ho && th <= 32; ++th) {
     if (g.Ho % th) continue;
     if (force_th && th != force_th) continue;
-    const int twp = H.TW + g.kw - 1, thp = th + g.kh - 1;
-    const size_t xc = ((size_t)thp * twp * cb * 2 + 1023) / 1024 * 1024, dc = ((size_t)th * H.TW * cbn * 2 + 1023) / 1024 * 1024;
-    const size_t smem = (size_t)H.stages * (xc * H.nchunks + dc * H.nbchunks) + sizeof(HwCtl) + 1024;
+    const int thp = th + g.kh - 1;
+    const size_t xc = ((size_t)thp * x_tw * cb * 2 + 1023) / 1024 * 1024, dc = ((size_t)th * dy_tw * cbn * 2 + 1023) / 1024 * 1024;
+    const size_t smem = (size_t)H.stages * (xc * H.nchunks + dc * H.nbchunks) + slack + sizeof(HwCtl) + 1024;
     if (smem <= 190 * 1024) best_th = th;
   }
   if (!best_th) return false;
   H.TH = best_th;
-  H.TWp = H.TW + g.kw - 1; H.THp = H.TH + g.kh - 1;
-  H.x_chunk_bytes = (int)(((size_t)H.THp * H.TWp * cb * 2 + 1023) / 1024 * 1024);
-  H.dy_chunk_bytes = (int)(((size_t)H.TH * H.TW * cbn * 2 + 1023) / 1024 * 1024);
+  H.x_tw = x_tw; H.x_th = H.TH + g.kh - 1; H.dy_tw = dy_tw; H.dy_th = H.TH;
+  H.x_dx = H.nstack ? 0 : -g.pl; H.x_dy = -g.pt; H.dy_dx = H.nstack ? -(g.kw - 1) + g.pl : 0;
+  H.x_chunk_bytes = (int)(((size_t)H.x_th * H.x_tw * cb * 2 + 1023) / 1024 * 1024);
+  H.dy_chunk_bytes = (int)(((size_t)H.dy_th * H.dy_tw * cbn * 2 + 1023) / 1024 * 1024);
   H.stage_bytes = H.x_chunk_bytes * H.nchunks + H.dy_chunk_bytes * H.nbchunks;
-  H.smem_bytes = (size_t)H.stages * H.stage_bytes + sizeof(HwCtl) + 1024;
+  H.smem_bytes = (size_t)H.stages * H.stage_bytes + slack + sizeof(HwCtl) + 1024;
+  const int pix = cb * 2;
+  H.a_lbo = H.mode == 1 ? H.x_chunk_bytes : (H.nstack ? H.x_tw * pix : pix);
+  H.b_lbo = H.nstack ? cbn * 2 : H.dy_chunk_bytes;
+  for (int gi = 0; gi < H.groups; ++gi) {
+    long long off;
+    if (H.nstack) {
+      if (H.mode == 0) off = (long long)(gi * H.nsub) * H.x_tw * pix;
+      else { const int a = gi / H.gpt, c0 = (gi % H.gpt) * H.nsub; off = (long long)c0 * H.x_chunk_bytes + (long long)a * H.x_tw * pix; }
+    } else {
+      if (H.mode == 0) { const int a = gi / H.gw, b0 = (gi % H.gw) * H.nsub; off = (long long)(a * H.x_tw + b0) * pix; }
+      else { const int tap = gi / H.gpt, c0 = (gi % H.gpt) * H.nsub; off = (long long)c0 * H.x_chunk_bytes + (long long)((tap / g.kw) * H.x_tw + tap % g.kw) * pix; }
+    }
+    H.goff[gi] = (uint32_t)(off >> 4);
+  }
   H.tiles_x = g.Wo / H.TW; H.tiles_y = g.Ho / H.TH; H.n_img = g.B;
   H.tiles = H.tiles_x * H.tiles_y * g.B;
   int ks = env_int("SV_HWG_SPLITS", 148) / H.m_splits;
@@ -1331,15 +1407,16 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
     if (t.wg_halo) {
       TcHaloWgrad& H = t.hw;
-      e = make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, H.nchunks * H.cb, H.cb, H.TWp, H.THp, 1, 1, H.x_swizzle);
+      e = make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, H.nchunks * H.cb, H.cb, H.x_tw, H.x_th, 1, 1, H.x_swizzle);
       if (e) return e;
-      e = make_act_map(&H.map_dy, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, H.n_pad, H.cbn, H.TW, H.TH, 1, 1, H.dy_swizzle);
+      e = make_act_map(&H.map_dy, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, H.nbchunks * H.cbn, H.cbn, H.dy_tw, H.dy_th, 1, 1, H.dy_swizzle);
       if (e) return e;
       H.partial = (float*)(ws + t.wg_partial_off);
       if (cudaFuncSetAttribute(halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
       if (env_int("SV_TC_VERBOSE", 0))
-        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d wgrad: HALO mode %d tile %dx%d groups %d (%d/CTA, m_splits %d) N %d tiles %d k_splits %d smem %zu\n", g.kh,
-                g.kw, g.stride, g.Ci, g.Co, H.mode, H.TW, H.TH, H.groups, H.groups_per_cta, H.m_splits, H.n_pad, H.tiles, H.k_splits, H.smem_bytes);
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d wgrad: HALO mode %d nstack %d tile %dx%d groups %d (%d/CTA, m_splits %d) N %d tiles %d k_splits %d smem %zu\n",
+                g.kh, g.kw, g.stride, g.Ci, g.Co, H.mode, H.nstack, H.TW, H.TH, H.groups, H.groups_per_cta, H.m_splits, H.n_pad, H.tiles, H.k_splits,
+                H.smem_bytes);
     }
   }
   return nullptr;
@@ -1447,7 +1524,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
     const TcHaloWgrad& H = t.hw;
     dim3 grid(H.m_splits, 1, H.k_splits);
     halo_wgrad_kernel<<<grid, kThreads, H.smem_bytes, s>>>(H);
-    const WgRowMap R{H.mode == 0 ? 2 : 3, g.kw, 0, H.cb, H.nsub, H.gw, H.gpt};
+    const WgRowMap R{(H.nstack ? 4 : 2) + (H.mode ? 1 : 0), g.kw, 0, H.cb, H.nsub, H.gw, H.gpt, H.nb};
     launch_wgrad_reduce(g, H.partial, H.k_splits, H.m_pad, H.n_pad, R, grads, s);
     return;
   }
@@ -1455,7 +1532,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
   const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
   dim3 grid(m_splits, L.n_tiles, L.k_splits);
   wgrad_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
-  const WgRowMap R{L.first ? 1 : 0, g.kw, L.ncb * L.cb, 0, 0, 0, 0};
+  const WgRowMap R{L.first ? 1 : 0, g.kw, L.ncb * L.cb, 0, 0, 0, 0, 0};
   launch_wgrad_reduce(g, L.partial, L.k_splits, L.m_pad, L.n_pad, R, grads, s);
 }
 

@@ -63,17 +63,26 @@ struct TcWgradLaunch {
 
 // Halo-resident weight gradient (stride-1 convolutions with W % 16 == 0): per pixel tile the X halo and the dY tile are loaded
 // once; every (filter tap, channel block) A operand is a shifted MN-major view of the same shared-memory halo.
-// An M = 128 row group stacks `nsub` sub-blocks of `cb` channels: horizontally adjacent taps (mode 0, LBO = one pixel) or
-// channel chunks of one tap (mode 1, LBO = one chunk).  K steps are 16 horizontally adjacent pixels.
+// An M = 128 row group stacks `nsub` sub-blocks of `cb` channels: adjacent taps (mode 0) or channel chunks of one tap (mode 1).
+// K steps are 16 horizontally adjacent pixels.  Two variants:
+//   plain   : D[(a,b,ci), co]          - groups enumerate (a,b); taps stacked horizontally (LBO = one pixel); N = Cout_pad
+//   N-stack : D[(a,ci), (kw-1-b, co)]  - the filter COLUMN moves to the N axis: B = kw shifted views of the dY tile
+//             (LBO = one pixel), taps stacked vertically in M (LBO = one tile row).  kw x fewer, kw x wider MMAs: the MMA
+//             rate is bound by the 128x16 A-operand read, so wide N is what makes the small-Cout layers efficient.
 struct TcHaloWgrad {
   CUtensorMap map_x, map_dy;
   int taps_h, taps_w, pad_t, pad_l;
   int cb, nchunks, x_swizzle;       // X channel chunk (elements), chunks per pixel
   int cbn, nbchunks, dy_swizzle;    // dY channel chunk, chunks
-  int n_pad;                        // UMMA N
-  int TW, TH, TWp, THp;
+  int n_pad;                        // UMMA N = columns of the partial buffer
+  int nstack, nb;                   // N-stacked variant: N = taps_w blocks of nb channels (block j = filter column taps_w-1-j)
+  int TW, TH;                       // pixel tile (K steps = 16 horizontally adjacent pixels)
+  int x_tw, x_th, dy_tw, dy_th;     // shared-memory tile extents (pixels) of X and dY
+  int x_dx, x_dy, dy_dx;            // TMA start = tile origin + these offsets
+  int a_lbo, b_lbo;                 // byte distance between the stacked sub-blocks of A (M) / B (N)
+  uint32_t goff[32];                // per 128-row group: (byte offset of its first sub-block inside the X tile) >> 4
   int x_chunk_bytes, dy_chunk_bytes, stage_bytes, stages;
-  int mode, nsub, gw, gpt;          // grouping (see above): gw = groups per filter row (mode 0), gpt = groups per tap (mode 1)
+  int mode, nsub, gw, gpt;          // grouping, used by the reduce kernel's row map
   int groups, groups_per_cta, m_splits;
   int tiles_x, tiles_y, n_img, tiles, tiles_per_split, k_splits;
   int m_pad;
