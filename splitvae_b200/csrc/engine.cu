@@ -65,7 +65,7 @@ struct sv_handle {
   GmEnc gm{};
   Decoder dec_x{}, dec_xh{};
   int ZCAT = -1, EPS_G = -1, EPS_L = -1, Z_G = -1, Z_L = -1, ZM_G = -1, ZS_G = -1, ZM_L = -1, ZS_L = -1;
-  int ZPM_OUT = -1, ZPS_OUT = -1, SCALARS = -1, PARTIALS = -1, COLSUM = -1, ADAM = -1, TCWS = -1;
+  int ZPM_OUT = -1, ZPS_OUT = -1, SCALARS = -1, PARTIALS = -1, KLPART = -1, COLSUM = -1, ADAM = -1, TCWS = -1;
   int XP[2] = {-1, -1};     // staged first-layer images (x, x_hat) for the tensor-core path
   long long seg_split = 0;  // arena offset where the decoders start
   // bound buffers
@@ -509,6 +509,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->ZPM_OUT = f32_buf(h, B * 128); h->ZPS_OUT = f32_buf(h, B * 128);
   h->SCALARS = f32_buf(h, 64);
   h->PARTIALS = f32_buf(h, 2 * 148 * 8 + 64);
+  h->KLPART = f32_buf(h, 2 * reparam_blocks(B) + 64);
   h->COLSUM = f32_buf(h, 256 * 8192);
   h->COLSUM2 = f32_buf(h, 256 * 8192);
   h->ADAM = new_buf(h, 1024);
@@ -623,7 +624,7 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
   conv_encoder_fwd(h, h->enc_xh, inputs, s2);
   join_side(h, s);
-  reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
+  reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), (float*)bp(h, h->KLPART), s);
   h->launches += 1;
   s2 = fork_side(h, s);
   decoder_fwd(h, h->dec_x, s);
@@ -651,7 +652,7 @@ sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
   pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), (const float*)bp(h, h->dec_xh.OUT), bp(h, h->dec_x.dOUT),
              bp(h, h->dec_xh.dOUT), h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
              (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s);
-  loss_scalars(latent_bufs(h), gm ? (const float*)bp(h, h->gm.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
+  loss_scalars((const float*)bp(h, h->KLPART), reparam_blocks(h->B), gm ? (const float*)bp(h, h->gm.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
                (const float*)bp(h, h->PARTIALS), pixel_loss_blocks(npix), (float*)bp(h, h->SCALARS), s);
   h->launches += 2;
   h->last_inputs = inputs;

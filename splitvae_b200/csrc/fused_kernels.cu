@@ -35,11 +35,15 @@ template <typename T>
 __device__ __forceinline__ T ld_as(const void* p, long long i) { return ((const T*)p)[i]; }
 
 // ------------------------------------------------------------------ reparameterisation
+// Also emits the per-block partial sums of the two Gaussian KL terms (vae/trainer.py:11-18) into kl_partials[2*block]
+// (fixed-order block reduction; loss_scalars adds the blocks up), so the scalar kernel does not re-read the latents.
 template <typename T>
-__global__ void reparam_kernel(LatentBufs L, int B, const float* __restrict__ ueg, const float* __restrict__ uel,
-                               unsigned long long seed, const unsigned long long* __restrict__ counter) {
+__global__ void __launch_bounds__(256) reparam_kernel(LatentBufs L, int B, const float* __restrict__ ueg, const float* __restrict__ uel,
+                                                      unsigned long long seed, const unsigned long long* __restrict__ counter,
+                                                      float* __restrict__ kl_partials) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * 128) return;
+  float kl_g = 0.f, kl_l = 0.f;
+  if (idx < B * 128) {
   const int b = idx >> 7, d = idx & 127;
   float eg, el;
   if (ueg && uel) {
@@ -60,13 +64,39 @@ __global__ void reparam_kernel(LatentBufs L, int B, const float* __restrict__ ue
   L.zm_g[idx] = mg; L.zs_g[idx] = sg; L.zm_l[idx] = ml; L.zs_l[idx] = sl;
   ((T*)L.zcat)[b * 256 + d] = from_f32<T>(zg);
   ((T*)L.zcat)[b * 256 + 128 + d] = from_f32<T>(zl);
+  if (L.yheads) {   // q(z_g) || p(z_g | y), q(z_l) || N(0, I)   (vae/trainer.py:157-158)
+    const float pm = L.yheads[b * 768 + 512 + d], ps = L.yheads[b * 768 + 640 + d];
+    kl_g = logf(ps) - logf(sg) + (sg * sg + (mg - pm) * (mg - pm)) / (2.f * ps * ps) - 0.5f;
+    kl_l = -logf(sl) + (sl * sl + ml * ml) * 0.5f - 0.5f;
+  } else {          // vae/trainer.py:11-15
+    kl_g = -0.5f * (1.f + logf(sg * sg) - mg * mg - sg * sg);
+    kl_l = -0.5f * (1.f + logf(sl * sl) - ml * ml - sl * sl);
+  }
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    kl_g += __shfl_xor_sync(0xffffffffu, kl_g, o);
+    kl_l += __shfl_xor_sync(0xffffffffu, kl_l, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = kl_g; red[1][threadIdx.x >> 5] = kl_l; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    kl_partials[2 * blockIdx.x] = a;
+    kl_partials[2 * blockIdx.x + 1] = c;
+  }
 }
 
+int reparam_blocks(int B) { return (B * 128 + 255) / 256; }
+
 void reparam(const LatentBufs& L, int B, int act_dt, const float* ueg, const float* uel, unsigned long long seed,
-             const unsigned long long* counter, cudaStream_t s) {
-  const int n = B * 128;
-  if (act_dt == DT_F32) reparam_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(L, B, ueg, uel, seed, counter);
-  else reparam_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>(L, B, ueg, uel, seed, counter);
+             const unsigned long long* counter, float* kl_partials, cudaStream_t s) {
+  const int nb = reparam_blocks(B);
+  if (act_dt == DT_F32) reparam_kernel<float><<<nb, 256, 0, s>>>(L, B, ueg, uel, seed, counter, kl_partials);
+  else reparam_kernel<bf16><<<nb, 256, 0, s>>>(L, B, ueg, uel, seed, counter, kl_partials);
 }
 
 // gradient w.r.t. the pre-activation encoder heads: reparam adjoint + KL gradient + softplus'
@@ -386,25 +416,16 @@ void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, vo
 #undef LAUNCH
 }
 
-// KL scalars (vae/trainer.py:11-18, 130-132, 157-161) + fixed-order reduction of the pixel partials.
-__global__ void __launch_bounds__(1024) loss_scalars_kernel(LatentBufs L, const float* __restrict__ y_logits, int B, int K,
+// Final scalars: fixed-order sum of the per-block partials of the pixel likelihood (pixel_loss_kernel) and of the Gaussian
+// KLs (reparam_kernel), plus the categorical KL of q(y|x) (vae/trainer.py:160-161, one thread per row), in double.
+__global__ void __launch_bounds__(1024) loss_scalars_kernel(const float* __restrict__ kl_partials, int kl_blocks,
+                                                            const float* __restrict__ y_logits, int B, int K,
                                                             int gm, float beta, float alpha,
                                                             const float* __restrict__ partials, int nblocks,
                                                             float* __restrict__ scalars) {
   __shared__ double red[5][32];
   double acc[5] = {0, 0, 0, 0, 0};  // kl_x, kl_x_hat, y_kl, recon_x, recon_x_hat
-  for (int idx = threadIdx.x; idx < B * 128; idx += blockDim.x) {
-    const int b = idx >> 7, d = idx & 127;
-    const float mg = L.zm_g[idx], sg = L.zs_g[idx], ml = L.zm_l[idx], sl = L.zs_l[idx];
-    if (gm) {
-      const float pm = L.yheads[b * 768 + 512 + d], ps = L.yheads[b * 768 + 640 + d];
-      acc[0] += logf(ps) - logf(sg) + (sg * sg + (mg - pm) * (mg - pm)) / (2.f * ps * ps) - 0.5f;
-      acc[1] += -logf(sl) + (sl * sl + ml * ml) * 0.5f - 0.5f;
-    } else {
-      acc[0] += -0.5f * (1.f + logf(sg * sg) - mg * mg - sg * sg);
-      acc[1] += -0.5f * (1.f + logf(sl * sl) - ml * ml - sl * sl);
-    }
-  }
+  for (int i = threadIdx.x; i < kl_blocks; i += blockDim.x) { acc[0] += kl_partials[2 * i]; acc[1] += kl_partials[2 * i + 1]; }
   if (gm) {
     for (int row = threadIdx.x; row < B; row += blockDim.x) {
       float mx = -INFINITY;
@@ -447,9 +468,9 @@ __global__ void __launch_bounds__(1024) loss_scalars_kernel(LatentBufs L, const 
   }
 }
 
-void loss_scalars(const LatentBufs& L, const float* y_logits, int B, int K, int gm, float beta, float alpha,
+void loss_scalars(const float* kl_partials, int kl_blocks, const float* y_logits, int B, int K, int gm, float beta, float alpha,
                   const float* partials, int nblocks, float* scalars, cudaStream_t s) {
-  loss_scalars_kernel<<<1, 1024, 0, s>>>(L, y_logits, B, K, gm, beta, alpha, partials, nblocks, scalars);
+  loss_scalars_kernel<<<1, 1024, 0, s>>>(kl_partials, kl_blocks, y_logits, B, K, gm, beta, alpha, partials, nblocks, scalars);
 }
 
 // ------------------------------------------------------------------ Keras Adam (ResourceApplyAdam)

@@ -40,8 +40,10 @@ struct LatentBufs {
   const float* yheads;    // [B,768] (h_top | z_prior_mean | z_prior_sig), fp32
 };
 
+// also writes the per-block partial sums of the two Gaussian KLs to kl_partials[2 * reparam_blocks(B)]
+int reparam_blocks(int B);
 void reparam(const LatentBufs& L, int B, int act_dt, const float* user_eps_g, const float* user_eps_l,
-             unsigned long long seed, const unsigned long long* counter_dev, cudaStream_t s);
+             unsigned long long seed, const unsigned long long* counter_dev, float* kl_partials, cudaStream_t s);
 void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s);
 
 void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, int act_dt, int B,
@@ -59,8 +61,8 @@ void gm_glue_b(const void* dy, const float* y, const float* logits, void* dlogit
 int pixel_loss_blocks(long long npix);
 void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, void* dout_x, void* dout_xh, int dout_dt,
                 int dout_ld, long long npix, float grad_scale, float* loss_partials, bool fast_math, cudaStream_t s);
-// KL scalars + final reduction of the pixel partials -> scalars[8]
-void loss_scalars(const LatentBufs& L, const float* y_logits, int B, int K, int gm, float beta, float alpha,
+// final reduction of the KL partials (reparam) and pixel partials (pixel_loss) + categorical KL -> scalars[8]
+void loss_scalars(const float* kl_partials, int kl_blocks, const float* y_logits, int B, int K, int gm, float beta, float alpha,
                   const float* loss_partials, int nblocks, float* scalars, cudaStream_t s);
 
 void dll_elementwise(const float* x, const float* m, const float* ls, float* out, long long n, cudaStream_t s);

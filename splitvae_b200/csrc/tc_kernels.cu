@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
   const int tiles_per_img = P.grid_h / P.tile_h;   // tile_w == grid_w
   const int n0 = (m_tile / tiles_per_img) * P.tile_n_img;
   const int y0 = (m_tile % tiles_per_img) * P.tile_h;
-  const int num_kb = P.taps_h * P.taps_w * P.kc;
+  const int kb_total = P.taps_h * P.taps_w * P.kc;
+  const int kb_first = P.k_splits > 1 ? blockIdx.z * P.kb_per_split : 0;          // split-K: this CTA's k-block range
+  const int num_kb = P.k_splits > 1 ? min(P.kb_per_split, kb_total - kb_first) : kb_total;
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&P.map_a);
@@ -236,9 +238,10 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int stage = kb % P.stages, phase = (kb / P.stages) & 1;
+      for (int it = 0; it < num_kb; ++it) {
+        const int stage = it % P.stages, phase = (it / P.stages) & 1;
         tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+        const int kb = kb_first + it;
         const int tap = kb / P.kc, chunk = kb - tap * P.kc;
         const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -273,6 +276,19 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
     tc::tc_fence_after();
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
+    if (P.k_splits > 1) {                       // split-K: raw fp32 partial, finished by splitk_finish_kernel
+      float* dst = P.partial + ((size_t)blockIdx.z * P.m_pad + (size_t)m_tile * 128 + row) * P.n_pad + (size_t)n_tile * P.tile_cols;
+      for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        const int ncol = min(32, P.tile_cols - c0);
+        if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          if (i < ncol) *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
     const int per_img = P.tile_h * P.tile_w;
     const int nn = row / per_img, rem = row - nn * per_img;
     const int hh = rem / P.tile_w, ww = rem - hh * P.tile_w;
@@ -280,6 +296,7 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
     const bool valid = n < P.n_img;
     const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
     epilogue_rows(P, epilogue_select(P, n_tile), tmem_base, quarter, valid, opix, n_tile);
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -289,6 +306,26 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
   }
 }
 
+// Split-K finish for dense layers (one output row per image): out[row][col] = epilogue(sum_z partial[z][row][col]).
+// Fixed summation order -> deterministic.  One thread per output element; consecutive threads = consecutive columns.
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ TcLaunch P) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int col = (int)(idx % P.n_valid);
+  const long long row = idx / P.n_valid;
+  if (row >= P.n_img) return;
+  const size_t zstride = (size_t)P.m_pad * P.n_pad;
+  const float* p = P.partial + (size_t)row * P.n_pad + col;
+  float acc = 0.f;
+  for (int z = 0; z < P.k_splits; ++z) acc += p[z * zstride];
+  if (P.bias) acc += P.bias[col];
+  int c = col, j = 0;
+  while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
+  acc = apply_act(acc, P.part_act[j]);
+  if (P.mask_act != ACT_NONE)
+    acc *= act_grad_from_out(__bfloat162float(((const bf16*)P.mask_src)[row * P.mask_ld + P.mask_coff + col]), P.mask_act);
+  const long long o = row * P.out_ld + col;
+  if (P.out_f32) ((float*)P.out)[o] = acc; else ((bf16*)P.out)[o] = __float2bfloat16_rn(acc);
+}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -840,6 +877,36 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const PackJob& J = jobs[lo];
+  if (J.kind == 0) {
+    // forward weights: dst[co][tap][ci] = W[tap][ci][co] is a transpose per tap -> 32x32 tiles through shared memory so
+    // that both the fp32 reads (along co) and the bf16 writes (along ci) are coalesced
+    __shared__ float tile[32][33];
+    const int tk_n = (J.k_pad + 31) >> 5, tr_n = (J.rows_pad + 31) >> 5;
+    int t = blockIdx.x - J.block_start;
+    const int tk = t % tk_n; t /= tk_n;
+    const int tr = t % tr_n;
+    const int tap = t / tr_n;
+    const int a = tap / J.taps_w, b = tap - a * J.taps_w;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int co = tr * 32 + tx;
+    int j = 0, lc = co;
+    while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+    const float* src = params + J.part_w[j] + (long long)(a * J.KW + b) * J.Ci * J.part_n[j] + lc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ci = tk * 32 + ty + 8 * i;
+      tile[ty + 8 * i][tx] = (co < J.Co && ci < J.Ci) ? src[(long long)ci * J.part_n[j]] : 0.f;
+    }
+    __syncthreads();
+    const int kk = tk * 32 + tx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = tr * 32 + ty + 8 * i;
+      if (r < J.rows_pad && kk < J.k_pad)
+        ((bf16*)J.dst)[((long long)r * (J.taps_h * J.taps_w) + tap) * J.k_pad + kk] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    return;
+  }
   const long long base = (long long)(blockIdx.x - J.block_start) * 2048;
   for (int t = threadIdx.x; t < 2048; t += 256) {
     const long long idx = base + t;
@@ -1002,13 +1069,38 @@ void finish_launch(TcLaunch& L, int n_cols_pad) {
 }
 
 
-// Converts an igemm launch (stride-1 A addressing) into a halo-resident launch when the output grid allows 8x16 row
-// groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
-// for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+
+// Split-K plan for a dense layer (1x1 "image", one tap) with few output tiles and a long K axis: heads (K = 8192 -> 256),
+// d1 dgrad, the GM y_block; without it 2-4 CTAs stream the whole weight matrix at TMA latency (78 us for 4 MB).
+void plan_split_k(TcLaunch& L, int n_img, size_t& off) {
+  L.k_splits = 1; L.kb_per_split = 0; L.partial = nullptr;
+  if (env_int("SV_NO_SPLITK", 0)) return;
+  if (L.halo || L.grid_h != 1 || L.grid_w != 1 || L.taps_h * L.taps_w != 1 || L.osy != 1 || L.osx != 1) return;
+  const int num_kb = L.kc;
+  const int m_tiles = (n_img + 127) / 128, ctas = m_tiles * L.n_tiles;
+  if (num_kb < 8 || ctas >= 74) return;
+  int splits = (148 + ctas - 1) / ctas;
+  if (splits > num_kb / 2) splits = num_kb / 2;
+  const int kbps = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kbps - 1) / kbps;
+  if (splits < 2) return;
+  L.k_splits = splits; L.kb_per_split = kbps;
+  L.m_pad = m_tiles * 128; L.n_pad = L.n_tiles * L.tile_cols;
+  if (L.stages > kbps) L.stages = kbps;
+  off = (off + 1023) / 1024 * 1024;
+  // (the caller records `off` as the partial-buffer offset)
+}
+size_t split_k_bytes(const TcLaunch& L) {
+  return L.k_splits > 1 ? ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024 : 0;
+}
+
+// Converts an igemm launch (stride-1 A addressing) into a halo-resident launch when the output grid allows 8x16 row
+// groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
+// for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
 
 void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
   L.halo = 0;
@@ -1248,8 +1340,11 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         L.mask_act = ACT_NONE;
         finish_launch(L, t.n_pad_fwd);
         if (cpad <= g.in_ld - g.in_coff) try_halo(L, g.Ho, g.Wo, g.B);
+        plan_split_k(L, g.B, off);
+        t.sk_fwd_off = off;
+        off += split_k_bytes(L);
         t.fwd_ok = true;
-        t.fwd_launches = 1;
+        t.fwd_launches = L.k_splits > 1 ? 2 : 1;
         t.w_fwd_off = off;
         off += round_up((int)((size_t)t.n_pad_fwd * g.kh * g.kw * cpad * 2), 1024);
         t.bias_off = off;
@@ -1284,10 +1379,15 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
       finish_launch(L, t.n_pad_dg);
       try_halo(L, GH, GW, g.B);
+      if (s == 1) {
+        plan_split_k(L, g.B, off);
+        t.sk_dgrad_off = off;
+        off += split_k_bytes(L);
+      }
     }
     if (ok) {
       t.dgrad_ok = true;
-      t.dgrad_launches = s * s;
+      t.dgrad_launches = s * s + (s == 1 && t.dgrad[0].k_splits > 1 ? 1 : 0);
       t.w_dgrad_off = off;
       off += (size_t)s * s * round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * copad * 2), 1024);
     }
@@ -1359,6 +1459,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     L.bias = (const float*)(ws + t.bias_off);
     L.out = out;
     L.mask_src = nullptr;
+    L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_fwd_off) : nullptr;
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   if (t.dgrad_ok) {
@@ -1378,6 +1479,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       L.mask_act = mask_act;
       L.mask_ld = g.in_ld;
       L.mask_coff = g.in_coff;
+      L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_dgrad_off) : nullptr;
     }
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
@@ -1389,8 +1491,8 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
                 g.kh, g.kw, g.stride, g.Ci, g.Co, what, L.TW, L.TH, L.TWp, L.THp, L.kc, L.chunk_bytes, L.tile_cols, L.n_tiles, L.w_stages,
                 L.w_stage_bytes, L.kb_per_stage, L.smem_bytes);
       else
-        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: per-tap tile %dx%dx%d bk %d N %d x%d stages %d smem %zu\n", g.kh, g.kw, g.stride, g.Ci, g.Co,
-                what, L.tile_n_img, L.tile_h, L.tile_w, L.bk, L.tile_cols, L.n_tiles, L.stages, L.smem_bytes);
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: per-tap tile %dx%dx%d bk %d N %d x%d stages %d smem %zu split-K %d x %d kb\n", g.kh, g.kw, g.stride, g.Ci, g.Co,
+                what, L.tile_n_img, L.tile_h, L.tile_w, L.bk, L.tile_cols, L.n_tiles, L.stages, L.smem_bytes, L.k_splits, L.kb_per_split);
     };
     if (t.fwd_ok) show("fwd", t.fwd);
     if (t.dgrad_ok) for (int c = 0; c < t.n_dgrad; ++c) show("dgrad", t.dgrad[c]);
@@ -1432,7 +1534,8 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
   int blocks = 0;
   auto push = [&](PackJob J) {
     J.block_start = blocks;
-    blocks += (int)((J.count + 2047) / 2048);
+    if (J.kind == 0) blocks += J.taps_h * J.taps_w * ((J.rows_pad + 31) / 32) * ((J.k_pad + 31) / 32);   // 32x32 transpose tiles
+    else blocks += (int)((J.count + 2047) / 2048);
     jobs.push_back(J);
   };
   for (int i = 0; i < n; ++i) {
@@ -1498,8 +1601,12 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
   }
   const int tiles_per_img = L.grid_h / L.tile_h;
   const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
-  dim3 grid(m_tiles, L.n_tiles);
+  dim3 grid(m_tiles, L.n_tiles, L.k_splits > 1 ? L.k_splits : 1);
   igemm_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+  if (L.k_splits > 1) {
+    const long long total = (long long)L.n_img * L.n_valid;
+    splitk_finish_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(L);
+  }
 }
 
 void tc_conv_fwd(TcLayer& t, cudaStream_t s) { launch(t.fwd, s); }

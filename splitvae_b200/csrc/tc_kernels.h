@@ -38,6 +38,10 @@ struct TcLaunch {
   int chunk_bytes;                              // bytes of one channel-chunk halo (1024-aligned)
   int kb_per_stage, w_stages, w_stage_bytes;    // weight ring: k-blocks (tap, chunk) per stage
   int tiles_x, tiles_y;
+  // split-K (skinny dense GEMMs: few output tiles, long K): blockIdx.z owns kb_per_split k-blocks and stores its raw fp32
+  // accumulator to partial[z][m_pad][n_pad]; splitk_finish_kernel sums the splits in a fixed order and applies the epilogue
+  int k_splits, kb_per_split, m_pad, n_pad;
+  float* partial;
 };
 
 // Weight gradient  dW[(tap,ci), co] = sum_pixels X[pixel+tap, ci] * dY[pixel, co]  as a GEMM whose K axis is the
@@ -105,6 +109,7 @@ struct TcLayer {
   int n_pad_dg = 0, co_pad = 0;       // dgrad: B = [classes][n_pad_dg][taps'][co_pad]
   int dg_taps_h = 0, dg_taps_w = 0;
   size_t w_fwd_off = 0, w_dgrad_off = 0, bias_off = 0, bytes = 0;   // offsets inside this layer's workspace slice
+  size_t sk_fwd_off = 0, sk_dgrad_off = 0;                            // split-K partial buffers
   char* ws = nullptr;
   int in_dt = 0, out_dt = 0;
 };
