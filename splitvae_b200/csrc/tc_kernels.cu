@@ -483,6 +483,301 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// N-stacked persistent convolution (see TcNsConv in tc_kernels.h).
+//   warp 0   : TMA producer - resident weights once, then one (R + kh - 1)-row input halo per tile (2 stages)
+//   warp 1   : single-thread tcgen05.mma issuer - kh * (C / 16) MMAs of N = kw * nb per tile (x ng N groups)
+//   warps 2-5: epilogue - for every block of 8 output channels: kw TMEM loads, lane shuffles by (b - pad_l) along x
+//              (W = 64: the 2-3 lanes that cross the two warps of an image row go through shared memory), bias,
+//              activation / mask, NHWC store.  Accumulators are double-buffered so this overlaps the next tile's MMAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNsMaxStages = 8;
+constexpr int kNsMaxGroups = 4;                  // epilogue groups = accumulator buffers in TMEM
+constexpr int kNsEpiWarps = 16;                  // epilogue warps per CTA = 4 TMEM quarters x groups x chunk lanes
+constexpr int kNsThreads = 64 + 32 * kNsEpiWarps;
+struct NsCtl {
+  uint64_t w_full, halo_full[kNsMaxStages], halo_empty[kNsMaxStages], acc_full[kNsMaxGroups], acc_empty[kNsMaxGroups];
+  uint32_t tmem_base;
+};
+constexpr int kNsXchSlots = 8;   // lanes 0..3 -> slots 0..3, lanes 28..31 -> slots 4..7
+
+// Epilogue of the N-stacked kernel for one warp.  A single warp per scheduler runs this dependent shuffle / FMA chain at ~8
+// cycles per instruction, so the work is spread over 16 warps: `groups` warp sets take whole tiles round-robin (group g owns
+// accumulator buffer g), and inside a group `lanes` warps per TMEM quarter q split a tile's 8-channel blocks.  The accumulator
+// is handed back to the MMA warp as soon as this warp's last block has been read from TMEM (before the shuffles and stores).
+// Everything that shapes the instruction stream is a template parameter (the first, fully runtime version was ~1700 SASS
+// instructions per 8-channel block and instruction-cache bound; this one is ~230).
+template <int KW, int ACT, bool WIDE, bool OUT_F32>
+__device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, float* xch_all, uint32_t tmem_base, int q, int grp, int cl, int lane) {
+  // loop-invariant parameters in registers (the asm memory clobbers would otherwise force reloads through the generic pointer)
+  const int W = P.W, H = P.H, R = P.R, nb = P.nb, pad_l = P.pad_l, tiles = P.tiles, tiles_per_img = P.tiles_per_img;
+  const int groups = P.groups, lanes = P.lanes, n_valid = P.n_valid, out_ld = P.out_ld, mask_act = P.mask_act;
+  const int mask_ld = P.mask_ld, mask_coff = P.mask_coff;
+  const float* bias = P.bias;
+  void* out = P.out;
+  const bf16* mask_src = (const bf16*)P.mask_src;
+  const int p = q * 32 + lane;
+  const int r = p / W, x = p - r * W;
+  const int nchunk8 = nb >> 3;
+  const int acc_cols = P.ng * P.ncols;
+  const int split = blockIdx.x % P.co_splits, cta = blockIdx.x / P.co_splits, ncta = gridDim.x / P.co_splits;
+  const int cbase = split * nb;               // first output channel of this CTA's split
+  const int my_last = cl + ((nchunk8 - 1 - cl) / lanes) * lanes;   // last block this warp reads (< 0: none)
+  float* xch = xch_all + (size_t)(grp * lanes + cl) * (2 * 4 * KW * kNsXchSlots * 8);
+  const int bar_id = 1 + grp * lanes + cl;
+  // per filter column b: source lane and whether the source pixel x + b - pad_l lies inside the image row (else: zero padding)
+  float keep[KW];
+  int src[KW];
+#pragma unroll
+  for (int b = 0; b < KW; ++b) {
+    const int d = b - pad_l;
+    keep[b] = (x + d >= 0 && x + d < W) ? 1.f : 0.f;
+    src[b] = (lane + d) & 31;
+  }
+  int xbuf = 0, i = 0;
+  for (int t = cta; t < tiles; t += ncta, ++i) {
+    if (i % groups != grp) continue;
+    const int aph = (i / groups) & 1;
+    const int n = t / tiles_per_img, y0 = (t - n * tiles_per_img) * R;
+    const long long opix = ((long long)n * H + (y0 + r)) * W + x;
+    tc::mbar_wait(&ctl->acc_full[grp], aph);
+    tc::tc_fence_after();
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * acc_cols);
+    if (cl >= nchunk8) {                          // more chunk lanes than blocks: nothing to read, but the barrier counts every warp
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&ctl->acc_empty[grp]);
+      continue;
+    }
+    for (int cc = cl; cc < nchunk8; cc += lanes) {
+      uint32_t v[KW][8];                          // [filter column b][channel]
+#pragma unroll
+      for (int b = 0; b < KW; ++b) tc::tmem_ld8(tacc + (uint32_t)(b * nb + cc * 8), v[b]);
+      tc::tmem_ld_wait();
+      if (cc == my_last) {                        // this warp is done with the accumulator: hand it back to the MMA warp
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&ctl->acc_empty[grp]);
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      if (WIDE) {
+        // an image row spans two warps (q even: left half, q odd: right half): lanes near the boundary publish their values
+        float* xb = xch + (size_t)xbuf * (4 * KW * kNsXchSlots * 8);
+        const int slot = lane < 4 ? lane : lane >= 28 ? lane - 24 : -1;
+        if (slot >= 0) {
+          float* xw = xb + (size_t)q * (KW * kNsXchSlots * 8);
+#pragma unroll
+          for (int b = 0; b < KW; ++b) {
+            uint4* dst = reinterpret_cast<uint4*>(xw + (b * kNsXchSlots + slot) * 8);
+            dst[0] = make_uint4(v[b][0], v[b][1], v[b][2], v[b][3]);
+            dst[1] = make_uint4(v[b][4], v[b][5], v[b][6], v[b][7]);
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the four quarter warps of this (group, chunk lane)
+#pragma unroll
+        for (int b = 0; b < KW; ++b) {
+          const int ls = lane + b - pad_l;
+          if (keep[b] != 0.f && (ls < 0 || ls > 31)) {   // source pixel lives in the neighbouring warp of this image row
+            const int qn = ls < 0 ? q - 1 : q + 1;
+            const int sl = ls < 0 ? ls + 8 : ls - 32;
+            const float4* xr = reinterpret_cast<const float4*>(xb + (size_t)qn * (KW * kNsXchSlots * 8) + (b * kNsXchSlots + sl) * 8);
+            const float4 lo = xr[0], hi = xr[1];
+            o[0] += lo.x; o[1] += lo.y; o[2] += lo.z; o[3] += lo.w; o[4] += hi.x; o[5] += hi.y; o[6] += hi.z; o[7] += hi.w;
+          }
+        }
+        xbuf ^= 1;
+      }
+#pragma unroll
+      for (int b = 0; b < KW; ++b) {
+        const int ls = lane + b - pad_l;
+        const float k = WIDE ? ((ls >= 0 && ls < 32) ? keep[b] : 0.f) : keep[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(k, __shfl_sync(0xffffffffu, __uint_as_float(v[b][j]), src[b]), o[j]);
+      }
+      const int c0 = cbase + cc * 8;
+      if (bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+      }
+      if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = act_t<ACT>(o[j]);
+      }
+      if (mask_act != ACT_NONE) {
+        const bf16* mrow = mask_src + opix * mask_ld + mask_coff + c0;
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < n_valid) o[j] *= act_grad_from_out(__bfloat162float(mrow[j]), mask_act);
+      }
+      if (OUT_F32) {
+        float* dst = (float*)out + opix * out_ld + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < n_valid) dst[j] = o[j];
+      } else {
+        bf16* dst = (bf16*)out + opix * out_ld + c0;
+        if ((out_ld & 7) == 0 && c0 + 8 <= n_valid) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]); pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dst) = pk;
+        } else {
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < n_valid) dst[j] = __float2bfloat16_rn(o[j]);
+        }
+      }
+    }
+  }
+}
+
+#define SV_NS_EPI_ARGS P, ctl, xch, tmem_base, q, grp, cl, lane
+template <int KW, int ACT>
+__device__ __forceinline__ void ns_epilogue_kw_act(const TcNsConv& P, NsCtl* ctl, float* xch, uint32_t tmem_base, int q, int grp, int cl, int lane) {
+  if (P.W > 32) {
+    if (P.out_f32) ns_epilogue_t<KW, ACT, true, true>(SV_NS_EPI_ARGS);
+    else ns_epilogue_t<KW, ACT, true, false>(SV_NS_EPI_ARGS);
+  } else {
+    if (P.out_f32) ns_epilogue_t<KW, ACT, false, true>(SV_NS_EPI_ARGS);
+    else ns_epilogue_t<KW, ACT, false, false>(SV_NS_EPI_ARGS);
+  }
+}
+template <int KW>
+__device__ __forceinline__ void ns_epilogue_kw(const TcNsConv& P, NsCtl* ctl, float* xch, uint32_t tmem_base, int q, int grp, int cl, int lane) {
+  if (P.act == ACT_RELU) ns_epilogue_kw_act<KW, ACT_RELU>(SV_NS_EPI_ARGS);
+  else if (P.act == ACT_ELU) ns_epilogue_kw_act<KW, ACT_ELU>(SV_NS_EPI_ARGS);
+  else ns_epilogue_kw_act<KW, ACT_NONE>(SV_NS_EPI_ARGS);   // (the planner admits relu / elu / linear only)
+}
+__device__ __forceinline__ void ns_epilogue(const TcNsConv& P, NsCtl* ctl, float* xch, uint32_t tmem_base, int q, int grp, int cl, int lane) {
+  if (P.kw == 6) ns_epilogue_kw<6>(SV_NS_EPI_ARGS);
+  else ns_epilogue_kw<4>(SV_NS_EPI_ARGS);                  // (the planner admits kw 4 and 6 only)
+}
+#undef SV_NS_EPI_ARGS
+
+// MMAs of one tile, fully unrolled: KH filter rows x KS k-steps of 16 channels x NG column groups.
+template <int KH, int KS, int NG>
+__device__ __forceinline__ void ns_issue_tile(uint64_t da0, uint64_t db0, uint32_t acc, uint32_t idesc, uint32_t row_step, uint32_t wk_step,
+                                              uint32_t grp_step, uint32_t ncols) {
+#pragma unroll
+  for (int a = 0; a < KH; ++a) {
+    const uint64_t da_a = da0 + (uint64_t)(a * row_step), db_a = db0 + (uint64_t)(a * wk_step);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+        tc::umma_bf16(acc + g * ncols, da_a + 2u * k, db_a + (uint64_t)(g * grp_step) + 2u * k, idesc, (a | k) != 0 ? 1u : 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_constant__ TcNsConv P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;
+  uint8_t* halo = smem + P.w_bytes;
+  NsCtl* ctl = reinterpret_cast<NsCtl*>(halo + (size_t)P.nstages * P.stage_bytes);
+  float* xch = reinterpret_cast<float*>(halo + (size_t)P.nstages * P.stage_bytes + P.xch_off);
+  const int split = blockIdx.x % P.co_splits, cta = blockIdx.x / P.co_splits, ncta = gridDim.x / P.co_splits;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_x);
+    tc::prefetch_tmap(&P.map_w);
+    tc::mbar_init(&ctl->w_full, 1);
+    for (int i = 0; i < P.nstages; ++i) { tc::mbar_init(&ctl->halo_full[i], 1); tc::mbar_init(&ctl->halo_empty[i], 1); }
+    for (int i = 0; i < P.groups; ++i) { tc::mbar_init(&ctl->acc_full[i], 1); tc::mbar_init(&ctl->acc_empty[i], 4 * P.lanes); }
+    tc::fence_barrier_init();
+  }
+  const int acc_cols = P.ng * P.ncols;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(P.groups * acc_cols)) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(P.num_kb * P.wk_bytes));
+      for (int j = 0; j < P.num_kb; ++j)
+        for (int r0 = 0; r0 < P.n_total; r0 += P.n_box)
+          tc::tma_load_2d(wsm + (size_t)j * P.wk_bytes + (size_t)r0 * P.pixB, &P.map_w, &ctl->w_full, j * P.ck, split * P.n_total + r0);
+      const uint32_t halo_tx = (uint32_t)(P.nchunks * P.halo_rows * P.W * P.pixB);
+      int i = 0;
+      for (int t = cta; t < P.tiles; t += ncta, ++i) {
+        const int st = i % P.nstages, ph = (i / P.nstages) & 1;
+        const int n = t / P.tiles_per_img, y0 = (t - n * P.tiles_per_img) * P.R;
+        tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
+        tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
+        for (int c = 0; c < P.nchunks; ++c)
+          tc::tma_load_4d(halo + (size_t)st * P.stage_bytes + (size_t)c * P.chunk_bytes, &P.map_x, &ctl->halo_full[st], c * P.ck, 0,
+                          y0 - P.pad_t, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.ncols, 0, 0);
+      const uint32_t lt = tc::layout_type_for(P.pixB);
+      const uint64_t tmpl = tc::make_smem_desc(0, 16, 8u * (uint32_t)P.pixB, lt);   // K-major, dense 8-row groups (A and B alike)
+      const uint32_t w_addr = tc::smem_u32(wsm) >> 4;
+      const uint32_t row_step = ((uint32_t)P.W * (uint32_t)P.pixB) >> 4;             // one image row of the halo
+      const uint32_t grp_step = ((uint32_t)P.ncols * (uint32_t)P.pixB) >> 4;         // next N group inside a weight k-block
+      const uint32_t wk_step = (uint32_t)P.wk_bytes >> 4, chunk_step = (uint32_t)P.chunk_bytes >> 4;
+      const int ksteps = P.ck / 16, kh = P.kh, nchunks = P.nchunks, ng = P.ng, tiles = P.tiles, nstages = P.nstages, groups = P.groups;
+      const uint32_t ncols = (uint32_t)P.ncols;
+      const uint32_t halo_addr = tc::smem_u32(halo) >> 4, stage_step = (uint32_t)P.stage_bytes >> 4;
+      const int shape = nchunks != 1 || kh != 6 ? 0
+                        : ng == 1 ? (ksteps == 4 ? 1 : ksteps == 2 ? 2 : ksteps == 1 ? 3 : 0)
+                                  : ng == 2 ? (ksteps == 2 ? 4 : ksteps == 4 ? 5 : 0) : 0;
+      tc::mbar_wait(&ctl->w_full, 0);
+      int i = 0;
+      for (int t = cta; t < tiles; t += ncta, ++i) {
+        const int st = i % nstages, ph = (i / nstages) & 1;
+        const int ab = i % groups, aph = (i / groups) & 1;
+        tc::mbar_wait(&ctl->halo_full[st], ph);
+        tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
+        tc::tc_fence_after();
+        const uint32_t h_addr = halo_addr + (uint32_t)st * stage_step;
+        const uint32_t acc = tmem_base + (uint32_t)(ab * acc_cols);
+        const uint64_t da0 = tmpl + h_addr, db0 = tmpl + w_addr;
+        // fully unrolled issue sequences for the shapes of this model family (the single issuing thread must spend only a
+        // few instructions per tcgen05.mma: the generic nest below costs ~75 and caps the tensor pipe at ~35 %)
+        if (shape == 1) ns_issue_tile<6, 4, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        else if (shape == 2) ns_issue_tile<6, 2, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        else if (shape == 3) ns_issue_tile<6, 1, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        else if (shape == 4) ns_issue_tile<6, 2, 2>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        else if (shape == 5) ns_issue_tile<6, 4, 2>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        else {
+          uint32_t b_addr = w_addr, accum = 0;
+          for (int a = 0; a < kh; ++a) {
+            uint32_t a_addr = h_addr + (uint32_t)a * row_step;
+            for (int c = 0; c < nchunks; ++c, a_addr += chunk_step, b_addr += wk_step) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = tmpl + a_addr + 2u * k;
+                uint64_t db = tmpl + b_addr + 2u * k;
+                uint32_t d = acc;
+                for (int g = 0; g < ng; ++g, db += grp_step, d += ncols) tc::umma_bf16(d, da, db, idesc, accum);
+                accum = 1u;
+              }
+            }
+          }
+        }
+        tc::umma_commit(&ctl->halo_empty[st]);
+        tc::umma_commit(&ctl->acc_full[ab]);
+      }
+    }
+  } else {
+    const int e = (warp - 2) >> 2;               // epilogue warp set: (group, chunk lane); the TMEM quarter is warp % 4
+    if (e < P.groups * P.lanes) ns_epilogue(P, ctl, xch, tmem_base, warp & 3, e / P.lanes, e % P.lanes, lane);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci), co] = sum over pixels; K axis = pixels (64 per stage), both operands MN-major.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgMaxA = 6, kWgMaxB = 2;
@@ -921,6 +1216,21 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
       ((float*)J.dst)[idx] = v;
       continue;
     }
+    if (J.kind >= 4) {           // N-stacked conv: dst[(b, n)][(a, c)] with rows_pad = nb channels per filter column, k_pad = C_pad
+      const int k_total = J.taps_h * J.k_pad;
+      const int k = (int)(idx % k_total);
+      int nrow = (int)(idx / k_total);
+      const int rows_per_split = J.taps_w * J.rows_pad;          // J.rows_pad = channels per filter column per split
+      const int split = nrow / rows_per_split;
+      nrow -= split * rows_per_split;
+      const int b = nrow / J.rows_pad, nn = split * J.rows_pad + (nrow - b * J.rows_pad);
+      const int a = k / J.k_pad, c = k - a * J.k_pad;
+      float v = 0.f;
+      if (J.kind == 4) { if (nn < J.Co && c < J.Ci) v = master_w(J, params, a, b, c, nn); }            // fwd: n = co, k = ci
+      else if (nn < J.Ci && c < J.Co) v = master_w(J, params, J.KH - 1 - a, J.KW - 1 - b, nn, c);      // dgrad: n = ci, k = co, flipped
+      ((bf16*)J.dst)[idx] = __float2bfloat16_rn(v);
+      continue;
+    }
     const int kk = (int)(idx % J.k_pad);
     const int tap = (int)((idx / J.k_pad) % (J.taps_h * J.taps_w));
     const int r = (int)(idx / ((long long)J.k_pad * J.taps_h * J.taps_w));
@@ -1238,6 +1548,76 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   return true;
 }
 
+// Plans the N-stacked persistent kernel for a stride-1 convolution C -> n_out over an H x W image (W in {16, 32, 64}).
+// Returns false when the layer is not eligible (then the per-tap / halo kernels are used).
+bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W, int n_img, int C, int n_out) {
+  if (env_int("SV_NO_NSCONV", 0)) return false;
+  if (!(kw == 4 || kw == 6) || pad_l > 4 || kw - 1 - pad_l > 4) return false;
+  if (!(W == 16 || W == 32 || W == 64)) return false;
+  const int R = 128 / W;
+  if (H % R) return false;
+  int ck, cpad;
+  choose_bk(C, ck, cpad);
+  const int pixB = ck * 2, nchunks = cpad / ck, num_kb = kh * nchunks;
+  int nb_all = round_up(n_out, 8);
+  if ((kw * nb_all) % 16) nb_all = round_up(n_out, 16);
+  // split the output channels over CTAs when the resident weights would leave room for fewer than 4 halo stages
+  const int chunk_bytes = round_up((R + kh - 1) * W * pixB, 1024), stage_bytes = chunk_bytes * nchunks;
+  const size_t xch_bytes = W > 32 ? (size_t)(kNsEpiWarps / 4) * 2 * 4 * kw * kNsXchSlots * 8 * 4 : 0;   // one area per (group, chunk lane)
+  const size_t budget = 227 * 1024 - 1024 - 256 - xch_bytes;
+  // (measured: the split costs more than it buys whenever the whole weight set fits beside two halo stages - d4 forward
+  // 35.6 us unsplit vs 41.8 us split - so it is only used where the layer would otherwise not fit at all: d3)
+  int co_splits = 1;
+  if ((size_t)kw * nb_all * num_kb * pixB + 2 * (size_t)stage_bytes > budget && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 &&
+      !env_int("SV_NS_NOSPLIT", 0))
+    co_splits = 2;
+  const int nb = nb_all / co_splits;
+  const int n_total = kw * nb;
+  int ng = 1;
+  if (n_total > 256) {
+    if ((kw % 2) || n_total / 2 > 256 || (n_total / 2) % 16) return false;
+    ng = 2;
+  }
+  P.kh = kh; P.kw = kw; P.pad_t = pad_t; P.pad_l = pad_l;
+  P.W = W; P.R = R; P.H = H; P.n_img = n_img;
+  P.tiles_per_img = H / R; P.tiles = n_img * P.tiles_per_img;
+  P.ck = ck; P.nchunks = nchunks; P.pixB = pixB;
+  P.nb = nb; P.ng = ng; P.ncols = n_total / ng; P.n_total = n_total; P.co_splits = co_splits;
+  // epilogue warp sets: `groups` accumulator buffers / tile round-robin, `lanes` warps per TMEM quarter splitting the 8-channel blocks
+  int groups = 512 / n_total;
+  if (groups > kNsMaxGroups) groups = kNsMaxGroups;
+  const int sets = kNsEpiWarps / 4;
+  int lanes = sets / groups;
+  if (lanes > nb / 8) lanes = nb / 8;
+  if (lanes < 1) lanes = 1;
+  { const int fg = env_int("SV_NS_GROUPS", 0), fl = env_int("SV_NS_LANES", 0);
+    if (fg >= 1 && fg <= groups) groups = fg;
+    if (fl >= 1 && fl * groups <= sets) lanes = fl; }
+  P.groups = groups; P.lanes = lanes;
+  P.nacc = groups;
+  P.halo_rows = R + kh - 1;
+  P.chunk_bytes = chunk_bytes;
+  P.stage_bytes = stage_bytes;
+  P.num_kb = num_kb;
+  P.wk_bytes = n_total * pixB;
+  if (P.wk_bytes % 1024) return false;            // every weight k-block starts on a swizzle-atom boundary
+  P.w_bytes = round_up(P.num_kb * P.wk_bytes, 1024);
+  P.n_box = n_total <= 256 ? n_total : P.ncols;
+  P.xch_off = 256;                                // after NsCtl
+  if ((size_t)P.w_bytes + 2 * (size_t)stage_bytes > budget) return false;
+  int nst = (int)((budget - P.w_bytes) / stage_bytes);
+  const int cap = env_int("SV_NS_STAGES", 6);
+  if (nst > cap) nst = cap;
+  if (nst > kNsMaxStages) nst = kNsMaxStages;
+  P.nstages = nst;
+  P.smem_bytes = (size_t)P.w_bytes + (size_t)nst * stage_bytes + 256 + xch_bytes + 1024;
+  P.grid = 148;
+  const int work = P.tiles * co_splits;
+  if (work < P.grid) P.grid = work;
+  P.grid -= P.grid % co_splits;
+  return true;
+}
+
 }  // namespace
 
 const char* tc_last_error() { return g_tc_error; }
@@ -1340,6 +1720,14 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         L.mask_act = ACT_NONE;
         finish_launch(L, t.n_pad_fwd);
         if (cpad <= g.in_ld - g.in_coff) try_halo(L, g.Ho, g.Wo, g.B);
+        if (g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
+            plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
+          TcNsConv& P = t.ns_fwd;
+          P.n_valid = g.Co; P.out_ld = g.out_ld; P.out_f32 = out_dt == DT_F32; P.act = g.part_act[0]; P.mask_act = ACT_NONE;
+          t.fwd_ns = true;
+          t.w_nsf_off = off;
+          off += (size_t)P.w_bytes * P.co_splits;
+        }
         plan_split_k(L, g.B, off);
         t.sk_fwd_off = off;
         off += split_k_bytes(L);
@@ -1385,9 +1773,22 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         off += split_k_bytes(L);
       }
     }
+    // (W = 64 dgrads - d5 - stay on the halo kernel: 4 shuffle blocks per tile with the cross-warp exchange make the
+    // N-stacked epilogue the bottleneck there, 124 us vs 102 us)
+    if (ok && s == 1 && g.Ho == g.Hi && g.Wo == g.Wi && (g.Wi <= 32 || env_int("SV_NS_WIDE_DGRAD", 0)) &&
+        plan_nsconv(t.ns_dgrad, g.kh, g.kw, g.kh - 1 - g.pt, g.kw - 1 - g.pl, g.Hi, g.Wi, g.B, g.Co, g.Ci)) {
+      TcNsConv& P = t.ns_dgrad;
+      P.n_valid = g.Ci; P.out_ld = g.din_ld; P.out_f32 = 0; P.act = ACT_NONE;
+      if (P.nchunks * P.ck <= g.dout_ld) {
+        t.dgrad_ns = true;
+        off = (off + 1023) / 1024 * 1024;
+        t.w_nsd_off = off;
+        off += (size_t)P.w_bytes * P.co_splits;
+      }
+    }
     if (ok) {
       t.dgrad_ok = true;
-      t.dgrad_launches = s * s + (s == 1 && t.dgrad[0].k_splits > 1 ? 1 : 0);
+      t.dgrad_launches = t.dgrad_ns ? 1 : s * s + (s == 1 && t.dgrad[0].k_splits > 1 ? 1 : 0);
       t.w_dgrad_off = off;
       off += (size_t)s * s * round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * copad * 2), 1024);
     }
@@ -1461,6 +1862,27 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     L.mask_src = nullptr;
     L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_fwd_off) : nullptr;
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  }
+  if (t.fwd_ns || t.dgrad_ns) {
+    if (cudaFuncSetAttribute(nsconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+    for (int which = 0; which < 2; ++which) {
+      if (!(which ? t.dgrad_ns : t.fwd_ns)) continue;
+      TcNsConv& P = which ? t.ns_dgrad : t.ns_fwd;
+      const char* e = which ? make_act_map(&P.map_x, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, P.nchunks * P.ck, P.ck, P.W, P.halo_rows, 1, 1, P.pixB)
+                            : make_act_map(&P.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, P.nchunks * P.ck, P.ck, P.W, P.halo_rows, 1, 1, P.pixB);
+      if (e) return e;
+      e = make_w_map(&P.map_w, ws + (which ? t.w_nsd_off : t.w_nsf_off), P.co_splits * P.n_total, (long long)P.kh * P.nchunks * P.ck, P.ck, P.n_box, P.pixB);
+      if (e) return e;
+      P.bias = which ? nullptr : (const float*)(ws + t.bias_off);
+      P.out = which ? din : out;
+      P.mask_src = which ? mask_src : nullptr;
+      P.mask_act = which ? mask_act : ACT_NONE;
+      P.mask_ld = g.in_ld; P.mask_coff = g.in_coff;
+      if (env_int("SV_TC_VERBOSE", 0))
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: NSCONV tile %dx%d halo rows %d chunks %d x %d B, N %d = %d x %d (ng %d, groups %d x lanes %d, co_splits %d), weights %d B resident, %d halo stages, smem %zu, grid %d\n",
+                g.kh, g.kw, g.stride, g.Ci, g.Co, which ? "dgrad" : "fwd", P.R, P.W, P.halo_rows, P.nchunks, P.chunk_bytes, P.n_total, P.kw, P.nb, P.ng,
+                P.groups, P.lanes, P.co_splits, P.w_bytes, P.nstages, P.smem_bytes, P.grid);
+    }
   }
   if (t.dgrad_ok) {
     const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
@@ -1544,6 +1966,20 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     PackJob B{};
     B.KH = g.kh; B.KW = g.kw; B.Ci = g.Ci; B.Co = g.Co; B.nparts = g.nparts;
     for (int j = 0; j < 3; ++j) { B.part_n[j] = g.part_n[j]; B.part_w[j] = g.part_w[j]; B.part_b[j] = g.part_b[j]; }
+    if (t.fwd_ns) {
+      PackJob J = B;
+      J.kind = 4; J.rows_pad = t.ns_fwd.nb; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = t.ns_fwd.nchunks * t.ns_fwd.ck;
+      J.dst = t.ws + t.w_nsf_off;
+      J.count = (long long)t.ns_fwd.co_splits * t.ns_fwd.n_total * g.kh * J.k_pad;
+      push(J);
+    }
+    if (t.dgrad_ns) {
+      PackJob J = B;
+      J.kind = 5; J.rows_pad = t.ns_dgrad.nb; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = t.ns_dgrad.nchunks * t.ns_dgrad.ck;
+      J.dst = t.ws + t.w_nsd_off;
+      J.count = (long long)t.ns_dgrad.co_splits * t.ns_dgrad.n_total * g.kh * J.k_pad;
+      push(J);
+    }
     if (t.fwd_ok) {
       PackJob J = B;
       J.kind = t.first ? 3 : 0; J.rows_pad = t.n_pad_fwd; J.taps_h = t.fwd.taps_h; J.taps_w = t.fwd.taps_w; J.k_pad = t.ci_pad;
@@ -1609,8 +2045,13 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
   }
 }
 
-void tc_conv_fwd(TcLayer& t, cudaStream_t s) { launch(t.fwd, s); }
+static void launch_ns(const TcNsConv& P, cudaStream_t s) { nsconv_kernel<<<P.grid, kNsThreads, P.smem_bytes, s>>>(P); }
+
+void tc_conv_fwd(TcLayer& t, cudaStream_t s) {
+  if (t.fwd_ns) launch_ns(t.ns_fwd, s); else launch(t.fwd, s);
+}
 void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
+  if (t.dgrad_ns) { launch_ns(t.ns_dgrad, s); return; }
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
 }
 static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_splits, int m_pad, int n_pad, const WgRowMap& R, float* grads,

@@ -94,6 +94,40 @@ struct TcHaloWgrad {
   size_t smem_bytes;
 };
 
+// N-stacked persistent convolution (stride-1 layers with few output channels: d4 / d5 forward and their dgrads).
+//   D[pixel, (b, co)] = sum_{a, ci} X[y + a - pad_t, x, ci] * W[a, b, ci, co]      (one accumulator, N = kw * nb columns)
+//   out[y, x, co]     = act(bias[co] + sum_b D[(y, x + b - pad_l), (b, co)])          (epilogue: lane shuffles along x)
+// The filter COLUMN b lives on the UMMA N axis, so one 128x16 A-operand read from shared memory feeds kw x more MACs: the
+// small-Cout layers stop being bound by the A read (44 cycles per MMA for N <= 32) and run at the tensor pipe's own rate.
+// The filter ROW a is a shifted view (whole image rows: offset a * W pixels) of a (R + kh - 1)-row halo that TMA loads once
+// per tile; the packed weights [kw*nb][kh*C] stay resident in shared memory for the whole persistent CTA; accumulators are
+// double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
+struct TcNsConv {
+  CUtensorMap map_x, map_w;
+  int kh, kw, pad_t, pad_l;
+  int W, R, H, n_img;               // tile = R rows x W pixels (R * W = 128)
+  int tiles_per_img, tiles;
+  int ck, nchunks, pixB;            // channel chunk (elements), chunks per pixel, bytes per pixel per chunk (= swizzle span)
+  int nb;                           // N block per filter column (padded output channels)
+  int ng, ncols, n_total;           // UMMA N groups (each ncols <= 256 columns), kw * nb
+  int nacc;                         // accumulator buffers in TMEM (= groups)
+  int groups, lanes;                // epilogue: `groups` warp sets take tiles round-robin (one accumulator each); inside a set
+                                    // `lanes` warps per TMEM quarter split the tile's 8-channel blocks
+  int co_splits;                    // output channels split over CTAs (CTA c serves split c % co_splits for its whole life): halves the
+                                    // resident weights so that more halo stages fit; nb / n_total / ncols are PER SPLIT
+  int nstages;                      // halo ring depth (the kernel is latency-bound on the halo loads below ~3 stages)
+  int halo_rows, chunk_bytes, stage_bytes;
+  int num_kb, wk_bytes, w_bytes;    // weight k-blocks (kh * nchunks), bytes per k-block, total (1024-aligned)
+  int n_box;                        // rows per weight TMA box (<= 256)
+  int xch_off;                      // W = 64: shared-memory exchange area for the shuffles that cross the two warps of a row
+  int n_valid, out_ld, out_f32, act, mask_act, mask_ld, mask_coff;
+  const float* bias;
+  void* out;
+  const void* mask_src;
+  size_t smem_bytes;
+  int grid;
+};
+
 struct TcLayer {
   bool fwd_ok = false, dgrad_ok = false, wgrad_ok = false;
   bool first = false;                 // first conv of an encoder: reads the staged, padded bf16 image (tc_stage_first)
@@ -103,6 +137,9 @@ struct TcLayer {
   TcWgradLaunch wg{};
   bool wg_halo = false;
   TcHaloWgrad hw{};
+  bool fwd_ns = false, dgrad_ns = false;   // N-stacked persistent kernel replaces the per-tap / halo kernel
+  TcNsConv ns_fwd{}, ns_dgrad{};
+  size_t w_nsf_off = 0, w_nsd_off = 0;
   size_t wg_partial_off = 0;
   // geometry of the packed operands
   int n_pad_fwd = 0, ci_pad = 0;      // fwd : B = [n_pad_fwd][taps][ci_pad]
