@@ -83,6 +83,10 @@ struct sv_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int COLSUM2 = -1;
   bool two_streams = true;
+  // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
+  bool cs_on = false;
+  int CSP[4] = {-1, -1, -1, -1};
+  ColsumTable* cs[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -265,6 +269,29 @@ Decoder build_decoder(sv_handle* h, const char* prefix, int L, int zcoff, int dz
 
 void* bp(sv_handle* h, int id) { return id < 0 ? nullptr : (void*)(h->ws + h->bufs[id].off); }
 
+std::vector<int> branch_layers(const sv_handle* h, int which) {
+  auto dec = [](const Decoder& d) { return std::vector<int>{d.d5, d.d4, d.d3, d.d2, d.d1}; };
+  auto enc = [](const ConvEnc& e) { return std::vector<int>{e.heads, e.e3, e.e2, e.e1}; };
+  if (which == 0) return dec(h->dec_x);
+  if (which == 1) return dec(h->dec_xh);
+  if (which == 3) return enc(h->enc_xh);
+  if (h->cfg.model == SV_MODEL_LGGMVAE) {
+    const GmEnc& e = h->gm;
+    return {e.zheads, e.yheads, e.ydense, e.yb2, e.yb0e1, e.h3, e.h2, e.h1};
+  }
+  return enc(h->enc_x);
+}
+std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, bool with_ptrs) {
+  std::vector<ColsumSpec> v;
+  for (int li : branch_layers(h, which)) {
+    ColsumSpec sp{};
+    sp.g = h->layers[li].g;
+    sp.dout = with_ptrs ? bp(h, h->layers[li].dout) : nullptr;
+    v.push_back(sp);
+  }
+  return v;
+}
+
 LatentBufs latent_bufs(sv_handle* h) {
   LatentBufs L{};
   const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
@@ -307,8 +334,10 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
     ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, h->round_w, s);
     h->launches += 1;
   }
-  bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, s == h->side ? h->COLSUM2 : h->COLSUM), h->grads, s);
-  h->launches += 2;
+  if (!h->cs_on) {   // (bf16 mode: one multi-tensor launch pair per branch instead, see branch_bias_grads)
+    bias_grad(L.g, bp(h, L.dout), T, (float*)bp(h, s == h->side ? h->COLSUM2 : h->COLSUM), h->grads, s);
+    h->launches += 2;
+  }
   if (L.din >= 0) {
     if (h->use_tc && L.tc.dgrad_ok) {
       tc_conv_dgrad(L.tc, s);
@@ -318,6 +347,10 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
       h->launches += 1;
     }
   }
+}
+
+void branch_bias_grads(sv_handle* h, int which, cudaStream_t s) {
+  if (h->cs_on) h->launches += colsum_table_run(h->cs[which], h->grads, s);
 }
 
 void conv_encoder_fwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaStream_t s) {
@@ -523,6 +556,20 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->dec_x = build_decoder(h, "decoder_x", 256, 0, dzcat, 256, dout_ld);
   h->dec_xh = build_decoder(h, "decoder_x_hat", 128, 128, dzl2, 128, dout_ld);
 
+  if (h->act_dt == DT_BF16 && !getenv("SV_NO_MULTI_COLSUM")) {
+    bool ok = true;
+    for (int b = 0; b < 4 && ok; ++b) {
+      const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
+      ok = colsum_multi_supported(sp.data(), (int)sp.size());
+    }
+    if (ok) {
+      h->cs_on = true;
+      for (int b = 0; b < 4; ++b) {
+        const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
+        h->CSP[b] = f32_buf(h, colsum_table_partial_floats(sp.data(), (int)sp.size()) + 64);
+      }
+    }
+  }
   if (h->use_tc) {
     for (auto& L : h->layers) {
       const bool first = L.in < 0;
@@ -543,6 +590,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 sv_status sv_destroy(sv_handle* h) {
   if (h) {
     tc_pack_table_destroy(h->pack);
+    for (int b = 0; b < 4; ++b) colsum_table_destroy(h->cs[b]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
@@ -591,6 +639,15 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     tc_pack_table_destroy(h->pack);
     h->pack = tc_pack_table_create(tl.data(), tg.data(), (int)tl.size(), &perr);
     if (!h->pack) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
+  }
+  if (h->cs_on) {
+    for (int b = 0; b < 4; ++b) {
+      const std::vector<ColsumSpec> sp = branch_specs(h, b, true);
+      const char* cerr = nullptr;
+      colsum_table_destroy(h->cs[b]);
+      h->cs[b] = colsum_table_create(sp.data(), (int)sp.size(), (float*)bp(h, h->CSP[b]), &cerr);
+      if (!h->cs[b]) return fail(h, SV_ERR_DEVICE, "bias-gradient table: %s", cerr ? cerr : "?");
+    }
   }
   if (!h->side) {
     const char* one = getenv("SV_ONE_STREAM");
@@ -675,7 +732,9 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
   if (seg == 0) {
     cudaStream_t s2 = fork_side(h, s);
     decoder_bwd(h, h->dec_x, s);
+    branch_bias_grads(h, 0, s);
     decoder_bwd(h, h->dec_xh, s2);
+    branch_bias_grads(h, 1, s2);
     join_side(h, s);
   } else if (seg == 1) {
     if (!inputs) return fail(h, SV_ERR_STATE, "sv_loss_fwd_bwd must precede sv_backward_segment");
@@ -685,7 +744,9 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
     h->launches += 1;
     cudaStream_t s2 = fork_side(h, s);
     conv_encoder_bwd(h, h->enc_xh, inputs, s2);
+    branch_bias_grads(h, 3, s2);
     if (gm) gm_encoder_bwd(h, inputs, s); else conv_encoder_bwd(h, h->enc_x, inputs, s);
+    branch_bias_grads(h, 2, s);
     join_side(h, s);
   } else {
     return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);

@@ -16,6 +16,14 @@ void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* do
                     cudaStream_t s);
 int colsum_chunks(long long rows);
 void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, float* grads, cudaStream_t s);
+// multi-tensor bias gradients (bf16 dY): all layers of one backward branch in two launches
+struct ColsumSpec { ConvGeom g; const void* dout; };
+struct ColsumTable;
+bool colsum_multi_supported(const ColsumSpec* specs, int n);
+long long colsum_table_partial_floats(const ColsumSpec* specs, int n);
+ColsumTable* colsum_table_create(const ColsumSpec* specs, int n, float* partial_ws, const char** err);
+void colsum_table_destroy(ColsumTable* t);
+int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s);   // returns #launches
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s);
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
                     int C, cudaStream_t s);

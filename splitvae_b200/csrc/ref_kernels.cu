@@ -6,6 +6,8 @@
 // Reference semantics: Keras Conv2D(padding='same') / Dense (vae/model.py:36-42,49-76,152-156),
 // tf.image.resize bilinear half-pixel (vae/model.py:163-167), tape.gradient (vae/trainer.py:137).
 #include "common.cuh"
+#include <vector>
+
 #include "kernels.h"
 
 namespace sv {
@@ -419,6 +421,161 @@ void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, f
   else
     colsum_partial_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dout, rows, g.Co, g.dout_ld, rpc, partial_ws);
   colsum_final_kernel<<<(g.Co + 31) / 32, dim3(32, 8), 0, s>>>(g, partial_ws, nch, grads);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-tensor bias gradients: the column sums of every dY of one backward branch (a decoder / an encoder) in two launches
+// instead of two per layer.  Job = (layer, slab of <= 256 columns); block = (job, row chunk): 256 threads = column groups of
+// 8 bf16 (one 128-bit load per row) x row lanes, fixed-order shared-memory reduction over the row lanes, then a second
+// kernel adds the chunks in order -> deterministic.
+// ---------------------------------------------------------------------------------------------
+struct ColsumJob {
+  const bf16* d;
+  long long rows;
+  int ld, col0, ncols, c_valid;     // slab [col0, col0 + ncols) of a [rows, ld] matrix; columns >= c_valid are padding
+  int rows_per_chunk, nchunks;
+  long long partial_off;            // floats; partial[chunk][ncols]
+  int block_start, fblock_start;    // first block of this job in the partial / final kernels
+  int nparts, part_n[3];
+  long long part_b[3];
+};
+
+__global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJob* __restrict__ jobs, int njobs, float* __restrict__ partial) {
+  __shared__ float red[2048];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ColsumJob J = jobs[lo];
+  const int chunk = blockIdx.x - J.block_start;
+  const int ngroups = J.ncols >> 3;              // 2 .. 32, power of two
+  const int lanes = 256 / ngroups;
+  const int gi = threadIdx.x % ngroups, ry = threadIdx.x / ngroups;
+  const long long r0 = (long long)chunk * J.rows_per_chunk;
+  long long r1 = r0 + J.rows_per_chunk;
+  if (r1 > J.rows) r1 = J.rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bf16* base = J.d + J.col0 + gi * 8;
+  long long r = r0 + ry;
+  for (; r + lanes < r1; r += 2 * lanes) {        // two independent loads in flight
+    const F8 a = ld_bf16x8(base + r * J.ld), b = ld_bf16x8(base + (r + lanes) * J.ld);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a.v[i] + b.v[i];
+  }
+  for (; r < r1; r += lanes) {
+    const F8 a = ld_bf16x8(base + r * J.ld);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a.v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ry * J.ncols + gi * 8 + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < J.ncols; c += 256) {
+    float t = 0.f;
+    for (int y = 0; y < lanes; ++y) t += red[y * J.ncols + c];
+    partial[J.partial_off + (long long)chunk * J.ncols + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs, const float* __restrict__ partial,
+                                                                 float* __restrict__ grads) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].fblock_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ColsumJob& J = jobs[lo];
+  const int c = threadIdx.x;
+  if (c >= J.ncols || J.col0 + c >= J.c_valid) return;
+  const float* p = partial + J.partial_off + c;
+  float t = 0.f;
+  for (int k = 0; k < J.nchunks; ++k) t += p[(long long)k * J.ncols];
+  int lc = J.col0 + c, j = 0;
+  while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+  grads[J.part_b[j] + lc] = t;
+}
+
+struct ColsumTable {
+  ColsumJob* dev = nullptr;
+  int njobs = 0, nblocks = 0, nfblocks = 0;
+  float* partial = nullptr;
+};
+
+static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>& jobs, long long& partial_floats, int& nblocks, int& nfblocks) {
+  jobs.clear();
+  partial_floats = 0; nblocks = 0; nfblocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const ConvGeom& g = specs[i].g;
+    const long long rows = (long long)g.B * g.Ho * g.Wo;
+    const int ld = g.dout_ld;
+    for (int col0 = 0; col0 < ld && col0 < ((g.Co + 7) & ~7); col0 += 256) {
+      ColsumJob J{};
+      J.d = (const bf16*)specs[i].dout;
+      J.rows = rows; J.ld = ld; J.col0 = col0; J.c_valid = g.Co;
+      int ncols = ld - col0 < 256 ? ld - col0 : 256;
+      int p2 = 16;                                   // slab width: power of two in [16, 256] (ld is one, or a multiple of 256)
+      while (p2 < ncols) p2 <<= 1;
+      J.ncols = p2 > 256 ? 256 : p2;
+      // chunks of >= 256 rows, at most 64 per job (the final kernel walks them serially)
+      long long nch = (rows + 255) / 256;
+      if (nch > 64) nch = 64;
+      if (nch < 1) nch = 1;
+      J.rows_per_chunk = (int)((rows + nch - 1) / nch);
+      J.nchunks = (int)((rows + J.rows_per_chunk - 1) / J.rows_per_chunk);
+      J.partial_off = partial_floats;
+      partial_floats += (long long)J.nchunks * J.ncols;
+      J.block_start = nblocks; nblocks += J.nchunks;
+      J.fblock_start = nfblocks; nfblocks += 1;
+      J.nparts = g.nparts;
+      for (int k = 0; k < 3; ++k) { J.part_n[k] = g.part_n[k]; J.part_b[k] = g.part_b[k]; }
+      jobs.push_back(J);
+    }
+  }
+}
+
+bool colsum_multi_supported(const ColsumSpec* specs, int n) {
+  for (int i = 0; i < n; ++i) {
+    const int ld = specs[i].g.dout_ld;
+    const bool pow2 = ld >= 16 && (ld & (ld - 1)) == 0;
+    if (!(pow2 || (ld % 256) == 0)) return false;
+  }
+  return n > 0;
+}
+
+long long colsum_table_partial_floats(const ColsumSpec* specs, int n) {
+  std::vector<ColsumJob> jobs;
+  long long pf; int nb, nf;
+  colsum_build(specs, n, jobs, pf, nb, nf);
+  return pf;
+}
+
+ColsumTable* colsum_table_create(const ColsumSpec* specs, int n, float* partial_ws, const char** err) {
+  std::vector<ColsumJob> jobs;
+  long long pf; int nb, nf;
+  colsum_build(specs, n, jobs, pf, nb, nf);
+  ColsumTable* T = new ColsumTable();
+  T->njobs = (int)jobs.size(); T->nblocks = nb; T->nfblocks = nf; T->partial = partial_ws;
+  if (T->njobs && (cudaMalloc(&T->dev, jobs.size() * sizeof(ColsumJob)) != cudaSuccess ||
+                   cudaMemcpy(T->dev, jobs.data(), jobs.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice) != cudaSuccess)) {
+    *err = "colsum table upload failed";
+    delete T;
+    return nullptr;
+  }
+  return T;
+}
+
+void colsum_table_destroy(ColsumTable* t) {
+  if (!t) return;
+  if (t->dev) cudaFree(t->dev);
+  delete t;
+}
+
+int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
+  if (!t || !t->njobs) return 0;
+  colsum_multi_partial_kernel<<<t->nblocks, 256, 0, s>>>(t->dev, t->njobs, t->partial);
+  colsum_multi_final_kernel<<<t->nfblocks, 256, 0, s>>>(t->dev, t->njobs, t->partial, grads);
+  return 2;
 }
 
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s) {

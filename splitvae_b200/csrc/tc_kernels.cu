@@ -1812,15 +1812,25 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.tile_cols = copad < 256 ? copad : 256;
       if (copad % L.tile_cols) L.tile_cols = 128;
       L.n_tiles = copad / L.tile_cols;
+      // Parallelism comes from the M axis first (few row groups per CTA) and only then from split-K: every K split costs a
+      // full fp32 copy of the weight gradient in the partial buffer, written once and re-read by the reduce kernel (64-way
+      // splits made that ~1.2 GB of traffic per step).
       L.groups_per_cta = 512 / L.tile_cols;
       if (L.groups_per_cta > L.groups) L.groups_per_cta = L.groups;
       if (L.groups_per_cta > 8) L.groups_per_cta = 8;
+      {
+        const int cap = env_int("SV_WG_GPC", 1);
+        if (cap >= 1 && L.groups_per_cta > cap) L.groups_per_cta = cap;
+      }
       L.m_pad = L.groups * 128;
       L.tile_w = g.Wo; L.tile_h = g.Ho < 64 / g.Wo ? g.Ho : 64 / g.Wo; L.tile_n_img = 64 / (L.tile_w * L.tile_h);
       L.grid_h = g.Ho; L.n_img = g.B;
       L.nchunks = L.tile_n_img > 1 ? (g.B + L.tile_n_img - 1) / L.tile_n_img : g.B * (g.Ho / L.tile_h);
       const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
-      int ks = (296 + m_splits * L.n_tiles - 1) / (m_splits * L.n_tiles);
+      // measured (B200, C2): convolutions like ~2 CTAs per SM (e2 48 vs 73 us), the dense layers ~1 (38 vs 48 us: their K axis
+      // is only the batch, so extra splits just add partial-buffer traffic)
+      const int target_ctas = env_int("SV_WG_CTAS", g.kh * g.kw > 1 ? 296 : 148);
+      int ks = (target_ctas + m_splits * L.n_tiles - 1) / (m_splits * L.n_tiles);
       if (ks > L.nchunks) ks = L.nchunks;
       if (ks < 1) ks = 1;
       L.chunks_per_split = (L.nchunks + ks - 1) / ks;
