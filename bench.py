@@ -210,16 +210,44 @@ def main():
     barrier()
     t_dev = ev0.elapsed_time(ev1) / 1000.0
 
-    # ---- (B) end to end: pinned host uint8 -> H2D -> scramble -> step -> D2H scalars, every step ---
-    for i in range(2):
-        stage(i); runner.step(); host_scalars.copy_(e.output("scalars"), non_blocking=True)
+    # ---- (B) end to end: pinned host uint8 -> H2D -> scramble -> step -> D2H scalars, every step.  The input pipeline is
+    # double-buffered: a copy stream uploads and scrambles batch i+1 into a staging tensor while the graph of step i runs;
+    # the main stream then copies the staged batch into the graph's input buffer (device to device) and replays.
+    main = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    staging = [torch.empty_like(runner.inputs) for _ in range(2)]
+    dev_u8s = [torch.empty_like(dev_u8) for _ in range(2)]
+    dev_perms = [torch.empty_like(dev_perm) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage_async(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_consumed[b])
+            dev_u8s[b].copy_(host_u8[i % pool], non_blocking=True)
+            dev_perms[b].copy_(host_perm[i % pool], non_blocking=True)
+            aug.scramble(dev_u8s[b], dev_perms[b], out=staging[b])
+            ev_ready[b].record(copy_stream)
+
+    def e2e_steps(n):
+        stage_async(0)
+        for i in range(n):
+            stage_async(i + 1)
+            main.wait_event(ev_ready[i % 2])
+            runner.inputs.copy_(staging[i % 2], non_blocking=True)
+            ev_consumed[i % 2].record(main)
+            runner.step()
+            host_scalars.copy_(e.output("scalars"), non_blocking=True)
+        main.wait_event(ev_ready[n % 2])    # the one batch staged ahead of the loop's end
+
+    for b in range(2):
+        ev_consumed[b].record(main)
+    e2e_steps(2)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
-    for i in range(K):
-        stage(i)
-        runner.step()
-        host_scalars.copy_(e.output("scalars"), non_blocking=True)
+    e2e_steps(K)
     ev3.record()
     barrier()
     t_e2e = ev2.elapsed_time(ev3) / 1000.0
@@ -231,26 +259,56 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = t.tolist()
 
-    # ---- roofline of the dominant kernel class, timed alone with an L2 flush between launches ------
+    # ---- roofline: every tensor-core launch of the step timed alone (CUDA events on the launching stream, L2 flushed
+    # before each launch), grouped by kernel; the kernel with the largest share of the step is the one reported ------
     peaks = measured_peaks()
     roof = None
     if rank == 0:
-        reps = 10
-        times = []
-        for i in range(reps):
-            l2_flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            e.loss_fwd_bwd(runner.inputs)
-            b.record()
-            torch.cuda.synchronize()
-            times.append(a.elapsed_time(b) / 1000.0)
-        t_loss = sorted(times)[len(times) // 2]
+        def timed(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                l2_flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) / 1000.0)
+            return sorted(ts)[len(ts) // 2]
+
+        from splitvae_b200._lib import KERNEL_NAMES
+        by_kernel = {}
+        for i, L in enumerate(e.debug_layers()):
+            flops = 2.0 * B * L.Ho * L.Wo * L.Co * L.kh * L.kw * L.Ci        # algorithmic (unpadded) FLOPs of one pass
+            for p, kern in ((0, L.kern_fwd), (1, L.kern_dgrad), (2, L.kern_wgrad)):
+                if not kern:
+                    continue
+                t = timed(lambda: e.debug_run_layer(i, p, 1, runner.inputs))
+                k = by_kernel.setdefault(KERNEL_NAMES[kern], {"launch_groups": 0, "us": 0.0, "gflop": 0.0})
+                k["launch_groups"] += 1
+                k["us"] += t * 1e6
+                k["gflop"] += flops / 1e9
+        for k in by_kernel.values():
+            k["tflops"] = k["gflop"] / k["us"] * 1e3 if k["us"] else 0.0   # GFLOP/us = PFLOP/s
+        dom = max(by_kernel, key=lambda n: by_kernel[n]["us"])
+        d = by_kernel[dom]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(wl, {}).get(dom)
+        roof = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": peaks["tensor_burst"], "unit": "TFLOP/s",
+                "frac": d["tflops"] / peaks["tensor_burst"], "traffic": traffic, "peak_source": peaks["source"],
+                "algorithmic_gflop": d["gflop"], "us": d["us"], "launch_groups": d["launch_groups"],
+                "note": "sum over this kernel's launches in one step of (2*MAC, unpadded) / sum of their CUDA-event times, each launch "
+                        "timed alone after an L2 flush; peak = bf16 burst (kernel timed in isolation); a 'launch group' is one layer pass "
+                        "(wgrad groups include their split-K reduce launch)",
+                "by_kernel": by_kernel}
+        t_loss = timed(lambda: e.loss_fwd_bwd(runner.inputs), reps=10)
         loss_bytes = B * LOSS_BYTES_PER_IMAGE[H]
         ach = loss_bytes / t_loss / 1e9
-        roof = {"kernel": "pixel_loss_kernel (fused likelihood fwd+bwd, both decoders)", "bound": "hbm", "achieved": ach,
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
-                "algorithmic_bytes_per_launch": loss_bytes, "us_per_launch": t_loss * 1e6}
+        roof["hbm_kernels"] = {"pixel_loss_kernel": {"achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                                                      "algorithmic_bytes_per_launch": loss_bytes, "us_per_launch": t_loss * 1e6}}
         step_flops = B * TRAIN_GFLOP_PER_IMAGE[wl] * 1e9
         roof["step_tensor"] = {"achieved_tflops": step_flops / (t_dev / K) / 1e12, "peak_tflops": peaks["tensor_sustained"],
                                "frac": step_flops / (t_dev / K) / 1e12 / peaks["tensor_sustained"],

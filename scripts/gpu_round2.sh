@@ -1,0 +1,16 @@
+#!/bin/bash
+TAG=${1:-r2}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+tail -4 $OUT/pytest_gpu.log
+timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; cut -c1-400 $OUT/bench_c2.json; tail -5 $OUT/bench_c2.err
+if [ -n "$DO_NCU" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_c2.csv \
+      python scripts/profile_step.py --workload c2 --steps 2 > $OUT/profile_step.log 2>&1
+  python scripts/summarize_launches.py $OUT/launches_c2.csv $(grep -o 'step 1: [0-9]*' $OUT/profile_step.log | grep -o '[0-9]*$') --all > $OUT/launches_c2_summary.txt 2>&1
+  tail -24 $OUT/launches_c2_summary.txt
+  timeout 600 ncu --set full --clock-control none -k 'regex:nsconv_kernel|pack_kernel|colsum_multi' -c 20 -f -o /tmp/prof_ns \
+      python scripts/profile_step.py --workload c2 --steps 1 > $OUT/ncu_ns.log 2>&1
+  ncu -i /tmp/prof_ns.ncu-rep --page raw --csv > $OUT/prof_ns_raw.csv 2>/dev/null
+fi

@@ -45,7 +45,11 @@ class SvLayerInfo(C.Structure):
                 ("kh", "kw", "stride", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "in_ld", "in_coff", "out_ld", "dout_ld", "din_ld",
                  "in_dt", "out_dt", "act_dt", "has_dgrad", "tc_fwd", "tc_dgrad", "tc_wgrad")] + \
                [(n, C.c_void_p) for n in ("in_", "out", "dout", "din")] + \
-               [(n, C.c_int64) for n in ("in_elems", "out_elems", "dout_elems", "din_elems")]
+               [(n, C.c_int64) for n in ("in_elems", "out_elems", "dout_elems", "din_elems")] + \
+               [(n, C.c_int32) for n in ("kern_fwd", "kern_dgrad", "kern_wgrad", "reserved")]
+
+
+KERNEL_NAMES = {0: "reference", 1: "igemm_kernel", 2: "halo_conv_kernel", 3: "nsconv_kernel", 4: "wgrad_kernel", 5: "halo_wgrad_kernel"}
 
 
 class SplitVaeError(RuntimeError):

@@ -83,6 +83,10 @@ struct sv_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int COLSUM2 = -1;
   bool two_streams = true;
+  // weight gradients run on one auxiliary stream per branch stream (dgrad chain = critical path, wgrad + reduce fill the gaps)
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_aux[2] = {nullptr, nullptr}, ev_aux_join[2] = {nullptr, nullptr};
+  bool wgrad_streams = false;
   // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
   bool cs_on = false;
   int CSP[4] = {-1, -1, -1, -1};
@@ -323,12 +327,27 @@ void layer_fwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
   }
 }
 
+// auxiliary stream paired with branch stream s (or s itself when the feature is off); makes it wait for everything issued on s
+cudaStream_t wgrad_stream(sv_handle* h, cudaStream_t s) {
+  if (!h->wgrad_streams || !h->cs_on) return s;
+  const int k = (s == h->side) ? 1 : 0;
+  cudaEventRecord(h->ev_aux[k], s);
+  cudaStreamWaitEvent(h->aux[k], h->ev_aux[k], 0);
+  return h->aux[k];
+}
+void join_wgrad_stream(sv_handle* h, cudaStream_t s) {
+  if (!h->wgrad_streams || !h->cs_on) return;
+  const int k = (s == h->side) ? 1 : 0;
+  cudaEventRecord(h->ev_aux_join[k], h->aux[k]);
+  cudaStreamWaitEvent(s, h->ev_aux_join[k], 0);
+}
+
 void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
   Layer& L = h->layers[li];
   const void* in = L.in < 0 ? (const void*)ext_in : bp(h, L.in);
   const int T = h->act_dt;
   if (h->use_tc && L.tc.wgrad_ok) {
-    tc_conv_wgrad(L.tc, L.g, h->grads, s);
+    tc_conv_wgrad(L.tc, L.g, h->grads, wgrad_stream(h, s));   // dY(L) and X(L) are complete on s at this point
     h->launches += L.tc.wgrad_launches;
   } else {
     ref_conv_wgrad(L.g, in, L.in_dt, bp(h, L.dout), T, h->grads, h->round_w, s);
@@ -351,6 +370,7 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
 
 void branch_bias_grads(sv_handle* h, int which, cudaStream_t s) {
   if (h->cs_on) h->launches += colsum_table_run(h->cs[which], h->grads, s);
+  join_wgrad_stream(h, s);
 }
 
 void conv_encoder_fwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaStream_t s) {
@@ -591,6 +611,11 @@ sv_status sv_destroy(sv_handle* h) {
   if (h) {
     tc_pack_table_destroy(h->pack);
     for (int b = 0; b < 4; ++b) colsum_table_destroy(h->cs[b]);
+    for (int k = 0; k < 2; ++k) {
+      if (h->ev_aux[k]) cudaEventDestroy(h->ev_aux[k]);
+      if (h->ev_aux_join[k]) cudaEventDestroy(h->ev_aux_join[k]);
+      if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
+    }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
@@ -657,6 +682,16 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "side stream / event creation failed");
+  }
+  if (!h->aux[0]) {
+    const char* off = getenv("SV_WGRAD_STREAMS");
+    h->wgrad_streams = !(off && *off == '0');
+    if (h->wgrad_streams)
+      for (int k = 0; k < 2; ++k)
+        if (cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_aux[k], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_aux_join[k], cudaEventDisableTiming) != cudaSuccess)
+          return fail(h, SV_ERR_DEVICE, "auxiliary stream / event creation failed");
   }
   h->bound = true;
   return SV_OK;
@@ -874,6 +909,11 @@ sv_status sv_debug_layer_info(const sv_handle* hc, int32_t i, sv_layer_info* o) 
   o->in_dt = L.in_dt; o->out_dt = L.out_dt; o->act_dt = h->act_dt;
   o->has_dgrad = L.din >= 0; o->tc_fwd = L.tc.fwd_ok; o->tc_dgrad = L.tc.dgrad_ok; o->tc_wgrad = L.tc.wgrad_ok;
   if (h->bound) { o->in = bp(h, L.in); o->out = bp(h, L.out); o->dout = bp(h, L.dout); o->din = bp(h, L.din); }
+  if (h->use_tc) {
+    o->kern_fwd = !L.tc.fwd_ok ? SV_KERN_NONE : L.tc.fwd_ns ? SV_KERN_NSCONV : L.tc.fwd.halo ? SV_KERN_HALO_CONV : SV_KERN_IGEMM;
+    o->kern_dgrad = !L.tc.dgrad_ok ? SV_KERN_NONE : L.tc.dgrad_ns ? SV_KERN_NSCONV : L.tc.dgrad[0].halo ? SV_KERN_HALO_CONV : SV_KERN_IGEMM;
+    o->kern_wgrad = !L.tc.wgrad_ok ? SV_KERN_NONE : L.tc.wg_halo ? SV_KERN_HALO_WGRAD : SV_KERN_WGRAD;
+  }
   o->in_elems = (int64_t)g.B * g.Hi * g.Wi * g.in_ld; o->out_elems = (int64_t)g.B * g.Ho * g.Wo * g.out_ld;
   o->dout_elems = (int64_t)g.B * g.Ho * g.Wo * g.dout_ld; o->din_elems = (int64_t)g.B * g.Hi * g.Wi * g.din_ld;
   return SV_OK;

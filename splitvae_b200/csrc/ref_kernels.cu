@@ -284,6 +284,47 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_vec_kernel(const bf16* __r
   }
 }
 
+// Quad variant: one thread = the 2x2 output pixels that lie BETWEEN four input pixels (iy, iy+1) x (ix, ix+1), i in [-1, n-1]
+// with clamped reads: out[2i+1] = in[i] + (in[i+1]-in[i])*.25, out[2i+2] = in[i] + (in[i+1]-in[i])*.75 - the same (x0, x1, weight)
+// triples as the per-pixel kernel above, so results are bit-identical, with 4 loads per 4 outputs instead of 16.
+__global__ void __launch_bounds__(256) upsample2x_fwd_quad_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
+                                                                  int B, int H, int W, int C8) {
+  const int total = B * (H + 1) * (W + 1) * C8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c8 = idx % C8;
+    int p = idx / C8;
+    const int qx = p % (W + 1) - 1;
+    p /= W + 1;
+    const int qy = p % (H + 1) - 1;
+    const int n = p / (H + 1);
+    const int y0 = max(qy, 0), y1 = min(qy + 1, H - 1), x0 = max(qx, 0), x1 = min(qx + 1, W - 1);
+    const bf16* b = in + ((size_t)n * H * W) * C8 * 8 + c8 * 8;
+    const F8 tl = ld_bf16x8(b + ((size_t)y0 * W + x0) * C8 * 8), tr = ld_bf16x8(b + ((size_t)y0 * W + x1) * C8 * 8);
+    const F8 bl = ld_bf16x8(b + ((size_t)y1 * W + x0) * C8 * 8), br = ld_bf16x8(b + ((size_t)y1 * W + x1) * C8 * 8);
+    bf16* ob = out + ((size_t)n * 4 * H * W) * C8 * 8 + c8 * 8;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int oy = 2 * qy + 1 + dy;
+      if (oy < 0 || oy >= 2 * H) continue;
+      const float ly = dy ? 0.75f : 0.25f;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ox = 2 * qx + 1 + dx;
+        if (ox < 0 || ox >= 2 * W) continue;
+        const float lx = dx ? 0.75f : 0.25f;
+        F8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float top = tl.v[i] + (tr.v[i] - tl.v[i]) * lx;
+          const float bot = bl.v[i] + (br.v[i] - bl.v[i]) * lx;
+          o.v[i] = top + (bot - top) * ly;
+        }
+        st_bf16x8(ob + ((size_t)oy * 2 * W + ox) * C8 * 8, o);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
                                                                  const bf16* __restrict__ mask_src, int mask_act,
                                                                  int B, int H, int W, int C8) {
@@ -458,10 +499,11 @@ __global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJ
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bf16* base = J.d + J.col0 + gi * 8;
   long long r = r0 + ry;
-  for (; r + lanes < r1; r += 2 * lanes) {        // two independent loads in flight
+  for (; r + 3 * lanes < r1; r += 4 * lanes) {    // four independent 128-bit loads in flight per thread
     const F8 a = ld_bf16x8(base + r * J.ld), b = ld_bf16x8(base + (r + lanes) * J.ld);
+    const F8 c = ld_bf16x8(base + (r + 2 * lanes) * J.ld), d = ld_bf16x8(base + (r + 3 * lanes) * J.ld);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += a.v[i] + b.v[i];
+    for (int i = 0; i < 8; ++i) acc[i] += (a.v[i] + b.v[i]) + (c.v[i] + d.v[i]);
   }
   for (; r < r1; r += lanes) {
     const F8 a = ld_bf16x8(base + r * J.ld);
@@ -485,15 +527,26 @@ __global__ void __launch_bounds__(256) colsum_multi_final_kernel(const ColsumJob
     const int mid = (lo + hi + 1) >> 1;
     if (jobs[mid].fblock_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
+  // block = 32 columns x 8 chunk lanes (lane y sums chunks y, y+8, ...), fixed-order combine through shared memory
+  __shared__ float red[8][33];
   const ColsumJob& J = jobs[lo];
-  const int c = threadIdx.x;
-  if (c >= J.ncols || J.col0 + c >= J.c_valid) return;
-  const float* p = partial + J.partial_off + c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x - J.fblock_start) * 32 + tx;
   float t = 0.f;
-  for (int k = 0; k < J.nchunks; ++k) t += p[(long long)k * J.ncols];
-  int lc = J.col0 + c, j = 0;
-  while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
-  grads[J.part_b[j] + lc] = t;
+  if (c < J.ncols) {
+    const float* p = partial + J.partial_off + c;
+    for (int k = ty; k < J.nchunks; k += 8) t += p[(long long)k * J.ncols];
+  }
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < J.ncols && J.col0 + c < J.c_valid) {
+    float u = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u += red[i][tx];
+    int lc = J.col0 + c, j = 0;
+    while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+    grads[J.part_b[j] + lc] = u;
+  }
 }
 
 struct ColsumTable {
@@ -517,16 +570,17 @@ static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>&
       int p2 = 16;                                   // slab width: power of two in [16, 256] (ld is one, or a multiple of 256)
       while (p2 < ncols) p2 <<= 1;
       J.ncols = p2 > 256 ? 256 : p2;
-      // chunks of >= 256 rows, at most 64 per job (the final kernel walks them serially)
-      long long nch = (rows + 255) / 256;
-      if (nch > 64) nch = 64;
+      // chunks of ~32 KB of dY (enough blocks to fill the GPU: the kernel is latency-bound per block), at most 512 per job
+      const long long rows_per = (32768 / (J.ncols * 2)) < 64 ? 64 : 32768 / (J.ncols * 2);
+      long long nch = (rows + rows_per - 1) / rows_per;
+      if (nch > 512) nch = 512;
       if (nch < 1) nch = 1;
       J.rows_per_chunk = (int)((rows + nch - 1) / nch);
       J.nchunks = (int)((rows + J.rows_per_chunk - 1) / J.rows_per_chunk);
       J.partial_off = partial_floats;
       partial_floats += (long long)J.nchunks * J.ncols;
       J.block_start = nblocks; nblocks += J.nchunks;
-      J.fblock_start = nfblocks; nfblocks += 1;
+      J.fblock_start = nfblocks; nfblocks += (J.ncols + 31) / 32;
       J.nparts = g.nparts;
       for (int k = 0; k < 3; ++k) { J.part_n[k] = g.part_n[k]; J.part_b[k] = g.part_b[k]; }
       jobs.push_back(J);
@@ -581,7 +635,8 @@ int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s) {
   const long long total = (long long)B * 4 * H * W * C;
   if (dt == DT_BF16 && (C % 8) == 0 && total / 8 < (1ll << 31)) {
-    upsample2x_fwd_vec_kernel<<<grid_for(total / 8, 256, 148 * 32), 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C / 8);
+    const long long quads = (long long)B * (H + 1) * (W + 1) * (C / 8);
+    upsample2x_fwd_quad_kernel<<<grid_for(quads, 256, 148 * 32), 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C / 8);
     return;
   }
   if (dt == DT_F32)

@@ -1122,6 +1122,30 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const flo
   }
 }
 
+// few splits, 4 consecutive output columns per thread (128-bit loads / stores); requires Co, every part width and n_pad to be
+// multiples of 4 and a row map with contiguous columns (mode < 4)
+__global__ void __launch_bounds__(256) wgrad_reduce_few4_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
+                                                                WgRowMap R, float* __restrict__ grads) {
+  const int co4 = g.Co >> 2;
+  const long long total = (long long)g.kh * g.kw * g.Ci * co4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % co4) * 4;
+    const int r = (int)(idx / co4);
+    const int ci = r % g.Ci, tap = r / g.Ci;
+    const size_t row = wg_row(R, tap, ci);
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = k < k_splits ? *reinterpret_cast<const float4*>(partial + ((size_t)k * m_pad + row) * n_pad + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t.x += v[k].x; t.y += v[k].y; t.z += v[k].z; t.w += v[k].w; }
+    int lc;
+    const int j = part_of(g, co, lc);
+    *reinterpret_cast<float4*>(grads + g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc) = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                                WgRowMap R, float* __restrict__ grads) {
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
@@ -1171,7 +1195,43 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     const int mid = (lo + hi + 1) >> 1;
     if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  const PackJob& J = jobs[lo];
+  __shared__ PackJob Js;                       // the job descriptor is read hundreds of times: keep it on chip
+  if (threadIdx.x < sizeof(PackJob) / 4) reinterpret_cast<uint32_t*>(&Js)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&jobs[lo])[threadIdx.x];
+  __syncthreads();
+  const PackJob& J = Js;
+  if (J.kind == 1) {
+    // dgrad weights: dst[ci][tap'][co] = W[kh][kw][ci][co] (flipped sub-kernel) keeps co contiguous on both sides: one thread
+    // converts 8 consecutive co (two 128-bit loads when the run lies inside one Keras variable, one 128-bit store)
+    const int k8 = J.k_pad >> 3, ntap = J.taps_h * J.taps_w;
+    const int base8 = (blockIdx.x - J.block_start) * 256;      // 2048 elements per block
+    const int i8 = base8 + threadIdx.x;
+    if (i8 * 8 >= (int)J.count) return;
+    const int kk = (i8 % k8) * 8;
+    const int rt = i8 / k8;
+    const int tap = rt % ntap, r = rt / ntap;
+    const int a = tap / J.taps_w, b = tap - a * J.taps_w;
+    const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (r < J.Ci) {
+      int j = 0, lc = kk;
+      while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+      const float* src = params + J.part_w[j] + ((long long)(kh * J.KW + kw) * J.Ci + r) * J.part_n[j] + lc;
+      if (lc + 8 <= J.part_n[j] && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(src)), p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (kk + i < J.Co) v[i] = master_w(J, params, kh, kw, r, kk + i);
+      }
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(J.dst)[i8] = pk;
+    return;
+  }
   if (J.kind == 0) {
     // forward weights: dst[co][tap][ci] = W[tap][ci][co] is a transpose per tap -> 32x32 tiles through shared memory so
     // that both the fp32 reads (along co) and the bf16 writes (along ci) are coalesced
@@ -1202,10 +1262,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     }
     return;
   }
-  const long long base = (long long)(blockIdx.x - J.block_start) * 2048;
+  const int base = (blockIdx.x - J.block_start) * 2048;     // every packed operand has < 2^31 elements: 32-bit index math
   for (int t = threadIdx.x; t < 2048; t += 256) {
-    const long long idx = base + t;
-    if (idx >= J.count) return;
+    const int idx = base + t;
+    if (idx >= (int)J.count) return;
     if (J.kind == 2) {
       int j = 0, lc = (int)idx;
       float v = 0.f;
@@ -1233,7 +1293,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     }
     const int kk = (int)(idx % J.k_pad);
     const int tap = (int)((idx / J.k_pad) % (J.taps_h * J.taps_w));
-    const int r = (int)(idx / ((long long)J.k_pad * J.taps_h * J.taps_w));
+    const int r = idx / (J.k_pad * J.taps_h * J.taps_w);
     const int a = tap / J.taps_w, b = tap % J.taps_w;
     float v = 0.f;
     if (J.kind == 0) {           // fwd: rows = co, k = ci
@@ -2068,9 +2128,12 @@ static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_s
                                 cudaStream_t s) {
   if (k_splits <= 8) {   // few splits, many outputs (dense layers): one thread per output, all splits in flight at once
     const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
-    long long blocks = (total + 255) / 256;
+    bool vec = R.mode < 4 && (g.Co % 4) == 0 && (n_pad % 4) == 0;
+    for (int j = 0; j < g.nparts; ++j) vec = vec && (g.part_n[j] % 4) == 0 && (g.part_w[j] % 4) == 0;
+    long long blocks = ((vec ? total / 4 : total) + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    if (vec) wgrad_reduce_few4_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    else wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
   } else {
     const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
     wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
