@@ -134,6 +134,11 @@ sv_status sv_backward_segment(sv_handle* h, int32_t segment, void* stream);
 /* optimizer.apply_gradients (vae/trainer.py:138,167): multi-tensor Keras-Adam over the arena,
  * step counter and (lggmvae) staircase LR schedule kept on the device (vae/main.py:65-68). */
 sv_status sv_adam_step(sv_handle* h, void* stream);
+/* The same update restricted to one backward segment's arena range (segment 0 also advances the step counter / bias-corrected
+ * step size, so segments must be applied in order 0..n-1, each exactly once per step).  Lets the host update the decoders
+ * (segment 0: its gradients are final - and all-reduced - first) while the encoders' backward pass is still running.
+ * sv_adam_step == sv_adam_segment(0) ; sv_adam_segment(1). */
+sv_status sv_adam_segment(sv_handle* h, int32_t segment, void* stream);
 
 /* Whole train_step_* (vae/trainer.py:120-144 / 146-173) = forward + loss + all segments + Adam. */
 sv_status sv_train_step(sv_handle* h, const float* inputs_dev, const float* eps_g_dev,

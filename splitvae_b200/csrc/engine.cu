@@ -77,6 +77,9 @@ struct sv_handle {
   const float* last_inputs = nullptr;  // inputs of the step in flight (first-layer wgrad reads them)
   unsigned long long seed = 0x5EEDull;
   TcPackTable* pack = nullptr;
+  TcPackTable* pack_seg[2] = {nullptr, nullptr};   // the same jobs split by backward segment (0: decoders, 1: encoders)
+  cudaStream_t opt = nullptr;                      // optimizer stream: Adam + re-pack of segment 0 overlap the encoders' backward
+  cudaEvent_t ev_opt_fork = nullptr, ev_opt_join = nullptr;
   // the x / x_hat encoders and the two decoders are independent: they run on two streams (fork/join with events, which
   // CUDA-graph capture turns into parallel branches)
   cudaStream_t side = nullptr;
@@ -610,6 +613,10 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 sv_status sv_destroy(sv_handle* h) {
   if (h) {
     tc_pack_table_destroy(h->pack);
+    for (int seg = 0; seg < 2; ++seg) tc_pack_table_destroy(h->pack_seg[seg]);
+    if (h->ev_opt_fork) cudaEventDestroy(h->ev_opt_fork);
+    if (h->ev_opt_join) cudaEventDestroy(h->ev_opt_join);
+    if (h->opt) cudaStreamDestroy(h->opt);
     for (int b = 0; b < 4; ++b) colsum_table_destroy(h->cs[b]);
     for (int k = 0; k < 2; ++k) {
       if (h->ev_aux[k]) cudaEventDestroy(h->ev_aux[k]);
@@ -664,6 +671,15 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     tc_pack_table_destroy(h->pack);
     h->pack = tc_pack_table_create(tl.data(), tg.data(), (int)tl.size(), &perr);
     if (!h->pack) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
+    for (int seg = 0; seg < 2; ++seg) {
+      std::vector<TcLayer*> sl;
+      std::vector<const ConvGeom*> sg;
+      for (auto& L : h->layers)
+        if ((L.g.part_w[0] >= h->seg_split) == (seg == 0)) { sl.push_back(&L.tc); sg.push_back(&L.g); }
+      tc_pack_table_destroy(h->pack_seg[seg]);
+      h->pack_seg[seg] = tc_pack_table_create(sl.data(), sg.data(), (int)sl.size(), &perr);
+      if (!h->pack_seg[seg]) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
+    }
   }
   if (h->cs_on) {
     for (int b = 0; b < 4; ++b) {
@@ -682,6 +698,14 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "side stream / event creation failed");
+  }
+  if (!h->opt) {
+    const char* off = getenv("SV_OPT_STREAM");
+    if (!(off && *off == '0') &&
+        (cudaStreamCreateWithFlags(&h->opt, cudaStreamNonBlocking) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_opt_fork, cudaEventDisableTiming) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_opt_join, cudaEventDisableTiming) != cudaSuccess))
+      return fail(h, SV_ERR_DEVICE, "optimizer stream / event creation failed");
   }
   if (!h->aux[0]) {
     const char* off = getenv("SV_WGRAD_STREAMS");
@@ -789,15 +813,26 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
   return check_launch(h, "sv_backward_segment");
 }
 
-sv_status sv_adam_step(sv_handle* h, void* stream) {
+sv_status sv_adam_segment(sv_handle* h, int32_t seg, void* stream) {
   REQUIRE_BOUND(h);
+  if (seg < 0 || seg > 1) return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
   cudaStream_t s = (cudaStream_t)stream;
   AdamState* st = (AdamState*)bp(h, h->ADAM);
-  adam_prepare(st, h->cfg.learning_rate, h->cfg.model == SV_MODEL_LGGMVAE, s);
-  adam_apply(h->params, h->grads, h->adam_m, h->adam_v, h->arena_floats, st, 0.f, s);
-  h->launches += 2;
-  if (h->use_tc) h->launches += tc_repack_all(h->pack, h->params, s);
-  return check_launch(h, "sv_adam_step");
+  if (seg == 0) {
+    adam_prepare(st, h->cfg.learning_rate, h->cfg.model == SV_MODEL_LGGMVAE, s);
+    h->launches += 1;
+  }
+  const long long off = seg == 0 ? h->seg_split : 0, cnt = seg == 0 ? h->arena_floats - h->seg_split : h->seg_split;
+  adam_apply(h->params + off, h->grads + off, h->adam_m + off, h->adam_v + off, cnt, st, 0.f, s);
+  h->launches += 1;
+  if (h->use_tc) h->launches += tc_repack_all(h->pack_seg[seg], h->params, s);
+  return check_launch(h, "sv_adam_segment");
+}
+
+sv_status sv_adam_step(sv_handle* h, void* stream) {
+  sv_status st = sv_adam_segment(h, 0, stream);
+  if (st) return st;
+  return sv_adam_segment(h, 1, stream);
 }
 
 sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u, void* stream) {
@@ -805,8 +840,16 @@ sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, c
   if (st) return st;
   if ((st = sv_loss_fwd_bwd(h, inputs, stream))) return st;
   if ((st = sv_backward_segment(h, 0, stream))) return st;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->opt) {   // decoders: gradients final -> Adam + re-pack on the optimizer stream while the encoders' backward runs
+    cudaEventRecord(h->ev_opt_fork, s);
+    cudaStreamWaitEvent(h->opt, h->ev_opt_fork, 0);
+    if ((st = sv_adam_segment(h, 0, h->opt))) return st;
+    cudaEventRecord(h->ev_opt_join, h->opt);
+  } else if ((st = sv_adam_segment(h, 0, stream))) return st;
   if ((st = sv_backward_segment(h, 1, stream))) return st;
-  return sv_adam_step(h, stream);
+  if (h->opt) cudaStreamWaitEvent(s, h->ev_opt_join, 0);
+  return sv_adam_segment(h, 1, stream);
 }
 
 sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t* count) {

@@ -204,7 +204,7 @@ __device__ __forceinline__ void halo_epilogue(const TcLaunch& P, EpiSel e, uint3
 }
 #undef SV_EPI_CALL
 
-__global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__ TcLaunch P) {
+__device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = 128 * P.bk * 2;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
   const int n0 = (m_tile / tiles_per_img) * P.tile_n_img;
   const int y0 = (m_tile % tiles_per_img) * P.tile_h;
   const int kb_total = P.taps_h * P.taps_w * P.kc;
-  const int kb_first = P.k_splits > 1 ? blockIdx.z * P.kb_per_split : 0;          // split-K: this CTA's k-block range
+  const int kb_first = P.k_splits > 1 ? zsplit * P.kb_per_split : 0;              // split-K: this CTA's k-block range
   const int num_kb = P.k_splits > 1 ? min(P.kb_per_split, kb_total - kb_first) : kb_total;
 
   if (threadIdx.x == 0) {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     if (P.k_splits > 1) {                       // split-K: raw fp32 partial, finished by splitk_finish_kernel
-      float* dst = P.partial + ((size_t)blockIdx.z * P.m_pad + (size_t)m_tile * 128 + row) * P.n_pad + (size_t)n_tile * P.tile_cols;
+      float* dst = P.partial + ((size_t)zsplit * P.m_pad + (size_t)m_tile * 128 + row) * P.n_pad + (size_t)n_tile * P.tile_cols;
       for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
@@ -305,6 +305,13 @@ __global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
+
+__global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__ TcLaunch P) { igemm_body(P, blockIdx.z); }
+
+// The s*s parity classes of a stride-s dgrad (each a small stride-1 convolution scattering into its own output parity)
+// as ONE launch: blockIdx.z selects the class.  4 x more CTAs in flight for layers whose single class does not fill the GPU.
+struct TcLaunch4 { TcLaunch l[4]; };
+__global__ void __launch_bounds__(kThreads) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { igemm_body(P4.l[blockIdx.z], 0); }
 
 // Split-K finish for dense layers (one output row per image): out[row][col] = epilogue(sum_z partial[z][row][col]).
 // Fixed summation order -> deterministic.  One thread per output element; consecutive threads = consecutive columns.
@@ -523,7 +530,7 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
   const int cbase = split * nb;               // first output channel of this CTA's split
   const int my_last = cl + ((nchunk8 - 1 - cl) / lanes) * lanes;   // last block this warp reads (< 0: none)
   float* xch = xch_all + (size_t)(grp * lanes + cl) * (2 * 4 * KW * kNsXchSlots * 8);
-  const int bar_id = 1 + grp * lanes + cl;
+  const int bar_id = 1 + (grp * lanes + cl) * 2 + (q >> 1);     // one named barrier per (warp set, image row of the tile)
   // per filter column b: source lane and whether the source pixel x + b - pad_l lies inside the image row (else: zero padding)
   float keep[KW];
   int src[KW];
@@ -558,12 +565,14 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&ctl->acc_empty[grp]);
       }
+      if (P.debug & 1) continue;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      float* xb = xch + (size_t)xbuf * (4 * KW * kNsXchSlots * 8);
       if (WIDE) {
         // an image row spans two warps (q even: left half, q odd: right half): lanes near the boundary publish their values
-        float* xb = xch + (size_t)xbuf * (4 * KW * kNsXchSlots * 8);
+        // first, the in-warp shuffles below hide the latency of the pair barrier
         const int slot = lane < 4 ? lane : lane >= 28 ? lane - 24 : -1;
         if (slot >= 0) {
           float* xw = xb + (size_t)q * (KW * kNsXchSlots * 8);
@@ -574,7 +583,16 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
             dst[1] = make_uint4(v[b][4], v[b][5], v[b][6], v[b][7]);
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // the four quarter warps of this (group, chunk lane)
+      }
+#pragma unroll
+      for (int b = 0; b < KW; ++b) {
+        const int ls = lane + b - pad_l;
+        const float k = WIDE ? ((ls >= 0 && ls < 32) ? keep[b] : 0.f) : keep[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(k, __shfl_sync(0xffffffffu, __uint_as_float(v[b][j]), src[b]), o[j]);
+      }
+      if (WIDE) {
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // the two warps of this image row: partner's values visible
 #pragma unroll
         for (int b = 0; b < KW; ++b) {
           const int ls = lane + b - pad_l;
@@ -587,13 +605,6 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
           }
         }
         xbuf ^= 1;
-      }
-#pragma unroll
-      for (int b = 0; b < KW; ++b) {
-        const int ls = lane + b - pad_l;
-        const float k = WIDE ? ((ls >= 0 && ls < 32) ? keep[b] : 0.f) : keep[b];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(k, __shfl_sync(0xffffffffu, __uint_as_float(v[b][j]), src[b]), o[j]);
       }
       const int c0 = cbase + cc * 8;
       if (bias) {
@@ -741,7 +752,8 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
         const uint64_t da0 = tmpl + h_addr, db0 = tmpl + w_addr;
         // fully unrolled issue sequences for the shapes of this model family (the single issuing thread must spend only a
         // few instructions per tcgen05.mma: the generic nest below costs ~75 and caps the tensor pipe at ~35 %)
-        if (shape == 1) ns_issue_tile<6, 4, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
+        if (P.debug & 2) { }
+        else if (shape == 1) ns_issue_tile<6, 4, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
         else if (shape == 2) ns_issue_tile<6, 2, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
         else if (shape == 3) ns_issue_tile<6, 1, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
         else if (shape == 4) ns_issue_tile<6, 2, 2>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
@@ -1675,6 +1687,7 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   const int work = P.tiles * co_splits;
   if (work < P.grid) P.grid = work;
   P.grid -= P.grid % co_splits;
+  P.debug = env_int("SV_NS_DEBUG", 0);
   return true;
 }
 
@@ -1846,9 +1859,18 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         off += (size_t)P.w_bytes * P.co_splits;
       }
     }
+    if (ok && s == 2 && !env_int("SV_NO_DGRAD_MERGE", 0)) {
+      bool same = true;
+      for (int cls = 0; cls < 4; ++cls) {
+        const TcLaunch &A = t.dgrad[0], &C = t.dgrad[cls];
+        same = same && !C.halo && C.k_splits <= 1 && C.smem_bytes == A.smem_bytes && C.n_tiles == A.n_tiles && C.tile_h == A.tile_h &&
+               C.tile_n_img == A.tile_n_img && C.grid_h == A.grid_h && C.n_img == A.n_img;
+      }
+      t.dgrad_merged = same;
+    }
     if (ok) {
       t.dgrad_ok = true;
-      t.dgrad_launches = t.dgrad_ns ? 1 : s * s + (s == 1 && t.dgrad[0].k_splits > 1 ? 1 : 0);
+      t.dgrad_launches = t.dgrad_ns || t.dgrad_merged ? 1 : s * s + (s == 1 && t.dgrad[0].k_splits > 1 ? 1 : 0);
       t.w_dgrad_off = off;
       off += (size_t)s * s * round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * copad * 2), 1024);
     }
@@ -1974,6 +1996,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_dgrad_off) : nullptr;
     }
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+    if (cudaFuncSetAttribute(igemm4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (env_int("SV_TC_VERBOSE", 0)) {
@@ -2122,6 +2145,15 @@ void tc_conv_fwd(TcLayer& t, cudaStream_t s) {
 }
 void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
   if (t.dgrad_ns) { launch_ns(t.ns_dgrad, s); return; }
+  if (t.dgrad_merged) {
+    TcLaunch4 P4;
+    for (int c = 0; c < 4; ++c) P4.l[c] = t.dgrad[c];
+    const TcLaunch& L = t.dgrad[0];
+    const int tiles_per_img = L.grid_h / L.tile_h;
+    const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
+    igemm4_kernel<<<dim3(m_tiles, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
+    return;
+  }
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
 }
 static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_splits, int m_pad, int n_pad, const WgRowMap& R, float* grads,

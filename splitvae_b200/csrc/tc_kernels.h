@@ -126,6 +126,7 @@ struct TcNsConv {
   const void* mask_src;
   size_t smem_bytes;
   int grid;
+  int debug;                        // SV_NS_DEBUG bit 0: epilogue only drains TMEM (no shuffles / stores); bit 1: no MMAs issued
 };
 
 struct TcLayer {
@@ -138,6 +139,7 @@ struct TcLayer {
   bool wg_halo = false;
   TcHaloWgrad hw{};
   bool fwd_ns = false, dgrad_ns = false;   // N-stacked persistent kernel replaces the per-tap / halo kernel
+  bool dgrad_merged = false;               // stride-2 dgrad: the 4 parity classes run as one launch (igemm4_kernel)
   TcNsConv ns_fwd{}, ns_dgrad{};
   size_t w_nsf_off = 0, w_nsd_off = 0;
   size_t wg_partial_off = 0;
