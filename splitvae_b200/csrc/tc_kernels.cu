@@ -372,12 +372,13 @@ struct HaloCtl {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_constant__ TcLaunch P) {
+__device__ __forceinline__ void halo_body(const TcLaunch& P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nchunks = P.kc;
+  const int sx = P.halo_sx, sy = P.halo_sy;     // input stride: sx parity planes per chunk, rows sy apart (1 = plain stride-1 conv)
   uint8_t* halo = smem;
-  uint8_t* wring = smem + (size_t)nchunks * P.chunk_bytes;
+  uint8_t* wring = smem + (size_t)nchunks * sx * P.chunk_bytes;
   HaloCtl* ctl = reinterpret_cast<HaloCtl*>(wring + (size_t)P.w_stages * P.w_stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -410,9 +411,11 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(&ctl->halo_full, (uint32_t)(nchunks * P.THp * P.TWp * P.bk * 2));
-      for (int c = 0; c < nchunks; ++c)
-        tc::tma_load_4d(halo + (size_t)c * P.chunk_bytes, &P.map_a, &ctl->halo_full, c * P.bk, x0 - P.pad_l, y0 - P.pad_t, n);
+      tc::mbar_expect_tx(&ctl->halo_full, (uint32_t)(nchunks * sx * P.THp * P.TWp * P.bk * 2));
+      for (int p = 0; p < sx; ++p)         // plane p holds input columns sx*x0 - pad_l + p + sx*j (TMA element stride sx)
+        for (int c = 0; c < nchunks; ++c)
+          tc::tma_load_4d(halo + (size_t)(p * nchunks + c) * P.chunk_bytes, &P.map_a, &ctl->halo_full, c * P.bk, sx * x0 - P.pad_l + p,
+                          sy * y0 - P.pad_t, n);
       for (int st = 0; st < num_stages_total; ++st) {
         const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
         tc::mbar_wait(&ctl->w_empty[slot], phase ^ 1);
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
       const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
       const uint32_t lt = tc::layout_type_for(P.swizzle);
       const uint32_t pix = (uint32_t)P.bk * 2u;              // bytes per pixel inside a chunk
-      const uint32_t a_sbo = (uint32_t)P.TWp * pix;          // next row group = next image row
+      const uint32_t a_sbo = (uint32_t)(sy * P.TWp) * pix;   // next row group = next output row = sy input rows
       const uint32_t b_sbo = 8u * pix;                       // weights: dense [tile_cols][bk]
       const uint32_t halo_addr = tc::smem_u32(halo);
       tc::mbar_wait(&ctl->halo_full, 0);
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 B): build one template per
       // operand and add offsets, so the single issuing thread spends a handful of instructions per MMA.
       const uint64_t a_tmpl = tc::make_smem_desc(0, 16, a_sbo, lt), b_tmpl = tc::make_smem_desc(0, 16, b_sbo, lt);
-      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)P.TWp * pix) >> 4;
+      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * P.TWp) * pix) >> 4;
       const uint32_t tile_cols = (uint32_t)P.tile_cols;
       const int ksteps = P.bk / 16;
       int kb = 0;
@@ -451,7 +454,10 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
         int tap = kb / nchunks, chunk = kb - tap * nchunks;
         int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
         for (; kb < kb_end; ++kb, b_addr += (uint32_t)kb_bytes >> 4) {
-          const uint32_t a_tap = (halo_addr + (uint32_t)chunk * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4;
+          // filter column tb = sx * b' + p: parity plane p, shifted by b' plane columns
+          const uint32_t a_tap = sx == 1 ? (halo_addr + (uint32_t)chunk * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4
+                                         : (halo_addr + (uint32_t)((tb % sx) * nchunks + chunk) * (uint32_t)P.chunk_bytes +
+                                            (uint32_t)(ta * P.TWp + tb / sx) * pix) >> 4;
           const uint64_t db = b_tmpl + b_addr;
           const uint32_t first = kb != 0;
           switch (P.mtx) {
@@ -488,6 +494,10 @@ __global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_consta
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
+
+__global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_constant__ TcLaunch P) { halo_body(P); }
+// the 4 parity classes of a stride-2 dgrad as one launch (blockIdx.z = class), as igemm4_kernel
+__global__ void __launch_bounds__(kThreads) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { halo_body(P4.l[blockIdx.z]); }
 
 // ------------------------------------------------------------------------------------------------
 // N-stacked persistent convolution (see TcNsConv in tc_kernels.h).
@@ -1134,6 +1144,72 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const flo
   }
 }
 
+// Many splits, VEC consecutive output columns per thread (128/64/32-bit loads): block = 32 column vectors x `blockDim.y` split
+// lanes; lane y sums splits y, y+L, ... with four independent loads in flight, then the L partial sums are combined in a fixed
+// order through shared memory (deterministic).  4x fewer threads / instructions per byte than wgrad_reduce_kernel, whose
+// scalar 128-byte rows ran at 1.1-1.8 TB/s out of L2.  Requires Co, every part width % VEC == 0.
+template <int VEC> struct VecF;
+template <> struct VecF<4> { typedef float4 T; };
+template <> struct VecF<2> { typedef float2 T; };
+template <> struct VecF<1> { typedef float T; };
+template <int VEC>
+__global__ void __launch_bounds__(1024) wgrad_reduce_vec_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
+                                                                WgRowMap R, float* __restrict__ grads) {
+  typedef typename VecF<VEC>::T V;
+  extern __shared__ float red_dyn[];   // [blockDim.y][32 * VEC]
+  const int cov = g.Co / VEC;
+  const long long items = (long long)g.kh * g.kw * g.Ci * cov;
+  const long long item = (long long)blockIdx.x * 32 + threadIdx.x;
+  const bool live = item < items;
+  float s[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = 0.f;
+  int tap = 0, ci = 0, co = 0;
+  if (live) {
+    co = (int)(item % cov) * VEC;
+    const int r = (int)(item / cov);
+    ci = r % g.Ci; tap = r / g.Ci;
+    const size_t zstride = (size_t)m_pad * n_pad;
+    const float* p = partial + wg_row(R, tap, ci) * n_pad + wg_col(R, tap, co);
+    const int L = blockDim.y;
+    int k = threadIdx.y;
+    for (; k + 3 * L < k_splits; k += 4 * L) {
+      const V a = *reinterpret_cast<const V*>(p + (size_t)k * zstride);
+      const V b = *reinterpret_cast<const V*>(p + (size_t)(k + L) * zstride);
+      const V c = *reinterpret_cast<const V*>(p + (size_t)(k + 2 * L) * zstride);
+      const V d = *reinterpret_cast<const V*>(p + (size_t)(k + 3 * L) * zstride);
+      const float* fa = reinterpret_cast<const float*>(&a); const float* fb = reinterpret_cast<const float*>(&b);
+      const float* fc = reinterpret_cast<const float*>(&c); const float* fd = reinterpret_cast<const float*>(&d);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) s[i] += (fa[i] + fb[i]) + (fc[i] + fd[i]);
+    }
+    for (; k < k_splits; k += L) {
+      const V a = *reinterpret_cast<const V*>(p + (size_t)k * zstride);
+      const float* fa = reinterpret_cast<const float*>(&a);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) s[i] += fa[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) red_dyn[(threadIdx.y * 32 + threadIdx.x) * VEC + i] = s[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    float t[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t[i] += red_dyn[(y * 32 + threadIdx.x) * VEC + i];
+    }
+    int lc;
+    const int j = part_of(g, co, lc);
+    float* o = grads + g.part_w[j] + ((long long)tap * g.Ci + ci) * g.part_n[j] + lc;
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(t[0], t[1], t[2], t[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(o) = make_float2(t[0], t[1]);
+    else o[0] = t[0];
+  }
+}
+
 // few splits, 4 consecutive output columns per thread (128-bit loads / stores); requires Co, every part width and n_pad to be
 // multiples of 4 and a row map with contiguous columns (mode < 4)
 __global__ void __launch_bounds__(256) wgrad_reduce_few4_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
@@ -1364,6 +1440,26 @@ const char* make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, 
   return nullptr;
 }
 
+// halo tile of an activation tensor [N][H][W][ld]: twp plane columns at element stride sx, thp consecutive rows
+const char* make_halo_map(CUtensorMap* m, const void* base, int N, int H, int W, int ld, int coff, int C, int bk, int twp, int thp, int sx,
+                          int swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(twp * sx - (sx - 1)), (cuuint32_t)thp, 1};   // ceil(box/stride) elements are loaded
+  cuuint32_t estr[4] = {1, (cuuint32_t)sx, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)((const bf16*)base + coff), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(halo) failed: %d (dims %d,%d,%d,%d ld %d box %u,%u,%u sx %d)", (int)r,
+             C, W, H, N, ld, box[0], box[1], box[2], sx);
+    return g_tc_error;
+  }
+  return nullptr;
+}
+
 // packed weights [rows][k_total] bf16: box = {bk, tile_rows}
 const char* make_w_map(CUtensorMap* m, const void* base, int rows, long long k_total, int bk, int tile_rows, int swizzle) {
   PFN_encodeTiled enc = get_encode();
@@ -1484,14 +1580,17 @@ size_t split_k_bytes(const TcLaunch& L) {
 // groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
 // for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
 
-void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
+void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false) {
   L.halo = 0;
+  L.halo_sx = 1; L.halo_sy = 1;
   if (env_int("SV_NO_HALO", 0)) return;
-  if (L.a_stride != 1 || (GH % 16) || (GW % 8) || L.taps_h * L.taps_w < 2) return;
+  if ((sx == 1 && sy == 1 && L.a_stride != 1) || (GH % 16) || (GW % 8) || L.taps_h * L.taps_w < 2) return;
   // measured on B200 (scripts/bench_layers.py): the halo kernel wins where the per-tap kernel is L2-bound with little
   // tensor work per byte (<= 32 channels per pixel and N <= 32: d5 forward 150 vs 221 us, d5 dgrad 103 vs 234 us); with 64+ channel
   // chunks the per-tap kernel (2 CTAs/SM, deep ring) is as fast or faster (d4 forward 97 vs 130 us) -> keep it there.
-  if ((L.bk > 32 || L.tile_cols > 32) && !env_int("SV_HALO_ALL", 0)) return;
+  // `force` (strided forward layers, stride-2 dgrad classes): the per-tap kernel re-reads every activation tile once per tap
+  // from L2 (e2 forward: 226 MB in 31 us), the halo kernel reads it once.
+  if ((L.bk > 32 || L.tile_cols > 32) && !force && !env_int("SV_HALO_ALL", 0)) return;
   const int pix = L.bk * 2, nch = L.kc;
   const int kb_bytes = L.tile_cols * L.bk * 2;
   const int num_kb = L.taps_h * L.taps_w * nch;
@@ -1502,6 +1601,7 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
   int best_tw = 0, best_th = 0, best_stages = 0;
   double best_cost = 1e30;
   const int force_tw = env_int("SV_HALO_TW", 0), force_th = env_int("SV_HALO_TH", 0);
+  const int wtaps = (L.taps_w + sx - 1) / sx;
   for (int TH = 16; TH <= 32 && TH <= GH; TH += 16) {
     if (GH % TH) continue;
     for (int TW = 8; TW <= 64 && TW <= GW; TW += 8) {
@@ -1510,18 +1610,18 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
       if (force_th && TH != force_th) continue;
       const int MT = (TW / 8) * (TH / 16);
       if (MT * L.tile_cols > 512) continue;
-      const int TWp = TW + L.taps_w - 1, THp = TH + L.taps_h - 1;
-      if (TWp > 256 || THp > 256) continue;
+      const int TWp = TW + wtaps - 1, THp = (TH - 1) * sy + L.taps_h;
+      if (TWp * sx > 256 || THp > 256) continue;
       const size_t chunk = ((size_t)THp * TWp * pix + 1023) / 1024 * 1024;
       for (int stages = 3; stages >= 2; --stages) {
-        const size_t smem = chunk * nch + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
+        const size_t smem = chunk * nch * sx + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
         if (smem > 200 * 1024) continue;
         int tmem_cols = 32;
         while (tmem_cols < MT * L.tile_cols) tmem_cols <<= 1;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
         if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
         if (per_sm < 1) continue;
-        const double traffic = ((double)chunk * nch + w_total) / (TW * TH);
+        const double traffic = ((double)chunk * nch * sx + w_total) / (TW * TH);
         double cost = traffic * (per_sm == 1 ? 1.6 : 1.0);
         if (TW == 32 && TH == 16) cost *= 0.5;   // measured best shape for the 64x64 layers
         if (cost < best_cost) { best_cost = cost; best_tw = TW; best_th = TH; best_stages = stages; }
@@ -1531,13 +1631,14 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img) {
   }
   if (!best_tw) return;
   L.halo = 1;
-  L.TW = best_tw; L.TH = best_th; L.TWp = best_tw + L.taps_w - 1; L.THp = best_th + L.taps_h - 1;
+  L.halo_sx = sx; L.halo_sy = sy;
+  L.TW = best_tw; L.TH = best_th; L.TWp = best_tw + wtaps - 1; L.THp = (best_th - 1) * sy + L.taps_h;
   L.mtx = best_tw / 8; L.mty = best_th / 16;
   L.chunk_bytes = (int)(((size_t)L.THp * L.TWp * pix + 1023) / 1024 * 1024);
   L.kb_per_stage = KB; L.w_stages = best_stages; L.w_stage_bytes = KB * kb_bytes;
   L.tiles_x = GW / best_tw; L.tiles_y = GH / best_th;
   L.n_img = n_img;
-  L.smem_bytes = (size_t)L.chunk_bytes * nch + (size_t)L.w_stages * L.w_stage_bytes + sizeof(HaloCtl) + 1024;
+  L.smem_bytes = (size_t)L.chunk_bytes * nch * sx + (size_t)L.w_stages * L.w_stage_bytes + sizeof(HaloCtl) + 1024;
 }
 
 
@@ -1731,6 +1832,16 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
     off += round_up(t.n_pad_fwd * 6 * 64 * 2, 1024);
     t.bias_off = off;
     off += round_up(t.n_pad_fwd * 4, 1024);
+    // Pixel-pair view on the halo kernel: the staged row [W+8][8 ch] is also [(W+8)/2][16 ch], so horizontally the 6x6 stride-2
+    // convolution is a 3-tap stride-1 convolution over pairs (K = 16 per pair-tap: one MMA) and vertically the UMMA row-group
+    // stride skips every other input row.  The tile's input halo is read once (the window kernel re-reads it per filter row).
+    if ((g.Wi % 2) == 0 && env_int("SV_FIRST_PAIR", 1)) {
+      TcLaunch P = L;
+      P.taps_h = 6; P.taps_w = 3; P.pad_l = 0; P.bk = 16; P.swizzle = 32; P.kc = 1;
+      finish_launch(P, t.n_pad_fwd);
+      try_halo(P, g.Ho, g.Wo, g.B, 1, 2, true);
+      if (P.halo) { L = P; t.first_pair = true; t.ci_pad = 16; }
+    }
   }
   {
     TcWgradLaunch& L = t.wg;
@@ -1792,7 +1903,10 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         for (int j = 0; j < 3; ++j) { L.part_n[j] = g.part_n[j]; L.part_act[j] = g.part_act[j]; }
         L.mask_act = ACT_NONE;
         finish_launch(L, t.n_pad_fwd);
-        if (cpad <= g.in_ld - g.in_coff) try_halo(L, g.Ho, g.Wo, g.B);
+        if (cpad <= g.in_ld - g.in_coff) {
+          if (g.stride == 1) try_halo(L, g.Ho, g.Wo, g.B);
+          else if (g.stride == 2 && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && env_int("SV_S2_FWD_HALO", 1)) try_halo(L, g.Ho, g.Wo, g.B, 2, 2, true);
+        }
         if (g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
             plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
           TcNsConv& P = t.ns_fwd;
@@ -1839,7 +1953,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.out_ld = g.din_ld; L.out_f32 = 0;
       L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
       finish_launch(L, t.n_pad_dg);
-      try_halo(L, GH, GW, g.B);
+      try_halo(L, GH, GW, g.B, 1, 1, s == 2 && L.tile_cols <= 64 && env_int("SV_S2_DGRAD_HALO", 1));
       if (s == 1) {
         plan_split_k(L, g.B, off);
         t.sk_dgrad_off = off;
@@ -1863,8 +1977,9 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       bool same = true;
       for (int cls = 0; cls < 4; ++cls) {
         const TcLaunch &A = t.dgrad[0], &C = t.dgrad[cls];
-        same = same && !C.halo && C.k_splits <= 1 && C.smem_bytes == A.smem_bytes && C.n_tiles == A.n_tiles && C.tile_h == A.tile_h &&
-               C.tile_n_img == A.tile_n_img && C.grid_h == A.grid_h && C.n_img == A.n_img;
+        same = same && C.halo == A.halo && C.k_splits <= 1 && C.smem_bytes == A.smem_bytes && C.n_tiles == A.n_tiles && C.tile_h == A.tile_h &&
+               C.tile_n_img == A.tile_n_img && C.grid_h == A.grid_h && C.n_img == A.n_img &&
+               (!C.halo || (C.TW == A.TW && C.TH == A.TH && C.tiles_x == A.tiles_x && C.tiles_y == A.tiles_y));
       }
       t.dgrad_merged = same;
     }
@@ -1941,8 +2056,10 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
   t.ws = ws;
   if (t.fwd_ok) {
     TcLaunch& L = t.fwd;
-    const char* e = t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
-                    : L.halo ? make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, 1, 1, L.swizzle)
+    // (first_pair: the staged image [B][H][W+8][8] seen as [B][H][(W+8)/2][16] - one K = 16 row per pixel pair)
+    const char* e = t.first_pair ? make_halo_map(&L.map_a, in, g.B, g.Hi, (g.Wi + 8) / 2, 16, 0, 16, 16, L.TWp, L.THp, 1, 32)
+                    : t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
+                    : L.halo ? make_halo_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, L.halo_sx, L.swizzle)
                             : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff,
                                            t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk, L.tile_w, L.tile_h, L.tile_n_img,
                                            g.stride, L.swizzle);
@@ -1980,7 +2097,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
     for (int cls = 0; cls < t.n_dgrad; ++cls) {
       TcLaunch& L = t.dgrad[cls];
-      const char* e = L.halo ? make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.TWp, L.THp, 1, 1, L.swizzle)
+      const char* e = L.halo ? make_halo_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
                              : make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.tile_w, L.tile_h, L.tile_n_img, 1,
                                             L.swizzle);
       if (e) return e;
@@ -1999,6 +2116,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (cudaFuncSetAttribute(igemm4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  if (cudaFuncSetAttribute(halo4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (env_int("SV_TC_VERBOSE", 0)) {
     auto show = [&](const char* what, const TcLaunch& L) {
       if (L.halo)
@@ -2076,6 +2194,7 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     if (t.fwd_ok) {
       PackJob J = B;
       J.kind = t.first ? 3 : 0; J.rows_pad = t.n_pad_fwd; J.taps_h = t.fwd.taps_h; J.taps_w = t.fwd.taps_w; J.k_pad = t.ci_pad;
+      if (t.first_pair) { J.kind = 0; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = 8; }   // K = (a, b, 8 channels): a pair-tap b' is the K block (b = 2b', 2b'+1)
       J.dst = t.ws + t.w_fwd_off;
       J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * t.ci_pad;
       push(J);
@@ -2151,7 +2270,8 @@ void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
     const TcLaunch& L = t.dgrad[0];
     const int tiles_per_img = L.grid_h / L.tile_h;
     const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
-    igemm4_kernel<<<dim3(m_tiles, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
+    if (L.halo) halo4_kernel<<<dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
+    else igemm4_kernel<<<dim3(m_tiles, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
     return;
   }
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
@@ -2166,6 +2286,23 @@ static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_s
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (vec) wgrad_reduce_few4_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
     else wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+  } else if (!env_int("SV_OLD_REDUCE", 0)) {
+    int vec = 4;
+    while (vec > 1) {
+      bool ok = (g.Co % vec) == 0 && (n_pad % vec) == 0 && (R.mode < 4 || (R.nb % vec) == 0);
+      for (int j = 0; j < g.nparts; ++j) ok = ok && (g.part_n[j] % vec) == 0 && (g.part_w[j] % vec) == 0;
+      if (ok) break;
+      vec >>= 1;
+    }
+    const long long items = (long long)g.kh * g.kw * g.Ci * (g.Co / vec);
+    const int blocks = (int)((items + 31) / 32);
+    // split lanes: enough that every lane has <= ~8 loads, more when the grid alone would not fill the GPU
+    int lanes = 8;
+    while (lanes < 32 && (k_splits > 8 * lanes || (long long)blocks * lanes < 148 * 16)) lanes <<= 1;
+    const size_t smem = (size_t)lanes * 32 * vec * sizeof(float);
+    if (vec == 4) wgrad_reduce_vec_kernel<4><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    else if (vec == 2) wgrad_reduce_vec_kernel<2><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    else wgrad_reduce_vec_kernel<1><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
   } else {
     const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
     wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);

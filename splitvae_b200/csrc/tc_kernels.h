@@ -38,6 +38,10 @@ struct TcLaunch {
   int chunk_bytes;                              // bytes of one channel-chunk halo (1024-aligned)
   int kb_per_stage, w_stages, w_stage_bytes;    // weight ring: k-blocks (tap, chunk) per stage
   int tiles_x, tiles_y;
+  // strided input (stride-2 forward convolutions): halo_sx parity planes per channel chunk (plane p = input columns
+  // sx*x0 - pad_l + p + sx*j, loaded with TMA element stride sx; filter column b = sx*b' + p reads plane p shifted by b'),
+  // halo_sy = input rows per output row (the UMMA row-group stride).  TWp = plane width, THp = (TH-1)*sy + taps_h.
+  int halo_sx, halo_sy;
   // split-K (skinny dense GEMMs: few output tiles, long K): blockIdx.z owns kb_per_split k-blocks and stores its raw fp32
   // accumulator to partial[z][m_pad][n_pad]; splitk_finish_kernel sums the splits in a fixed order and applies the epilogue
   int k_splits, kb_per_split, m_pad, n_pad;
@@ -139,7 +143,8 @@ struct TcLayer {
   bool wg_halo = false;
   TcHaloWgrad hw{};
   bool fwd_ns = false, dgrad_ns = false;   // N-stacked persistent kernel replaces the per-tap / halo kernel
-  bool dgrad_merged = false;               // stride-2 dgrad: the 4 parity classes run as one launch (igemm4_kernel)
+  bool dgrad_merged = false;               // stride-2 dgrad: the 4 parity classes run as one launch (igemm4_kernel / halo4_kernel)
+  bool first_pair = false;                 // first layer forward on the halo kernel through the pixel-PAIR view of the staged image
   TcNsConv ns_fwd{}, ns_dgrad{};
   size_t w_nsf_off = 0, w_nsd_off = 0;
   size_t wg_partial_off = 0;

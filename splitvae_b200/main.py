@@ -32,6 +32,8 @@ def build_parser():
     parser.add_argument('--report_every', type=int, default=10000)
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--no_graph', action='store_true')
+    parser.add_argument('--test_batches', type=int, default=4, help='synthetic test batches per evaluation pass (0: no evaluation)')
+    parser.add_argument('--save_weights', type=str, default='', help='write the trained weights (.npz, Keras variable names) here')
     return parser
 
 
@@ -52,7 +54,7 @@ def main(argv=None):
     augmentor = Augmentator(type=config.augmentation, size=config.patch_size)
     train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=False,
                                                                 batch_size=config.batch_size, augmentor=augmentor,
-                                                                seed=config.seed)
+                                                                seed=config.seed, test_batches=config.test_batches)
     config.label = False  # synthetic data carries no labels
     if config.model == 'lgvae':
         model = LGVae(global_latent_dims=config.global_latent_dims, local_latent_dims=config.local_latent_dims,
@@ -66,7 +68,10 @@ def main(argv=None):
     else:
         raise NotImplementedError("--model %s is outside the hot path of this build (lgvae | lggmvae)" % config.model)
     print('Training local-global autoencoder')
-    return trainer.train_local_global_autoencoder(model, optimizer, config.dataset, train_dataset, test_dataset, config=config)
+    history = trainer.train_local_global_autoencoder(model, optimizer, config.dataset, train_dataset, test_dataset, config=config)
+    if config.save_weights:                       # vae/trainer.py:421
+        print('saved', model.save_weights(config.save_weights, include_optimizer=True))
+    return history
 
 
 if __name__ == '__main__':

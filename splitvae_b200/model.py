@@ -28,6 +28,7 @@ class _SplitModel:
         self.precision = precision
         self._engine_kwargs = dict(engine_kwargs)
         self.engine = None
+        self._eval_engines = {}
         self._pending_params = None
 
     # -- engine management -------------------------------------------------------------------
@@ -58,6 +59,61 @@ class _SplitModel:
     def configure(self, **kw):
         """Loss weights / optimizer settings that live in the reference's `config` and optimizer objects."""
         self._engine_kwargs.update(kw)
+
+    def eval_engine(self, batch_size):
+        """A second engine for the evaluation batch size that shares nothing with the training engine but the parameter
+        VALUES (copied device to device before every evaluation pass): rebuilding the training engine for a different
+        batch would drop its Adam state and captured graph."""
+        b = int(batch_size)
+        if self.engine is not None and self.engine.B == b and not self._eval_engines:
+            return self.engine
+        ev = self._eval_engines.get(b)
+        if ev is None:
+            kw = dict(self._engine_kwargs)
+            H, W = int(self.image_shape[1]), int(self.image_shape[2])
+            ev = Engine(model=self._kind, height=H, width=W, batch=b, y_size=self.y_size or 30, tau=self.tau or 0.4,
+                        precision=self.precision, **kw)
+            self._eval_engines[b] = ev
+        if self.engine is not None:
+            ev.params.copy_(self.engine.params)
+        elif self._pending_params is not None:
+            ev.load_params(self._pending_params)
+        ev.params_updated()
+        return ev
+
+    # -- checkpoints (vae/trainer.py:421 model.save_weights; Keras variable names and layouts) ----
+    def save_weights(self, path, include_optimizer=False):
+        """The reference writes Keras HDF5 (`model.save_weights('models/<run>.h5')`); h5py is not part of this image, so the
+        same variables (Keras names, conv HWIO / dense [in,out] layouts) go into a NumPy `.npz`.  With include_optimizer the
+        Adam moments and the iteration counter are stored too (the reference cannot resume; this build can)."""
+        import numpy as np
+        e = self.engine
+        blob = {name: a for name, a in e.get_params().items()}
+        if include_optimizer:
+            for name, a in e._export(e.adam_m).items():
+                blob["adam_m/" + name] = a
+            for name, a in e._export(e.adam_v).items():
+                blob["adam_v/" + name] = a
+            blob["optimizer/iterations"] = np.asarray(e.iterations, dtype=np.int64)
+        if not str(path).endswith(".npz"):
+            path = str(path) + ".npz"
+        np.savez(path, **blob)
+        return path
+
+    def load_weights(self, path):
+        import numpy as np
+        with np.load(path) as z:
+            blob = {k: z[k] for k in z.files}
+        named = {k: v for k, v in blob.items() if "/" not in k}
+        self.set_weights_by_name(named)
+        if self.engine is not None and "optimizer/iterations" in blob:
+            e = self.engine
+            for arena, prefix in ((e.adam_m, "adam_m/"), (e.adam_v, "adam_v/")):
+                host = arena.cpu()
+                for name, shape, off, cnt in e.table:
+                    host[off:off + cnt] = torch.from_numpy(np.asarray(blob[prefix + name], dtype=np.float32).reshape(-1))
+                arena.copy_(host)
+            e.iterations = int(blob["optimizer/iterations"])
 
     def set_weights_by_name(self, named):
         self._pending_params = named

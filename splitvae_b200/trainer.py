@@ -6,7 +6,9 @@
 
 The step itself (forward, fused loss fwd+bwd, backward, Adam) runs inside libsplitvae; this module
 adds the CUDA-graph capture of the whole step and the data-parallel gradient all-reduce.
-Evaluation, classifier scoring and visualisation (vae/trainer.py:313-416) are out of scope.
+The evaluation steps (test_step_lg_vae / test_step_lg_gm_vae, vae/trainer.py:199-274) and the periodic report
+(313-382) reuse the forward and the fused loss kernel without the backward pass; classifier scoring, cluster accuracy
+and visualisation need SVHN labels / the missing classifier blob and stay out of scope.
 """
 from __future__ import annotations
 
@@ -141,6 +143,119 @@ class StepRunner:
         return dict(zip(names, s))
 
 
+class Mean:
+    """tf.keras.metrics.Mean: running mean with result() / reset_states() (vae/trainer.py:99-113).  result() of an empty
+    metric is 0, as in Keras."""
+
+    def __init__(self, name=None):
+        self.name = name
+        self.total, self.count = 0.0, 0
+
+    def __call__(self, value):
+        self.total += float(value)
+        self.count += 1
+
+    update_state = __call__
+
+    def result(self):
+        return self.total / self.count if self.count else 0.0
+
+    def reset_states(self):
+        self.total, self.count = 0.0, 0
+
+
+METRIC_NAMES = ("x_recon", "x_kl", "x_hat_recon", "x_hat_kl", "total_kl", "y_kl")
+
+
+def make_metrics():
+    """The train/test Keras Mean metrics of vae/trainer.py:99-113 (classifier accuracies stay at Keras' empty value 0)."""
+    return {f"{n}_{split}_loss": Mean(f"{n}_{split}_loss") for split in ("train", "test") for n in METRIC_NAMES}
+
+
+def _update_metrics(metrics, split, sc, gm):
+    metrics[f"x_recon_{split}_loss"](sc["recon_x"])
+    metrics[f"x_kl_{split}_loss"](sc["kl_x"])
+    metrics[f"x_hat_recon_{split}_loss"](sc["recon_x_hat"])
+    metrics[f"x_hat_kl_{split}_loss"](sc["kl_x_hat"])
+    if gm:
+        metrics[f"y_kl_{split}_loss"](sc["y_kl"])
+    else:
+        metrics[f"total_kl_{split}_loss"](sc["total_kl"])
+
+
+def _test_step(model, images, config=None, eps_g=None, eps_l=None, u=None):
+    """Forward + loss terms, no backward, no parameter update.  Runs sv_forward and the fused loss kernel (whose gradient
+    outputs land in workspace buffers nobody reads here).  Returns (scalars dict, engine)."""
+    kw = {}
+    if config is not None:
+        kw["beta"] = float(config.get("beta", 40.0))
+        kw["alpha"] = float(config.get("alpha", 40.0) or 40.0)
+        model.configure(**kw)
+    if model.engine is None and not model._eval_engines:
+        model.build(images.shape[0])
+    e = model.eval_engine(images.shape[0])
+    images = images.contiguous().float()
+    e.forward(images, eps_g, eps_l, u)
+    e.loss_fwd_bwd(images)
+    return e.scalars(), e
+
+
+def test_step_lg_vae(model, images, labels=None, config=None, metrics=None, eps_g=None, eps_l=None):
+    """vae/trainer.py:199-232 without the classifier block (labels are accepted and ignored: the SVHN classifier weights
+    are not part of the reference checkout).  Returns {recon_x, recon_x_hat, kl_x, kl_x_hat, total_kl, total}."""
+    sc, _ = _test_step(model, images, config, eps_g, eps_l)
+    if metrics is not None:
+        _update_metrics(metrics, "test", sc, gm=False)
+    return sc
+
+
+def test_step_lg_gm_vae(model, images, labels=None, config=None, metrics=None, eps_g=None, eps_l=None, u=None):
+    """vae/trainer.py:235-274: updates the test metrics and returns the model's 14-tuple like the reference."""
+    sc, e = _test_step(model, images, config, eps_g, eps_l, u)
+    if metrics is not None:
+        _update_metrics(metrics, "test", sc, gm=True)
+    o = e.output
+    dx, dxh = o("dec_x"), o("dec_x_hat")
+    test_step_lg_gm_vae.last_scalars = sc
+    return (dx[..., :3], dx[..., 3:], o("z_x"), o("z_mean_x"), o("z_sig_x"), o("z_x_hat"), dxh[..., :3], dxh[..., 3:],
+            o("z_mean_x_hat"), o("z_sig_x_hat"), o("y"), o("y_logits"), o("z_prior_mean"), o("z_prior_sig"))
+
+
+test_step_lg_vae.__test__ = False       # not pytest tests, whatever their names
+test_step_lg_gm_vae.__test__ = False
+
+REPORT_TEMPLATE = ('Training step {}\n'
+                   '            X Recon Loss: {:.4f}, X KLD loss: {:.4f}, Total X loss: {:.4f} \n'
+                   '            X hat Recon Loss: {:.4f}, X hat KLD loss: {:.4f}, Total X hat loss: {:.4f} \n'
+                   '            Test X Recon Loss: {:.4f}, Test X KLD loss: {:.4f}, Test Total X loss: {:.4f} \n'
+                   '            Test X hat Recon Loss: {:.4f}, Test X hat KLD loss: {:.4f}, Test Total X hat loss: {:.4f}\n'
+                   '            Total KL train loss: {:.4f}, Total KL test loss: {:.4f}\n'
+                   '            Classifier recon acc: {:.4f}, Classifier random z_g acc: {:.4f}, Classifier random z_l acc: {:.4f}\n'
+                   '            Classifier cluster acc: {:.4f}\n'
+                   '            Y KL train loss: {:.4f}, Y KL test loss: {:.4f}')
+
+
+def format_report(step, m):
+    """The stdout report of vae/trainer.py:354-382 (same template, same argument order)."""
+    r = lambda k: m[k].result()
+    return REPORT_TEMPLATE.format(
+        step,
+        r("x_recon_train_loss"), r("x_kl_train_loss"), r("x_recon_train_loss") + r("x_kl_train_loss"),
+        r("x_hat_recon_train_loss"), r("x_hat_kl_train_loss"), r("x_hat_recon_train_loss") + r("x_hat_kl_train_loss"),
+        r("x_recon_test_loss"), r("x_kl_test_loss"), r("x_recon_test_loss") + r("x_kl_test_loss"),
+        r("x_hat_recon_test_loss"), r("x_hat_kl_test_loss"), r("x_hat_recon_test_loss") + r("x_hat_kl_test_loss"),
+        r("total_kl_train_loss"), r("total_kl_test_loss"),
+        0.0, 0.0, 0.0, 0.0,
+        r("y_kl_train_loss"), r("y_kl_test_loss"))
+
+
+def reset_reported(m):
+    """Only the metrics the reference resets after a report (vae/trainer.py:405-414): x_hat_* and y_kl_* keep running."""
+    for k in ("x_recon_train_loss", "x_kl_train_loss", "x_recon_test_loss", "x_kl_test_loss", "total_kl_test_loss",
+              "total_kl_train_loss"):
+        m[k].reset_states()
+
+
 _RUNNERS = {}
 
 
@@ -182,7 +297,10 @@ def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, tes
         train_step = train_step_lg_gm_vae
     else:
         raise NotImplementedError(type(model).__name__)
+    gm = isinstance(model, LGGMVae)
+    test_step = test_step_lg_gm_vae if gm else test_step_lg_vae
     report_every = int(config.get("report_every", 10000) or 10000)
+    metrics = make_metrics()
     start = time.time()
     history = []
     for step, train_data in enumerate(train_dataset):
@@ -191,10 +309,22 @@ def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, tes
             images = images.cuda(non_blocking=True)
         train_step(model, images, optimizer, config)
         if step % report_every == 0:
+            # (the reference updates its train metrics every step inside the tf.function; reading the device scalars every
+            # step would put a host synchronisation into the hot loop, so they are sampled at the report steps)
             sc = _RUNNERS[id(model)].scalars()
+            _update_metrics(metrics, "train", sc, gm)
             history.append((step, sc))
             print("Training time: {:.2f}".format(time.time() - start))
-            print("step {}: ".format(step) + ", ".join("{}: {:.4f}".format(k, v) for k, v in sc.items()), flush=True)
+            start = time.time()
+            if test_dataset is not None:                      # evaluation pass, vae/trainer.py:316-352
+                for test_data in test_dataset:
+                    test_images = test_data[0] if config.get("label") else test_data
+                    if not test_images.is_cuda:
+                        test_images = test_images.cuda(non_blocking=True)
+                    test_step(model, test_images, config=config, metrics=metrics)
+                print("Testing time: {:.2f}".format(time.time() - start))
+            print(format_report(step, metrics), flush=True)
+            reset_reported(metrics)
             start = time.time()
         if step >= int(config.get("training_steps")):  # vae/trainer.py:417-419
             print('Training done!')
