@@ -25,7 +25,7 @@ SYMBOLS = ["sv_create", "sv_destroy", "sv_last_error", "sv_version", "sv_param_c
            "sv_num_segments", "sv_segment_range", "sv_backward_segment", "sv_adam_step", "sv_adam_segment", "sv_train_step",
            "sv_output_ptr", "sv_decode", "sv_encode_y", "sv_get_iterations", "sv_set_iterations", "sv_launch_count",
            "sv_discretised_logistic_loss", "sv_adam_flat", "sv_stage_scramble", "sv_debug_layer_count",
-           "sv_debug_layer_info", "sv_debug_run_layer"]
+           "sv_debug_layer_info", "sv_debug_run_layer", "sv_debug_halo_trace"]
 
 
 class SvConfig(C.Structure):
@@ -104,6 +104,8 @@ def load():
     lib.sv_debug_layer_count.argtypes = [vp]
     lib.sv_debug_layer_info.argtypes = [vp, i32, C.POINTER(SvLayerInfo)]
     lib.sv_debug_run_layer.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.sv_debug_halo_trace.argtypes = [vp, i32]
+    lib.sv_debug_halo_trace.restype = i32
     _lib = lib
     return lib
 

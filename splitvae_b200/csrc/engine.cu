@@ -985,6 +985,12 @@ sv_status sv_debug_run_layer(sv_handle* h, int32_t i, int32_t pass, int32_t impl
   return check_launch(h, "sv_debug_run_layer");
 }
 
+int32_t sv_debug_halo_trace(uint64_t* out_host, int32_t max_ctas) {
+  if (!out_host || max_ctas < 1) return -1;
+  cudaDeviceSynchronize();
+  return tc_halo_trace_read((unsigned long long*)out_host, max_ctas);
+}
+
 sv_status sv_stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int32_t B, int32_t H, int32_t W, int32_t p, void* stream) {
   if (!u8 || !perm || !inputs || B < 1 || p < 1 || H % p || W % p) return SV_ERR_INVALID;
   stage_scramble(u8, perm, inputs, B, H, W, p, (cudaStream_t)stream);

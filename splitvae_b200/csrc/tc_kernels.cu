@@ -60,87 +60,131 @@ __device__ __forceinline__ float mask_t(float y) {
   return 1.f;
 }
 
+// Loop-invariant epilogue parameters, read ONCE into registers.  (ncu, round 1: with the launch descriptor read in place, every
+// asm("memory") clobber - each tcgen05.ld / wait - forced the fields to be re-read through a generic pointer, LD.E + long
+// scoreboard stall per field per block, and the epilogue took ~70 % of a halo CTA's lifetime.)
+struct EpiRegs {
+  const float* bias;
+  const bf16* mask_src;
+  void* out;
+  int tile_cols, n_valid, out_ld, mask_ld, mask_coff;
+};
+__device__ __forceinline__ EpiRegs load_epi_regs(const TcLaunch& P) {
+  EpiRegs E;
+  E.bias = P.bias; E.mask_src = (const bf16*)P.mask_src; E.out = P.out;
+  E.tile_cols = P.tile_cols; E.n_valid = P.n_valid; E.out_ld = P.out_ld; E.mask_ld = P.mask_ld; E.mask_coff = P.mask_coff;
+  return E;
+}
+
+// Finishes one block of 16 accumulator columns whose tcgen05.ld into v[] is in flight: the block's mask loads are issued first
+// (they overlap the TMEM load), then the wait, then the NEXT block's tcgen05.ld is started into vn[] so that its latency hides
+// behind this block's arithmetic and stores.  (Blocks of 16: two register sets of 32 columns spilled at 3 CTAs per SM.)
+constexpr int kEpiBW = 16;
 template <int ACT, int MASK, bool OUT_F32>
-__device__ __forceinline__ void epilogue_rows_t(const TcLaunch& P, uint32_t tmem_acc, int quarter, bool valid, long long opix, int n_tile) {
-  const int col_base = n_tile * P.tile_cols;
+__device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpiBW], int cfirst, long long opix, bool valid,
+                                            uint32_t next_taddr, uint32_t (&vn)[kEpiBW]) {
   const int esz = OUT_F32 ? 4 : 2;
-  const bool vec_ok = ((P.out_ld * esz) % 16) == 0;
-  const bool mask_vec = MASK != ACT_NONE && (P.mask_ld % 8) == 0 && (P.mask_coff % 8) == 0;
-  const bf16* mrow = MASK != ACT_NONE ? (const bf16*)P.mask_src + opix * P.mask_ld + P.mask_coff : nullptr;
-  for (int c0 = 0; c0 < P.tile_cols; c0 += 32) {
-    uint32_t v[32];
-    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-    const int ncol = min(32, P.tile_cols - c0);
-    if (ncol >= 32) tc::tmem_ld32(taddr, v); else tc::tmem_ld16(taddr, v);
-    tc::tmem_ld_wait();
-    if (!valid) continue;
-    const int cfirst = col_base + c0;
-    float f[32];
+  const bool vec_ok = ((E.out_ld * esz) % 16) == 0;
+  const bool mask_vec = MASK != ACT_NONE && (E.mask_ld % 8) == 0 && (E.mask_coff % 8) == 0 && cfirst + kEpiBW <= E.n_valid;
+  const bf16* mrow = MASK != ACT_NONE ? E.mask_src + opix * E.mask_ld + E.mask_coff + cfirst : nullptr;
+  uint4 mq[kEpiBW / 8];
+  if (MASK != ACT_NONE && mask_vec && valid) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-    if (P.bias) {   // packed bias is padded to n_pad (zeros beyond n_valid), 16-byte aligned
-      const float4* bp = reinterpret_cast<const float4*>(P.bias + cfirst);
+    for (int i = 0; i < kEpiBW / 8; ++i) mq[i] = __ldg(reinterpret_cast<const uint4*>(mrow + i * 8));
+  }
+  tc::tmem_ld_wait();
+  if (next_taddr != 0u) tc::tmem_ld16(next_taddr, vn);
+  if (!valid) return;
+  float f[kEpiBW];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i * 4 < ncol) {
-          const float4 b = __ldg(bp + i);
-          f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
-        }
-      }
+  for (int i = 0; i < kEpiBW; ++i) f[i] = __uint_as_float(v[i]);
+  if (E.bias) {   // packed bias is padded to n_pad (zeros beyond n_valid), 16-byte aligned; L1-resident after the first block
+    const float4* bp = reinterpret_cast<const float4*>(E.bias + cfirst);
+#pragma unroll
+    for (int i = 0; i < kEpiBW / 4; ++i) {
+      const float4 b = __ldg(bp + i);
+      f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
     }
-    if (ACT != ACT_NONE) {
+  }
+  if (ACT != ACT_NONE) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = act_t<ACT>(f[i]);
-    }
-    if (MASK != ACT_NONE) {
-      if (mask_vec && cfirst + ncol <= P.n_valid) {
+    for (int i = 0; i < kEpiBW; ++i) f[i] = act_t<ACT>(f[i]);
+  }
+  if (MASK != ACT_NONE) {
+    if (mask_vec) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          if (i < ncol) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow + cfirst + i));
-            f[i + 0] *= mask_t<MASK>(__uint_as_float(q.x << 16)); f[i + 1] *= mask_t<MASK>(__uint_as_float(q.x & 0xffff0000u));
-            f[i + 2] *= mask_t<MASK>(__uint_as_float(q.y << 16)); f[i + 3] *= mask_t<MASK>(__uint_as_float(q.y & 0xffff0000u));
-            f[i + 4] *= mask_t<MASK>(__uint_as_float(q.z << 16)); f[i + 5] *= mask_t<MASK>(__uint_as_float(q.z & 0xffff0000u));
-            f[i + 6] *= mask_t<MASK>(__uint_as_float(q.w << 16)); f[i + 7] *= mask_t<MASK>(__uint_as_float(q.w & 0xffff0000u));
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < ncol && cfirst + i < P.n_valid) f[i] *= mask_t<MASK>(__bfloat162float(mrow[cfirst + i]));
-      }
-    }
-    if (OUT_F32) {
-      float* o = (float*)P.out + opix * P.out_ld + cfirst;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (i < ncol) {
-          if (vec_ok && cfirst + i + 4 <= P.n_valid) {
-            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (cfirst + i + q < P.n_valid) o[i + q] = f[i + q];
-          }
-        }
+      for (int i = 0; i < kEpiBW / 8; ++i) {
+        const uint4 q = mq[i];
+        const int o = 8 * i;
+        f[o + 0] *= mask_t<MASK>(__uint_as_float(q.x << 16)); f[o + 1] *= mask_t<MASK>(__uint_as_float(q.x & 0xffff0000u));
+        f[o + 2] *= mask_t<MASK>(__uint_as_float(q.y << 16)); f[o + 3] *= mask_t<MASK>(__uint_as_float(q.y & 0xffff0000u));
+        f[o + 4] *= mask_t<MASK>(__uint_as_float(q.z << 16)); f[o + 5] *= mask_t<MASK>(__uint_as_float(q.z & 0xffff0000u));
+        f[o + 6] *= mask_t<MASK>(__uint_as_float(q.w << 16)); f[o + 7] *= mask_t<MASK>(__uint_as_float(q.w & 0xffff0000u));
       }
     } else {
-      bf16* o = (bf16*)P.out + opix * P.out_ld + cfirst;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (i < ncol) {
-          if (vec_ok && cfirst + i + 8 <= P.n_valid) {
-            uint4 pk;
-            pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
-            pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
-            *reinterpret_cast<uint4*>(o + i) = pk;
-          } else {
+      for (int i = 0; i < kEpiBW; ++i)
+        if (cfirst + i < E.n_valid) f[i] *= mask_t<MASK>(__bfloat162float(mrow[i]));
+    }
+  }
+  if (OUT_F32) {
+    float* o = (float*)E.out + opix * E.out_ld + cfirst;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (cfirst + i + q < P.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
-          }
-        }
+    for (int i = 0; i < kEpiBW; i += 4) {
+      if (vec_ok && cfirst + i + 4 <= E.n_valid) {
+        *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (cfirst + i + q < E.n_valid) o[i + q] = f[i + q];
       }
+    }
+  } else {
+    bf16* o = (bf16*)E.out + opix * E.out_ld + cfirst;
+#pragma unroll
+    for (int i = 0; i < kEpiBW; i += 8) {
+      if (vec_ok && cfirst + i + 8 <= E.n_valid) {
+        uint4 pk;
+        pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
+        pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
+        *reinterpret_cast<uint4*>(o + i) = pk;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (cfirst + i + q < E.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
+      }
+    }
+  }
+}
+
+// Drains `n_acc` accumulators (each tile_cols columns - a multiple of 16 -, `acc_stride` TMEM columns apart) of this thread's TMEM
+// lane.  Accumulator a belongs to output pixel opix0 + (a / mtx) * step_ty + (a % mtx) * step_tx (igemm: one accumulator; halo
+// kernel: mtx x mty).  Blocks of 16 columns are software-pipelined through two register sets (see epi_block_t).
+template <int ACT, int MASK, bool OUT_F32>
+__device__ __forceinline__ void epilogue_acc_t(const EpiRegs& E, uint32_t tmem_lane, int n_acc, int acc_stride, int mtx, long long opix0,
+                                               long long step_tx, long long step_ty, bool valid, int col_base) {
+  const int cpb = E.tile_cols / kEpiBW;                // column blocks per accumulator
+  const int nblk = n_acc * cpb;
+  uint32_t va[kEpiBW], vb[kEpiBW];
+  int cb = 0, tx = 0;                                  // current block: column block cb of the accumulator at (.., tx)
+  uint32_t taddr = tmem_lane;                          // TMEM address of the current block
+  long long opix = opix0;
+  const uint32_t acc_skip = (uint32_t)(acc_stride - (cpb - 1) * kEpiBW);   // last block of an accumulator -> first of the next
+  tc::tmem_ld16(taddr, va);
+  for (int j = 0; j < nblk; j += 2) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (j + half >= nblk) break;
+      const bool last_cb = cb + 1 == cpb;
+      const uint32_t next = taddr + (last_cb ? acc_skip : (uint32_t)kEpiBW);
+      const uint32_t next_taddr = j + half + 1 < nblk ? next : 0u;
+      if (half == 0) epi_block_t<ACT, MASK, OUT_F32>(E, va, col_base + cb * kEpiBW, opix, valid, next_taddr, vb);
+      else epi_block_t<ACT, MASK, OUT_F32>(E, vb, col_base + cb * kEpiBW, opix, valid, next_taddr, va);
+      taddr = next;
+      if (last_cb) {
+        cb = 0;
+        if (++tx == mtx) { tx = 0; opix += step_ty - (long long)(mtx - 1) * step_tx; } else opix += step_tx;
+      } else ++cb;
     }
   }
 }
@@ -152,41 +196,10 @@ __device__ __forceinline__ EpiSel epilogue_select(const TcLaunch& P, int n_tile)
   while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
   return EpiSel{P.part_act[j], P.mask_act, P.out_f32};
 }
-#define SV_EPI_CALL(A, M, F) epilogue_rows_t<A, M, F>(P, tmem_acc, quarter, valid, opix, n_tile)
-__device__ __forceinline__ void epilogue_rows(const TcLaunch& P, EpiSel e, uint32_t tmem_acc, int quarter, bool valid, long long opix, int n_tile) {
+#define SV_EPI_CALL(A, M, F) epilogue_acc_t<A, M, F>(E, tmem_lane, n_acc, acc_stride, mtx, opix0, step_tx, step_ty, valid, col_base)
+__device__ __forceinline__ void epilogue_dispatch(const EpiRegs& E, EpiSel e, uint32_t tmem_lane, int n_acc, int acc_stride, int mtx, long long opix0,
+                                                  long long step_tx, long long step_ty, bool valid, int col_base) {
   if (e.mask != ACT_NONE) {            // dgrad: linear, bf16 out
-    if (e.mask == ACT_RELU) SV_EPI_CALL(ACT_NONE, ACT_RELU, false);
-    else if (e.mask == ACT_ELU) SV_EPI_CALL(ACT_NONE, ACT_ELU, false);
-    else SV_EPI_CALL(ACT_NONE, ACT_SOFTPLUS, false);
-  } else if (e.f32) {
-    if (e.act == ACT_NONE) SV_EPI_CALL(ACT_NONE, ACT_NONE, true);
-    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, true);
-    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, true);
-    else SV_EPI_CALL(ACT_RELU, ACT_NONE, true);
-  } else {
-    if (e.act == ACT_RELU) SV_EPI_CALL(ACT_RELU, ACT_NONE, false);
-    else if (e.act == ACT_ELU) SV_EPI_CALL(ACT_ELU, ACT_NONE, false);
-    else if (e.act == ACT_SOFTPLUS) SV_EPI_CALL(ACT_SOFTPLUS, ACT_NONE, false);
-    else SV_EPI_CALL(ACT_NONE, ACT_NONE, false);
-  }
-}
-#undef SV_EPI_CALL
-
-// halo kernel: the loop over the CTA's accumulators lives INSIDE each instantiation (one dispatch per thread)
-template <int ACT, int MASK, bool OUT_F32>
-__device__ __noinline__ void halo_epilogue_t(const TcLaunch& P, uint32_t tmem_base, int quarter, int lane, int n, int y0, int x0, int n_tile) {
-  const int row = quarter * 32 + lane;
-  const int g = row >> 3, i = row & 7;
-  for (int ty = 0; ty < P.mty; ++ty)
-    for (int tx = 0; tx < P.mtx; ++tx) {
-      const int y = y0 + ty * 16 + g, x = x0 + tx * 8 + i;
-      const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
-      epilogue_rows_t<ACT, MASK, OUT_F32>(P, tmem_base + (uint32_t)((ty * P.mtx + tx) * P.tile_cols), quarter, true, opix, n_tile);
-    }
-}
-#define SV_EPI_CALL(A, M, F) halo_epilogue_t<A, M, F>(P, tmem_base, quarter, lane, n, y0, x0, n_tile)
-__device__ __forceinline__ void halo_epilogue(const TcLaunch& P, EpiSel e, uint32_t tmem_base, int quarter, int lane, int n, int y0, int x0, int n_tile) {
-  if (e.mask != ACT_NONE) {
     if (e.mask == ACT_RELU) SV_EPI_CALL(ACT_NONE, ACT_RELU, false);
     else if (e.mask == ACT_ELU) SV_EPI_CALL(ACT_NONE, ACT_ELU, false);
     else SV_EPI_CALL(ACT_NONE, ACT_SOFTPLUS, false);
@@ -272,6 +285,8 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global -----------------------------------------
+    const EpiRegs E = load_epi_regs(P);         // (before the wait: these loads overlap the main loop)
+    const EpiSel esel = epilogue_select(P, n_tile);
     tc::mbar_wait(&ctl->tmem_full, 0);
     tc::tc_fence_after();
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
@@ -295,7 +310,7 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
     const int n = n0 + nn, y = y0 + hh, x = ww;
     const bool valid = n < P.n_img;
     const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
-    epilogue_rows(P, epilogue_select(P, n_tile), tmem_base, quarter, valid, opix, n_tile);
+    epilogue_dispatch(E, esel, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, 0, 1, opix, 0, 0, valid, n_tile * P.tile_cols);
     }
   }
   tc::tc_fence_before();
@@ -306,12 +321,12 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
   }
 }
 
-__global__ void __launch_bounds__(kThreads) igemm_kernel(const __grid_constant__ TcLaunch P) { igemm_body(P, blockIdx.z); }
+__global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constant__ TcLaunch P) { igemm_body(P, blockIdx.z); }
 
 // The s*s parity classes of a stride-s dgrad (each a small stride-1 convolution scattering into its own output parity)
 // as ONE launch: blockIdx.z selects the class.  4 x more CTAs in flight for layers whose single class does not fill the GPU.
 struct TcLaunch4 { TcLaunch l[4]; };
-__global__ void __launch_bounds__(kThreads) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { igemm_body(P4.l[blockIdx.z], 0); }
+__global__ void __launch_bounds__(kThreads, 3) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { igemm_body(P4.l[blockIdx.z], 0); }
 
 // Split-K finish for dense layers (one output row per image): out[row][col] = epilogue(sum_z partial[z][row][col]).
 // Fixed summation order -> deterministic.  One thread per output element; consecutive threads = consecutive columns.
@@ -364,6 +379,18 @@ __device__ __forceinline__ void halo_issue_kb(uint64_t da0, uint64_t db0, uint32
   }
 }
 
+// SV_HALO_TRACE=1: every halo CTA records the SM clock at its phase boundaries (sv_debug_halo_trace reads the buffer back):
+//   [0] smid  [1] CTA start  [2] setup done  [3] halo landed (MMA warp)  [4] last MMA issued  [5] accumulators complete
+//   (epilogue warp)  [6] epilogue done  [7] globaltimer at start
+constexpr int kTraceSlots = 8, kTraceCtas = 8192;
+__device__ unsigned long long g_halo_trace[kTraceSlots * kTraceCtas];
+__device__ __forceinline__ void trace_mark(int on, int slot) {
+  if (on) {
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta < kTraceCtas) g_halo_trace[cta * kTraceSlots + slot] = (unsigned long long)clock64();
+  }
+}
+
 struct HaloCtl {
   uint64_t halo_full;
   uint64_t w_full[kMaxStages];
@@ -392,7 +419,18 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
   const int num_stages_total = (num_kb + P.kb_per_stage - 1) / P.kb_per_stage;
   const int MT = P.mtx * P.mty;
 
+  const int tr = P.trace;
   if (threadIdx.x == 0) {
+    if (tr) {
+      const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if (cta < kTraceCtas) {
+        unsigned smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_halo_trace[cta * kTraceSlots + 0] = smid; g_halo_trace[cta * kTraceSlots + 7] = gt;
+      }
+      trace_mark(tr, 1);
+    }
     tc::prefetch_tmap(&P.map_a);
     tc::prefetch_tmap(&P.map_b);
     tc::mbar_init(&ctl->halo_full, 1);
@@ -435,8 +473,10 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
       const uint32_t a_sbo = (uint32_t)(sy * P.TWp) * pix;   // next row group = next output row = sy input rows
       const uint32_t b_sbo = 8u * pix;                       // weights: dense [tile_cols][bk]
       const uint32_t halo_addr = tc::smem_u32(halo);
+      trace_mark(tr, 2);
       tc::mbar_wait(&ctl->halo_full, 0);
       tc::tc_fence_after();
+      trace_mark(tr, 3);
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 B): build one template per
       // operand and add offsets, so the single issuing thread spends a handful of instructions per MMA.
       const uint64_t a_tmpl = tc::make_smem_desc(0, 16, a_sbo, lt), b_tmpl = tc::make_smem_desc(0, 16, b_sbo, lt);
@@ -481,11 +521,21 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
         tc::umma_commit(&ctl->w_empty[slot]);
       }
       tc::umma_commit(&ctl->tmem_full);
+      trace_mark(tr, 4);
     }
   } else {
+    const EpiRegs E = load_epi_regs(P);         // (before the wait: these loads overlap the main loop)
+    const EpiSel esel = epilogue_select(P, n_tile);
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const int y = y0 + (row >> 3), x = x0 + (row & 7);             // accumulator (0,0): row group = image row, 8 pixels wide
+    const long long opix0 = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
+    const long long step_tx = 8LL * P.osx, step_ty = 16LL * P.osy * P.OW;
+    const int mtx = P.mtx, n_acc = MT, acc_stride = P.tile_cols, col_base = n_tile * P.tile_cols;
     tc::mbar_wait(&ctl->tmem_full, 0);
     tc::tc_fence_after();
-    halo_epilogue(P, epilogue_select(P, n_tile), tmem_base, warp & 3, lane, n, y0, x0, n_tile);
+    if (threadIdx.x == 64) trace_mark(tr, 5);
+    epilogue_dispatch(E, esel, tmem_base + ((uint32_t)(quarter * 32) << 16), n_acc, acc_stride, mtx, opix0, step_tx, step_ty, true, col_base);
+    if (threadIdx.x == 64) trace_mark(tr, 6);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -495,9 +545,9 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) halo_conv_kernel(const __grid_constant__ TcLaunch P) { halo_body(P); }
+__global__ void __launch_bounds__(kThreads, 3) halo_conv_kernel(const __grid_constant__ TcLaunch P) { halo_body(P); }
 // the 4 parity classes of a stride-2 dgrad as one launch (blockIdx.z = class), as igemm4_kernel
-__global__ void __launch_bounds__(kThreads) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { halo_body(P4.l[blockIdx.z]); }
+__global__ void __launch_bounds__(kThreads, 3) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { halo_body(P4.l[blockIdx.z]); }
 
 // ------------------------------------------------------------------------------------------------
 // N-stacked persistent convolution (see TcNsConv in tc_kernels.h).
@@ -1631,6 +1681,7 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
   }
   if (!best_tw) return;
   L.halo = 1;
+  L.trace = env_int("SV_HALO_TRACE", 0);
   L.halo_sx = sx; L.halo_sy = sy;
   L.TW = best_tw; L.TH = best_th; L.TWp = best_tw + wtaps - 1; L.THp = (best_th - 1) * sy + L.taps_h;
   L.mtx = best_tw / 8; L.mty = best_th / 16;
@@ -1713,7 +1764,7 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   }
   H.tiles_x = g.Wo / H.TW; H.tiles_y = g.Ho / H.TH; H.n_img = g.B;
   H.tiles = H.tiles_x * H.tiles_y * g.B;
-  int ks = env_int("SV_HWG_SPLITS", 148) / H.m_splits;
+  int ks = env_int("SV_HWG_SPLITS", 37) / H.m_splits;   // measured (B200, C2 step): 148 -> 1.78 ms, 74 -> 1.71, 37 -> 1.68, 26 -> 1.71, 18 -> 1.83 (the wgrads share the GPU with the dgrad chain)
   if (ks < 1) ks = 1;
   if (ks > H.tiles) ks = H.tiles;
   H.tiles_per_split = (H.tiles + ks - 1) / ks;
@@ -2258,6 +2309,12 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
 }
 
 static void launch_ns(const TcNsConv& P, cudaStream_t s) { nsconv_kernel<<<P.grid, kNsThreads, P.smem_bytes, s>>>(P); }
+
+int tc_halo_trace_read(unsigned long long* out, int max_ctas) {
+  const int n = max_ctas < kTraceCtas ? max_ctas : kTraceCtas;
+  if (cudaMemcpyFromSymbol(out, g_halo_trace, (size_t)n * kTraceSlots * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  return n;
+}
 
 void tc_conv_fwd(TcLayer& t, cudaStream_t s) {
   if (t.fwd_ns) launch_ns(t.ns_fwd, s); else launch(t.fwd, s);

@@ -42,6 +42,7 @@ struct TcLaunch {
   // sx*x0 - pad_l + p + sx*j, loaded with TMA element stride sx; filter column b = sx*b' + p reads plane p shifted by b'),
   // halo_sy = input rows per output row (the UMMA row-group stride).  TWp = plane width, THp = (TH-1)*sy + taps_h.
   int halo_sx, halo_sy;
+  int trace;                                    // SV_HALO_TRACE: record per-CTA phase clocks (debugging)
   // split-K (skinny dense GEMMs: few output tiles, long K): blockIdx.z owns kb_per_split k-blocks and stores its raw fp32
   // accumulator to partial[z][m_pad][n_pad]; splitk_finish_kernel sums the splits in a fixed order and applies the epilogue
   int k_splits, kb_per_split, m_pad, n_pad;
@@ -176,5 +177,6 @@ void tc_conv_fwd(TcLayer& t, cudaStream_t s);
 void tc_conv_dgrad(TcLayer& t, cudaStream_t s);
 void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s);
 const char* tc_last_error();
+int tc_halo_trace_read(unsigned long long* out, int max_ctas);   // 8 words per CTA, see g_halo_trace
 
 }  // namespace sv
