@@ -82,7 +82,7 @@ __device__ __forceinline__ EpiRegs load_epi_regs(const TcLaunch& P) {
 constexpr int kEpiBW = 16;
 template <int ACT, int MASK, bool OUT_F32>
 __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpiBW], int cfirst, long long opix, bool valid,
-                                            uint32_t next_taddr, uint32_t (&vn)[kEpiBW]) {
+                                            uint32_t next_taddr, uint32_t (&vn)[kEpiBW], uint64_t* release_bar = nullptr) {
   const int esz = OUT_F32 ? 4 : 2;
   const bool vec_ok = ((E.out_ld * esz) % 16) == 0;
   const bool mask_vec = MASK != ACT_NONE && (E.mask_ld % 8) == 0 && (E.mask_coff % 8) == 0 && cfirst + kEpiBW <= E.n_valid;
@@ -94,6 +94,11 @@ __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpi
   }
   tc::tmem_ld_wait();
   if (next_taddr != 0u) tc::tmem_ld16(next_taddr, vn);
+  else if (release_bar) {       // persistent kernel: the last block has left TMEM -> hand the accumulator set back to the MMA warp
+    tc::tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(release_bar);
+  }
   if (!valid) return;
   float f[kEpiBW];
 #pragma unroll
@@ -162,7 +167,7 @@ __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpi
 // kernel: mtx x mty).  Blocks of 16 columns are software-pipelined through two register sets (see epi_block_t).
 template <int ACT, int MASK, bool OUT_F32>
 __device__ __forceinline__ void epilogue_acc_t(const EpiRegs& E, uint32_t tmem_lane, int n_acc, int acc_stride, int mtx, long long opix0,
-                                               long long step_tx, long long step_ty, bool valid, int col_base) {
+                                               long long step_tx, long long step_ty, bool valid, int col_base, uint64_t* release_bar = nullptr) {
   const int cpb = E.tile_cols / kEpiBW;                // column blocks per accumulator
   const int nblk = n_acc * cpb;
   uint32_t va[kEpiBW], vb[kEpiBW];
@@ -178,8 +183,8 @@ __device__ __forceinline__ void epilogue_acc_t(const EpiRegs& E, uint32_t tmem_l
       const bool last_cb = cb + 1 == cpb;
       const uint32_t next = taddr + (last_cb ? acc_skip : (uint32_t)kEpiBW);
       const uint32_t next_taddr = j + half + 1 < nblk ? next : 0u;
-      if (half == 0) epi_block_t<ACT, MASK, OUT_F32>(E, va, col_base + cb * kEpiBW, opix, valid, next_taddr, vb);
-      else epi_block_t<ACT, MASK, OUT_F32>(E, vb, col_base + cb * kEpiBW, opix, valid, next_taddr, va);
+      if (half == 0) epi_block_t<ACT, MASK, OUT_F32>(E, va, col_base + cb * kEpiBW, opix, valid, next_taddr, vb, release_bar);
+      else epi_block_t<ACT, MASK, OUT_F32>(E, vb, col_base + cb * kEpiBW, opix, valid, next_taddr, va, release_bar);
       taddr = next;
       if (last_cb) {
         cb = 0;
@@ -196,9 +201,9 @@ __device__ __forceinline__ EpiSel epilogue_select(const TcLaunch& P, int n_tile)
   while (j + 1 < P.nparts && c >= P.part_n[j]) { c -= P.part_n[j]; ++j; }
   return EpiSel{P.part_act[j], P.mask_act, P.out_f32};
 }
-#define SV_EPI_CALL(A, M, F) epilogue_acc_t<A, M, F>(E, tmem_lane, n_acc, acc_stride, mtx, opix0, step_tx, step_ty, valid, col_base)
+#define SV_EPI_CALL(A, M, F) epilogue_acc_t<A, M, F>(E, tmem_lane, n_acc, acc_stride, mtx, opix0, step_tx, step_ty, valid, col_base, release_bar)
 __device__ __forceinline__ void epilogue_dispatch(const EpiRegs& E, EpiSel e, uint32_t tmem_lane, int n_acc, int acc_stride, int mtx, long long opix0,
-                                                  long long step_tx, long long step_ty, bool valid, int col_base) {
+                                                  long long step_tx, long long step_ty, bool valid, int col_base, uint64_t* release_bar = nullptr) {
   if (e.mask != ACT_NONE) {            // dgrad: linear, bf16 out
     if (e.mask == ACT_RELU) SV_EPI_CALL(ACT_NONE, ACT_RELU, false);
     else if (e.mask == ACT_ELU) SV_EPI_CALL(ACT_NONE, ACT_ELU, false);
@@ -548,6 +553,210 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
 __global__ void __launch_bounds__(kThreads, 3) halo_conv_kernel(const __grid_constant__ TcLaunch P) { halo_body(P); }
 // the 4 parity classes of a stride-2 dgrad as one launch (blockIdx.z = class), as igemm4_kernel
 __global__ void __launch_bounds__(kThreads, 3) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { halo_body(P4.l[blockIdx.z]); }
+
+// ------------------------------------------------------------------------------------------------
+// Persistent, pipelined variant of the halo convolution (same operand addressing as halo_body).
+// The one-tile-per-CTA kernel above runs its phases back to back and co-resident CTAs fall into lockstep (per-CTA phase trace,
+// d5 dgrad: 900 setup + 2400 halo wait + 23500 MMA phase shared by 3 CTAs + 4000 epilogue of a 31400-cycle lifetime): the tensor
+// pipe idles a third of the time and every CTA re-fetches the weights.  Here one CTA per SM keeps the packed weights resident,
+// streams halos through an `p_stages`-deep ring and double-buffers the accumulators in TMEM:
+//   warp 0      TMA producer: weights once, then one halo per tile
+//   warp 1      single-thread MMA issuer: tile i -> accumulator set i % 2
+//   warps 2-5   epilogue of the even tiles (set 0),  warps 6-9: odd tiles (set 1); a set hands its accumulators back as soon as
+//               its last TMEM read has completed, so load(i+1), MMA(i) and the epilogues of i-1 / i-2 overlap.
+// blockIdx.y selects one of up to 4 launches (the parity classes of a stride-2 dgrad) that share the geometry.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPcThreads = 64 + 8 * 32;
+constexpr int kPcMaxStages = 6;
+struct PcCtl {
+  uint64_t w_full, halo_full[kPcMaxStages], halo_empty[kPcMaxStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+// MMAs of one tile, fully unrolled for the shapes of this model family (one channel chunk, unit column stride, one accumulator
+// row): KH x KW taps x KS k-steps x MTX accumulators.  The single issuing thread must spend only a few instructions per
+// tcgen05.mma - the generic nest costs ~60 per k-block and capped d5 dgrad at 85 cycles per MMA (44 is the pipe's own rate).
+template <int KH, int KW, int KS, int MTX>
+__device__ __forceinline__ void pc_issue_tile(uint64_t da0, uint64_t db0, uint32_t acc, uint32_t tile_cols, uint32_t idesc, uint32_t row_step,
+                                              uint32_t pix_step, uint32_t kb_step, uint32_t tx_step) {
+#pragma unroll
+  for (int a = 0; a < KH; ++a) {
+#pragma unroll
+    for (int b = 0; b < KW; ++b) {
+      const uint64_t da = da0 + (uint64_t)(a * row_step + b * pix_step);
+      const uint64_t db = db0 + (uint64_t)((a * KW + b) * kb_step);
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+#pragma unroll
+        for (int tx = 0; tx < MTX; ++tx)
+          tc::umma_bf16(acc + tx * tile_cols, da + (uint64_t)(tx * tx_step + 2u * k), db + 2u * k, idesc, (a | b | k) != 0 ? 1u : 0u);
+      }
+    }
+  }
+}
+
+template <int ACT, int MASK, bool OUT_F32>
+__device__ __noinline__ void pconv_epilogue_t(const TcLaunch& P, PcCtl* ctl, uint32_t tmem_base, int set, int quarter, int lane) {
+  const int row = quarter * 32 + lane;
+  const EpiRegs E = load_epi_regs(P);
+  const long long step_tx = 8LL * P.osx, step_ty = 16LL * P.osy * P.OW;
+  const int mtx = P.mtx, MT = P.mtx * P.mty, TW = P.TW, TH = P.TH, tiles_x = P.tiles_x, OH = P.OH, OW = P.OW;
+  const int osy = P.osy, ooy = P.ooy, osx = P.osx, oox = P.oox;
+  const int acc_stride = P.tile_cols, acc_cols = MT * P.tile_cols;
+  const int tiles_per_img = P.tiles_x * P.tiles_y, tiles = tiles_per_img * P.n_img;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * acc_cols);
+  uint64_t* full = &ctl->acc_full[set];
+  uint64_t* empty = &ctl->acc_empty[set];
+  int i = set;
+  for (int t = blockIdx.x + set * gridDim.x; t < tiles; t += 2 * gridDim.x, i += 2) {
+    const int aph = (i >> 1) & 1;
+    const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+    const int tile_y = r / tiles_x, tile_x = r - tile_y * tiles_x;
+    const int y = tile_y * TH + (row >> 3), x = tile_x * TW + (row & 7);
+    const long long opix0 = ((long long)n * OH + (y * osy + ooy)) * OW + (x * osx + oox);
+    tc::mbar_wait(full, aph);
+    tc::tc_fence_after();
+    epilogue_acc_t<ACT, MASK, OUT_F32>(E, tmem_lane, MT, acc_stride, mtx, opix0, step_tx, step_ty, true, 0, empty);
+  }
+}
+
+__device__ __forceinline__ void pconv_body(const TcLaunch& P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nchunks = P.kc, sx = P.halo_sx, sy = P.halo_sy, nst = P.p_stages;
+  const int stage_bytes = nchunks * sx * P.chunk_bytes;
+  uint8_t* wsm = smem;
+  uint8_t* halo = smem + P.p_wbytes;
+  PcCtl* ctl = reinterpret_cast<PcCtl*>(halo + (size_t)nst * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int num_kb = P.taps_h * P.taps_w * nchunks;
+  const int MT = P.mtx * P.mty;
+  const int acc_cols = MT * P.tile_cols;
+  const int tiles_per_img = P.tiles_x * P.tiles_y;
+  const int tiles = tiles_per_img * P.n_img;
+  const int kb_bytes = P.tile_cols * P.bk * 2;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&P.map_a);
+    tc::prefetch_tmap(&P.map_b);
+    tc::mbar_init(&ctl->w_full, 1);
+    for (int i = 0; i < nst; ++i) { tc::mbar_init(&ctl->halo_full[i], 1); tc::mbar_init(&ctl->halo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&ctl->acc_full[i], 1); tc::mbar_init(&ctl->acc_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * acc_cols)) tmem_cols <<= 1;
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(num_kb * kb_bytes));
+      for (int kb = 0; kb < num_kb; ++kb) tc::tma_load_2d(wsm + (size_t)kb * kb_bytes, &P.map_b, &ctl->w_full, kb * P.bk, 0);
+      const uint32_t halo_tx = (uint32_t)(nchunks * sx * P.THp * P.TWp * P.bk * 2);
+      int i = 0;
+      for (int t = cta; t < tiles; t += ncta, ++i) {
+        const int st = i % nst, ph = (i / nst) & 1;
+        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+        const int tile_y = r / P.tiles_x, tile_x = r - tile_y * P.tiles_x;
+        const int x0 = tile_x * P.TW, y0 = tile_y * P.TH;
+        tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
+        tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
+        for (int p = 0; p < sx; ++p)
+          for (int c = 0; c < nchunks; ++c)
+            tc::tma_load_4d(halo + (size_t)st * stage_bytes + (size_t)(p * nchunks + c) * P.chunk_bytes, &P.map_a, &ctl->halo_full[st], c * P.bk,
+                            sx * x0 - P.pad_l + p, sy * y0 - P.pad_t, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
+      const uint32_t lt = tc::layout_type_for(P.swizzle);
+      const uint32_t pix = (uint32_t)P.bk * 2u;
+      const uint32_t a_sbo = (uint32_t)(sy * P.TWp) * pix, b_sbo = 8u * pix;
+      const uint64_t a_tmpl = tc::make_smem_desc(0, 16, a_sbo, lt), b_tmpl = tc::make_smem_desc(0, 16, b_sbo, lt);
+      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * P.TWp) * pix) >> 4;
+      const uint32_t tile_cols = (uint32_t)P.tile_cols, chunk_bytes = (uint32_t)P.chunk_bytes;
+      const int ksteps = P.bk / 16, mtx = P.mtx, mty = P.mty, taps_w = P.taps_w, TWp = P.TWp;
+      const uint32_t halo_addr = tc::smem_u32(halo), w_addr = tc::smem_u32(wsm) >> 4, kb_step = (uint32_t)kb_bytes >> 4;
+      const bool env_shape_off = (P.trace & 2) != 0;      // SV_HALO_TRACE=2: generic issue loop (A/B)
+      // unrolled issue sequences: 1 = 6x6 taps, K 16, 4 accumulators (d5 dgrad); 2 = 6x3 pair taps (first layer, 64x64 images);
+      // 3 = 3x3 taps, K 64, 2 accumulators (e2 dgrad classes); 4 = first layer, 32x32 images
+      const int shape = (nchunks != 1 || sx != 1 || mty != 1 || env_shape_off) ? 0
+                        : (P.taps_h == 6 && taps_w == 6 && ksteps == 1 && mtx == 4) ? 1
+                        : (P.taps_h == 6 && taps_w == 3 && ksteps == 1 && mtx == 4) ? 2
+                        : (P.taps_h == 3 && taps_w == 3 && ksteps == 4 && mtx == 2) ? 3
+                        : (P.taps_h == 6 && taps_w == 3 && ksteps == 1 && mtx == 2) ? 4 : 0;
+      tc::mbar_wait(&ctl->w_full, 0);
+      int i = 0;
+      for (int t = cta; t < tiles; t += ncta, ++i) {
+        const int st = i % nst, ph = (i / nst) & 1;
+        const int ab = i & 1, aph = (i >> 1) & 1;
+        tc::mbar_wait(&ctl->halo_full[st], ph);
+        tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
+        tc::tc_fence_after();
+        const uint32_t h_addr = halo_addr + (uint32_t)st * (uint32_t)stage_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)(ab * acc_cols);
+        uint32_t b_addr = w_addr;
+        int ta = 0, tb = 0, chunk = 0;
+        if (shape) {
+          const uint64_t da0 = a_tmpl + (h_addr >> 4), db0 = b_tmpl + w_addr;
+          const uint32_t row_step = ((uint32_t)TWp * pix) >> 4, pix_step = pix >> 4;
+          if (shape == 1) pc_issue_tile<6, 6, 1, 4>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 2) pc_issue_tile<6, 3, 1, 4>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 3) pc_issue_tile<3, 3, 4, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else pc_issue_tile<6, 3, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+        } else
+        for (int kb = 0; kb < num_kb; ++kb, b_addr += kb_step) {
+          const uint32_t a_tap = sx == 1 ? (h_addr + (uint32_t)chunk * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
+                                         : (h_addr + (uint32_t)((tb % sx) * nchunks + chunk) * chunk_bytes + (uint32_t)(ta * TWp + tb / sx) * pix) >> 4;
+          const uint64_t db = b_tmpl + b_addr;
+          const uint32_t first = kb != 0;
+          switch (mtx) {
+            case 1: halo_issue_kb<1>(a_tmpl + a_tap, db, acc, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            case 2: halo_issue_kb<2>(a_tmpl + a_tap, db, acc, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            case 4: halo_issue_kb<4>(a_tmpl + a_tap, db, acc, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            default: halo_issue_kb<8>(a_tmpl + a_tap, db, acc, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+          }
+          if (++chunk == nchunks) { chunk = 0; if (++tb == taps_w) { tb = 0; ++ta; } }
+        }
+        tc::umma_commit(&ctl->halo_empty[st]);
+        tc::umma_commit(&ctl->acc_full[ab]);
+      }
+    }
+  } else {
+    const int set = (warp - 2) >> 2;            // accumulator set this warp drains (tiles i with i % 2 == set)
+    const EpiSel e = epilogue_select(P, 0);
+    // one dispatch per thread with the tile loop INSIDE each instantiation (with the dispatch inside the loop the compiler
+    // hoisted the loop invariants of all eleven variants at once: 168 registers and 20 KB of spill code)
+#define SV_PC_CALL(A, M, F) pconv_epilogue_t<A, M, F>(P, ctl, tmem_base, set, warp & 3, lane)
+    if (e.mask != ACT_NONE) {
+      if (e.mask == ACT_RELU) SV_PC_CALL(ACT_NONE, ACT_RELU, false);
+      else if (e.mask == ACT_ELU) SV_PC_CALL(ACT_NONE, ACT_ELU, false);
+      else SV_PC_CALL(ACT_NONE, ACT_SOFTPLUS, false);
+    } else if (e.f32) {
+      if (e.act == ACT_NONE) SV_PC_CALL(ACT_NONE, ACT_NONE, true);
+      else if (e.act == ACT_ELU) SV_PC_CALL(ACT_ELU, ACT_NONE, true);
+      else SV_PC_CALL(ACT_RELU, ACT_NONE, true);
+    } else {
+      if (e.act == ACT_RELU) SV_PC_CALL(ACT_RELU, ACT_NONE, false);
+      else if (e.act == ACT_ELU) SV_PC_CALL(ACT_ELU, ACT_NONE, false);
+      else SV_PC_CALL(ACT_NONE, ACT_NONE, false);
+    }
+#undef SV_PC_CALL
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+__global__ void __launch_bounds__(kPcThreads, 1) pconv_kernel(const __grid_constant__ TcLaunch4 P4) { pconv_body(P4.l[blockIdx.y]); }
 
 // ------------------------------------------------------------------------------------------------
 // N-stacked persistent convolution (see TcNsConv in tc_kernels.h).
@@ -1693,6 +1902,30 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
 }
 
 
+// Upgrades a halo launch to the persistent pipelined kernel when the packed weights fit beside two halo stages and two
+// accumulator sets fit in TMEM.  `n_classes` launches share the GPU (stride-2 dgrad: 4 parity classes, 37 CTAs each).
+void plan_persist(TcLaunch& L, int n_classes) {
+  L.persist = 0;
+  if (!L.halo || !env_int("SV_PCONV", 1)) return;
+  const int MT = L.mtx * L.mty;
+  if (L.n_tiles != 1 || 2 * MT * L.tile_cols > 512 || (L.tile_cols % kEpiBW) || L.nparts != 1) return;
+  const int num_kb = L.taps_h * L.taps_w * L.kc, kb_bytes = L.tile_cols * L.bk * 2;
+  const size_t w_bytes = ((size_t)num_kb * kb_bytes + 1023) / 1024 * 1024;
+  const size_t stage_bytes = (size_t)L.kc * L.halo_sx * L.chunk_bytes;
+  const size_t budget = 225 * 1024 - 1024 - sizeof(PcCtl);
+  if (w_bytes + 2 * stage_bytes > budget) return;
+  int nst = (int)((budget - w_bytes) / stage_bytes);
+  const int cap = env_int("SV_PCONV_STAGES", kPcMaxStages);
+  if (nst > cap) nst = cap;
+  if (nst > kPcMaxStages) nst = kPcMaxStages;
+  const int tiles = L.tiles_x * L.tiles_y * L.n_img;
+  int grid = env_int("SV_PCONV_GRID", 148) / n_classes;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  L.persist = 1; L.p_stages = nst; L.p_wbytes = (int)w_bytes; L.p_grid = grid;
+  L.p_smem = w_bytes + (size_t)nst * stage_bytes + sizeof(PcCtl) + 1024;
+}
+
 // Plans the halo-resident wgrad for a stride-1 convolution; returns false when the layer is not eligible.
 bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int cbn, int copad) {
   if (env_int("SV_NO_HALO_WGRAD", 0)) return false;
@@ -1891,7 +2124,7 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
       P.taps_h = 6; P.taps_w = 3; P.pad_l = 0; P.bk = 16; P.swizzle = 32; P.kc = 1;
       finish_launch(P, t.n_pad_fwd);
       try_halo(P, g.Ho, g.Wo, g.B, 1, 2, true);
-      if (P.halo) { L = P; t.first_pair = true; t.ci_pad = 16; }
+      if (P.halo) { plan_persist(P, 1); L = P; t.first_pair = true; t.ci_pad = 16; }
     }
   }
   {
@@ -1955,8 +2188,11 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         L.mask_act = ACT_NONE;
         finish_launch(L, t.n_pad_fwd);
         if (cpad <= g.in_ld - g.in_coff) {
+          // (stride-2 forward on the halo kernel: parity-tested, but the weights of e2 - 144 KB - cannot stay resident beside the
+          //  halo, and streaming them through the 3-stage ring is latency-bound: 39 us vs 32 us per-tap -> off by default)
           if (g.stride == 1) try_halo(L, g.Ho, g.Wo, g.B);
-          else if (g.stride == 2 && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && env_int("SV_S2_FWD_HALO", 1)) try_halo(L, g.Ho, g.Wo, g.B, 2, 2, true);
+          else if (g.stride == 2 && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && env_int("SV_S2_FWD_HALO", 0)) try_halo(L, g.Ho, g.Wo, g.B, 2, 2, true);
+          plan_persist(L, 1);
         }
         if (g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
             plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
@@ -2005,6 +2241,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
       finish_launch(L, t.n_pad_dg);
       try_halo(L, GH, GW, g.B, 1, 1, s == 2 && L.tile_cols <= 64 && env_int("SV_S2_DGRAD_HALO", 1));
+      plan_persist(L, s * s);
       if (s == 1) {
         plan_split_k(L, g.B, off);
         t.sk_dgrad_off = off;
@@ -2030,7 +2267,8 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         const TcLaunch &A = t.dgrad[0], &C = t.dgrad[cls];
         same = same && C.halo == A.halo && C.k_splits <= 1 && C.smem_bytes == A.smem_bytes && C.n_tiles == A.n_tiles && C.tile_h == A.tile_h &&
                C.tile_n_img == A.tile_n_img && C.grid_h == A.grid_h && C.n_img == A.n_img &&
-               (!C.halo || (C.TW == A.TW && C.TH == A.TH && C.tiles_x == A.tiles_x && C.tiles_y == A.tiles_y));
+               (!C.halo || (C.TW == A.TW && C.TH == A.TH && C.tiles_x == A.tiles_x && C.tiles_y == A.tiles_y)) &&
+               C.persist == A.persist && (!C.persist || (C.p_smem == A.p_smem && C.p_grid == A.p_grid));
       }
       t.dgrad_merged = same;
     }
@@ -2168,9 +2406,14 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
   }
   if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(halo4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  if (cudaFuncSetAttribute(pconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (env_int("SV_TC_VERBOSE", 0)) {
     auto show = [&](const char* what, const TcLaunch& L) {
-      if (L.halo)
+      if (L.halo && L.persist)
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: PCONV tile %dx%d halo %dx%d x%d planes, chunks %d x %d B, N %d, weights %d B resident, %d halo stages, smem %zu, grid %d\n",
+                g.kh, g.kw, g.stride, g.Ci, g.Co, what, L.TW, L.TH, L.TWp, L.THp, L.halo_sx, L.kc, L.chunk_bytes, L.tile_cols, L.p_wbytes, L.p_stages,
+                L.p_smem, L.p_grid);
+      else if (L.halo)
         fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: HALO tile %dx%d halo %dx%d chunks %d x %d B, N %d x%d, w ring %d x %d B (%d kb/stage), smem %zu\n",
                 g.kh, g.kw, g.stride, g.Ci, g.Co, what, L.TW, L.TH, L.TWp, L.THp, L.kc, L.chunk_bytes, L.tile_cols, L.n_tiles, L.w_stages,
                 L.w_stage_bytes, L.kb_per_stage, L.smem_bytes);
@@ -2293,6 +2536,12 @@ int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
 }
 
 static void launch(const TcLaunch& L, cudaStream_t s) {
+  if (L.halo && L.persist) {
+    TcLaunch4 P4;
+    P4.l[0] = L;
+    pconv_kernel<<<dim3(L.p_grid, 1), kPcThreads, L.p_smem, s>>>(P4);
+    return;
+  }
   if (L.halo) {
     dim3 grid(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles);
     halo_conv_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
@@ -2327,7 +2576,8 @@ void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
     const TcLaunch& L = t.dgrad[0];
     const int tiles_per_img = L.grid_h / L.tile_h;
     const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
-    if (L.halo) halo4_kernel<<<dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
+    if (L.halo && L.persist) pconv_kernel<<<dim3(L.p_grid, 4), kPcThreads, L.p_smem, s>>>(P4);
+    else if (L.halo) halo4_kernel<<<dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
     else igemm4_kernel<<<dim3(m_tiles, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
     return;
   }

@@ -43,6 +43,9 @@ struct TcLaunch {
   // halo_sy = input rows per output row (the UMMA row-group stride).  TWp = plane width, THp = (TH-1)*sy + taps_h.
   int halo_sx, halo_sy;
   int trace;                                    // SV_HALO_TRACE: record per-CTA phase clocks (debugging)
+  // persistent pipelined variant (pconv_kernel): weights resident in shared memory, halo ring, two accumulator sets in TMEM
+  int persist, p_stages, p_wbytes, p_grid;
+  size_t p_smem;
   // split-K (skinny dense GEMMs: few output tiles, long K): blockIdx.z owns kb_per_split k-blocks and stores its raw fp32
   // accumulator to partial[z][m_pad][n_pad]; splitk_finish_kernel sums the splits in a fixed order and applies the epilogue
   int k_splits, kb_per_split, m_pad, n_pad;
