@@ -2028,6 +2028,10 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   if ((size_t)kw * nb_all * num_kb * pixB + 2 * (size_t)stage_bytes > budget && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 &&
       !env_int("SV_NS_NOSPLIT", 0))
     co_splits = 2;
+  // N wider than one MMA (d4 dgrad: 6 x 64 = 384 columns) leaves room for a single accumulator set in TMEM, so the MMAs and the
+  // epilogue of a tile serialise; splitting the output channels over CTA pairs halves N and restores the double buffering
+  if (co_splits == 1 && kw * nb_all > 256 && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 && env_int("SV_NS_SPLIT_WIDE", 0))
+    co_splits = 2;
   const int nb = nb_all / co_splits;
   const int n_total = kw * nb;
   int ng = 1;
