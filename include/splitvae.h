@@ -186,7 +186,7 @@ typedef struct sv_layer_info {
   /* which tensor-core kernel serves each pass (SV_KERN_*; 0 = reference SIMT kernel) */
   int32_t kern_fwd, kern_dgrad, kern_wgrad, reserved;
 } sv_layer_info;
-enum { SV_KERN_NONE = 0, SV_KERN_IGEMM = 1, SV_KERN_HALO_CONV = 2, SV_KERN_NSCONV = 3, SV_KERN_WGRAD = 4, SV_KERN_HALO_WGRAD = 5 };
+enum { SV_KERN_NONE = 0, SV_KERN_IGEMM = 1, SV_KERN_HALO_CONV = 2, SV_KERN_NSCONV = 3, SV_KERN_WGRAD = 4, SV_KERN_HALO_WGRAD = 5, SV_KERN_PCONV = 6 };
 enum { SV_PASS_FWD = 0, SV_PASS_DGRAD = 1, SV_PASS_WGRAD = 2 };
 enum { SV_IMPL_REF = 0, SV_IMPL_TC = 1 };
 int32_t sv_debug_layer_count(const sv_handle* h);

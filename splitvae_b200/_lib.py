@@ -49,7 +49,7 @@ class SvLayerInfo(C.Structure):
                [(n, C.c_int32) for n in ("kern_fwd", "kern_dgrad", "kern_wgrad", "reserved")]
 
 
-KERNEL_NAMES = {0: "reference", 1: "igemm_kernel", 2: "halo_conv_kernel", 3: "nsconv_kernel", 4: "wgrad_kernel", 5: "halo_wgrad_kernel"}
+KERNEL_NAMES = {0: "reference", 1: "igemm_kernel", 2: "halo_conv_kernel", 3: "nsconv_kernel", 4: "wgrad_kernel", 5: "halo_wgrad_kernel", 6: "pconv_kernel"}
 
 
 class SplitVaeError(RuntimeError):

@@ -953,8 +953,8 @@ sv_status sv_debug_layer_info(const sv_handle* hc, int32_t i, sv_layer_info* o) 
   o->has_dgrad = L.din >= 0; o->tc_fwd = L.tc.fwd_ok; o->tc_dgrad = L.tc.dgrad_ok; o->tc_wgrad = L.tc.wgrad_ok;
   if (h->bound) { o->in = bp(h, L.in); o->out = bp(h, L.out); o->dout = bp(h, L.dout); o->din = bp(h, L.din); }
   if (h->use_tc) {
-    o->kern_fwd = !L.tc.fwd_ok ? SV_KERN_NONE : L.tc.fwd_ns ? SV_KERN_NSCONV : L.tc.fwd.halo ? SV_KERN_HALO_CONV : SV_KERN_IGEMM;
-    o->kern_dgrad = !L.tc.dgrad_ok ? SV_KERN_NONE : L.tc.dgrad_ns ? SV_KERN_NSCONV : L.tc.dgrad[0].halo ? SV_KERN_HALO_CONV : SV_KERN_IGEMM;
+    o->kern_fwd = !L.tc.fwd_ok ? SV_KERN_NONE : L.tc.fwd_ns ? SV_KERN_NSCONV : L.tc.fwd.halo ? (L.tc.fwd.persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;
+    o->kern_dgrad = !L.tc.dgrad_ok ? SV_KERN_NONE : L.tc.dgrad_ns ? SV_KERN_NSCONV : L.tc.dgrad[0].halo ? (L.tc.dgrad[0].persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;
     o->kern_wgrad = !L.tc.wgrad_ok ? SV_KERN_NONE : L.tc.wg_halo ? SV_KERN_HALO_WGRAD : SV_KERN_WGRAD;
   }
   o->in_elems = (int64_t)g.B * g.Hi * g.Wi * g.in_ld; o->out_elems = (int64_t)g.B * g.Ho * g.Wo * g.out_ld;

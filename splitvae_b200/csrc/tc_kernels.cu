@@ -794,7 +794,8 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
   const int p = q * 32 + lane;
   const int r = p / W, x = p - r * W;
   const int nchunk8 = nb >> 3;
-  const int acc_cols = P.ng * P.ncols;
+  const int mb = P.mb;                          // 128-pixel blocks per tile (each R rows), one accumulator per block
+  const int acc1 = P.ng * P.ncols, acc_cols = mb * acc1;
   const int split = blockIdx.x % P.co_splits, cta = blockIdx.x / P.co_splits, ncta = gridDim.x / P.co_splits;
   const int cbase = split * nb;               // first output channel of this CTA's split
   const int my_last = cl + ((nchunk8 - 1 - cl) / lanes) * lanes;   // last block this warp reads (< 0: none)
@@ -813,23 +814,24 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
   for (int t = cta; t < tiles; t += ncta, ++i) {
     if (i % groups != grp) continue;
     const int aph = (i / groups) & 1;
-    const int n = t / tiles_per_img, y0 = (t - n * tiles_per_img) * R;
-    const long long opix = ((long long)n * H + (y0 + r)) * W + x;
+    const int n = t / tiles_per_img, y0 = (t - n * tiles_per_img) * R * mb;
     tc::mbar_wait(&ctl->acc_full[grp], aph);
     tc::tc_fence_after();
-    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * acc_cols);
     if (cl >= nchunk8) {                          // more chunk lanes than blocks: nothing to read, but the barrier counts every warp
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&ctl->acc_empty[grp]);
       continue;
     }
+    for (int mbi = 0; mbi < mb; ++mbi) {
+    const long long opix = ((long long)n * H + (y0 + mbi * R + r)) * W + x;
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * acc_cols + mbi * acc1);
     for (int cc = cl; cc < nchunk8; cc += lanes) {
       uint32_t v[KW][8];                          // [filter column b][channel]
 #pragma unroll
       for (int b = 0; b < KW; ++b) tc::tmem_ld8(tacc + (uint32_t)(b * nb + cc * 8), v[b]);
       tc::tmem_ld_wait();
-      if (cc == my_last) {                        // this warp is done with the accumulator: hand it back to the MMA warp
+      if (cc == my_last && mbi == mb - 1) {       // this warp is done with the accumulators: hand them back to the MMA warp
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&ctl->acc_empty[grp]);
@@ -906,6 +908,7 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
         }
       }
     }
+    }
   }
 }
 
@@ -966,7 +969,7 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
     for (int i = 0; i < P.groups; ++i) { tc::mbar_init(&ctl->acc_full[i], 1); tc::mbar_init(&ctl->acc_empty[i], 4 * P.lanes); }
     tc::fence_barrier_init();
   }
-  const int acc_cols = P.ng * P.ncols;
+  const int acc1 = P.ng * P.ncols, acc_cols = P.mb * acc1;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(P.groups * acc_cols)) tmem_cols <<= 1;
   if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
@@ -985,7 +988,7 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
       int i = 0;
       for (int t = cta; t < P.tiles; t += ncta, ++i) {
         const int st = i % P.nstages, ph = (i / P.nstages) & 1;
-        const int n = t / P.tiles_per_img, y0 = (t - n * P.tiles_per_img) * P.R;
+        const int n = t / P.tiles_per_img, y0 = (t - n * P.tiles_per_img) * P.R * P.mb;
         tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
         tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
         for (int c = 0; c < P.nchunks; ++c)
@@ -1005,6 +1008,8 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
       const int ksteps = P.ck / 16, kh = P.kh, nchunks = P.nchunks, ng = P.ng, tiles = P.tiles, nstages = P.nstages, groups = P.groups;
       const uint32_t ncols = (uint32_t)P.ncols;
       const uint32_t halo_addr = tc::smem_u32(halo) >> 4, stage_step = (uint32_t)P.stage_bytes >> 4;
+      const int mb = P.mb;
+      const uint32_t blk_step = ((uint32_t)(P.R * P.W) * (uint32_t)P.pixB) >> 4;     // R image rows: next 128-pixel block of the tile
       const int shape = nchunks != 1 || kh != 6 ? 0
                         : ng == 1 ? (ksteps == 4 ? 1 : ksteps == 2 ? 2 : ksteps == 1 ? 3 : 0)
                                   : ng == 2 ? (ksteps == 2 ? 4 : ksteps == 4 ? 5 : 0) : 0;
@@ -1016,8 +1021,9 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
         tc::mbar_wait(&ctl->halo_full[st], ph);
         tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
         tc::tc_fence_after();
-        const uint32_t h_addr = halo_addr + (uint32_t)st * stage_step;
-        const uint32_t acc = tmem_base + (uint32_t)(ab * acc_cols);
+        for (int mbi = 0; mbi < mb; ++mbi) {    // block mbi of the tile: rows mbi*R .. of the shared halo, its own accumulator
+        const uint32_t h_addr = halo_addr + (uint32_t)st * stage_step + (uint32_t)mbi * blk_step;
+        const uint32_t acc = tmem_base + (uint32_t)(ab * acc_cols + mbi * acc1);
         const uint64_t da0 = tmpl + h_addr, db0 = tmpl + w_addr;
         // fully unrolled issue sequences for the shapes of this model family (the single issuing thread must spend only a
         // few instructions per tcgen05.mma: the generic nest below costs ~75 and caps the tensor pipe at ~35 %)
@@ -1041,6 +1047,7 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
               }
             }
           }
+        }
         }
         tc::umma_commit(&ctl->halo_empty[st]);
         tc::umma_commit(&ctl->acc_full[ab]);
@@ -2018,8 +2025,18 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   const int pixB = ck * 2, nchunks = cpad / ck, num_kb = kh * nchunks;
   int nb_all = round_up(n_out, 8);
   if ((kw * nb_all) % 16) nb_all = round_up(n_out, 16);
+  // Blocks per tile: a tile of mb * R rows shares one (mb*R + kh - 1)-row halo.  With R = 2 (64-wide images) a single block
+  // re-reads its input 3.5x through the 7-row halo of a 6x6 filter and d5 forward is L2->SMEM bound (235 MB per launch); two
+  // blocks per tile cut that to 2.25x.  Needs two accumulators per buffer in TMEM (two buffers: 4 * N <= 512) and one channel chunk.
+  int mb = 1;
+  {
+    const bool can2 = nchunks == 1 && (H % (2 * R)) == 0 && 4 * kw * nb_all <= 512;
+    if (R + kh - 1 > 3 * R && can2) mb = 2;
+    const int f = env_int("SV_NS_MB", 0);
+    if (f == 1 || (f == 2 && can2)) mb = f;
+  }
   // split the output channels over CTAs when the resident weights would leave room for fewer than 4 halo stages
-  const int chunk_bytes = round_up((R + kh - 1) * W * pixB, 1024), stage_bytes = chunk_bytes * nchunks;
+  const int chunk_bytes = round_up((mb * R + kh - 1) * W * pixB, 1024), stage_bytes = chunk_bytes * nchunks;
   const size_t xch_bytes = W > 32 ? (size_t)(kNsEpiWarps / 4) * 2 * 4 * kw * kNsXchSlots * 8 * 4 : 0;   // one area per (group, chunk lane)
   const size_t budget = 227 * 1024 - 1024 - 256 - xch_bytes;
   // (measured: the split costs more than it buys whenever the whole weight set fits beside two halo stages - d4 forward
@@ -2030,7 +2047,7 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
     co_splits = 2;
   // N wider than one MMA (d4 dgrad: 6 x 64 = 384 columns) leaves room for a single accumulator set in TMEM, so the MMAs and the
   // epilogue of a tile serialise; splitting the output channels over CTA pairs halves N and restores the double buffering
-  if (co_splits == 1 && kw * nb_all > 256 && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 && env_int("SV_NS_SPLIT_WIDE", 0))
+  if (co_splits == 1 && kw * nb_all > 256 && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 && env_int("SV_NS_SPLIT_WIDE", 1))   // d4 dgrad 55 -> 45 us, 1.538 -> 1.514 ms/step
     co_splits = 2;
   const int nb = nb_all / co_splits;
   const int n_total = kw * nb;
@@ -2041,11 +2058,12 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   }
   P.kh = kh; P.kw = kw; P.pad_t = pad_t; P.pad_l = pad_l;
   P.W = W; P.R = R; P.H = H; P.n_img = n_img;
-  P.tiles_per_img = H / R; P.tiles = n_img * P.tiles_per_img;
+  P.mb = mb;
+  P.tiles_per_img = H / (R * mb); P.tiles = n_img * P.tiles_per_img;
   P.ck = ck; P.nchunks = nchunks; P.pixB = pixB;
   P.nb = nb; P.ng = ng; P.ncols = n_total / ng; P.n_total = n_total; P.co_splits = co_splits;
   // epilogue warp sets: `groups` accumulator buffers / tile round-robin, `lanes` warps per TMEM quarter splitting the 8-channel blocks
-  int groups = 512 / n_total;
+  int groups = 512 / (n_total * mb);
   if (groups > kNsMaxGroups) groups = kNsMaxGroups;
   const int sets = kNsEpiWarps / 4;
   int lanes = sets / groups;
@@ -2056,7 +2074,7 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
     if (fl >= 1 && fl * groups <= sets) lanes = fl; }
   P.groups = groups; P.lanes = lanes;
   P.nacc = groups;
-  P.halo_rows = R + kh - 1;
+  P.halo_rows = mb * R + kh - 1;
   P.chunk_bytes = chunk_bytes;
   P.stage_bytes = stage_bytes;
   P.num_kb = num_kb;
@@ -2381,7 +2399,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       P.mask_act = which ? mask_act : ACT_NONE;
       P.mask_ld = g.in_ld; P.mask_coff = g.in_coff;
       if (env_int("SV_TC_VERBOSE", 0))
-        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: NSCONV tile %dx%d halo rows %d chunks %d x %d B, N %d = %d x %d (ng %d, groups %d x lanes %d, co_splits %d), weights %d B resident, %d halo stages, smem %zu, grid %d\n",
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d %s: NSCONV block %dx%d halo rows %d chunks %d x %d B, N %d = %d x %d (ng %d, groups %d x lanes %d, co_splits %d), weights %d B resident, %d halo stages, smem %zu, grid %d\n",
                 g.kh, g.kw, g.stride, g.Ci, g.Co, which ? "dgrad" : "fwd", P.R, P.W, P.halo_rows, P.nchunks, P.chunk_bytes, P.n_total, P.kw, P.nb, P.ng,
                 P.groups, P.lanes, P.co_splits, P.w_bytes, P.nstages, P.smem_bytes, P.grid);
     }

@@ -113,7 +113,8 @@ struct TcHaloWgrad {
 struct TcNsConv {
   CUtensorMap map_x, map_w;
   int kh, kw, pad_t, pad_l;
-  int W, R, H, n_img;               // tile = R rows x W pixels (R * W = 128)
+  int W, R, H, n_img;               // block = R rows x W pixels (R * W = 128)
+  int mb;                           // blocks per tile (tile = mb * R rows sharing one halo; one accumulator per block)
   int tiles_per_img, tiles;
   int ck, nchunks, pixB;            // channel chunk (elements), chunks per pixel, bytes per pixel per chunk (= swizzle span)
   int nb;                           // N block per filter column (padded output channels)
