@@ -87,8 +87,11 @@ struct sv_handle {
   int COLSUM2 = -1;
   bool two_streams = true;
   // weight gradients run on one auxiliary stream per branch stream (dgrad chain = critical path, wgrad + reduce fill the gaps)
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t ev_aux[2] = {nullptr, nullptr}, ev_aux_join[2] = {nullptr, nullptr};
+  // (SV_WGRAD_STREAMS = n streams per branch, used round-robin by consecutive layers; 0 = none.  Two per branch let wgrad(L-1) start
+  // while wgrad(L) and its split-K reduce are still queued: on one in-order stream the encoders' last wgrads formed a serial tail)
+  cudaStream_t aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t ev_aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, ev_aux_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int aux_n = 0, aux_rr[2] = {0, 0};
   bool wgrad_streams = false;
   // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
   bool cs_on = false;
@@ -334,15 +337,20 @@ void layer_fwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
 cudaStream_t wgrad_stream(sv_handle* h, cudaStream_t s) {
   if (!h->wgrad_streams || !h->cs_on) return s;
   const int k = (s == h->side) ? 1 : 0;
-  cudaEventRecord(h->ev_aux[k], s);
-  cudaStreamWaitEvent(h->aux[k], h->ev_aux[k], 0);
-  return h->aux[k];
+  const int j = h->aux_rr[k]++ % h->aux_n;
+  cudaEventRecord(h->ev_aux[k][j], s);
+  cudaStreamWaitEvent(h->aux[k][j], h->ev_aux[k][j], 0);
+  return h->aux[k][j];
 }
 void join_wgrad_stream(sv_handle* h, cudaStream_t s) {
   if (!h->wgrad_streams || !h->cs_on) return;
   const int k = (s == h->side) ? 1 : 0;
-  cudaEventRecord(h->ev_aux_join[k], h->aux[k]);
-  cudaStreamWaitEvent(s, h->ev_aux_join[k], 0);
+  const int used = h->aux_rr[k] < h->aux_n ? h->aux_rr[k] : h->aux_n;   // (an untouched stream is not part of a graph capture)
+  for (int j = 0; j < used; ++j) {
+    cudaEventRecord(h->ev_aux_join[k][j], h->aux[k][j]);
+    cudaStreamWaitEvent(s, h->ev_aux_join[k][j], 0);
+  }
+  h->aux_rr[k] = 0;
 }
 
 void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
@@ -618,11 +626,12 @@ sv_status sv_destroy(sv_handle* h) {
     if (h->ev_opt_join) cudaEventDestroy(h->ev_opt_join);
     if (h->opt) cudaStreamDestroy(h->opt);
     for (int b = 0; b < 4; ++b) colsum_table_destroy(h->cs[b]);
-    for (int k = 0; k < 2; ++k) {
-      if (h->ev_aux[k]) cudaEventDestroy(h->ev_aux[k]);
-      if (h->ev_aux_join[k]) cudaEventDestroy(h->ev_aux_join[k]);
-      if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
-    }
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < 2; ++j) {
+        if (h->ev_aux[k][j]) cudaEventDestroy(h->ev_aux[k][j]);
+        if (h->ev_aux_join[k][j]) cudaEventDestroy(h->ev_aux_join[k][j]);
+        if (h->aux[k][j]) cudaStreamDestroy(h->aux[k][j]);
+      }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
@@ -707,14 +716,16 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
          cudaEventCreateWithFlags(&h->ev_opt_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "optimizer stream / event creation failed");
   }
-  if (!h->aux[0]) {
+  if (!h->aux[0][0]) {
     const char* off = getenv("SV_WGRAD_STREAMS");
-    h->wgrad_streams = !(off && *off == '0');
-    if (h->wgrad_streams)
-      for (int k = 0; k < 2; ++k)
-        if (cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_aux[k], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_aux_join[k], cudaEventDisableTiming) != cudaSuccess)
+    h->aux_n = off && *off ? atoi(off) : 2;
+    if (h->aux_n > 2) h->aux_n = 2;
+    h->wgrad_streams = h->aux_n > 0;
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < h->aux_n; ++j)
+        if (cudaStreamCreateWithFlags(&h->aux[k][j], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_aux[k][j], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_aux_join[k][j], cudaEventDisableTiming) != cudaSuccess)
           return fail(h, SV_ERR_DEVICE, "auxiliary stream / event creation failed");
   }
   h->bound = true;
