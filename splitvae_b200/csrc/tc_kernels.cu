@@ -576,14 +576,15 @@ struct PcCtl {
 // MMAs of one tile, fully unrolled for the shapes of this model family (one channel chunk, unit column stride, one accumulator
 // row): KH x KW taps x KS k-steps x MTX accumulators.  The single issuing thread must spend only a few instructions per
 // tcgen05.mma - the generic nest costs ~60 per k-block and capped d5 dgrad at 85 cycles per MMA (44 is the pipe's own rate).
-template <int KH, int KW, int KS, int MTX>
+template <int KH, int KW, int KS, int MTX, int SX = 1>
 __device__ __forceinline__ void pc_issue_tile(uint64_t da0, uint64_t db0, uint32_t acc, uint32_t tile_cols, uint32_t idesc, uint32_t row_step,
-                                              uint32_t pix_step, uint32_t kb_step, uint32_t tx_step) {
+                                              uint32_t pix_step, uint32_t kb_step, uint32_t tx_step, uint32_t plane_step = 0) {
 #pragma unroll
   for (int a = 0; a < KH; ++a) {
 #pragma unroll
     for (int b = 0; b < KW; ++b) {
-      const uint64_t da = da0 + (uint64_t)(a * row_step + b * pix_step);
+      // (SX parity planes: filter column b lives in plane b % SX, shifted by b / SX plane columns)
+      const uint64_t da = da0 + (uint64_t)(a * row_step + (b / SX) * pix_step + (b % SX) * plane_step);
       const uint64_t db = db0 + (uint64_t)((a * KW + b) * kb_step);
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
@@ -602,7 +603,7 @@ __device__ __noinline__ void pconv_epilogue_t(const TcLaunch& P, PcCtl* ctl, uin
   const long long step_tx = 8LL * P.osx, step_ty = 16LL * P.osy * P.OW;
   const int mtx = P.mtx, MT = P.mtx * P.mty, TW = P.TW, TH = P.TH, tiles_x = P.tiles_x, OH = P.OH, OW = P.OW;
   const int osy = P.osy, ooy = P.ooy, osx = P.osx, oox = P.oox;
-  const int acc_stride = P.tile_cols, acc_cols = MT * P.tile_cols;
+  const int acc_stride = P.tile_cols, acc_cols = MT * P.tile_cols, col_base = P.p_ntile * P.tile_cols;
   const int tiles_per_img = P.tiles_x * P.tiles_y, tiles = tiles_per_img * P.n_img;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * acc_cols);
   uint64_t* full = &ctl->acc_full[set];
@@ -616,7 +617,7 @@ __device__ __noinline__ void pconv_epilogue_t(const TcLaunch& P, PcCtl* ctl, uin
     const long long opix0 = ((long long)n * OH + (y * osy + ooy)) * OW + (x * osx + oox);
     tc::mbar_wait(full, aph);
     tc::tc_fence_after();
-    epilogue_acc_t<ACT, MASK, OUT_F32>(E, tmem_lane, MT, acc_stride, mtx, opix0, step_tx, step_ty, true, 0, empty);
+    epilogue_acc_t<ACT, MASK, OUT_F32>(E, tmem_lane, MT, acc_stride, mtx, opix0, step_tx, step_ty, true, col_base, empty);
   }
 }
 
@@ -656,7 +657,8 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
   if (warp == 0) {
     if (tc::elect_one()) {
       tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(num_kb * kb_bytes));
-      for (int kb = 0; kb < num_kb; ++kb) tc::tma_load_2d(wsm + (size_t)kb * kb_bytes, &P.map_b, &ctl->w_full, kb * P.bk, 0);
+      for (int kb = 0; kb < num_kb; ++kb)
+        tc::tma_load_2d(wsm + (size_t)kb * kb_bytes, &P.map_b, &ctl->w_full, kb * P.bk, P.p_ntile * P.tile_cols);
       const uint32_t halo_tx = (uint32_t)(nchunks * sx * P.THp * P.TWp * P.bk * 2);
       int i = 0;
       for (int t = cta; t < tiles; t += ncta, ++i) {
@@ -686,11 +688,16 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
       const bool env_shape_off = (P.trace & 2) != 0;      // SV_HALO_TRACE=2: generic issue loop (A/B)
       // unrolled issue sequences: 1 = 6x6 taps, K 16, 4 accumulators (d5 dgrad); 2 = 6x3 pair taps (first layer, 64x64 images);
       // 3 = 3x3 taps, K 64, 2 accumulators (e2 dgrad classes); 4 = first layer, 32x32 images
-      const int shape = (nchunks != 1 || sx != 1 || mty != 1 || env_shape_off) ? 0
+      // 5 / 6 = 6x6 stride-2 forward over two parity planes, K 32, one / two accumulators (e2 forward)
+      const int shape = (nchunks != 1 || mty != 1 || env_shape_off) ? 0
+                        : sx == 2 ? ((P.taps_h == 6 && taps_w == 6 && ksteps == 2 && mtx == 1) ? 5
+                                     : (P.taps_h == 6 && taps_w == 6 && ksteps == 2 && mtx == 2) ? 6 : 0)
+                        : sx != 1 ? 0
                         : (P.taps_h == 6 && taps_w == 6 && ksteps == 1 && mtx == 4) ? 1
                         : (P.taps_h == 6 && taps_w == 3 && ksteps == 1 && mtx == 4) ? 2
                         : (P.taps_h == 3 && taps_w == 3 && ksteps == 4 && mtx == 2) ? 3
-                        : (P.taps_h == 6 && taps_w == 3 && ksteps == 1 && mtx == 2) ? 4 : 0;
+                        : (P.taps_h == 6 && taps_w == 3 && ksteps == 1 && mtx == 2) ? 4
+                        : (P.taps_h == 6 && taps_w == 3 && ksteps == 4 && mtx == 1) ? 7 : 0;   // 7 = e2 forward in the pixel-pair view
       tc::mbar_wait(&ctl->w_full, 0);
       int i = 0;
       for (int t = cta; t < tiles; t += ncta, ++i) {
@@ -709,7 +716,10 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
           if (shape == 1) pc_issue_tile<6, 6, 1, 4>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
           else if (shape == 2) pc_issue_tile<6, 3, 1, 4>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
           else if (shape == 3) pc_issue_tile<3, 3, 4, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
-          else pc_issue_tile<6, 3, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 4) pc_issue_tile<6, 3, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 7) pc_issue_tile<6, 3, 4, 1>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 5) pc_issue_tile<6, 6, 2, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
+          else pc_issue_tile<6, 6, 2, 2, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
         } else
         for (int kb = 0; kb < num_kb; ++kb, b_addr += kb_step) {
           const uint32_t a_tap = sx == 1 ? (h_addr + (uint32_t)chunk * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
@@ -730,7 +740,7 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
     }
   } else {
     const int set = (warp - 2) >> 2;            // accumulator set this warp drains (tiles i with i % 2 == set)
-    const EpiSel e = epilogue_select(P, 0);
+    const EpiSel e = epilogue_select(P, P.p_ntile);
     // one dispatch per thread with the tile loop INSIDE each instantiation (with the dispatch inside the loop the compiler
     // hoisted the loop invariants of all eleven variants at once: 168 registers and 20 KB of spill code)
 #define SV_PC_CALL(A, M, F) pconv_epilogue_t<A, M, F>(P, ctl, tmem_base, set, warp & 3, lane)
@@ -1846,7 +1856,7 @@ size_t split_k_bytes(const TcLaunch& L) {
 // groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
 // for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
 
-void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false) {
+void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false, size_t max_halo_bytes = 0) {
   L.halo = 0;
   L.halo_sx = 1; L.halo_sy = 1;
   if (env_int("SV_NO_HALO", 0)) return;
@@ -1879,6 +1889,7 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
       const int TWp = TW + wtaps - 1, THp = (TH - 1) * sy + L.taps_h;
       if (TWp * sx > 256 || THp > 256) continue;
       const size_t chunk = ((size_t)THp * TWp * pix + 1023) / 1024 * 1024;
+      if (max_halo_bytes && chunk * nch * sx > max_halo_bytes) continue;
       for (int stages = 3; stages >= 2; --stages) {
         const size_t smem = chunk * nch * sx + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
         if (smem > 200 * 1024) continue;
@@ -1915,7 +1926,7 @@ void plan_persist(TcLaunch& L, int n_classes) {
   L.persist = 0;
   if (!L.halo || !env_int("SV_PCONV", 1)) return;
   const int MT = L.mtx * L.mty;
-  if (L.n_tiles != 1 || 2 * MT * L.tile_cols > 512 || (L.tile_cols % kEpiBW) || L.nparts != 1) return;
+  if (L.n_tiles > 4 || (L.n_tiles > 1 && n_classes != L.n_tiles) || 2 * MT * L.tile_cols > 512 || (L.tile_cols % kEpiBW) || L.nparts != 1) return;
   const int num_kb = L.taps_h * L.taps_w * L.kc, kb_bytes = L.tile_cols * L.bk * 2;
   const size_t w_bytes = ((size_t)num_kb * kb_bytes + 1023) / 1024 * 1024;
   const size_t stage_bytes = (size_t)L.kc * L.halo_sx * L.chunk_bytes;
@@ -1929,7 +1940,7 @@ void plan_persist(TcLaunch& L, int n_classes) {
   int grid = env_int("SV_PCONV_GRID", 148) / n_classes;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  L.persist = 1; L.p_stages = nst; L.p_wbytes = (int)w_bytes; L.p_grid = grid;
+  L.persist = 1; L.p_stages = nst; L.p_wbytes = (int)w_bytes; L.p_grid = grid; L.p_ntile = 0;
   L.p_smem = w_bytes + (size_t)nst * stage_bytes + sizeof(PcCtl) + 1024;
 }
 
@@ -2215,6 +2226,31 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
           if (g.stride == 1) try_halo(L, g.Ho, g.Wo, g.B);
           else if (g.stride == 2 && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && env_int("SV_S2_FWD_HALO", 0)) try_halo(L, g.Ho, g.Wo, g.B, 2, 2, true);
           plan_persist(L, 1);
+          // Stride-2 forward on the persistent kernel: split the output channels over up to 4 CTA classes until the class's
+          // weights stay resident beside two halo stages (e2: 2 x 32 columns, 72 KB of weights, 8x16 tiles); the halo is then
+          // read once per class instead of once per filter tap (per-tap kernel: 226 MB L2->SMEM, 31 us).
+          if (g.stride == 2 && !L.persist && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && g.nparts == 1 && env_int("SV_S2_FWD_PCONV", 1)) {
+            // Pixel-pair view (as for the first layer): with an even filter width and an even left pad the NHWC row [W][C] read
+            // as [W/2][2C] turns the stride-2 convolution into kw/2 unit-stride pair taps of K = 2C, so the halo is ONE
+            // contiguous TMA box (the parity-plane form needs element-strided boxes, which the TMA unit gathers at ~11 cycles per
+            // 64-byte pixel: e2 forward stayed at 29 us).  Needs a dense input tensor and 2C <= 64 channels per swizzle row.
+            const bool pair_ok = (g.kw % 2) == 0 && (g.pl % 2) == 0 && g.in_coff == 0 && g.in_ld == cpad && L.kc == 1 && 2 * cpad <= 64 &&
+                                 (g.Wi % 2) == 0 && env_int("SV_S2_FWD_PAIR", 1);
+            for (int split = 1; split <= 4; split *= 2) {
+              const int cols = t.n_pad_fwd / split;
+              if (cols < 16 || (cols % 16) || cols > 128) continue;
+              TcLaunch Q = L;
+              Q.tile_cols = cols; Q.n_tiles = split;
+              if (pair_ok) { Q.taps_w = g.kw / 2; Q.pad_l = g.pl / 2; Q.bk = 2 * L.bk; Q.swizzle = 2 * L.swizzle; }
+              const size_t w_bytes = ((size_t)g.kh * g.kw * L.kc * cols * L.bk * 2 + 1023) / 1024 * 1024;
+              const size_t budget = 225 * 1024 - 1024 - sizeof(PcCtl);
+              if (w_bytes + 4096 >= budget) continue;
+              try_halo(Q, g.Ho, g.Wo, g.B, pair_ok ? 1 : 2, 2, true, (budget - w_bytes) / 2);
+              if (!Q.halo) continue;
+              plan_persist(Q, split);
+              if (Q.persist) { L = Q; t.fwd_pair = pair_ok; if (pair_ok) t.ci_pad = 2 * cpad; break; }
+            }
+          }
         }
         if (g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
             plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
@@ -2369,6 +2405,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     TcLaunch& L = t.fwd;
     // (first_pair: the staged image [B][H][W+8][8] seen as [B][H][(W+8)/2][16] - one K = 16 row per pixel pair)
     const char* e = t.first_pair ? make_halo_map(&L.map_a, in, g.B, g.Hi, (g.Wi + 8) / 2, 16, 0, 16, 16, L.TWp, L.THp, 1, 32)
+                    : t.fwd_pair ? make_halo_map(&L.map_a, in, g.B, g.Hi, g.Wi / 2, 2 * g.in_ld, 0, t.ci_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
                     : t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
                     : L.halo ? make_halo_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, L.halo_sx, L.swizzle)
                             : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff,
@@ -2511,8 +2548,9 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
       PackJob J = B;
       J.kind = t.first ? 3 : 0; J.rows_pad = t.n_pad_fwd; J.taps_h = t.fwd.taps_h; J.taps_w = t.fwd.taps_w; J.k_pad = t.ci_pad;
       if (t.first_pair) { J.kind = 0; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = 8; }   // K = (a, b, 8 channels): a pair-tap b' is the K block (b = 2b', 2b'+1)
+      if (t.fwd_pair) { J.taps_w = g.kw; J.k_pad = t.ci_pad / 2; }                       // same memory as [co][kh][kw][ci_pad/2]
       J.dst = t.ws + t.w_fwd_off;
-      J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * t.ci_pad;
+      J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * J.k_pad;
       push(J);
       PackJob Jb = B;
       Jb.kind = 2; Jb.dst = t.ws + t.bias_off; Jb.count = t.n_pad_fwd;
@@ -2560,8 +2598,8 @@ int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
 static void launch(const TcLaunch& L, cudaStream_t s) {
   if (L.halo && L.persist) {
     TcLaunch4 P4;
-    P4.l[0] = L;
-    pconv_kernel<<<dim3(L.p_grid, 1), kPcThreads, L.p_smem, s>>>(P4);
+    for (int j = 0; j < L.n_tiles; ++j) { P4.l[j] = L; P4.l[j].p_ntile = j; }   // (n_tiles > 1: one CTA class per column tile)
+    pconv_kernel<<<dim3(L.p_grid, L.n_tiles), kPcThreads, L.p_smem, s>>>(P4);
     return;
   }
   if (L.halo) {

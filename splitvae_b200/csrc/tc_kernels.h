@@ -45,6 +45,7 @@ struct TcLaunch {
   int trace;                                    // SV_HALO_TRACE: record per-CTA phase clocks (debugging)
   // persistent pipelined variant (pconv_kernel): weights resident in shared memory, halo ring, two accumulator sets in TMEM
   int persist, p_stages, p_wbytes, p_grid;
+  int p_ntile;                                  // column tile (of n_tiles) this launch descriptor serves: weight rows / output columns p_ntile * tile_cols
   size_t p_smem;
   // split-K (skinny dense GEMMs: few output tiles, long K): blockIdx.z owns kb_per_split k-blocks and stores its raw fp32
   // accumulator to partial[z][m_pad][n_pad]; splitk_finish_kernel sums the splits in a fixed order and applies the epilogue
@@ -149,6 +150,7 @@ struct TcLayer {
   TcHaloWgrad hw{};
   bool fwd_ns = false, dgrad_ns = false;   // N-stacked persistent kernel replaces the per-tap / halo kernel
   bool dgrad_merged = false;               // stride-2 dgrad: the 4 parity classes run as one launch (igemm4_kernel / halo4_kernel)
+  bool fwd_pair = false;                   // stride-2 forward on the persistent kernel through the pixel-pair view [W/2][2C]
   bool first_pair = false;                 // first layer forward on the halo kernel through the pixel-PAIR view of the staged image
   TcNsConv ns_fwd{}, ns_dgrad{};
   size_t w_nsf_off = 0, w_nsd_off = 0;

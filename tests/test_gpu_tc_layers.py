@@ -83,3 +83,22 @@ def test_tc_layers_match_reference(model, H, B):
             n_checked += 1
     assert n_checked > 0
     print(f"{model} H={H} B={B}: {n_checked} tensor-core kernels checked")
+
+
+# Planner alternatives that are off by default or only chosen for other shapes: the same per-layer check with the knob set
+# (the planner reads the environment when the engine is created).
+@pytest.mark.parametrize("env", [
+    {"SV_S2_FWD_HALO": "1"},                       # stride-2 forward on the halo kernel (parity planes, TMA element stride 2)
+    {"SV_PCONV": "0"},                             # one-tile-per-CTA halo kernel + merged 4-class launch (halo4_kernel)
+    {"SV_PCONV": "0", "SV_S2_FWD_HALO": "1"},
+    {"SV_HALO_TRACE": "2"},                        # persistent kernel with the generic (not unrolled) issue loop
+    {"SV_FIRST_PAIR": "0", "SV_S2_DGRAD_HALO": "0"},   # first layer through the window map, stride-2 dgrad per tap
+    {"SV_NS_MB": "1", "SV_NS_SPLIT_WIDE": "0"},    # N-stacked conv: one block per tile, unsplit wide N (single accumulator set)
+    {"SV_OLD_REDUCE": "1", "SV_HWG_SPLITS": "148", "SV_WGRAD_STREAMS": "1"},
+], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_tc_layers_planner_variants(env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_tc_layers_match_reference("lgvae", 64, 3)
+    if "SV_NS_MB" in env or "SV_PCONV" in env:
+        test_tc_layers_match_reference("lggmvae", 64, 2)
