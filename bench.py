@@ -121,10 +121,34 @@ def run_reference(args, wl):
                              "sample": f"{args.steps} oracle train steps of {sample_batch} images ({H}x{H}x3), torch CPU fp32"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _stdout_json_only():
+    """The driver reads ONE JSON line from stdout: send everything else that lands on fd 1 (NCCL's 'NCCL version ...' banner, library
+    chatter) to stderr and keep a private duplicate of the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def main():
+    _stdout_json_only()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -342,7 +366,7 @@ def main():
             "launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "final_total_loss": final_total,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # release the captured graph (it holds NCCL kernels) before tearing the communicator down; destroy_process_group()
         # was observed to block forever with a live captured collective, so leave the teardown to process exit
