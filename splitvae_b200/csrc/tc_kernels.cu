@@ -1218,7 +1218,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
 // Halo-resident wgrad (see TcHaloWgrad in tc_kernels.h).
 // ------------------------------------------------------------------------------------------------
 struct HwCtl {
-  uint64_t full[2], empty[2], tmem_full;
+  uint64_t full[4], empty[4], tmem_full;
   uint32_t tmem_base;
   uint32_t goff[32];   // per row group: byte offset >> 4 of its first sub-block inside a stage's X halo
 };
@@ -1809,11 +1809,17 @@ bool tile_grid(TcLaunch& L, int GH, int GW, int n_img) {
   return true;
 }
 
-void finish_launch(TcLaunch& L, int n_cols_pad) {
+int env_int(const char* name, int dflt);
+void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concurrent: launches of this shape sharing the GPU
   L.tile_cols = n_cols_pad < 128 ? n_cols_pad : 128;
   L.n_tiles = n_cols_pad / L.tile_cols;
   const int a_bytes = 128 * L.bk * 2, b_bytes = round_up(L.tile_cols * L.bk * 2, 1024);
-  int stages = (100 * 1024) / (a_bytes + b_bytes);
+  // ring budget: 100 KB keeps two CTAs per SM; a launch with at most one CTA per SM anyway (the 8x8-pixel layers: 128 CTAs)
+  // takes the whole shared memory for a deeper ring instead
+  const int tiles_per_img = L.tile_h > 0 ? L.grid_h / L.tile_h : 1;
+  const long long m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : (long long)L.n_img * tiles_per_img;
+  const bool one_wave = m_tiles * L.n_tiles * concurrent <= 148 && env_int("SV_IGEMM_DEEP", 1);
+  int stages = ((one_wave ? 192 : 100) * 1024) / (a_bytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   const int num_kb = L.taps_h * L.taps_w * L.kc;
@@ -1978,7 +1984,9 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   const int force_th = env_int("SV_HWG_TH", 0), force_tw = env_int("SV_HWG_TW", 0);
   H.TW = force_tw ? force_tw : ((g.Wo % 32) == 0 ? 32 : 16);
   if (g.Wo % H.TW) return false;
-  H.stages = 2;
+  H.stages = env_int("SV_HWG_STAGES", 2);
+  if (H.stages < 2) H.stages = 2;
+  if (H.stages > 4) H.stages = 4;
   const int x_tw = H.nstack ? H.TW : H.TW + g.kw - 1, dy_tw = H.nstack ? H.TW + g.kw - 1 : H.TW;
   // garbage sub-blocks of a partially filled group read up to (nsub-1) rows (N-stack) / pixels (plain) past the X tile
   const size_t slack = H.nstack ? (size_t)(H.nsub - 1) * x_tw * cb * 2 : (size_t)H.nsub * cb * 2;
@@ -2297,7 +2305,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       L.OH = g.Hi; L.OW = g.Wi; L.osy = s; L.ooy = ph; L.osx = s; L.oox = pw;
       L.out_ld = g.din_ld; L.out_f32 = 0;
       L.nparts = 1; L.part_n[0] = t.n_pad_dg; L.part_act[0] = ACT_NONE;
-      finish_launch(L, t.n_pad_dg);
+      finish_launch(L, t.n_pad_dg, s * s);
       try_halo(L, GH, GW, g.B, 1, 1, s == 2 && L.tile_cols <= 64 && env_int("SV_S2_DGRAD_HALO", 1));
       plan_persist(L, s * s);
       if (s == 1) {
