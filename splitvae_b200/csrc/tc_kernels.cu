@@ -1862,7 +1862,8 @@ size_t split_k_bytes(const TcLaunch& L) {
 // groups.  Tile choice: minimise estimated L2->SMEM bytes per output pixel (halo + streamed weights), with a 25 % penalty
 // for configurations that leave a single CTA per SM (no cross-CTA overlap of the load / MMA / epilogue phases).
 
-void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false, size_t max_halo_bytes = 0) {
+void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false, size_t max_halo_bytes = 0,
+              int tmem_limit = 512) {
   L.halo = 0;
   L.halo_sx = 1; L.halo_sy = 1;
   if (env_int("SV_NO_HALO", 0)) return;
@@ -1891,7 +1892,7 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
       if (force_tw && TW != force_tw) continue;
       if (force_th && TH != force_th) continue;
       const int MT = (TW / 8) * (TH / 16);
-      if (MT * L.tile_cols > 512) continue;
+      if (MT * L.tile_cols > tmem_limit) continue;
       const int TWp = TW + wtaps - 1, THp = (TH - 1) * sy + L.taps_h;
       if (TWp * sx > 256 || THp > 256) continue;
       const size_t chunk = ((size_t)THp * TWp * pix + 1023) / 1024 * 1024;
@@ -2165,7 +2166,15 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
       P.taps_h = 6; P.taps_w = 3; P.pad_l = 0; P.bk = 16; P.swizzle = 32; P.kc = 1;
       finish_launch(P, t.n_pad_fwd);
       try_halo(P, g.Ho, g.Wo, g.B, 1, 2, true);
-      if (P.halo) { plan_persist(P, 1); L = P; t.first_pair = true; t.ci_pad = 16; }
+      if (P.halo) plan_persist(P, 1);
+      if (P.halo && !P.persist) {       // wide first layers (GM h_block.0: 128 columns): a tile whose two accumulator sets fit in TMEM
+        TcLaunch Q = L;
+        Q.taps_h = 6; Q.taps_w = 3; Q.pad_l = 0; Q.bk = 16; Q.swizzle = 32; Q.kc = 1;
+        finish_launch(Q, t.n_pad_fwd);
+        try_halo(Q, g.Ho, g.Wo, g.B, 1, 2, true, 0, 256);
+        if (Q.halo) { plan_persist(Q, 1); if (Q.persist) P = Q; }
+      }
+      if (P.halo) { L = P; t.first_pair = true; t.ci_pad = 16; }
     }
   }
   {

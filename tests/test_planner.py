@@ -1,0 +1,46 @@
+"""CPU: the kernel planner (pure host code inside libsplitvae, reached through a plan-only handle - no CUDA call is made).
+
+Pins which tensor-core kernel serves every layer pass of the BASELINE.json configurations, that every conv / dense pass of the
+hot path HAS a tensor-core kernel (nothing silently falls back to the SIMT reference kernels in bf16 mode), and that the
+workspace stays far below one B200's 180 GB."""
+import pytest
+
+from splitvae_b200._lib import KERNEL_NAMES
+from splitvae_b200.engine import Engine
+
+
+def _plan(model, H, B, **env):
+    e = Engine(model=model, height=H, width=H, batch=B, plan_only=True)
+    return e, {L.name.decode(): (KERNEL_NAMES[L.kern_fwd], KERNEL_NAMES[L.kern_dgrad], KERNEL_NAMES[L.kern_wgrad]) for L in e.debug_layers()}
+
+
+def test_c2_layer_to_kernel_map():
+    e, plan = _plan("lgvae", 64, 256)
+    for enc in ("encoder_x", "encoder_x_hat"):
+        assert plan[f"{enc}.e1"] == ("pconv_kernel", "reference", "wgrad_kernel")        # first conv: no input gradient
+        assert plan[f"{enc}.e2"] == ("pconv_kernel", "pconv_kernel", "wgrad_kernel")
+        assert plan[f"{enc}.e3"] == ("igemm_kernel", "igemm_kernel", "wgrad_kernel")
+    for dec in ("decoder_x", "decoder_x_hat"):
+        assert plan[f"{dec}.d3"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
+        assert plan[f"{dec}.d4"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
+        assert plan[f"{dec}.d5"] == ("nsconv_kernel", "pconv_kernel", "halo_wgrad_kernel")
+    assert e.workspace_bytes < 4 << 30
+
+
+@pytest.mark.parametrize("model,H,B", [("lgvae", 32, 64), ("lgvae", 64, 256), ("lggmvae", 32, 256), ("lggmvae", 64, 256), ("lgvae", 16, 3)])
+def test_every_pass_of_the_hot_path_has_a_tensor_core_kernel(model, H, B):
+    e, plan = _plan(model, H, B)
+    assert len(plan) == (18 if model == "lgvae" else 22)
+    for name, (fwd, dgrad, wgrad) in plan.items():
+        assert fwd != "reference" and wgrad != "reference", (name, fwd, wgrad)
+        first_conv = name.endswith(".e1") and "encoder_x_hat" in name or name in ("encoder_x.e1", "encoder_x.h_block.0")
+        if not first_conv:
+            assert dgrad != "reference", name
+
+
+def test_planner_knobs_are_read_at_plan_time(monkeypatch):
+    monkeypatch.setenv("SV_PCONV", "0")
+    monkeypatch.setenv("SV_NO_NSCONV", "1")
+    _, plan = _plan("lgvae", 64, 256)
+    assert plan["decoder_x.d5"][1] == "halo_conv_kernel"
+    assert plan["decoder_x.d4"][0] == "igemm_kernel"
