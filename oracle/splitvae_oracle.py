@@ -15,7 +15,9 @@ reference itself: its own source, executed here against a stand-in for the few `
     graph, concat / slice order, activations, return-tuple order) and the forward + loss lines of
     train_step_lg_vae / train_step_lg_gm_vae (beta / alpha weighting), with noise drawn from a queue
     and weights injected by Keras variable name (scripts/make_reference_model_golden.py) - the oracle's
-    model_forward / step_losses agree to 1e-10 on every output tensor and scalar.
+    model_forward / step_losses agree to 1e-10 on every output tensor and scalar;
+  * the patch scramble: augmentation.py imported UNMODIFIED, Augmentator.scramble driven by an injected patch
+    permutation (scripts/make_reference_scramble_golden.py) - oracle.scramble agrees bit for bit.
 What stays UNPINNED (restated from the published TF/Keras semantics listed below, checked only by
 analytic known-answer tests and fp64 finite differences): the library primitives themselves -
 Conv2D 'same' padding, bilinear resize, activations, Keras Adam / ExponentialDecay - and autodiff,

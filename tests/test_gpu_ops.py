@@ -98,3 +98,21 @@ def test_loss_kernel_matches_the_reference_source_vectors():
     pm, ps = (torch.tensor(G["inputs"][k], dtype=torch.float32).cuda() for k in ("prior_mean", "prior_sig"))
     assert abs(float(trainer.kl_divergence(zm, zs)) - G["kl_divergence"]) <= 1e-5 * G["kl_divergence"]
     assert abs(float(trainer.kl_divergence_two_gauss(zm, zs, pm, ps)) - G["kl_divergence_two_gauss"]) <= 1e-5 * G["kl_divergence_two_gauss"]
+
+
+def test_stage_scramble_matches_the_reference_source_vectors():
+    """sv_stage_scramble against tests/golden/reference_scramble.json (the reference's own Augmentator.scramble executed by
+    scripts/make_reference_scramble_golden.py): bit-exact on the k/255*2-1 grid."""
+    import json
+    import os
+    from splitvae_b200.augmentation import Augmentator
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_scramble.json")) as f:
+        G = json.load(f)
+    for c in G["cases"]:
+        H, p = c["H"], c["p"]
+        u8 = torch.tensor(c["x"], dtype=torch.uint8).reshape(1, H, H, 3).cuda()
+        perm = torch.tensor(c["perm"], dtype=torch.int32).reshape(1, -1).cuda()
+        out = Augmentator("scramble", p).scramble(u8, perm).cpu().numpy()[0]
+        scale = lambda k: (np.asarray(k, np.float64).reshape(H, H, 3) / 255.0 * 2 - 1).astype(np.float32)   # vae/data.py:52
+        assert np.array_equal(out[..., :3], scale(c["x"])), (H, p)
+        assert np.array_equal(out[..., 3:], scale(c["x_hat"])), (H, p)

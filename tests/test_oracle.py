@@ -258,3 +258,19 @@ def test_oracle_forward_and_losses_match_the_reference_source(kind):
     assert set(L.keys()) == set(G["scalars"].keys())
     for k, v in G["scalars"].items():
         assert abs(float(L[k]) - v) <= 1e-10 * max(1.0, abs(v)), (k, float(L[k]), v)
+
+
+def test_scramble_matches_the_reference_source():
+    """oracle.scramble against tests/golden/reference_scramble.json: the reference's own Augmentator.scramble (augmentation.py:43-57,
+    imported unmodified by scripts/make_reference_scramble_golden.py) driven by an injected patch permutation."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_scramble.json")) as f:
+        G = json.load(f)
+    assert len(G["cases"]) >= 5
+    for c in G["cases"]:
+        H, p = c["H"], c["p"]
+        x = np.asarray(c["x"], np.float64).reshape(H, H, 3)
+        out = O.scramble(x, p, np.asarray(c["perm"]))
+        assert out.shape == (H, H, 6)
+        assert np.array_equal(out[..., :3], x)
+        assert np.array_equal(out[..., 3:], np.asarray(c["x_hat"], np.float64).reshape(H, H, 3)), (H, p)
