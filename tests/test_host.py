@@ -96,3 +96,26 @@ def test_data_parallel_world_size_2_equals_global_batch():
     full = np.concatenate([grads[k].reshape(-1) for k in ret["names"]])
     assert np.allclose(ret["flat"], full, rtol=1e-9, atol=1e-12)
     assert np.allclose(ret["scal"], [sc["total"], sc["recon_x"]], rtol=1e-12)
+
+
+def test_cli_matches_the_reference_parser():
+    """splitvae_b200.main's parser against tests/golden/reference_cli.json: the reference's own argparse block (vae/main.py:15-31)
+    executed verbatim by scripts/make_reference_cli_golden.py, and every `python main.py ...` command of its README parsed by it."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_cli.json")) as f:
+        G = json.load(f)
+    mine = {a.dest: a for a in cli.build_parser()._actions}
+    assert len(G["flags"]) == 16
+    for dest, spec in G["flags"].items():
+        assert dest in mine, dest
+        a = mine[dest]
+        assert a.option_strings == spec["options"], dest                     # same spelling, including the single-dash flags
+        assert a.default == spec["default"], dest
+        assert getattr(a.type, "__name__", None) == spec["type"], dest
+    assert len(G["commands"]) >= 7
+    for c in G["commands"]:
+        got = vars(cli.build_parser().parse_args(c["argv"]))
+        for k, v in c["parsed"].items():
+            assert got[k] == v, (c["argv"], k)
+        cfg = cli.make_config(c["argv"])
+        assert cfg.label == (not c["parsed"]["no_label"])                   # vae/main.py:49
