@@ -205,11 +205,24 @@ def main():
         assert len(tup) == len(names) and not NOISE["normal"] and not NOISE["uniform"]
         queue()
         sc = step(model, inputs, types.SimpleNamespace(beta=beta, alpha=alpha))
+        # the rest of the model surface the visualiser / test steps call (vae/model.py:204-218, 252-275), on regenerable inputs
+        api = {}
+        queue()
+        api["encode"] = [digest(t) for t in model.encode(inputs)]
+        z_a, z_b = 0.5 * t64(b["eps_g"]), 0.5 * t64(b["eps_l"])
+        api["decode_rescaled"] = [digest(t) for t in model.decode(z_a, z_b)]
+        api["decode_raw"] = [digest(t) for t in model.decode(z_a, z_b, rescale=False)]
+        if kind == "lggmvae":
+            y_in = torch.softmax(torch.log(t64(b["u"])), dim=1)
+            api["encode_y"] = [digest(t) for t in model.encode_y(y_in)]
+            queue()
+            api["get_y"] = [digest(t) for t in model.get_y(inputs[..., :3])]     # (the 3-channel image: model.py:272-275 does not slice)
         G = {"source": f"{REF_MODEL} (unmodified) + {REF_TRAINER} lines {lines[0]}-{lines[1]} and 11-38, executed against the torch float64 "
                        f"stand-in for tensorflow defined in scripts/make_reference_model_golden.py",
              "case": {"model": kind, "H": H, "B": B, "patch": patch, "beta": beta, "alpha": alpha, "seed_base": seed_base},
              "inputs_sum": float(np.asarray(b["inputs"], np.float64).sum()),
              "outputs": {n: digest(t) for n, t in zip(names, tup)},
+             "output_order": names, "api": api,
              "scalars": {k: float(v) for k, v in sc.items()}}
         path = os.path.join(ROOT, "tests", "golden", f"reference_model_{kind}.json")
         with open(path, "w") as f:
