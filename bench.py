@@ -84,9 +84,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(model, H, batch, patch, beta, alpha, steps, threads=None):
+def cpu_baseline(model, H, batch, patch, beta, alpha, steps, threads=None, min_seconds=0.0):
     """The oracle (CPU restatement of the TF reference; TF itself is not installable) timed on the host
-    cores over a bounded sample: `steps` train steps of `batch` images of this workload's shape."""
+    cores over a bounded sample: `steps` train steps of `batch` images of this workload's shape (more steps
+    until `min_seconds` of CPU work have been timed)."""
     import torch
     from oracle import splitvae_oracle as O
     threads = threads or os.cpu_count() or 1
@@ -97,11 +98,11 @@ def cpu_baseline(model, H, batch, patch, beta, alpha, steps, threads=None):
     u = b["u"] if model == "lggmvae" else None
     O.train_step(st, model, b["inputs"], b["eps_g"], b["eps_l"], u, beta=beta, alpha=alpha)  # warm-up
     times = []
-    for _ in range(steps):
+    while len(times) < steps or sum(times) < min_seconds:
         t0 = time.perf_counter()
         O.train_step(st, model, b["inputs"], b["eps_g"], b["eps_l"], u, beta=beta, alpha=alpha)
         times.append(time.perf_counter() - t0)
-    return batch * steps / sum(times), threads, times
+    return batch * len(times) / sum(times), threads, times
 
 
 def run_reference(args, wl):
@@ -349,9 +350,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             sb = 16 if H == 64 else 64
-            ips, threads, times = cpu_baseline(model, H, sb, patch, beta, alpha, 2)
+            ips, threads, times = cpu_baseline(model, H, sb, patch, beta, alpha, 5, min_seconds=10.0)
             cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                   "sample": f"2 oracle train steps of {sb} images ({H}x{H}x3) after 1 warm-up, torch CPU fp32 (TF 2.0 not installable)"}
+                   "sample": f"{len(times)} oracle train steps of {sb} images ({H}x{H}x3) = {sum(times):.1f} s of CPU work after 1 warm-up, "
+                             f"torch CPU fp32 on {threads} threads (TF 2.0 not installable)"}
         total_images = world * B * K
         line = {
             "metric": "train images/sec", "value": total_images / t_dev, "unit": "images/s", "n_gpus": world, "steps": K,
