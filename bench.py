@@ -348,7 +348,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # (the CPU baseline is reported by the 1-GPU run only)
             sb = 16 if H == 64 else 64
             ips, threads, times = cpu_baseline(model, H, sb, patch, beta, alpha, 5, min_seconds=10.0)
             cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
