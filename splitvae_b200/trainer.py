@@ -143,6 +143,50 @@ class StepRunner:
         return dict(zip(names, s))
 
 
+def linear_assignment(labels, pred):
+    """vae/trainer.py:40-67: majority-vote mapping of clusters to classes.  labels [n, num_class] one-hot, pred [n, num_cluster]
+    scores; every sample of cluster i is assigned the most frequent true class inside that cluster (ties: the class met first,
+    as tf.unique_with_counts + tf.argmax do); returns the assignment one-hot [n, num_class].  Host-side metric code: runs on
+    whatever device the tensors live on (it is not part of the train hot path)."""
+    num_class, num_cluster = labels.shape[1], pred.shape[1]
+    lab = torch.argmax(labels, dim=1)
+    cluster = torch.argmax(pred, dim=1)
+    cluster_pred = torch.zeros_like(lab)
+    for i in range(num_cluster):
+        members = lab[cluster == i]
+        if members.numel() == 0:           # skip if the cluster does not exist
+            continue
+        seen, counts = [], {}
+        for v in members.tolist():         # unique values in order of first occurrence
+            if v not in counts:
+                seen.append(v)
+                counts[v] = 0
+            counts[v] += 1
+        best = max(range(len(seen)), key=lambda j: (counts[seen[j]], -j))
+        cluster_pred = torch.where(cluster == i, torch.full_like(cluster_pred, seen[best]), cluster_pred)
+    return torch.nn.functional.one_hot(cluster_pred, num_class).to(labels.dtype)
+
+
+class CategoricalAccuracy:
+    """tf.keras.metrics.CategoricalAccuracy (vae/trainer.py:114-118): running fraction of rows whose argmax matches."""
+
+    def __init__(self, name=None):
+        self.name = name
+        self.correct, self.count = 0, 0
+
+    def __call__(self, y_true, y_pred):
+        self.correct += int((torch.argmax(y_true, dim=1) == torch.argmax(y_pred, dim=1)).sum())
+        self.count += int(y_true.shape[0])
+
+    update_state = __call__
+
+    def result(self):
+        return self.correct / self.count if self.count else 0.0
+
+    def reset_states(self):
+        self.correct, self.count = 0, 0
+
+
 class Mean:
     """tf.keras.metrics.Mean: running mean with result() / reset_states() (vae/trainer.py:99-113).  result() of an empty
     metric is 0, as in Keras."""
@@ -235,8 +279,9 @@ REPORT_TEMPLATE = ('Training step {}\n'
                    '            Y KL train loss: {:.4f}, Y KL test loss: {:.4f}')
 
 
-def format_report(step, m):
-    """The stdout report of vae/trainer.py:354-382 (same template, same argument order)."""
+def format_report(step, m, cluster_acc=0.0):
+    """The stdout report of vae/trainer.py:354-382 (same template, same argument order).  The three classifier accuracies need the
+    SVHN classifier (weights blob missing upstream) and print as Keras' empty-metric value 0."""
     r = lambda k: m[k].result()
     return REPORT_TEMPLATE.format(
         step,
@@ -245,7 +290,7 @@ def format_report(step, m):
         r("x_recon_test_loss"), r("x_kl_test_loss"), r("x_recon_test_loss") + r("x_kl_test_loss"),
         r("x_hat_recon_test_loss"), r("x_hat_kl_test_loss"), r("x_hat_recon_test_loss") + r("x_hat_kl_test_loss"),
         r("total_kl_train_loss"), r("total_kl_test_loss"),
-        0.0, 0.0, 0.0, 0.0,
+        0.0, 0.0, 0.0, float(cluster_acc),
         r("y_kl_train_loss"), r("y_kl_test_loss"))
 
 
@@ -316,14 +361,22 @@ def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, tes
             history.append((step, sc))
             print("Training time: {:.2f}".format(time.time() - start))
             start = time.time()
+            cluster_acc = CategoricalAccuracy("classifier_cluster_acc")
             if test_dataset is not None:                      # evaluation pass, vae/trainer.py:316-352
+                all_labels, all_pred = [], []
                 for test_data in test_dataset:
                     test_images = test_data[0] if config.get("label") else test_data
                     if not test_images.is_cuda:
                         test_images = test_images.cuda(non_blocking=True)
-                    test_step(model, test_images, config=config, metrics=metrics)
+                    outs = test_step(model, test_images, config=config, metrics=metrics)
+                    if config.get("label") and gm:            # trainer.py:323-328: labels and y_logits of the whole test set
+                        all_labels.append(test_data[1].detach().cpu())
+                        all_pred.append(outs[11].detach().cpu().clone())
+                if all_labels:                                # trainer.py:345-349: majority-vote cluster accuracy
+                    labels = torch.cat(all_labels)
+                    cluster_acc(labels, linear_assignment(labels, torch.cat(all_pred)))
                 print("Testing time: {:.2f}".format(time.time() - start))
-            print(format_report(step, metrics), flush=True)
+            print(format_report(step, metrics, cluster_acc.result()), flush=True)
             reset_reported(metrics)
             start = time.time()
         if step >= int(config.get("training_steps")):  # vae/trainer.py:417-419

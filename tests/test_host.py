@@ -119,3 +119,21 @@ def test_cli_matches_the_reference_parser():
             assert got[k] == v, (c["argv"], k)
         cfg = cli.make_config(c["argv"])
         assert cfg.label == (not c["parsed"]["no_label"])                   # vae/main.py:49
+
+
+def test_linear_assignment_matches_the_reference_source():
+    """trainer.linear_assignment / CategoricalAccuracy against tests/golden/reference_cluster.json (the reference's own
+    linear_assignment, vae/trainer.py:40-67, executed by scripts/make_reference_cluster_golden.py), including exact ties."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_cluster.json")) as f:
+        G = json.load(f)
+    for c in G["cases"]:
+        lab = torch.tensor(c["labels"])
+        labels = torch.nn.functional.one_hot(lab, c["num_class"]).float()
+        pred = torch.tensor(c["pred"], dtype=torch.float64)
+        out = trainer.linear_assignment(labels, pred)
+        assert out.shape == labels.shape
+        assert torch.argmax(out, dim=1).tolist() == c["assigned"]
+        acc = trainer.CategoricalAccuracy()
+        acc(labels, out)
+        assert abs(acc.result() - c["accuracy"]) < 1e-12
