@@ -341,6 +341,24 @@ def main():
         ach = loss_bytes / t_loss / 1e9
         roof["hbm_kernels"] = {"pixel_loss_kernel": {"achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                                                       "algorithmic_bytes_per_launch": loss_bytes, "us_per_launch": t_loss * 1e6}}
+        try:   # multi-tensor Keras Adam over an arena-sized scratch copy: 28 B / parameter; never allowed to break the line
+            import ctypes as C
+            from splitvae_b200 import _lib
+            n = int(e.arena_floats)
+            bufs = [torch.zeros(n, device=dev) for _ in range(4)]
+            bufs[1].normal_()
+            lib = _lib.load()
+            vp = lambda t: C.c_void_p(t.data_ptr())
+            run = lambda: lib.sv_adam_flat(vp(bufs[0]), vp(bufs[1]), vp(bufs[2]), vp(bufs[3]), C.c_int64(n), C.c_float(1e-4),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            t_adam = timed(run, reps=10)
+            adam_bytes = 28 * n
+            roof["hbm_kernels"]["adam_kernel"] = {"achieved": adam_bytes / t_adam / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                                  "frac": adam_bytes / t_adam / 1e9 / peaks["hbm"],
+                                                  "algorithmic_bytes_per_launch": adam_bytes, "us_per_launch": t_adam * 1e6}
+            del bufs
+        except Exception as ex:   # pragma: no cover
+            roof["hbm_kernels"]["adam_kernel"] = {"error": str(ex)[:200]}
         step_flops = B * TRAIN_GFLOP_PER_IMAGE[wl] * 1e9
         roof["step_tensor"] = {"achieved_tflops": step_flops / (t_dev / K) / 1e12, "peak_tflops": peaks["tensor_sustained"],
                                "frac": step_flops / (t_dev / K) / 1e12 / peaks["tensor_sustained"],
