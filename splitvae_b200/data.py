@@ -1,5 +1,6 @@
-"""Synthetic stand-ins for vae/data.py:get_dataset (the real SVHN / CelebA readers need the network
-and the datasets).  Shapes and value grid follow the reference:
+"""vae/data.py:get_dataset for this build: synthetic batches by default (the datasets need the network, SURVEY.md section 2
+row 5), plus a reader for local SVHN `.mat` files (`data_root=`); CelebA (zip of JPEGs -> crop 178 -> resize 64 -> TFRecord,
+data.py:77-134) is not read.  Shapes and value grid follow the reference:
 uint8 pixels mapped k/255*2-1 (vae/data.py:52); `svhn*` -> 32x32x3, `celeba64` -> 64x64x3."""
 from __future__ import annotations
 
@@ -44,10 +45,75 @@ class SyntheticBatches:
         return self.aug.scramble(self.u8)
 
 
-def get_dataset(dataset, get_label=False, batch_size=64, augmentor=None, seed=0, test_batches=4):
+class SvhnBatches:
+    """The SVHN cropped-digits `.mat` files of vae/data.py:23-75 (`train_32x32.mat`, `extra_32x32.mat`, `test_32x32.mat` with
+    X [32,32,3,N] uint8 and y [N,1], digit 0 stored as label 10), read from `root` (no download: there is no network here).
+    Images stay uint8 in pinned host memory; a batch is gathered on the host, copied to the device and handed to the scramble
+    kernel, which applies the reference's /255*2-1 scaling (data.py:52) and builds x_hat (augmentation.py:43-57).
+      train: shuffled, repeating, full batches only (`shuffle(20000).repeat()...batch(B)`, vae/main.py:57)
+      test : one pass, the last batch may be partial (`batch(B)` without drop_remainder, vae/main.py:58)
+    With get_label the iterator yields (images, one_hot(y - 1, 10)) like the reference ("0 one-hot at the last index")."""
+
+    def __init__(self, root, split, batch_size, augmentor, get_label=False, extra=True, seed=0, device="cuda"):
+        import os
+
+        import numpy as np
+        from scipy.io import loadmat
+        files = {"train": ["train_32x32.mat"] + (["extra_32x32.mat"] if extra else []), "test": ["test_32x32.mat"]}[split]
+        xs, ys = [], []
+        for f in files:
+            path = os.path.join(root, f)
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"{path} (the SVHN files are not downloaded by this build; see vae/data.py:35-43 for the URLs)")
+            m = loadmat(path)
+            xs.append(np.ascontiguousarray(m["X"].transpose((3, 0, 1, 2))))      # data.py:46
+            ys.append(np.asarray(m["y"]).reshape(-1).astype(np.int64))
+        self.x = torch.from_numpy(np.concatenate(xs))
+        self.y = torch.from_numpy(np.concatenate(ys))
+        if torch.cuda.is_available():
+            self.x = self.x.pin_memory()
+        self.split, self.B, self.aug, self.get_label, self.device = split, int(batch_size), augmentor, get_label, device
+        self.gen = torch.Generator().manual_seed(seed)
+        self.shape = [-1, 32, 32, 3]
+        self._order, self._pos = None, 0
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def host_batch(self):
+        """(uint8 images [b,32,32,3], one-hot labels [b,10]) of the next batch; raises StopIteration at the end of a test pass."""
+        n = self.x.shape[0]
+        if self.split == "train":
+            if self._order is None or self._pos + self.B > n:      # a new shuffled epoch (full batches only)
+                self._order, self._pos = torch.randperm(n, generator=self.gen), 0
+            idx = self._order[self._pos:self._pos + self.B]
+        else:
+            if self._pos >= n:
+                raise StopIteration
+            idx = torch.arange(self._pos, min(self._pos + self.B, n))
+        self._pos += idx.numel()
+        labels = torch.nn.functional.one_hot((self.y[idx] - 1) % 10, 10).float()   # data.py:56: digit 0 (label 10) -> index 9
+        return self.x[idx], labels
+
+    def __iter__(self):
+        if self.split != "train":
+            self._pos = 0
+        return self
+
+    def __next__(self):
+        u8, labels = self.host_batch()
+        images = self.aug.scramble(u8.to(self.device, non_blocking=True))
+        return (images, labels) if self.get_label else images
+
+
+def get_dataset(dataset, get_label=False, batch_size=64, augmentor=None, seed=0, test_batches=4, data_root=None):
     """Same return contract as vae/data.py:11-21: (train_dataset, test_dataset, image_shape).  The test set is a finite
     pass of `test_batches` synthetic batches of the same batch size (vae/main.py:58-61 batches the test split the same way)."""
     shp = image_shape(dataset)
+    if data_root is not None and dataset.lower() in ("svhn", "svhn_no_extra"):     # the real files, when the caller has them
+        extra = dataset.lower() == "svhn"
+        return (SvhnBatches(data_root, "train", batch_size, augmentor, get_label, extra, seed),
+                SvhnBatches(data_root, "test", batch_size, augmentor, get_label, extra, seed), shp)
     train = SyntheticBatches(dataset, batch_size, augmentor, seed=seed)
     test = SyntheticBatches(dataset, batch_size, augmentor, seed=seed + 7919, pool=max(1, test_batches), length=test_batches) \
         if test_batches else None

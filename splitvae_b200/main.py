@@ -33,6 +33,7 @@ def build_parser():
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--no_graph', action='store_true')
     parser.add_argument('--test_batches', type=int, default=4, help='synthetic test batches per evaluation pass (0: no evaluation)')
+    parser.add_argument('--data_root', type=str, default='', help='directory with the SVHN .mat files (train/extra/test_32x32.mat); default: synthetic data')
     parser.add_argument('--save_weights', type=str, default='', help='write the trained weights (.npz, Keras variable names) here')
     return parser
 
@@ -52,10 +53,13 @@ def main(argv=None):
     from .augmentation import Augmentator
     from .model import LGGMVae, LGVae
     augmentor = Augmentator(type=config.augmentation, size=config.patch_size)
-    train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=False,
+    real = bool(config.data_root)
+    train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=real and config.label,
                                                                 batch_size=config.batch_size, augmentor=augmentor,
-                                                                seed=config.seed, test_batches=config.test_batches)
-    config.label = False  # synthetic data carries no labels
+                                                                seed=config.seed, test_batches=config.test_batches,
+                                                                data_root=config.data_root or None)
+    if not real:
+        config.label = False  # synthetic data carries no labels
     if config.model == 'lgvae':
         model = LGVae(global_latent_dims=config.global_latent_dims, local_latent_dims=config.local_latent_dims,
                       image_shape=input_shape, precision=config.precision)

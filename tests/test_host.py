@@ -137,3 +137,48 @@ def test_linear_assignment_matches_the_reference_source():
         acc = trainer.CategoricalAccuracy()
         acc(labels, out)
         assert abs(acc.result() - c["accuracy"]) < 1e-12
+
+
+def test_svhn_mat_reader_host_side(tmp_path):
+    """data.SvhnBatches (vae/data.py:23-75 without the download): file layout X [32,32,3,N] / y [N,1], digit 0 stored as label 10 ->
+    one-hot index 9, train = shuffled repeating full batches over train+extra, test = one pass with a partial last batch."""
+    from scipy.io import savemat
+    from splitvae_b200 import data
+    rng = np.random.default_rng(0)
+    sets = {}
+    for name, n in (("train", 10), ("extra", 6), ("test", 7)):
+        X = rng.integers(0, 256, (32, 32, 3, n), dtype=np.uint8)
+        y = rng.integers(1, 11, (n, 1)).astype(np.uint8)
+        y[0, 0] = 10
+        savemat(str(tmp_path / f"{name}_32x32.mat"), {"X": X, "y": y})
+        sets[name] = (X.transpose(3, 0, 1, 2), y.reshape(-1))
+    tr = data.SvhnBatches(str(tmp_path), "train", 4, None, get_label=True, extra=True, seed=1)
+    assert len(tr) == 16 and tr.shape == [-1, 32, 32, 3]
+    allx = np.concatenate([sets["train"][0], sets["extra"][0]])
+    ally = np.concatenate([sets["train"][1], sets["extra"][1]])
+    seen = []
+    for _ in range(4):                                   # one epoch = 4 full batches, every image exactly once
+        u8, lab = tr.host_batch()
+        assert u8.shape == (4, 32, 32, 3) and u8.dtype == torch.uint8 and lab.shape == (4, 10)
+        for img, l in zip(u8.numpy(), lab.numpy()):
+            j = next(i for i in range(16) if np.array_equal(allx[i], img))
+            seen.append(j)
+            assert np.argmax(l) == (ally[j] - 1) % 10 and l.sum() == 1
+    assert sorted(seen) == list(range(16))
+    u8, _ = tr.host_batch()                              # repeats: a new shuffled epoch
+    assert u8.shape[0] == 4
+    te = data.SvhnBatches(str(tmp_path), "test", 4, None, get_label=True)
+    sizes = []
+    while True:
+        try:
+            u8, lab = te.host_batch()
+        except StopIteration:
+            break
+        sizes.append(u8.shape[0])
+    assert sizes == [4, 3]                               # batch(B) keeps the partial last batch (vae/main.py:58)
+    assert np.array_equal(te.x.numpy(), sets["test"][0])
+    assert int(np.argmax(data.SvhnBatches(str(tmp_path), "test", 7, None, True).host_batch()[1][0])) == 9    # label 10 -> index 9
+    nx = data.SvhnBatches(str(tmp_path), "train", 4, None, extra=False)
+    assert len(nx) == 10                                 # svhn_no_extra
+    with pytest.raises(FileNotFoundError):
+        data.SvhnBatches(str(tmp_path / "missing"), "train", 4, None)
