@@ -96,6 +96,10 @@ def layer_table(model: str, H: int, W: int, global_latent: int = 128, local_late
         rows.append((prefix + ".d4", "conv", (6, 6, 64, 32), 0.0))
         rows.append((prefix + ".d5", "conv", (6, 6, 32, 6), 0.0))
 
+    if model == "gmvae":            # plain GMVAE (vae/model.py:277-286): gm encoder + ONE decoder fed by z only; not built on the
+        gm_encoder("encoder_x", global_latent)      # device yet - the oracle is ahead of the product here
+        decoder("decoder_x", global_latent)
+        return rows
     if model == "lgvae":
         conv_encoder("encoder_x", global_latent)
     elif model == "lggmvae":
@@ -230,6 +234,11 @@ def model_forward(P, model, inputs, eps_g, eps_l, u=None, tau=0.4):
     H, W = inputs.shape[1], inputs.shape[2]
     x, x_hat = inputs[..., :3], inputs[..., 3:]
     out = {}
+    if model == "gmvae":            # GMVae.call, vae/model.py:288-299 (9-tuple)
+        z_x, zm_x, zs_x, y, y_logits, zpm, zps = encoder_gmvae(P, "encoder_x", x, eps_g, u, tau)
+        x_mean, x_ls = decoder(P, "decoder_x", z_x, H, W)
+        return dict(x_mean=x_mean, x_log_scale=x_ls, z_x=z_x, z_mean_x=zm_x, z_sig_x=zs_x, y=y, y_logits=y_logits,
+                    z_prior_mean=zpm, z_prior_sig=zps)
     if model == "lgvae":
         z_x, zm_x, zs_x = encoder_conv(P, "encoder_x", x, eps_g)
     else:
@@ -288,6 +297,12 @@ def step_losses(out, inputs, model, beta, alpha=40.0, y_size=30):
     x, x_hat = inputs[..., :3], inputs[..., 3:]
     L = {}
     L["recon_x"] = torch.mean(torch.sum(discretised_logistic_loss(x, out["x_mean"], out["x_log_scale"]), dim=[1, 2, 3]))
+    if model == "gmvae":            # train_step_gm_vae, vae/trainer.py:175-195
+        L["kl_x"] = kl_divergence_two_gauss(out["z_mean_x"], out["z_sig_x"], out["z_prior_mean"], out["z_prior_sig"])
+        py = torch.softmax(out["y_logits"], dim=1)
+        L["y_kl"] = torch.mean(torch.sum(py * (torch.log(py + 1e-8) - math.log(1.0 / y_size)), dim=1))
+        L["total"] = L["recon_x"] + beta * L["kl_x"] + alpha * L["y_kl"]
+        return L
     L["recon_x_hat"] = torch.mean(torch.sum(discretised_logistic_loss(x_hat, out["x_hat_mean"], out["x_hat_log_scale"]), dim=[1, 2, 3]))
     if model == "lgvae":
         L["total_kl"] = beta * kl_divergence(torch.cat([out["z_mean_x"], out["z_mean_x_hat"]], dim=1),

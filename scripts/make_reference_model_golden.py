@@ -179,7 +179,7 @@ def digest(t):
 def main():
     tf = install()
     ref = load_reference_model()
-    for kind, H, B, patch, beta, alpha in (("lgvae", 32, 3, 4, 7.0, 40.0), ("lggmvae", 32, 3, 4, 5.0, 3.0)):
+    for kind, H, B, patch, beta, alpha in (("lgvae", 32, 3, 4, 7.0, 40.0), ("lggmvae", 32, 3, 4, 5.0, 3.0), ("gmvae", 32, 3, 4, 6.0, 2.0)):
         seed_base = 70
         params = O.init_params(kind, H, H, seed=5 + seed_base)
         b = O.synthetic_batch(B, H, patch, seed_base=seed_base)
@@ -190,6 +190,11 @@ def main():
             outs = {"recon_x": "x_recon_loss", "recon_x_hat": "x_hat_recon_loss", "total_kl": "total_kl_loss", "kl_x": "x_kl_loss",
                     "kl_x_hat": "x_hat_kl_loss", "total": "total_loss"}
             step, lines = reference_step("train_step_lg_vae", tf, outs)
+        elif kind == "gmvae":
+            model = ref.GMVae(global_latent_dims=128, image_shape=[-1, H, H, 3], y_size=30, tau=0.4)
+            names = ["x_mean", "x_log_scale", "z_x", "z_mean_x", "z_sig_x", "y", "y_logits", "z_prior_mean", "z_prior_sig"]
+            outs = {"recon_x": "x_recon_loss", "kl_x": "x_kl_loss", "y_kl": "y_kl_loss", "total": "total_loss"}
+            step, lines = reference_step("train_step_gm_vae", tf, outs)
         else:
             model = ref.LGGMVae(global_latent_dims=128, local_latent_dims=128, image_shape=[-1, H, H, 3], y_size=30, tau=0.4)
             names = ["x_mean", "x_log_scale", "z_x", "z_mean_x", "z_sig_x", "z_x_hat", "x_hat_mean", "x_hat_log_scale", "z_mean_x_hat", "z_sig_x_hat",
@@ -199,7 +204,8 @@ def main():
             step, lines = reference_step("train_step_lg_gm_vae", tf, outs)
         inject(model, params)
         inputs = t64(b["inputs"])
-        queue = lambda: NOISE.update(normal=[t64(b["eps_g"]), t64(b["eps_l"])], uniform=[t64(b["u"])] if kind == "lggmvae" else [])
+        queue = lambda: NOISE.update(normal=[t64(b["eps_g"])] + ([] if kind == "gmvae" else [t64(b["eps_l"])]),
+                                     uniform=[] if kind == "lgvae" else [t64(b["u"])])
         queue()
         tup = model(inputs) if kind == "lgvae" else model(inputs, training=True)
         assert len(tup) == len(names) and not NOISE["normal"] and not NOISE["uniform"]
@@ -207,11 +213,12 @@ def main():
         sc = step(model, inputs, types.SimpleNamespace(beta=beta, alpha=alpha))
         # the rest of the model surface the visualiser / test steps call (vae/model.py:204-218, 252-275), on regenerable inputs
         api = {}
-        queue()
-        api["encode"] = [digest(t) for t in model.encode(inputs)]
         z_a, z_b = 0.5 * t64(b["eps_g"]), 0.5 * t64(b["eps_l"])
-        api["decode_rescaled"] = [digest(t) for t in model.decode(z_a, z_b)]
-        api["decode_raw"] = [digest(t) for t in model.decode(z_a, z_b, rescale=False)]
+        if kind != "gmvae":
+            queue()
+            api["encode"] = [digest(t) for t in model.encode(inputs)]
+            api["decode_rescaled"] = [digest(t) for t in model.decode(z_a, z_b)]
+            api["decode_raw"] = [digest(t) for t in model.decode(z_a, z_b, rescale=False)]
         if kind == "lggmvae":
             y_in = torch.softmax(torch.log(t64(b["u"])), dim=1)
             api["encode_y"] = [digest(t) for t in model.encode_y(y_in)]

@@ -234,7 +234,7 @@ def test_oracle_losses_match_the_reference_source():
 # forward/loss lines of its train steps under a torch stand-in for the few tensorflow names they use
 # (scripts/make_reference_model_golden.py).  The stand-in supplies library semantics only (the oracle's primitives); layer graph,
 # concat / slice order, activations, tuple order, beta / alpha weighting come from the reference's code.
-@pytest.mark.parametrize("kind", ["lgvae", "lggmvae"])
+@pytest.mark.parametrize("kind", ["lgvae", "lggmvae", "gmvae"])     # (gmvae: oracle only so far - SURVEY.md 8f #4 is not built on the device)
 def test_oracle_forward_and_losses_match_the_reference_source(kind):
     import json
     with open(os.path.join(os.path.dirname(__file__), "golden", f"reference_model_{kind}.json")) as f:
@@ -246,7 +246,7 @@ def test_oracle_forward_and_losses_match_the_reference_source(kind):
     P = O.to_torch(params, torch.float64, requires_grad=False)
     t64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
     inputs = t64(b["inputs"])
-    out = O.model_forward(P, kind, inputs, t64(b["eps_g"]), t64(b["eps_l"]), t64(b["u"]) if kind == "lggmvae" else None)
+    out = O.model_forward(P, kind, inputs, t64(b["eps_g"]), t64(b["eps_l"]), t64(b["u"]) if kind != "lgvae" else None)
     assert set(out.keys()) == set(G["outputs"].keys())
     for name, d in G["outputs"].items():
         t = out[name].detach().reshape(-1)
