@@ -35,8 +35,11 @@ enum {
 };
 
 enum { SV_MODEL_LGVAE = 0, SV_MODEL_LGGMVAE = 1 };      /* vae/main.py:63-69  --model */
-enum { SV_PRECISION_BF16_TC = 0,   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */
-       SV_PRECISION_FP32_REF = 1   /* fp32 SIMT reference kernels (debug / tight parity) */ };
+enum { SV_PRECISION_BF16_TC = 0,   /* single-bf16 operands on tcgen05 tensor cores, fp32 accumulate: fastest; gradients 5-10 % from
+                                      fp32 (ReLU masks of near-zero units flip under 2^-9 forward roundings) */
+       SV_PRECISION_FP32_REF = 1,  /* fp32 SIMT reference kernels (debug / tight parity) */
+       SV_PRECISION_BF16X3 = 2     /* the parity mode: forward products on bf16 PAIRS (hi + lo, three tcgen05 MMAs hi*hi + lo*hi +
+                                      hi*lo, fp32 accumulate), backward on single bf16: gradients < 1e-2, KL / ELBO < 1e-3 from fp64 */ };
 
 /* Mirrors the reference's CLI/config (vae/main.py:16-31) + model ctor args (vae/model.py:175,222). */
 typedef struct sv_config {
@@ -184,7 +187,9 @@ typedef struct sv_layer_info {
   void *in, *out, *dout, *din;            /* device pointers; in == NULL: the layer reads the caller's inputs */
   int64_t in_elems, out_elems, dout_elems, din_elems;
   /* which tensor-core kernel serves each pass (SV_KERN_*; 0 = reference SIMT kernel) */
-  int32_t kern_fwd, kern_dgrad, kern_wgrad, reserved;
+  int32_t kern_fwd, kern_dgrad, kern_wgrad;
+  int32_t split_fwd;                      /* 1: the forward product multiplies bf16 pairs (SV_PRECISION_BF16X3) */
+  void *in_lo, *out_lo;                   /* lo planes of in / out (value = hi + lo) in the bf16x3 mode, else NULL */
 } sv_layer_info;
 enum { SV_KERN_NONE = 0, SV_KERN_IGEMM = 1, SV_KERN_HALO_CONV = 2, SV_KERN_NSCONV = 3, SV_KERN_WGRAD = 4, SV_KERN_HALO_WGRAD = 5, SV_KERN_PCONV = 6 };
 enum { SV_PASS_FWD = 0, SV_PASS_DGRAD = 1, SV_PASS_WGRAD = 2 };

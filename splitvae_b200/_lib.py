@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsplitvae.so")
 
 SV_OK = 0
 SV_MODEL = {"lgvae": 0, "lggmvae": 1}
-SV_PRECISION = {"bf16": 0, "fp32": 1}
+SV_PRECISION = {"bf16": 0, "fp32": 1, "bf16x3": 2}
 SV_FLAG_PLAN_ONLY = 1
 SV_FLAG_NO_TC = 2
 
@@ -46,7 +46,8 @@ class SvLayerInfo(C.Structure):
                  "in_dt", "out_dt", "act_dt", "has_dgrad", "tc_fwd", "tc_dgrad", "tc_wgrad")] + \
                [(n, C.c_void_p) for n in ("in_", "out", "dout", "din")] + \
                [(n, C.c_int64) for n in ("in_elems", "out_elems", "dout_elems", "din_elems")] + \
-               [(n, C.c_int32) for n in ("kern_fwd", "kern_dgrad", "kern_wgrad", "reserved")]
+               [(n, C.c_int32) for n in ("kern_fwd", "kern_dgrad", "kern_wgrad", "split_fwd")] + \
+               [(n, C.c_void_p) for n in ("in_lo", "out_lo")]
 
 
 KERNEL_NAMES = {0: "reference", 1: "igemm_kernel", 2: "halo_conv_kernel", 3: "nsconv_kernel", 4: "wgrad_kernel", 5: "halo_wgrad_kernel", 6: "pconv_kernel"}

@@ -36,6 +36,8 @@ struct Layer {
   int in_dt = DT_F32, out_dt = DT_F32;
   int mask_act = ACT_NONE;                    // activation of the producer of `in`
   int xp = -1;                                // first conv of an encoder: staged padded bf16 image (tensor-core path)
+  bool split_fwd = false;                     // bf16x3: the forward product multiplies bf16 pairs (every layer but the decoders' d5)
+  int in_lo = -1, out_lo = -1;                // lo planes of the input / output activation (bf16x3)
   TcLayer tc;                                 // tensor-core plan (tc_kernels.h)
 };
 
@@ -55,6 +57,8 @@ struct sv_handle {
   sv_config cfg{};
   int act_dt = DT_BF16;
   bool round_w = true, plan_only = false, use_tc = true;
+  bool split = false;                         // SV_PRECISION_BF16X3: forward operands are bf16 pairs (hi + lo), backward single bf16
+  std::vector<int> lo_of;                     // buffer id -> id of its lo plane (-1: none)
   int B = 0, H = 0, W = 0, F = 0, K = 0;
   std::vector<Var> vars;
   long long arena_floats = 0;
@@ -126,6 +130,17 @@ int new_buf(sv_handle* h, size_t bytes) {
 }
 size_t esz(int dt) { return dt == DT_F32 ? 4 : 2; }
 int act_buf(sv_handle* h, long long elems) { return new_buf(h, (size_t)elems * esz(h->act_dt)); }
+// forward activation that feeds another forward layer: in the bf16x3 mode it is a bf16 PAIR, the lo plane is a twin buffer
+int fwd_buf(sv_handle* h, long long elems) {
+  const int hi = act_buf(h, elems);
+  if (h->split) {
+    const int lo = act_buf(h, elems);
+    h->lo_of.resize(h->bufs.size(), -1);
+    h->lo_of[hi] = lo;
+  }
+  return hi;
+}
+int lo_buf(const sv_handle* h, int id) { return (id >= 0 && id < (int)h->lo_of.size()) ? h->lo_of[id] : -1; }
 int f32_buf(sv_handle* h, long long elems) { return new_buf(h, (size_t)elems * 4); }
 
 long long add_var(sv_handle* h, const std::string& name, int ndim, const int* shape) {
@@ -192,9 +207,9 @@ ConvEnc build_conv_encoder(sv_handle* h, const char* prefix, int coff) {
   e.e2 = add_layer(h, prefix, 6, 6, 2, H / 2, W / 2, 32, {{"e2", 64, ACT_RELU}});
   e.e3 = add_layer(h, prefix, 4, 4, 2, H / 4, W / 4, 64, {{"e3", 128, ACT_RELU}});
   e.heads = add_layer(h, prefix, 1, 1, 1, 1, 1, h->F, {{"e4_mean", 128, ACT_NONE}, {"e4_sd", 128, ACT_SOFTPLUS}});
-  e.A1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 32); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 32);
-  e.A2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 64); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 64);
-  e.A3 = act_buf(h, (long long)B * h->F); e.dA3 = act_buf(h, (long long)B * h->F);
+  e.A1 = fwd_buf(h, (long long)B * (H / 2) * (W / 2) * 32); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 32);
+  e.A2 = fwd_buf(h, (long long)B * (H / 4) * (W / 4) * 64); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 64);
+  e.A3 = fwd_buf(h, (long long)B * h->F); e.dA3 = act_buf(h, (long long)B * h->F);
   e.HEADS = f32_buf(h, (long long)B * 256); e.dHEADS = act_buf(h, (long long)B * 256);
   wire(h, e.e1, -1, DT_F32, 6, coff, e.A1, T, 32, e.dA1, 32, -1, 0, ACT_NONE);
   wire(h, e.e2, e.A1, T, 32, 0, e.A2, T, 64, e.dA2, 64, e.dA1, 32, ACT_RELU);
@@ -228,16 +243,16 @@ GmEnc build_gm_encoder(sv_handle* h, const char* prefix) {
   }
   e.zheads = add_layer(h, prefix, 1, 1, 1, 1, 1, 512, {{"z_mean", 128, ACT_NONE}, {"z_sig", 128, ACT_SOFTPLUS}});
 
-  e.A1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 128); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 128);
-  e.A2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 128); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 128);
-  e.A3 = act_buf(h, (long long)B * F); e.dA3 = act_buf(h, (long long)B * F);
-  e.YB0E1 = act_buf(h, (long long)B * 1536); e.dYB0E1 = act_buf(h, (long long)B * 1536);
-  e.YH2 = act_buf(h, (long long)B * 128); e.dYH2 = act_buf(h, (long long)B * 128);
+  e.A1 = fwd_buf(h, (long long)B * (H / 2) * (W / 2) * 128); e.dA1 = act_buf(h, (long long)B * (H / 2) * (W / 2) * 128);
+  e.A2 = fwd_buf(h, (long long)B * (H / 4) * (W / 4) * 128); e.dA2 = act_buf(h, (long long)B * (H / 4) * (W / 4) * 128);
+  e.A3 = fwd_buf(h, (long long)B * F); e.dA3 = act_buf(h, (long long)B * F);
+  e.YB0E1 = fwd_buf(h, (long long)B * 1536); e.dYB0E1 = act_buf(h, (long long)B * 1536);
+  e.YH2 = fwd_buf(h, (long long)B * 128); e.dYH2 = act_buf(h, (long long)B * 128);
   e.LOGITS = f32_buf(h, (long long)B * 32); e.dLOGITS = act_buf(h, (long long)B * 32);
-  e.Y = f32_buf(h, (long long)B * 32); e.YT = act_buf(h, (long long)B * 32); e.U = f32_buf(h, (long long)B * 32);
+  e.Y = f32_buf(h, (long long)B * 32); e.YT = fwd_buf(h, (long long)B * 32); e.U = f32_buf(h, (long long)B * 32);
   e.dY = act_buf(h, (long long)B * 32);
   e.YHEADS = f32_buf(h, (long long)B * 768); e.dYHEADS = act_buf(h, (long long)B * 768);
-  e.HSUM = act_buf(h, (long long)B * 512); e.dHSUM = act_buf(h, (long long)B * 512);
+  e.HSUM = fwd_buf(h, (long long)B * 512); e.dHSUM = act_buf(h, (long long)B * 512);
   e.HEADS = f32_buf(h, (long long)B * 256); e.dHEADS = act_buf(h, (long long)B * 256);
 
   wire(h, e.h1, -1, DT_F32, 6, 0, e.A1, T, 128, e.dA1, 128, -1, 0, ACT_NONE);
@@ -260,13 +275,13 @@ Decoder build_decoder(sv_handle* h, const char* prefix, int L, int zcoff, int dz
   d.d4 = add_layer(h, prefix, 6, 6, 1, H / 2, W / 2, 64, {{"d4", 32, ACT_RELU}});
   d.d5 = add_layer(h, prefix, 6, 6, 1, H, W, 32, {{"d5", 6, ACT_NONE}});
   const long long p8 = (long long)B * (H / 8) * (W / 8), p4 = p8 * 4, p2 = p8 * 16, p1 = p8 * 64;
-  d.D1 = act_buf(h, p8 * 128); d.dD1 = act_buf(h, p8 * 128);
-  d.D2 = act_buf(h, p8 * 128); d.dD2 = act_buf(h, p8 * 128);
-  d.U1 = act_buf(h, p4 * 128); d.dU1 = act_buf(h, p4 * 128);
-  d.D3 = act_buf(h, p4 * 64); d.dD3 = act_buf(h, p4 * 64);
-  d.U2 = act_buf(h, p2 * 64); d.dU2 = act_buf(h, p2 * 64);
-  d.D4 = act_buf(h, p2 * 32); d.dD4 = act_buf(h, p2 * 32);
-  d.U3 = act_buf(h, p1 * 32); d.dU3 = act_buf(h, p1 * 32);
+  d.D1 = fwd_buf(h, p8 * 128); d.dD1 = act_buf(h, p8 * 128);
+  d.D2 = fwd_buf(h, p8 * 128); d.dD2 = act_buf(h, p8 * 128);
+  d.U1 = fwd_buf(h, p4 * 128); d.dU1 = act_buf(h, p4 * 128);
+  d.D3 = fwd_buf(h, p4 * 64); d.dD3 = act_buf(h, p4 * 64);
+  d.U2 = fwd_buf(h, p2 * 64); d.dU2 = act_buf(h, p2 * 64);
+  d.D4 = fwd_buf(h, p2 * 32); d.dD4 = act_buf(h, p2 * 32);
+  d.U3 = act_buf(h, p1 * 32); d.dU3 = act_buf(h, p1 * 32);      // (input of d5: single bf16 in every mode)
   d.OUT = f32_buf(h, p1 * 6); d.dOUT = act_buf(h, p1 * dout_ld);
   d.dz = dz_buf;
   wire(h, d.d1, h->ZCAT, T, 256, zcoff, d.D1, T, F, d.dD1, F, dz_buf, dz_ld, ACT_NONE);
@@ -312,6 +327,7 @@ LatentBufs latent_bufs(sv_handle* h) {
   L.zm_g = (float*)bp(h, h->ZM_G); L.zs_g = (float*)bp(h, h->ZS_G);
   L.zm_l = (float*)bp(h, h->ZM_L); L.zs_l = (float*)bp(h, h->ZS_L);
   L.zcat = bp(h, h->ZCAT);
+  L.zcat_lo = (bf16*)bp(h, lo_buf(h, h->ZCAT));
   L.dzcat = bp(h, h->dec_x.dz);
   L.dzl2 = bp(h, h->dec_xh.dz);
   L.dheads_g = bp(h, gm ? h->gm.dHEADS : h->enc_x.dHEADS);
@@ -405,10 +421,10 @@ void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStrea
   layer_fwd(h, e.yb0e1, nullptr, s);
   layer_fwd(h, e.yb2, nullptr, s);
   layer_fwd(h, e.ydense, nullptr, s);
-  gumbel_fwd((const float*)bp(h, e.LOGITS), u, (float*)bp(h, e.U), (float*)bp(h, e.Y), bp(h, e.YT), h->act_dt, h->B,
+  gumbel_fwd((const float*)bp(h, e.LOGITS), u, (float*)bp(h, e.U), (float*)bp(h, e.Y), bp(h, e.YT), bp(h, lo_buf(h, e.YT)), h->act_dt, h->B,
              h->K, h->cfg.tau, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
   layer_fwd(h, e.yheads, nullptr, s);
-  gm_add(bp(h, e.YB0E1), (const float*)bp(h, e.YHEADS), bp(h, e.HSUM), h->act_dt, h->B, s);
+  gm_add(bp(h, e.YB0E1), bp(h, lo_buf(h, e.YB0E1)), (const float*)bp(h, e.YHEADS), bp(h, e.HSUM), bp(h, lo_buf(h, e.HSUM)), h->act_dt, h->B, s);
   layer_fwd(h, e.zheads, nullptr, s);
   h->launches += 2;
 }
@@ -433,13 +449,17 @@ void gm_encoder_bwd(sv_handle* h, const float* inputs, cudaStream_t s) {
 
 void decoder_fwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
   const int B = h->B, H = h->H, W = h->W, T = h->act_dt;
+  auto up = [&](int src, int dst, int hh, int ww, int c) {
+    if (h->split) upsample2x_fwd_pair(bp(h, src), bp(h, lo_buf(h, src)), bp(h, dst), bp(h, lo_buf(h, dst)), B, hh, ww, c, s);
+    else upsample2x_fwd(bp(h, src), bp(h, dst), T, B, hh, ww, c, s);
+  };
   layer_fwd(h, d.d1, nullptr, s);
   layer_fwd(h, d.d2, nullptr, s);
-  upsample2x_fwd(bp(h, d.D2), bp(h, d.U1), T, B, H / 8, W / 8, 128, s);
+  up(d.D2, d.U1, H / 8, W / 8, 128);
   layer_fwd(h, d.d3, nullptr, s);
-  upsample2x_fwd(bp(h, d.D3), bp(h, d.U2), T, B, H / 4, W / 4, 64, s);
+  up(d.D3, d.U2, H / 4, W / 4, 64);
   layer_fwd(h, d.d4, nullptr, s);
-  upsample2x_fwd(bp(h, d.D4), bp(h, d.U3), T, B, H / 2, W / 2, 32, s);
+  up(d.D4, d.U3, H / 2, W / 2, 32);
   layer_fwd(h, d.d5, nullptr, s);
   h->launches += 3;
 }
@@ -457,19 +477,24 @@ void decoder_bwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
   h->launches += 3;
 }
 
-__global__ void pack_z_kernel(const float* __restrict__ zg, const float* __restrict__ zl, void* zcat, int dt, int B) {
+__global__ void pack_z_kernel(const float* __restrict__ zg, const float* __restrict__ zl, void* zcat, bf16* zcat_lo, int dt, int B) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 128) return;
   const int b = idx >> 7, d = idx & 127;
   if (dt == DT_F32) { ((float*)zcat)[b * 256 + d] = zg[idx]; ((float*)zcat)[b * 256 + 128 + d] = zl[idx]; }
   else { ((bf16*)zcat)[b * 256 + d] = __float2bfloat16_rn(zg[idx]); ((bf16*)zcat)[b * 256 + 128 + d] = __float2bfloat16_rn(zl[idx]); }
+  if (zcat_lo) {
+    zcat_lo[b * 256 + d] = __float2bfloat16_rn(zg[idx] - round_bf16(zg[idx]));
+    zcat_lo[b * 256 + 128 + d] = __float2bfloat16_rn(zl[idx] - round_bf16(zl[idx]));
+  }
 }
-__global__ void pack_y_kernel(const float* __restrict__ y, void* yt, int dt, int B, int K) {
+__global__ void pack_y_kernel(const float* __restrict__ y, void* yt, bf16* yt_lo, int dt, int B, int K) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 32) return;
   const int b = idx >> 5, k = idx & 31;
   const float v = k < K ? y[b * K + k] : 0.f;
   if (dt == DT_F32) ((float*)yt)[idx] = v; else ((bf16*)yt)[idx] = __float2bfloat16_rn(v);
+  if (yt_lo) yt_lo[idx] = __float2bfloat16_rn(v - round_bf16(v));
 }
 __global__ void copy_cols_kernel(const float* __restrict__ src, int ld, int coff, float* __restrict__ dst, int B, int n) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -481,7 +506,7 @@ void stage_first_inputs(sv_handle* h, const float* inputs, cudaStream_t s) {
   if (!h->use_tc) return;
   for (int i = 0; i < 2; ++i)
     if (h->XP[i] >= 0) {
-      tc_stage_first(inputs, bp(h, h->XP[i]), i ? 3 : 0, h->B, h->H, h->W, s);
+      tc_stage_first(inputs, bp(h, h->XP[i]), i ? 3 : 0, h->B, h->H, h->W, h->split, s);
       h->launches += 1;
     }
 }
@@ -537,7 +562,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   if (cfg->model == SV_MODEL_LGGMVAE && (cfg->y_size < 2 || cfg->y_size > 32))
     return fail(nullptr, SV_ERR_INVALID, "y_size %d unsupported (2..32)", cfg->y_size);
   if (cfg->world_size < 1) return fail(nullptr, SV_ERR_INVALID, "world_size must be >= 1");
-  if (cfg->precision != SV_PRECISION_BF16_TC && cfg->precision != SV_PRECISION_FP32_REF)
+  if (cfg->precision != SV_PRECISION_BF16_TC && cfg->precision != SV_PRECISION_FP32_REF && cfg->precision != SV_PRECISION_BF16X3)
     return fail(nullptr, SV_ERR_INVALID, "unknown precision %d", cfg->precision);
   const bool plan_only = (cfg->flags & SV_FLAG_PLAN_ONLY) != 0;
   if (!plan_only) {
@@ -556,7 +581,8 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->plan_only = plan_only;
   h->act_dt = cfg->precision == SV_PRECISION_FP32_REF ? DT_F32 : DT_BF16;
   h->round_w = h->act_dt == DT_BF16;
-  h->use_tc = cfg->precision == SV_PRECISION_BF16_TC && !(cfg->flags & SV_FLAG_NO_TC);
+  h->split = cfg->precision == SV_PRECISION_BF16X3;
+  h->use_tc = (cfg->precision == SV_PRECISION_BF16_TC && !(cfg->flags & SV_FLAG_NO_TC)) || h->split;
   h->B = cfg->batch; h->H = cfg->height; h->W = cfg->width;
   h->F = ((cfg->height / 8) * cfg->width) / 8 * 128;  // vae/model.py:152 precedence
   h->K = cfg->model == SV_MODEL_LGGMVAE ? cfg->y_size : 0;
@@ -565,7 +591,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   const int dout_ld = h->act_dt == DT_F32 ? 6 : 16;
 
   // shared latent buffers first (decoders reference ZCAT)
-  h->ZCAT = act_buf(h, (long long)B * 256);
+  h->ZCAT = fwd_buf(h, (long long)B * 256);
   h->EPS_G = f32_buf(h, B * 128); h->EPS_L = f32_buf(h, B * 128);
   h->Z_G = f32_buf(h, B * 128); h->Z_L = f32_buf(h, B * 128);
   h->ZM_G = f32_buf(h, B * 128); h->ZS_G = f32_buf(h, B * 128);
@@ -601,10 +627,23 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
       }
     }
   }
+  if (h->split) {     // every forward product but the decoders' last layer multiplies bf16 pairs
+    h->lo_of.resize(h->bufs.size(), -1);
+    for (size_t li = 0; li < h->layers.size(); ++li) {
+      Layer& L = h->layers[li];
+      L.split_fwd = (int)li != h->dec_x.d5 && (int)li != h->dec_xh.d5;
+      if (L.split_fwd) { L.in_lo = lo_buf(h, L.in); L.out_lo = lo_buf(h, L.out); }
+    }
+  }
   if (h->use_tc) {
     for (auto& L : h->layers) {
       const bool first = L.in < 0;
-      tc_plan_layer(L.tc, L.g, L.in_dt, L.out_dt, L.in >= 0, L.din >= 0, first);
+      tc_plan_layer(L.tc, L.g, L.in_dt, L.out_dt, L.in >= 0, L.din >= 0, first, L.split_fwd);
+      if (h->split && !L.tc.fwd_ok) {
+        const sv_status st = fail(nullptr, SV_ERR_NOT_IMPLEMENTED, "bf16x3: no tensor-core forward plan for layer %s at this shape", L.name.c_str());
+        delete h;
+        return st;
+      }
       if (first && (L.tc.fwd_ok || L.tc.wgrad_ok)) {
         if (h->XP[L.g.in_coff ? 1 : 0] < 0) h->XP[L.g.in_coff ? 1 : 0] = new_buf(h, tc_first_stage_bytes(h->B, h->H, h->W));
         L.xp = h->XP[L.g.in_coff ? 1 : 0];
@@ -669,7 +708,8 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     char* tcws = (char*)bp(h, h->TCWS);
     for (auto& L : h->layers) {
       const char* err = tc_bind_layer(L.tc, L.g, L.in >= 0 ? bp(h, L.in) : bp(h, L.xp), bp(h, L.out), bp(h, L.dout),
-                                      L.din >= 0 ? bp(h, L.din) : nullptr, L.in >= 0 ? bp(h, L.in) : nullptr, L.mask_act, tcws);
+                                      L.din >= 0 ? bp(h, L.din) : nullptr, L.in >= 0 ? bp(h, L.in) : nullptr, L.mask_act, tcws,
+                                      bp(h, L.in_lo), bp(h, L.out_lo));
       if (err) return fail(h, SV_ERR_DEVICE, "tensor-core plan for %s: %s", L.name.c_str(), err);
       tcws += tc_workspace_bytes(L.tc, L.g);
     }
@@ -897,7 +937,7 @@ sv_status sv_decode(sv_handle* h, const float* z_x, const float* z_x_hat, void* 
   REQUIRE_BOUND(h);
   if (!z_x || !z_x_hat) return fail(h, SV_ERR_INVALID, "null latent");
   cudaStream_t s = (cudaStream_t)stream;
-  pack_z_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>(z_x, z_x_hat, bp(h, h->ZCAT), h->act_dt, h->B);
+  pack_z_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>(z_x, z_x_hat, bp(h, h->ZCAT), (bf16*)bp(h, lo_buf(h, h->ZCAT)), h->act_dt, h->B);
   h->launches += 1;
   cudaStream_t s2 = fork_side(h, s);
   decoder_fwd(h, h->dec_x, s);
@@ -911,7 +951,7 @@ sv_status sv_encode_y(sv_handle* h, const float* y, void* stream) {
   if (h->cfg.model != SV_MODEL_LGGMVAE) return fail(h, SV_ERR_INVALID, "encode_y needs the lggmvae model");
   if (!y) return fail(h, SV_ERR_INVALID, "null y");
   cudaStream_t s = (cudaStream_t)stream;
-  pack_y_kernel<<<(h->B * 32 + 255) / 256, 256, 0, s>>>(y, bp(h, h->gm.YT), h->act_dt, h->B, h->K);
+  pack_y_kernel<<<(h->B * 32 + 255) / 256, 256, 0, s>>>(y, bp(h, h->gm.YT), (bf16*)bp(h, lo_buf(h, h->gm.YT)), h->act_dt, h->B, h->K);
   layer_fwd(h, h->gm.yheads, nullptr, s);
   copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
   copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
@@ -962,7 +1002,8 @@ sv_status sv_debug_layer_info(const sv_handle* hc, int32_t i, sv_layer_info* o) 
   o->in_ld = g.in_ld; o->in_coff = g.in_coff; o->out_ld = g.out_ld; o->dout_ld = g.dout_ld; o->din_ld = g.din_ld;
   o->in_dt = L.in_dt; o->out_dt = L.out_dt; o->act_dt = h->act_dt;
   o->has_dgrad = L.din >= 0; o->tc_fwd = L.tc.fwd_ok; o->tc_dgrad = L.tc.dgrad_ok; o->tc_wgrad = L.tc.wgrad_ok;
-  if (h->bound) { o->in = bp(h, L.in); o->out = bp(h, L.out); o->dout = bp(h, L.dout); o->din = bp(h, L.din); }
+  if (h->bound) { o->in = bp(h, L.in); o->out = bp(h, L.out); o->dout = bp(h, L.dout); o->din = bp(h, L.din); o->in_lo = bp(h, L.in_lo); o->out_lo = bp(h, L.out_lo); }
+  o->split_fwd = L.split_fwd;
   if (h->use_tc) {
     o->kern_fwd = !L.tc.fwd_ok ? SV_KERN_NONE : L.tc.fwd_ns ? SV_KERN_NSCONV : L.tc.fwd.halo ? (L.tc.fwd.persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;
     o->kern_dgrad = !L.tc.dgrad_ok ? SV_KERN_NONE : L.tc.dgrad_ns ? SV_KERN_NSCONV : L.tc.dgrad[0].halo ? (L.tc.dgrad[0].persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;

@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(256) reparam_kernel(LatentBufs L, int B, const
   L.zm_g[idx] = mg; L.zs_g[idx] = sg; L.zm_l[idx] = ml; L.zs_l[idx] = sl;
   ((T*)L.zcat)[b * 256 + d] = from_f32<T>(zg);
   ((T*)L.zcat)[b * 256 + 128 + d] = from_f32<T>(zl);
+  if (L.zcat_lo) {   // bf16x3: z as a bf16 pair
+    L.zcat_lo[b * 256 + d] = __float2bfloat16_rn(zg - round_bf16(zg));
+    L.zcat_lo[b * 256 + 128 + d] = __float2bfloat16_rn(zl - round_bf16(zl));
+  }
   if (L.yheads) {   // q(z_g) || p(z_g | y), q(z_l) || N(0, I)   (vae/trainer.py:157-158)
     const float pm = L.yheads[b * 768 + 512 + d], ps = L.yheads[b * 768 + 640 + d];
     kl_g = logf(ps) - logf(sg) + (sg * sg + (mg - pm) * (mg - pm)) / (2.f * ps * ps) - 0.5f;
@@ -136,7 +140,7 @@ void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, floa
 // ------------------------------------------------------------------ gumbel softmax (one warp per row)
 template <typename T>
 __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ user_u,
-                                  float* __restrict__ u_saved, float* __restrict__ y, T* __restrict__ y_act, int B,
+                                  float* __restrict__ u_saved, float* __restrict__ y, T* __restrict__ y_act, bf16* __restrict__ y_act_lo, int B,
                                   int K, float tau, unsigned long long seed,
                                   const unsigned long long* __restrict__ counter) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -164,27 +168,33 @@ __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, const float*
   u_saved[row * 32 + k] = u;
   y[row * 32 + k] = yv;
   y_act[row * 32 + k] = from_f32<T>(yv);
+  if (y_act_lo) y_act_lo[row * 32 + k] = __float2bfloat16_rn(yv - round_bf16(yv));
 }
 
-void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, int act_dt, int B,
+void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, void* y_act_lo, int act_dt, int B,
                 int K, float tau, unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
   const int rows_per_block = 8;
   dim3 grid((B + rows_per_block - 1) / rows_per_block), block(32 * rows_per_block);
-  if (act_dt == DT_F32) gumbel_fwd_kernel<float><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (float*)y_act, B, K, tau, seed, counter);
-  else gumbel_fwd_kernel<bf16><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (bf16*)y_act, B, K, tau, seed, counter);
+  if (act_dt == DT_F32) gumbel_fwd_kernel<float><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (float*)y_act, nullptr, B, K, tau, seed, counter);
+  else gumbel_fwd_kernel<bf16><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (bf16*)y_act, (bf16*)y_act_lo, B, K, tau, seed, counter);
 }
 
 template <typename T>
-__global__ void gm_add_kernel(const T* __restrict__ yb0e1, const float* __restrict__ yheads, T* __restrict__ hsum, int B) {
+__global__ void gm_add_kernel(const T* __restrict__ yb0e1, const bf16* __restrict__ yb0e1_lo, const float* __restrict__ yheads,
+                              T* __restrict__ hsum, bf16* __restrict__ hsum_lo, int B) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 512) return;
   const int b = idx >> 9, j = idx & 511;
-  hsum[idx] = from_f32<T>(to_f32(yb0e1[(long long)b * 1536 + 1024 + j]) + yheads[b * 768 + j]);  // model.py:130
+  float e1o = to_f32(yb0e1[(long long)b * 1536 + 1024 + j]);
+  if (yb0e1_lo) e1o += __bfloat162float(yb0e1_lo[(long long)b * 1536 + 1024 + j]);       // bf16x3: e1's output is a bf16 pair
+  const float h = e1o + yheads[b * 768 + j];                                               // model.py:130
+  hsum[idx] = from_f32<T>(h);
+  if (hsum_lo) hsum_lo[idx] = __float2bfloat16_rn(h - round_bf16(h));
 }
-void gm_add(const void* yb0e1_out, const float* yheads, void* hsum, int act_dt, int B, cudaStream_t s) {
+void gm_add(const void* yb0e1_out, const void* yb0e1_lo, const float* yheads, void* hsum, void* hsum_lo, int act_dt, int B, cudaStream_t s) {
   const int n = B * 512;
-  if (act_dt == DT_F32) gm_add_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)yb0e1_out, yheads, (float*)hsum, B);
-  else gm_add_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)yb0e1_out, yheads, (bf16*)hsum, B);
+  if (act_dt == DT_F32) gm_add_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)yb0e1_out, nullptr, yheads, (float*)hsum, nullptr, B);
+  else gm_add_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)yb0e1_out, (const bf16*)yb0e1_lo, yheads, (bf16*)hsum, (bf16*)hsum_lo, B);
 }
 
 template <typename T>

@@ -25,6 +25,8 @@ ColsumTable* colsum_table_create(const ColsumSpec* specs, int n, float* partial_
 void colsum_table_destroy(ColsumTable* t);
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s);   // returns #launches
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s);
+// bf16x3: input and output are bf16 pairs (value = hi + lo); out_lo may be NULL (the consumer reads single bf16: d5)
+void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C, cudaStream_t s);
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
                     int C, cudaStream_t s);
 
@@ -39,6 +41,7 @@ struct LatentBufs {
   float* z_l;
   float* zm_g; float* zs_g; float* zm_l; float* zs_l;   // contiguous copies for the output tuple
   void* zcat;             // [B,256] activation dtype: decoder_x input (z_g | z_l)
+  bf16* zcat_lo;          // bf16x3: lo plane of zcat (NULL otherwise)
   // backward
   const void* dzcat;      // [B,256] activation dtype: dgrad of decoder_x.d1
   const void* dzl2;       // [B,128] activation dtype: dgrad of decoder_x_hat.d1
@@ -54,10 +57,11 @@ void reparam(const LatentBufs& L, int B, int act_dt, const float* user_eps_g, co
              unsigned long long seed, const unsigned long long* counter_dev, float* kl_partials, cudaStream_t s);
 void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s);
 
-void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, int act_dt, int B,
+// (y_act_lo / *_lo: lo planes of the bf16x3 mode, NULL otherwise)
+void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float* y, void* y_act, void* y_act_lo, int act_dt, int B,
                 int K, float tau, unsigned long long seed, const unsigned long long* counter_dev, cudaStream_t s);
 // h = e1out + h_top  (vae/model.py:130)
-void gm_add(const void* yb0e1_out, const float* yheads, void* hsum, int act_dt, int B, cudaStream_t s);
+void gm_add(const void* yb0e1_out, const void* yb0e1_lo, const float* yheads, void* hsum, void* hsum_lo, int act_dt, int B, cudaStream_t s);
 // glue A: gradients entering the (y_block.0|e1) and (h_top|z_prior_mean|z_prior_sig) fused layers
 void gm_glue_a(const void* dhsum, const void* yb0e1_out, const float* yheads, const float* zm_g, const float* zs_g,
                void* d_yb0e1, void* d_yheads, int act_dt, int B, float beta, float inv_batch, cudaStream_t s);

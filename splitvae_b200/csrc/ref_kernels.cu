@@ -325,6 +325,56 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_quad_kernel(const bf16* __
   }
 }
 
+// bf16x3 forward: the low-resolution tensor is a bf16 pair (hi + lo), interpolated in fp32 and written back as a pair
+// (out_lo == NULL: the consumer multiplies single bf16 - the input of d5).  Same quad decomposition as upsample2x_fwd_quad_kernel.
+__device__ __forceinline__ F8 ld_pair8(const bf16* hi, const bf16* lo, size_t off) {
+  F8 a = ld_bf16x8(hi + off);
+  const F8 b = ld_bf16x8(lo + off);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
+  return a;
+}
+__global__ void __launch_bounds__(256) upsample2x_fwd_pair_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                                                  bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W, int C8) {
+  const int total = B * (H + 1) * (W + 1) * C8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c8 = idx % C8;
+    int p = idx / C8;
+    const int qx = p % (W + 1) - 1;
+    p /= W + 1;
+    const int qy = p % (H + 1) - 1;
+    const int n = p / (H + 1);
+    const int y0 = max(qy, 0), y1 = min(qy + 1, H - 1), x0 = max(qx, 0), x1 = min(qx + 1, W - 1);
+    const size_t base = ((size_t)n * H * W) * C8 * 8 + c8 * 8;
+    const F8 tl = ld_pair8(in_hi, in_lo, base + ((size_t)y0 * W + x0) * C8 * 8), tr = ld_pair8(in_hi, in_lo, base + ((size_t)y0 * W + x1) * C8 * 8);
+    const F8 bl = ld_pair8(in_hi, in_lo, base + ((size_t)y1 * W + x0) * C8 * 8), br = ld_pair8(in_hi, in_lo, base + ((size_t)y1 * W + x1) * C8 * 8);
+    const size_t obase = ((size_t)n * 4 * H * W) * C8 * 8 + c8 * 8;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int oy = 2 * qy + 1 + dy;
+      if (oy < 0 || oy >= 2 * H) continue;
+      const float ly = dy ? 0.75f : 0.25f;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ox = 2 * qx + 1 + dx;
+        if (ox < 0 || ox >= 2 * W) continue;
+        const float lx = dx ? 0.75f : 0.25f;
+        F8 o, l;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float top = tl.v[i] + (tr.v[i] - tl.v[i]) * lx;
+          const float bot = bl.v[i] + (br.v[i] - bl.v[i]) * lx;
+          o.v[i] = top + (bot - top) * ly;
+          l.v[i] = o.v[i] - round_bf16(o.v[i]);
+        }
+        const size_t off = obase + ((size_t)oy * 2 * W + ox) * C8 * 8;
+        st_bf16x8(out_hi + off, o);
+        if (out_lo) st_bf16x8(out_lo + off, l);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
                                                                  const bf16* __restrict__ mask_src, int mask_act,
                                                                  int B, int H, int W, int C8) {
@@ -643,6 +693,12 @@ void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int 
     upsample2x_fwd_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)in, (float*)out, B, H, W, C);
   else
     upsample2x_fwd_kernel<bf16><<<grid_for(total), 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C);
+}
+
+void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C, cudaStream_t s) {
+  const long long quads = (long long)B * (H + 1) * (W + 1) * (C / 8);     // (C % 8 == 0 for every decoder tensor: 128 / 64 / 32)
+  upsample2x_fwd_pair_kernel<<<grid_for(quads, 256, 148 * 32), 256, 0, s>>>((const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo,
+                                                                           B, H, W, C / 8);
 }
 
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,

@@ -67,11 +67,12 @@ struct EpiRegs {
   const float* bias;
   const bf16* mask_src;
   void* out;
+  bf16* out_lo;          // bf16x3 forward: lo plane of the output (value = hi + lo), same indexing as `out`
   int tile_cols, n_valid, out_ld, mask_ld, mask_coff;
 };
 __device__ __forceinline__ EpiRegs load_epi_regs(const TcLaunch& P) {
   EpiRegs E;
-  E.bias = P.bias; E.mask_src = (const bf16*)P.mask_src; E.out = P.out;
+  E.bias = P.bias; E.mask_src = (const bf16*)P.mask_src; E.out = P.out; E.out_lo = (bf16*)P.out_lo;
   E.tile_cols = P.tile_cols; E.n_valid = P.n_valid; E.out_ld = P.out_ld; E.mask_ld = P.mask_ld; E.mask_coff = P.mask_coff;
   return E;
 }
@@ -159,6 +160,24 @@ __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpi
           if (cfirst + i + q < E.n_valid) o[i + q] = __float2bfloat16_rn(f[i + q]);
       }
     }
+    if (E.out_lo) {     // bf16 pair: lo = bf16(v - hi)
+      bf16* ol = E.out_lo + opix * E.out_ld + cfirst;
+#pragma unroll
+      for (int i = 0; i < kEpiBW; ++i) f[i] -= round_bf16(f[i]);
+#pragma unroll
+      for (int i = 0; i < kEpiBW; i += 8) {
+        if (vec_ok && cfirst + i + 8 <= E.n_valid) {
+          uint4 pk;
+          pk.x = pack_bf16x2(f[i], f[i + 1]); pk.y = pack_bf16x2(f[i + 2], f[i + 3]);
+          pk.z = pack_bf16x2(f[i + 4], f[i + 5]); pk.w = pack_bf16x2(f[i + 6], f[i + 7]);
+          *reinterpret_cast<uint4*>(ol + i) = pk;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (cfirst + i + q < E.n_valid) ol[i + q] = __float2bfloat16_rn(f[i + q]);
+        }
+      }
+    }
   }
 }
 
@@ -235,13 +254,14 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
   const int tiles_per_img = P.grid_h / P.tile_h;   // tile_w == grid_w
   const int n0 = (m_tile / tiles_per_img) * P.tile_n_img;
   const int y0 = (m_tile % tiles_per_img) * P.tile_h;
-  const int kb_total = P.taps_h * P.taps_w * P.kc;
+  const int kb_total = P.taps_h * P.taps_w * P.kcl;                               // logical k-blocks (see TcLaunch::split)
   const int kb_first = P.k_splits > 1 ? zsplit * P.kb_per_split : 0;              // split-K: this CTA's k-block range
   const int num_kb = P.k_splits > 1 ? min(P.kb_per_split, kb_total - kb_first) : kb_total;
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&P.map_a);
     tc::prefetch_tmap(&P.map_b);
+    if (P.kca > P.kc) tc::prefetch_tmap(&P.map_a_lo);
     for (int i = 0; i < P.stages; ++i) { tc::mbar_init(&ctl->full[i], 1); tc::mbar_init(&ctl->empty[i], 1); }
     tc::mbar_init(&ctl->tmem_full, 1);
     tc::fence_barrier_init();
@@ -260,12 +280,15 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
         const int stage = it % P.stages, phase = (it / P.stages) & 1;
         tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
         const int kb = kb_first + it;
-        const int tap = kb / P.kc, chunk = kb - tap * P.kc;
+        const int tap = kb / P.kcl, chunk = kb - tap * P.kcl;                 // logical chunk -> physical A chunk / weight k-block
+        const int ap = chunk % P.a_wrap, bp = chunk < P.b_fold ? chunk : chunk - P.b_sub;
+        const bool a_is_lo = ap >= P.kc;
         const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         tc::mbar_expect_tx(&ctl->full[stage], a_bytes + P.tile_cols * P.bk * 2);
-        tc::tma_load_4d(sa, &P.map_a, &ctl->full[stage], chunk * P.bk, tb - P.pad_l, y0 * P.a_stride + ta - P.pad_t, n0);
-        tc::tma_load_2d(sa + a_bytes, &P.map_b, &ctl->full[stage], kb * P.bk, n_tile * P.tile_cols);
+        tc::tma_load_4d(sa, a_is_lo ? &P.map_a_lo : &P.map_a, &ctl->full[stage], (a_is_lo ? ap - P.kc : ap) * P.bk, tb - P.pad_l,
+                        y0 * P.a_stride + ta - P.pad_t, n0);
+        tc::tma_load_2d(sa + a_bytes, &P.map_b, &ctl->full[stage], (tap * P.kcb + bp) * P.bk, n_tile * P.tile_cols);
       }
     }
   } else if (warp == 1) {
@@ -351,7 +374,12 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constan
   if (P.mask_act != ACT_NONE)
     acc *= act_grad_from_out(__bfloat162float(((const bf16*)P.mask_src)[row * P.mask_ld + P.mask_coff + col]), P.mask_act);
   const long long o = row * P.out_ld + col;
-  if (P.out_f32) ((float*)P.out)[o] = acc; else ((bf16*)P.out)[o] = __float2bfloat16_rn(acc);
+  if (P.out_f32) ((float*)P.out)[o] = acc;
+  else {
+    const bf16 hi = __float2bfloat16_rn(acc);
+    ((bf16*)P.out)[o] = hi;
+    if (P.out_lo) ((bf16*)P.out_lo)[o] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+  }
 }
 
 
@@ -407,10 +435,11 @@ struct HaloCtl {
 __device__ __forceinline__ void halo_body(const TcLaunch& P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nchunks = P.kc;
+  const int nchunks = P.kcl;                    // LOGICAL chunks per tap; the halo holds P.kca physical chunks (TcLaunch::split)
+  const int nphys = P.kca;
   const int sx = P.halo_sx, sy = P.halo_sy;     // input stride: sx parity planes per chunk, rows sy apart (1 = plain stride-1 conv)
   uint8_t* halo = smem;
-  uint8_t* wring = smem + (size_t)nchunks * sx * P.chunk_bytes;
+  uint8_t* wring = smem + (size_t)nphys * sx * P.chunk_bytes;
   HaloCtl* ctl = reinterpret_cast<HaloCtl*>(wring + (size_t)P.w_stages * P.w_stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -438,6 +467,7 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
     }
     tc::prefetch_tmap(&P.map_a);
     tc::prefetch_tmap(&P.map_b);
+    if (P.kca > P.kc) tc::prefetch_tmap(&P.map_a_lo);
     tc::mbar_init(&ctl->halo_full, 1);
     for (int i = 0; i < P.w_stages; ++i) { tc::mbar_init(&ctl->w_full[i], 1); tc::mbar_init(&ctl->w_empty[i], 1); }
     tc::mbar_init(&ctl->tmem_full, 1);
@@ -454,20 +484,23 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(&ctl->halo_full, (uint32_t)(nchunks * sx * P.THp * P.TWp * P.bk * 2));
+      tc::mbar_expect_tx(&ctl->halo_full, (uint32_t)(nphys * sx * P.THp * P.TWp * P.bk * 2));
       for (int p = 0; p < sx; ++p)         // plane p holds input columns sx*x0 - pad_l + p + sx*j (TMA element stride sx)
-        for (int c = 0; c < nchunks; ++c)
-          tc::tma_load_4d(halo + (size_t)(p * nchunks + c) * P.chunk_bytes, &P.map_a, &ctl->halo_full, c * P.bk, sx * x0 - P.pad_l + p,
-                          sy * y0 - P.pad_t, n);
+        for (int c = 0; c < nphys; ++c)    // physical chunks: the hi plane's chunks, then the lo plane's
+          tc::tma_load_4d(halo + (size_t)(p * nphys + c) * P.chunk_bytes, c < P.kc ? &P.map_a : &P.map_a_lo, &ctl->halo_full,
+                          (c < P.kc ? c : c - P.kc) * P.bk, sx * x0 - P.pad_l + p, sy * y0 - P.pad_t, n);
       for (int st = 0; st < num_stages_total; ++st) {
         const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
         tc::mbar_wait(&ctl->w_empty[slot], phase ^ 1);
         const int kb0 = st * P.kb_per_stage;
         const int nkb = min(P.kb_per_stage, num_kb - kb0);
         tc::mbar_expect_tx(&ctl->w_full[slot], (uint32_t)(nkb * kb_bytes));
-        for (int j = 0; j < nkb; ++j)
-          tc::tma_load_2d(wring + (size_t)slot * P.w_stage_bytes + (size_t)j * kb_bytes, &P.map_b, &ctl->w_full[slot], (kb0 + j) * P.bk,
-                          n_tile * P.tile_cols);
+        for (int j = 0; j < nkb; ++j) {
+          const int kbl = kb0 + j, tapl = kbl / nchunks, cl = kbl - tapl * nchunks;     // logical k-block -> physical weight k-block
+          const int bp = cl < P.b_fold ? cl : cl - P.b_sub;
+          tc::tma_load_2d(wring + (size_t)slot * P.w_stage_bytes + (size_t)j * kb_bytes, &P.map_b, &ctl->w_full[slot],
+                          (tapl * P.kcb + bp) * P.bk, n_tile * P.tile_cols);
+        }
       }
     }
   } else if (warp == 1) {
@@ -500,8 +533,9 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
         int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
         for (; kb < kb_end; ++kb, b_addr += (uint32_t)kb_bytes >> 4) {
           // filter column tb = sx * b' + p: parity plane p, shifted by b' plane columns
-          const uint32_t a_tap = sx == 1 ? (halo_addr + (uint32_t)chunk * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4
-                                         : (halo_addr + (uint32_t)((tb % sx) * nchunks + chunk) * (uint32_t)P.chunk_bytes +
+          const int ap = chunk % P.a_wrap;     // physical halo chunk of this logical chunk
+          const uint32_t a_tap = sx == 1 ? (halo_addr + (uint32_t)ap * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4
+                                         : (halo_addr + (uint32_t)((tb % sx) * nphys + ap) * (uint32_t)P.chunk_bytes +
                                             (uint32_t)(ta * P.TWp + tb / sx) * pix) >> 4;
           const uint64_t db = b_tmpl + b_addr;
           const uint32_t first = kb != 0;
@@ -624,8 +658,8 @@ __device__ __noinline__ void pconv_epilogue_t(const TcLaunch& P, PcCtl* ctl, uin
 __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nchunks = P.kc, sx = P.halo_sx, sy = P.halo_sy, nst = P.p_stages;
-  const int stage_bytes = nchunks * sx * P.chunk_bytes;
+  const int nchunks = P.kcl, nphys = P.kca, sx = P.halo_sx, sy = P.halo_sy, nst = P.p_stages;   // logical / physical chunks (TcLaunch::split)
+  const int stage_bytes = nphys * sx * P.chunk_bytes;
   uint8_t* wsm = smem;
   uint8_t* halo = smem + P.p_wbytes;
   PcCtl* ctl = reinterpret_cast<PcCtl*>(halo + (size_t)nst * stage_bytes);
@@ -641,6 +675,7 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&P.map_a);
     tc::prefetch_tmap(&P.map_b);
+    if (P.kca > P.kc) tc::prefetch_tmap(&P.map_a_lo);
     tc::mbar_init(&ctl->w_full, 1);
     for (int i = 0; i < nst; ++i) { tc::mbar_init(&ctl->halo_full[i], 1); tc::mbar_init(&ctl->halo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&ctl->acc_full[i], 1); tc::mbar_init(&ctl->acc_empty[i], 4); }
@@ -656,10 +691,11 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(num_kb * kb_bytes));
-      for (int kb = 0; kb < num_kb; ++kb)
+      const int num_kb_phys = P.taps_h * P.taps_w * P.kcb;          // resident weights: the PHYSICAL k-blocks
+      tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(num_kb_phys * kb_bytes));
+      for (int kb = 0; kb < num_kb_phys; ++kb)
         tc::tma_load_2d(wsm + (size_t)kb * kb_bytes, &P.map_b, &ctl->w_full, kb * P.bk, P.p_ntile * P.tile_cols);
-      const uint32_t halo_tx = (uint32_t)(nchunks * sx * P.THp * P.TWp * P.bk * 2);
+      const uint32_t halo_tx = (uint32_t)(nphys * sx * P.THp * P.TWp * P.bk * 2);
       int i = 0;
       for (int t = cta; t < tiles; t += ncta, ++i) {
         const int st = i % nst, ph = (i / nst) & 1;
@@ -669,9 +705,9 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
         tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
         tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
         for (int p = 0; p < sx; ++p)
-          for (int c = 0; c < nchunks; ++c)
-            tc::tma_load_4d(halo + (size_t)st * stage_bytes + (size_t)(p * nchunks + c) * P.chunk_bytes, &P.map_a, &ctl->halo_full[st], c * P.bk,
-                            sx * x0 - P.pad_l + p, sy * y0 - P.pad_t, n);
+          for (int c = 0; c < nphys; ++c)
+            tc::tma_load_4d(halo + (size_t)st * stage_bytes + (size_t)(p * nphys + c) * P.chunk_bytes, c < P.kc ? &P.map_a : &P.map_a_lo,
+                            &ctl->halo_full[st], (c < P.kc ? c : c - P.kc) * P.bk, sx * x0 - P.pad_l + p, sy * y0 - P.pad_t, n);
       }
     }
   } else if (warp == 1) {
@@ -684,6 +720,7 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
       const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * P.TWp) * pix) >> 4;
       const uint32_t tile_cols = (uint32_t)P.tile_cols, chunk_bytes = (uint32_t)P.chunk_bytes;
       const int ksteps = P.bk / 16, mtx = P.mtx, mty = P.mty, taps_w = P.taps_w, TWp = P.TWp;
+      const int a_wrap = P.a_wrap, b_fold = P.b_fold, b_sub = P.b_sub, kcb = P.kcb;
       const uint32_t halo_addr = tc::smem_u32(halo), w_addr = tc::smem_u32(wsm) >> 4, kb_step = (uint32_t)kb_bytes >> 4;
       const bool env_shape_off = (P.trace & 2) != 0;      // SV_HALO_TRACE=2: generic issue loop (A/B)
       // unrolled issue sequences: 1 = 6x6 taps, K 16, 4 accumulators (d5 dgrad); 2 = 6x3 pair taps (first layer, 64x64 images);
@@ -721,9 +758,11 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
           else if (shape == 5) pc_issue_tile<6, 6, 2, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
           else pc_issue_tile<6, 6, 2, 2, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
         } else
-        for (int kb = 0; kb < num_kb; ++kb, b_addr += kb_step) {
-          const uint32_t a_tap = sx == 1 ? (h_addr + (uint32_t)chunk * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
-                                         : (h_addr + (uint32_t)((tb % sx) * nchunks + chunk) * chunk_bytes + (uint32_t)(ta * TWp + tb / sx) * pix) >> 4;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int ap = chunk % a_wrap, bp = chunk < b_fold ? chunk : chunk - b_sub;   // logical chunk -> physical halo chunk / weight k-block
+          b_addr = w_addr + (uint32_t)((ta * taps_w + tb) * kcb + bp) * kb_step;
+          const uint32_t a_tap = sx == 1 ? (h_addr + (uint32_t)ap * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
+                                         : (h_addr + (uint32_t)((tb % sx) * nphys + ap) * chunk_bytes + (uint32_t)(ta * TWp + tb / sx) * pix) >> 4;
           const uint64_t db = b_tmpl + b_addr;
           const uint32_t first = kb != 0;
           switch (mtx) {
@@ -1536,11 +1575,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const
 // weight packing: one multi-tensor kernel refreshes every bf16 operand copy from the fp32 masters
 // ------------------------------------------------------------------------------------------------
 struct PackJob {
-  int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias, 3: first-layer fwd weights
+  int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias, 4 / 5: N-stacked fwd / dgrad weights
   int KH, KW, Ci, Co;       // layer geometry (logical)
   int nparts, part_n[3];
   long long part_w[3], part_b[3];
   int rows_pad, taps_h, taps_w, k_pad;   // dst = [rows_pad][taps_h*taps_w][k_pad]
+  // kind 0: one k-block row = [nsec sections][ppx pixels][cpp channels] (k_pad = nsec * ppx * cpp); k-block tap (a, b') covers the
+  // filter columns b = b' * ppx + px.  ppx = 1: one pixel per tap; 2: the pixel-pair views; 8: the first layer's window view.
+  // nsec = 2 (bf16x3): section 0 = bf16(W) = W_hi, section 1 = bf16(W - W_hi) = W_lo.  first_cat (first layer, bf16x3): the staged
+  // pixel holds [x_hi(3) x_lo(3) 0 0], so section 0 = [W_hi W_hi 0 0] (x_hi*W_hi + x_lo*W_hi) and section 1 = [W_lo 0 0 0].
+  int ppx, cpp, nsec, first_cat;
   int stride, rh, rw;       // dgrad: kh = stride*(taps_h-1-a) + rh  (stride 1: rh = 0)
   void* dst;
   long long count;
@@ -1597,24 +1641,39 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     return;
   }
   if (J.kind == 0) {
-    // forward weights: dst[co][tap][ci] = W[tap][ci][co] is a transpose per tap -> 32x32 tiles through shared memory so
-    // that both the fp32 reads (along co) and the bf16 writes (along ci) are coalesced
+    // forward weights: dst[co][tap][k] = W[tap][ci(k)][co] is a transpose per tap -> 32x32 tiles through shared memory so
+    // that both the fp32 reads (along co) and the bf16 writes (along k) are coalesced
     __shared__ float tile[32][33];
     const int tk_n = (J.k_pad + 31) >> 5, tr_n = (J.rows_pad + 31) >> 5;
     int t = blockIdx.x - J.block_start;
     const int tk = t % tk_n; t /= tk_n;
     const int tr = t % tr_n;
     const int tap = t / tr_n;
-    const int a = tap / J.taps_w, b = tap - a * J.taps_w;
+    const int a = tap / J.taps_w, bq = tap - a * J.taps_w;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int co = tr * 32 + tx;
     int j = 0, lc = co;
     while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
-    const float* src = params + J.part_w[j] + (long long)(a * J.KW + b) * J.Ci * J.part_n[j] + lc;
+    const float* src = params + J.part_w[j] + lc;
+    const int sec_len = J.ppx * J.cpp;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int ci = tk * 32 + ty + 8 * i;
-      tile[ty + 8 * i][tx] = (co < J.Co && ci < J.Ci) ? src[(long long)ci * J.part_n[j]] : 0.f;
+      const int kk = tk * 32 + ty + 8 * i;
+      const int sec = kk / sec_len, rem = kk - sec * sec_len;
+      const int px = rem / J.cpp, c = rem - px * J.cpp;
+      const int b = bq * J.ppx + px;
+      int ci = c, plane = sec;                       // plane: 0 = hi, 1 = lo, -1 = zero
+      if (J.first_cat) {
+        if (c < 3) { ci = c; plane = sec; }
+        else if (c < 6) { ci = c - 3; plane = sec == 0 ? 0 : -1; }
+        else plane = -1;
+      }
+      float v = 0.f;
+      if (kk < J.k_pad && plane >= 0 && co < J.Co && ci < J.Ci && b < J.KW) {
+        v = src[((long long)(a * J.KW + b) * J.Ci + ci) * J.part_n[j]];
+        if (plane == 1) v -= round_bf16(v);
+      }
+      tile[ty + 8 * i][tx] = v;
     }
     __syncthreads();
     const int kk = tk * 32 + tx;
@@ -1660,12 +1719,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     const int r = idx / (J.k_pad * J.taps_h * J.taps_w);
     const int a = tap / J.taps_w, b = tap % J.taps_w;
     float v = 0.f;
-    if (J.kind == 0) {           // fwd: rows = co, k = ci
-      if (r < J.Co && kk < J.Ci) v = master_w(J, params, a, b, kk, r);
-    } else if (J.kind == 3) {    // first layer: one K block per kernel row, k = (kw, c) with 8 pixels x 8 channels
-      const int kw = kk >> 3, c = kk & 7;
-      if (r < J.Co && kw < J.KW && c < J.Ci) v = master_w(J, params, tap, kw, c, r);
-    } else {                     // dgrad: rows = ci, k = co, flipped (sub-)kernel
+    {                            // dgrad (generic path): rows = ci, k = co, flipped (sub-)kernel
       const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
       if (r < J.Ci && kk < J.Co) v = master_w(J, params, kh, kw, r, kk);
     }
@@ -1773,16 +1827,25 @@ const char* make_window_map(CUtensorMap* m, const void* xp, int N, int H, int W,
   return nullptr;
 }
 
-__global__ void __launch_bounds__(256) stage_first_kernel(const float* __restrict__ inputs, bf16* __restrict__ xp, int coff, int B, int H, int W) {
+__global__ void __launch_bounds__(256) stage_first_kernel(const float* __restrict__ inputs, bf16* __restrict__ xp, int coff, int B, int H, int W,
+                                                          int split) {
   const long long total = (long long)B * H * W;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % W);
     const long long row = idx / W;  // n*H + y
     const float* ip = inputs + idx * 6 + coff;
+    const float v0 = ip[0], v1 = ip[1], v2 = ip[2];
     uint4 pk;
-    pk.x = pack_bf16x2(ip[0], ip[1]);
-    pk.y = pack_bf16x2(ip[2], 0.f);
-    pk.z = 0u; pk.w = 0u;
+    pk.x = pack_bf16x2(v0, v1);
+    if (split) {      // bf16 pairs inside the pixel: channels 0-2 hi, 3-5 lo = bf16(v - hi)
+      const float l0 = v0 - round_bf16(v0), l1 = v1 - round_bf16(v1), l2 = v2 - round_bf16(v2);
+      pk.y = pack_bf16x2(v2, l0);
+      pk.z = pack_bf16x2(l1, l2);
+    } else {
+      pk.y = pack_bf16x2(v2, 0.f);
+      pk.z = 0u;
+    }
+    pk.w = 0u;
     *reinterpret_cast<uint4*>(xp + (row * (W + 8) + x + 2) * 8) = pk;
   }
 }
@@ -1810,7 +1873,14 @@ bool tile_grid(TcLaunch& L, int GH, int GW, int n_img) {
 }
 
 int env_int(const char* name, int dflt);
+// logical / physical chunk bookkeeping of a launch (TcLaunch::split: 0 plain, 1 bf16 pairs, 2 first layer with in-pixel pairs)
+void set_chunks(TcLaunch& L) {
+  if (L.split == 1) { L.kcl = 3 * L.kc; L.kca = L.a_wrap = 2 * L.kc; L.kcb = 2 * L.kc; L.b_fold = L.kc; L.b_sub = L.kc; }
+  else if (L.split == 2) { L.kcl = 2; L.kca = L.a_wrap = 1; L.kcb = 2; L.b_fold = 2; L.b_sub = 0; }      // (kc == 1)
+  else { L.kcl = L.kca = L.a_wrap = L.kcb = L.b_fold = L.kc; L.b_sub = 0; }
+}
 void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concurrent: launches of this shape sharing the GPU
+  set_chunks(L);
   L.tile_cols = n_cols_pad < 128 ? n_cols_pad : 128;
   L.n_tiles = n_cols_pad / L.tile_cols;
   const int a_bytes = 128 * L.bk * 2, b_bytes = round_up(L.tile_cols * L.bk * 2, 1024);
@@ -1822,7 +1892,7 @@ void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concu
   int stages = ((one_wave ? 192 : 100) * 1024) / (a_bytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  const int num_kb = L.taps_h * L.taps_w * L.kc;
+  const int num_kb = L.taps_h * L.taps_w * L.kcl;
   if (stages > num_kb) stages = num_kb < 1 ? 1 : num_kb;
   L.stages = stages;
   L.smem_bytes = (size_t)stages * (a_bytes + b_bytes) + sizeof(SmemCtl) + 1024;
@@ -1840,7 +1910,7 @@ void plan_split_k(TcLaunch& L, int n_img, size_t& off) {
   L.k_splits = 1; L.kb_per_split = 0; L.partial = nullptr;
   if (env_int("SV_NO_SPLITK", 0)) return;
   if (L.halo || L.grid_h != 1 || L.grid_w != 1 || L.taps_h * L.taps_w != 1 || L.osy != 1 || L.osx != 1) return;
-  const int num_kb = L.kc;
+  const int num_kb = L.kcl;
   const int m_tiles = (n_img + 127) / 128, ctas = m_tiles * L.n_tiles;
   if (num_kb < 8 || ctas >= 74) return;
   int splits = (148 + ctas - 1) / ctas;
@@ -1874,9 +1944,10 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
   // `force` (strided forward layers, stride-2 dgrad classes): the per-tap kernel re-reads every activation tile once per tap
   // from L2 (e2 forward: 226 MB in 31 us), the halo kernel reads it once.
   if ((L.bk > 32 || L.tile_cols > 32) && !force && !env_int("SV_HALO_ALL", 0)) return;
-  const int pix = L.bk * 2, nch = L.kc;
+  set_chunks(L);
+  const int pix = L.bk * 2, nch = L.kca;                 // physical chunks held by the halo
   const int kb_bytes = L.tile_cols * L.bk * 2;
-  const int num_kb = L.taps_h * L.taps_w * nch;
+  const int num_kb = L.taps_h * L.taps_w * L.kcl;        // (logical) weight k-blocks streamed per tile
   const double w_total = (double)num_kb * kb_bytes;
   int KB = 8192 / kb_bytes;
   if (KB < 1) KB = 1;
@@ -1934,9 +2005,10 @@ void plan_persist(TcLaunch& L, int n_classes) {
   if (!L.halo || !env_int("SV_PCONV", 1)) return;
   const int MT = L.mtx * L.mty;
   if (L.n_tiles > 4 || (L.n_tiles > 1 && n_classes != L.n_tiles) || 2 * MT * L.tile_cols > 512 || (L.tile_cols % kEpiBW) || L.nparts != 1) return;
-  const int num_kb = L.taps_h * L.taps_w * L.kc, kb_bytes = L.tile_cols * L.bk * 2;
+  set_chunks(L);
+  const int num_kb = L.taps_h * L.taps_w * L.kcb, kb_bytes = L.tile_cols * L.bk * 2;     // resident: the physical k-blocks
   const size_t w_bytes = ((size_t)num_kb * kb_bytes + 1023) / 1024 * 1024;
-  const size_t stage_bytes = (size_t)L.kc * L.halo_sx * L.chunk_bytes;
+  const size_t stage_bytes = (size_t)L.kca * L.halo_sx * L.chunk_bytes;
   const size_t budget = 225 * 1024 - 1024 - sizeof(PcCtl);
   if (w_bytes + 2 * stage_bytes > budget) return;
   int nst = (int)((budget - w_bytes) / stage_bytes);
@@ -2124,16 +2196,16 @@ const char* tc_last_error() { return g_tc_error; }
 
 size_t tc_first_stage_bytes(int B, int H, int W) { return (size_t)B * H * (W + 8) * 16; }
 
-void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, cudaStream_t s) {
+void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, bool split, cudaStream_t s) {
   const long long total = (long long)B * H * W;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stage_first_kernel<<<(int)blocks, 256, 0, s>>>(inputs, (bf16*)xp, coff, B, H, W);
+  stage_first_kernel<<<(int)blocks, 256, 0, s>>>(inputs, (bf16*)xp, coff, B, H, W, split ? 1 : 0);
 }
 
 // First conv of an encoder (6x6, stride 2, 3 input channels): the staged image is read as overlapping
 // 8-pixel x 8-channel windows, one K block of 64 per kernel row (48 of the 64 K entries carry weights).
-static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& off) {
+static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& off, bool split_fwd) {
   if (!(g.Ci == 3 && g.kh == 6 && g.kw == 6 && g.stride == 2 && g.pl == 2 && is_pow2(g.Ho) && is_pow2(g.Wo) && g.Wo <= 64 &&
         g.Wi == 2 * g.Wo && g.Hi == 2 * g.Ho && (g.dout_ld % 8) == 0))
     return;
@@ -2143,6 +2215,7 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
     if (!tile_grid(L, g.Ho, g.Wo, g.B)) return;
     L.taps_h = 6; L.taps_w = 1; L.pad_t = g.pt; L.pad_l = 0; L.a_stride = 2;
     L.bk = 64; L.swizzle = 128; L.kc = 1;
+    L.split = split_fwd ? 2 : 0;          // the staged pixel carries [hi lo] itself: two weight k-blocks per tap, one A chunk
     t.ci_pad = 64;
     t.n_pad_fwd = pad_cols(g.Co);
     L.n_valid = g.Co;
@@ -2155,7 +2228,7 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
     t.fwd_ok = true;
     t.fwd_launches = 1;
     t.w_fwd_off = off;
-    off += round_up(t.n_pad_fwd * 6 * 64 * 2, 1024);
+    off += round_up(t.n_pad_fwd * 6 * 64 * 2 * (split_fwd ? 2 : 1), 1024);
     t.bias_off = off;
     off += round_up(t.n_pad_fwd * 4, 1024);
     // Pixel-pair view on the halo kernel: the staged row [W+8][8 ch] is also [(W+8)/2][16 ch], so horizontally the 6x6 stride-2
@@ -2210,12 +2283,14 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
   }
 }
 
-void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer) {
+void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer,
+                   bool split_fwd) {
   t.in_dt = in_dt;
   t.out_dt = out_dt;
+  t.split_fwd = split_fwd;
   size_t off = 0;
   if (first_layer) {
-    plan_first_layer(t, g, out_dt, off);
+    plan_first_layer(t, g, out_dt, off, split_fwd);
     t.bytes = off;
     return;
   }
@@ -2228,6 +2303,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
       if (tile_grid(L, g.Ho, g.Wo, g.B)) {
         L.taps_h = g.kh; L.taps_w = g.kw; L.pad_t = g.pt; L.pad_l = g.pl; L.a_stride = g.stride;
         L.bk = bk; L.swizzle = bk * 2; L.kc = cpad / bk;
+        L.split = split_fwd ? 1 : 0;
         t.ci_pad = cpad;
         t.n_pad_fwd = pad_cols(g.Co);
         L.n_valid = g.Co;
@@ -2240,7 +2316,8 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         if (cpad <= g.in_ld - g.in_coff) {
           // (stride-2 forward on the halo kernel: parity-tested, but the weights of e2 - 144 KB - cannot stay resident beside the
           //  halo, and streaming them through the 3-stage ring is latency-bound: 39 us vs 32 us per-tap -> off by default)
-          if (g.stride == 1) try_halo(L, g.Ho, g.Wo, g.B);
+          // (bf16x3: twice the operand bytes per tap make the per-tap kernel L2-bound everywhere -> halo-resident wherever the grid allows)
+          if (g.stride == 1) try_halo(L, g.Ho, g.Wo, g.B, 1, 1, split_fwd);
           else if (g.stride == 2 && g.Hi == 2 * g.Ho && g.Wi == 2 * g.Wo && env_int("SV_S2_FWD_HALO", 0)) try_halo(L, g.Ho, g.Wo, g.B, 2, 2, true);
           plan_persist(L, 1);
           // Stride-2 forward on the persistent kernel: split the output channels over up to 4 CTA classes until the class's
@@ -2259,7 +2336,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
               TcLaunch Q = L;
               Q.tile_cols = cols; Q.n_tiles = split;
               if (pair_ok) { Q.taps_w = g.kw / 2; Q.pad_l = g.pl / 2; Q.bk = 2 * L.bk; Q.swizzle = 2 * L.swizzle; }
-              const size_t w_bytes = ((size_t)g.kh * g.kw * L.kc * cols * L.bk * 2 + 1023) / 1024 * 1024;
+              const size_t w_bytes = ((size_t)g.kh * g.kw * L.kc * cols * L.bk * 2 * (split_fwd ? 2 : 1) + 1023) / 1024 * 1024;
               const size_t budget = 225 * 1024 - 1024 - sizeof(PcCtl);
               if (w_bytes + 4096 >= budget) continue;
               try_halo(Q, g.Ho, g.Wo, g.B, pair_ok ? 1 : 2, 2, true, (budget - w_bytes) / 2);
@@ -2269,7 +2346,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
             }
           }
         }
-        if (g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
+        if (!split_fwd && g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
             plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
           TcNsConv& P = t.ns_fwd;
           P.n_valid = g.Co; P.out_ld = g.out_ld; P.out_f32 = out_dt == DT_F32; P.act = g.part_act[0]; P.mask_act = ACT_NONE;
@@ -2283,7 +2360,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         t.fwd_ok = true;
         t.fwd_launches = L.k_splits > 1 ? 2 : 1;
         t.w_fwd_off = off;
-        off += round_up((int)((size_t)t.n_pad_fwd * g.kh * g.kw * cpad * 2), 1024);
+        off += round_up((int)((size_t)t.n_pad_fwd * g.kh * g.kw * cpad * 2 * (split_fwd ? 2 : 1)), 1024);
         t.bias_off = off;
         off += round_up(t.n_pad_fwd * 4, 1024);
       }
@@ -2416,23 +2493,31 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
 size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom&) { return t.bytes; }
 
 const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din, const void* mask_src,
-                          int mask_act, char* ws) {
+                          int mask_act, char* ws, const void* in_lo, void* out_lo) {
   t.ws = ws;
   if (t.fwd_ok) {
     TcLaunch& L = t.fwd;
-    // (first_pair: the staged image [B][H][W+8][8] seen as [B][H][(W+8)/2][16] - one K = 16 row per pixel pair)
-    const char* e = t.first_pair ? make_halo_map(&L.map_a, in, g.B, g.Hi, (g.Wi + 8) / 2, 16, 0, 16, 16, L.TWp, L.THp, 1, 32)
-                    : t.fwd_pair ? make_halo_map(&L.map_a, in, g.B, g.Hi, g.Wi / 2, 2 * g.in_ld, 0, t.ci_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
-                    : t.first ? make_window_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
-                    : L.halo ? make_halo_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, L.halo_sx, L.swizzle)
-                            : make_act_map(&L.map_a, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff,
-                                           t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk, L.tile_w, L.tile_h, L.tile_n_img,
-                                           g.stride, L.swizzle);
+    auto make_a = [&](CUtensorMap* m, const void* base) -> const char* {
+      // (first_pair: the staged image [B][H][W+8][8] seen as [B][H][(W+8)/2][16] - one K = 16 row per pixel pair)
+      return t.first_pair ? make_halo_map(m, base, g.B, g.Hi, (g.Wi + 8) / 2, 16, 0, 16, 16, L.TWp, L.THp, 1, 32)
+             : t.fwd_pair ? make_halo_map(m, base, g.B, g.Hi, g.Wi / 2, 2 * g.in_ld, 0, t.ci_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
+             : t.first    ? make_window_map(m, base, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
+             : L.halo     ? make_halo_map(m, base, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, L.halo_sx, L.swizzle)
+                          : make_act_map(m, base, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk,
+                                         L.tile_w, L.tile_h, L.tile_n_img, g.stride, L.swizzle);
+    };
+    const char* e = make_a(&L.map_a, in);
     if (e) return e;
-    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * t.ci_pad, L.bk, L.tile_cols, L.swizzle);
+    if (L.kca > L.kc) {          // bf16x3: the lo plane of the input, same geometry
+      if (!in_lo) return "bf16x3 forward needs the lo plane of the layer input";
+      e = make_a(&L.map_a_lo, in_lo);
+      if (e) return e;
+    }
+    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * L.kcb * L.bk, L.bk, L.tile_cols, L.swizzle);
     if (e) return e;
     L.bias = (const float*)(ws + t.bias_off);
     L.out = out;
+    L.out_lo = (t.split_fwd && !L.out_f32) ? out_lo : nullptr;
     L.mask_src = nullptr;
     L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_fwd_off) : nullptr;
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -2563,9 +2648,14 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     }
     if (t.fwd_ok) {
       PackJob J = B;
-      J.kind = t.first ? 3 : 0; J.rows_pad = t.n_pad_fwd; J.taps_h = t.fwd.taps_h; J.taps_w = t.fwd.taps_w; J.k_pad = t.ci_pad;
-      if (t.first_pair) { J.kind = 0; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = 8; }   // K = (a, b, 8 channels): a pair-tap b' is the K block (b = 2b', 2b'+1)
-      if (t.fwd_pair) { J.taps_w = g.kw; J.k_pad = t.ci_pad / 2; }                       // same memory as [co][kh][kw][ci_pad/2]
+      const TcLaunch& L = t.fwd;
+      J.kind = 0; J.rows_pad = t.n_pad_fwd; J.taps_h = L.taps_h; J.taps_w = L.taps_w;
+      // pixels per k-block: 8 for the first layer's window view (one k-block per filter row), 2 for the pixel-pair views
+      J.ppx = (t.first && !t.first_pair) ? 8 : (t.first_pair || t.fwd_pair) ? 2 : 1;
+      J.cpp = (L.kc * L.bk) / J.ppx;                  // channels per pixel slot of one plane
+      J.nsec = L.kcb / L.kc;                          // [W_hi | W_lo] sections (bf16x3) or one
+      J.first_cat = L.split == 2;
+      J.k_pad = J.nsec * J.ppx * J.cpp;
       J.dst = t.ws + t.w_fwd_off;
       J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * J.k_pad;
       push(J);

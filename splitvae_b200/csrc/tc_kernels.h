@@ -13,8 +13,17 @@ namespace sv {
 //   B = a packed bf16 weight matrix [n_pad][taps*c_pad] read through a 2-D TMA map.
 struct TcLaunch {
   CUtensorMap map_a, map_b;
+  CUtensorMap map_a_lo;                         // bf16x3 forward: the lo plane of the A tensor (same geometry as map_a)
   int taps_h, taps_w, pad_t, pad_l, a_stride;   // A coordinate of (out y, tap a) = y*a_stride + a - pad_t
   int kc;                                       // channel chunks per tap (c_pad / bk)
+  // bf16x3 forward (operands are bf16 pairs hi + lo, product = hi*hi + lo*hi + hi*lo): per tap the K loop runs over `kcl` LOGICAL
+  // chunks that address `kca` physical A chunks (hi chunks then lo chunks, c -> c % a_wrap) and `kcb` physical weight
+  // k-blocks ([W_hi | W_lo] per tap, c -> c < b_fold ? c : c - b_sub).  Plain launches: kcl = kca = kcb = a_wrap = b_fold = kc.
+  //   split, kc chunks:   logical (hi,Whi)*kc (lo,Whi)*kc (hi,Wlo)*kc    -> kcl 3kc, kca 2kc, a_wrap 2kc, kcb 2kc, b_fold kc, b_sub kc
+  //   split, first layer: the 8-channel staged pixel holds [hi(3) lo(3) 0 0]; k-block 0 = [Whi Whi 0 0], k-block 1 = [Wlo 0 0 0]
+  //                                                                       -> kcl 2, kca 1, a_wrap 1, kcb 2, b_fold 2, b_sub 0
+  int split, kcl, kca, a_wrap, kcb, b_fold, b_sub;
+  void* out_lo;                                 // lo plane of a bf16 output (NULL: single bf16 / fp32 output)
   int bk, swizzle;                              // K elements per stage, swizzle bytes (= 2*bk)
   int tile_n_img, tile_h, tile_w;               // M tile = tile_n_img x tile_h x tile_w = 128 output pixels
   int grid_h, grid_w, n_img;                    // output grid per image (before scatter) and image count
@@ -148,6 +157,7 @@ struct TcLayer {
   TcWgradLaunch wg{};
   bool wg_halo = false;
   TcHaloWgrad hw{};
+  bool split_fwd = false;                  // bf16x3: the forward pass multiplies bf16 pairs (see TcLaunch::split)
   bool fwd_ns = false, dgrad_ns = false;   // N-stacked persistent kernel replaces the per-tap / halo kernel
   bool dgrad_merged = false;               // stride-2 dgrad: the 4 parity classes run as one launch (igemm4_kernel / halo4_kernel)
   bool fwd_pair = false;                   // stride-2 forward on the persistent kernel through the pixel-pair view [W/2][2C]
@@ -166,13 +176,16 @@ struct TcLayer {
 };
 
 // plan (no CUDA calls), workspace size, bind (creates TMA descriptors; returns NULL or an error text)
-void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer);
+void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool has_internal_input, bool has_dgrad, bool first_layer,
+                   bool split_fwd = false);
 // staged first-layer input: [B][H][W+8][8] bf16, real pixel x at column x+2, channels 3..7 and the borders zero
+// (split: channels 0-2 = hi, 3-5 = lo of the image value, 6-7 zero)
 size_t tc_first_stage_bytes(int B, int H, int W);
-void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, cudaStream_t s);
+void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W, bool split, cudaStream_t s);
 size_t tc_workspace_bytes(const TcLayer& t, const ConvGeom& g);
+// in_lo / out_lo: the lo planes of the layer input / output (bf16x3 forward; NULL otherwise)
 const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* out, void* dout, void* din,
-                          const void* mask_src, int mask_act, char* ws);
+                          const void* mask_src, int mask_act, char* ws, const void* in_lo = nullptr, void* out_lo = nullptr);
 // One multi-tensor launch that refreshes every packed operand from the fp32 master weights.
 struct TcPackTable;
 TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const* geoms, int n, const char** err);

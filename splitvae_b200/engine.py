@@ -26,7 +26,7 @@ class Engine:
     """One model replica on one GPU (vae/main.py:63-74 builds the same objects in TF)."""
 
     def __init__(self, model="lgvae", height=32, width=32, batch=64, y_size=30, tau=0.4, beta=40.0, alpha=40.0,
-                 learning_rate=1e-4, world_size=1, precision="bf16", device=None, rng_stream=0, no_tc=False,
+                 learning_rate=1e-4, world_size=1, precision="bf16x3", device=None, rng_stream=0, no_tc=False,
                  plan_only=False):
         self.lib = _lib.load()
         self.model, self.H, self.W, self.B = model, int(height), int(width), int(batch)

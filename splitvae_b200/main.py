@@ -28,7 +28,8 @@ def build_parser():
     parser.add_argument('--alpha', type=float, nargs='?', default=40)
     parser.add_argument('-allow_growth', action='store_true')  # TF session option; no effect here
     # new in this build
-    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument('--precision', type=str, default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'],
+                        help='bf16x3 (default): forward on bf16 pairs, gradients within 1e-2 of fp32; bf16: single-bf16 operands, fastest; fp32: SIMT reference kernels')
     parser.add_argument('--report_every', type=int, default=10000)
     parser.add_argument('--seed', type=int, default=0)
     parser.add_argument('--no_graph', action='store_true')

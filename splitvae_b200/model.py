@@ -16,7 +16,7 @@ class _SplitModel:
     _kind = None
 
     def __init__(self, global_latent_dims, local_latent_dims, image_shape=None, y_size=30, tau=0.4,
-                 variational=True, precision="bf16", **engine_kwargs):
+                 variational=True, precision="bf16x3", **engine_kwargs):
         if not variational:
             raise NotImplementedError("Determiistic LG-AE not implemented")  # vae/model.py:202,250
         self.global_latent_dims = global_latent_dims

@@ -1,9 +1,11 @@
 """GPU parity: libsplitvae (through the C-ABI) vs the CPU oracle on identical weights, inputs, noise.
 
-Tolerances (stated per SURVEY.md section 7 "Precision"):
+Tolerances:
+  * bf16x3 (DEFAULT, benchmarked: forward on bf16 pairs, backward on single bf16, fp32 accumulate): every scalar (ELBO and KL terms)
+    rel 1e-3, every gradient tensor rel-L2 1e-2 against the fp64 oracle.
   * fp32 reference-kernel mode: scalars rel 1e-5, every gradient tensor rel-L2 2e-4 (fp32 summation order only).
-  * bf16 tensor-core mode (bf16 operands, fp32 accumulate): scalars rel 1e-3 (the north-star tolerance),
-    gradient tensors rel-L2 3e-2 (bf16 has 8 mantissa bits; activations and activation-gradients are stored in bf16).
+  * bf16 (fast mode, single-bf16 operands everywhere): ELBO terms rel 1e-3; KL terms 2e-2; gradients only to 0.2 against fp64 and
+    8e-2 against the oracle with the same rounding points: 2^-9 forward roundings flip the ReLU masks of near-zero units.
 """
 import numpy as np
 import pytest
@@ -64,11 +66,58 @@ def test_step_bf16(model, H, B, p, beta, alpha, no_tc):
     #     which flips ~1e-3 of the bf16 roundings per layer; the same 3x-per-layer amplification turns that into
     #     up to 4e-2 on decoder d1 (it stays ~7x below the bf16 storage noise itself) -> rel-L2 <= 8e-2.
     u = batch["u"] if model == "lggmvae" else None
-    emu_sc, emu_g = E.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha)
+    emu_sc, emu_g = E.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha, mode="bf16")
     for k, v in emu_sc.items():
         assert abs(sc[k] - v) <= (1e-4 if no_tc else 1e-3) * max(1.0, abs(v)), (k, sc[k], v)
     worst, bad = compare_grads(grads, emu_g, 3e-2 if no_tc else 8e-2)
     assert not bad, bad
+
+
+# The benchmarked default mode.  Gates (VERDICT r1 / north_star "rel 1e-3 in fp32-accumulate"): EVERY scalar of the step - ELBO terms AND
+# KL terms - within rel 1e-3 of the fp64 oracle, every gradient tensor within rel-L2 1e-2 of the fp64 oracle (measured 3-7e-3: the
+# single-bf16 backward operands; the fp64-vs-fp32 floor is 3e-6), and within 1e-2 of the oracle with the device's rounding points.
+X3_CASES = CASES + [("lgvae", 32, 64, 1, 1.0, 40.0)]      # + C1 at its real batch (the fp64 oracle needs ~20 s for it)
+
+
+@pytest.mark.parametrize("model,H,B,p,beta,alpha", X3_CASES)
+def test_step_bf16x3(model, H, B, p, beta, alpha):
+    params, batch = make_case(model, H, B, p)
+    e = make_engine(model, H, B, "bf16x3", beta, alpha)
+    e.load_params(params)
+    sc, grads = run_engine_step(e, batch, model, adam=False)
+    ref_sc, ref_g = _oracle(model, params, batch, beta, alpha, torch.float64)
+    for k, v in ref_sc.items():
+        assert abs(sc[k] - v) <= 1e-3 * max(abs(v), 1e-3), (k, sc[k], v)
+    worst, bad = compare_grads(grads, ref_g, 1e-2)
+    assert not bad, bad
+    u = batch["u"] if model == "lggmvae" else None
+    emu_sc, emu_g = E.forward_backward(params, model, batch["inputs"], batch["eps_g"], batch["eps_l"], u, beta=beta, alpha=alpha, mode="bf16x3")
+    for k, v in emu_sc.items():
+        assert abs(sc[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, sc[k], v)
+    worst_emu, bad = compare_grads(grads, emu_g, 1e-2)
+    assert not bad, bad
+    print(f"{model} H={H} B={B} bf16x3: worst gradient rel-L2 vs fp64 {worst:.2e}, vs rounding-point oracle {worst_emu:.2e}")
+
+
+@pytest.mark.parametrize("model", ["lgvae", "lggmvae"])
+def test_forward_outputs_bf16x3(model):
+    """Every output of the model call in the default mode against the fp64 oracle: the forward is 2^-16-accurate up to d5's input."""
+    H, B = 32, 4
+    params, batch = make_case(model, H, B, 4, seed_base=10)
+    e = make_engine(model, H, B, "bf16x3", 40.0)
+    e.load_params(params)
+    x = to_dev(batch["inputs"])
+    e.forward(x, to_dev(batch["eps_g"]), to_dev(batch["eps_l"]), to_dev(batch["u"]) if model == "lggmvae" else None)
+    torch.cuda.synchronize()
+    _, _, out = _oracle(model, params, batch, 40.0, 40.0, torch.float64, outputs=True)
+    dx = e.output("dec_x").cpu().numpy()
+    assert rel_l2(dx[..., :3], out["x_mean"]) < 3e-3        # d5 multiplies single bf16 (smooth error, no ReLU after it)
+    assert rel_l2(dx[..., 3:], out["x_log_scale"]) < 3e-3
+    for name in ("z_x", "z_mean_x", "z_sig_x", "z_x_hat", "z_mean_x_hat", "z_sig_x_hat"):
+        assert rel_l2(e.output(name).cpu().numpy(), out[name]) < 5e-5, name
+    if model == "lggmvae":
+        for name in ("y", "y_logits", "z_prior_mean", "z_prior_sig"):
+            assert rel_l2(e.output(name).cpu().numpy(), out[name]) < 5e-5, name
 
 
 @pytest.mark.parametrize("model", ["lgvae", "lggmvae"])

@@ -9,8 +9,8 @@ from splitvae_b200._lib import KERNEL_NAMES
 from splitvae_b200.engine import Engine
 
 
-def _plan(model, H, B, **env):
-    e = Engine(model=model, height=H, width=H, batch=B, plan_only=True)
+def _plan(model, H, B, precision="bf16"):
+    e = Engine(model=model, height=H, width=H, batch=B, plan_only=True, precision=precision)
     return e, {L.name.decode(): (KERNEL_NAMES[L.kern_fwd], KERNEL_NAMES[L.kern_dgrad], KERNEL_NAMES[L.kern_wgrad]) for L in e.debug_layers()}
 
 
@@ -28,8 +28,9 @@ def test_c2_layer_to_kernel_map():
 
 
 @pytest.mark.parametrize("model,H,B", [("lgvae", 32, 64), ("lgvae", 64, 256), ("lggmvae", 32, 256), ("lggmvae", 64, 256), ("lgvae", 16, 3)])
-def test_every_pass_of_the_hot_path_has_a_tensor_core_kernel(model, H, B):
-    e, plan = _plan(model, H, B)
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_every_pass_of_the_hot_path_has_a_tensor_core_kernel(model, H, B, precision):
+    e, plan = _plan(model, H, B, precision)
     assert len(plan) == (18 if model == "lgvae" else 22)
     for name, (fwd, dgrad, wgrad) in plan.items():
         assert fwd != "reference" and wgrad != "reference", (name, fwd, wgrad)
@@ -44,3 +45,19 @@ def test_planner_knobs_are_read_at_plan_time(monkeypatch):
     _, plan = _plan("lgvae", 64, 256)
     assert plan["decoder_x.d5"][1] == "halo_conv_kernel"
     assert plan["decoder_x.d4"][0] == "igemm_kernel"
+
+
+def test_c2_layer_to_kernel_map_bf16x3():
+    """The default mode: forward products on bf16 pairs (three MMAs) need twice the operand bytes, so the planner moves the
+    resident-weight forward kernels of d3 / d4 to the halo kernel with streamed weights; d5 forward (single bf16 by design)
+    and the whole backward pass keep the single-bf16 plan."""
+    e, plan = _plan("lgvae", 64, 256, "bf16x3")
+    _, fast = _plan("lgvae", 64, 256, "bf16")
+    for name in plan:
+        assert plan[name][1:] == fast[name][1:], name                      # dgrad / wgrad kernels unchanged
+    for dec in ("decoder_x", "decoder_x_hat"):
+        assert plan[f"{dec}.d5"][0] == "nsconv_kernel"
+        assert plan[f"{dec}.d4"][0] in ("halo_conv_kernel", "pconv_kernel", "nsconv_kernel")
+    info = {L.name.decode(): L for L in e.debug_layers()}
+    assert all(L.split_fwd == (0 if n.endswith(".d5") else 1) for n, L in info.items())
+    assert e.workspace_bytes < 4 << 30
