@@ -14,9 +14,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--filter", default="")
+ap.add_argument("--precision", default="bf16x3")
 args = ap.parse_args()
 model, H, B, patch, beta, alpha, desc = WORKLOADS[args.workload]
-e = Engine(model=model, height=H, width=H, batch=B, beta=beta, alpha=alpha)
+e = Engine(model=model, height=H, width=H, batch=B, beta=beta, alpha=alpha, precision=args.precision)
 e.init_params(seed=5)
 x = torch.rand(B, H, H, 6, device="cuda") * 2 - 1
 e.train_step(x)

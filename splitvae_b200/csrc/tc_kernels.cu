@@ -40,6 +40,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// bf16x3 forward (TcLaunch::split): a tap's K loop in LOGICAL chunks -> physical A chunk (hi chunks 0..kc-1, lo chunks kc..2kc-1)
+// and physical weight k-block (per tap [W_hi(ch) W_lo(ch)] interleaved by chunk: block 2*ch + sec).
+//   split 1: logical (hi,Whi) x kc, (lo,Whi) x kc, (hi,Wlo) x kc;  split 2 (first layer, pairs inside the pixel): (x, [Whi Whi]), (x, [Wlo 0])
+__device__ __forceinline__ void logical_chunk(int split, int kc, int c, int& ap, int& bp) {
+  if (split == 1) { const int cls = c / kc, ch = c - cls * kc; ap = cls == 1 ? kc + ch : ch; bp = 2 * ch + (cls == 2 ? 1 : 0); }
+  else if (split == 2) { ap = 0; bp = c; }
+  else { ap = c; bp = c; }
+}
+// the same products driven by the PHYSICAL weight block jj of a tap (streamed-weight kernels read every block once): the A chunks
+// it multiplies; returns how many (1 or 2)
+__device__ __forceinline__ int phys_block_chunks(int split, int kc, int jj, int& a0, int& a1) {
+  if (split == 1) { const int ch = jj >> 1; a0 = ch; a1 = kc + ch; return (jj & 1) ? 1 : 2; }
+  a1 = 0;
+  if (split == 2) { a0 = 0; return 1; }
+  a0 = jj;
+  return 1;
+}
+
 
 // One epilogue thread = one accumulator row (TMEM lane) = one output pixel: reads tile_cols fp32 columns, adds the bias,
 // applies the activation (forward) or multiplies by the activation derivative of the producer layer (dgrad), stores NHWC.
@@ -69,11 +87,13 @@ struct EpiRegs {
   void* out;
   bf16* out_lo;          // bf16x3 forward: lo plane of the output (value = hi + lo), same indexing as `out`
   int tile_cols, n_valid, out_ld, mask_ld, mask_coff;
+  int stack_off;         // N-stacked pair accumulators (TcLaunch::nstack2): the correction columns sit stack_off TMEM columns further
 };
 __device__ __forceinline__ EpiRegs load_epi_regs(const TcLaunch& P) {
   EpiRegs E;
   E.bias = P.bias; E.mask_src = (const bf16*)P.mask_src; E.out = P.out; E.out_lo = (bf16*)P.out_lo;
   E.tile_cols = P.tile_cols; E.n_valid = P.n_valid; E.out_ld = P.out_ld; E.mask_ld = P.mask_ld; E.mask_coff = P.mask_coff;
+  E.stack_off = P.nstack2 ? P.tile_cols : 0;
   return E;
 }
 
@@ -83,7 +103,7 @@ __device__ __forceinline__ EpiRegs load_epi_regs(const TcLaunch& P) {
 constexpr int kEpiBW = 16;
 template <int ACT, int MASK, bool OUT_F32>
 __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpiBW], int cfirst, long long opix, bool valid,
-                                            uint32_t next_taddr, uint32_t (&vn)[kEpiBW], uint64_t* release_bar = nullptr) {
+                                            uint32_t next_taddr, uint32_t (&vn)[kEpiBW], uint64_t* release_bar = nullptr, uint32_t cur_taddr = 0u) {
   const int esz = OUT_F32 ? 4 : 2;
   const bool vec_ok = ((E.out_ld * esz) % 16) == 0;
   const bool mask_vec = MASK != ACT_NONE && (E.mask_ld % 8) == 0 && (E.mask_coff % 8) == 0 && cfirst + kEpiBW <= E.n_valid;
@@ -94,6 +114,13 @@ __device__ __forceinline__ void epi_block_t(const EpiRegs& E, uint32_t (&v)[kEpi
     for (int i = 0; i < kEpiBW / 8; ++i) mq[i] = __ldg(reinterpret_cast<const uint4*>(mrow + i * 8));
   }
   tc::tmem_ld_wait();
+  if (E.stack_off) {            // D = D_main + D_corr (hi*W_lo accumulated in its own columns by the N-stacked MMA)
+    uint32_t w[kEpiBW];
+    tc::tmem_ld16(cur_taddr + (uint32_t)E.stack_off, w);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < kEpiBW; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+  }
   if (next_taddr != 0u) tc::tmem_ld16(next_taddr, vn);
   else if (release_bar) {       // persistent kernel: the last block has left TMEM -> hand the accumulator set back to the MMA warp
     tc::tc_fence_before();
@@ -202,8 +229,8 @@ __device__ __forceinline__ void epilogue_acc_t(const EpiRegs& E, uint32_t tmem_l
       const bool last_cb = cb + 1 == cpb;
       const uint32_t next = taddr + (last_cb ? acc_skip : (uint32_t)kEpiBW);
       const uint32_t next_taddr = j + half + 1 < nblk ? next : 0u;
-      if (half == 0) epi_block_t<ACT, MASK, OUT_F32>(E, va, col_base + cb * kEpiBW, opix, valid, next_taddr, vb, release_bar);
-      else epi_block_t<ACT, MASK, OUT_F32>(E, vb, col_base + cb * kEpiBW, opix, valid, next_taddr, va, release_bar);
+      if (half == 0) epi_block_t<ACT, MASK, OUT_F32>(E, va, col_base + cb * kEpiBW, opix, valid, next_taddr, vb, release_bar, taddr);
+      else epi_block_t<ACT, MASK, OUT_F32>(E, vb, col_base + cb * kEpiBW, opix, valid, next_taddr, va, release_bar, taddr);
       taddr = next;
       if (last_cb) {
         cb = 0;
@@ -281,7 +308,8 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
         tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
         const int kb = kb_first + it;
         const int tap = kb / P.kcl, chunk = kb - tap * P.kcl;                 // logical chunk -> physical A chunk / weight k-block
-        const int ap = chunk % P.a_wrap, bp = chunk < P.b_fold ? chunk : chunk - P.b_sub;
+        int ap, bp;
+        logical_chunk(P.split, P.kc, chunk, ap, bp);
         const bool a_is_lo = ap >= P.kc;
         const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -424,6 +452,30 @@ __device__ __forceinline__ void trace_mark(int on, int slot) {
   }
 }
 
+// bf16x3, N-stacked weight pairs: all MMAs of ONE filter tap (= one weight-ring stage: [W_hi(ch) W_lo(ch)] per channel chunk), fully
+// unrolled - per chunk A_hi x [W_hi ; W_lo] (2N columns) then A_lo x W_hi (N columns), KS k-steps, MTX accumulators.  The generic
+// nest spends ~150 cycles of single-thread issue per tcgen05.mma (phase trace, d4: 85 k cycles for 576 MMAs); this one a few.
+template <int KS, int MTX, int KC>
+__device__ __forceinline__ void halo_issue_tap_pairs(uint64_t da_hi, uint64_t db0, uint32_t acc0, uint32_t spacing, uint32_t idesc1, uint32_t idesc2,
+                                                     uint32_t tx_step, uint32_t chunk_step, uint32_t lo_off, uint32_t blk_step, uint32_t first) {
+#pragma unroll
+  for (int ch = 0; ch < KC; ++ch) {
+    const uint64_t da = da_hi + (uint64_t)(ch * chunk_step), db = db0 + (uint64_t)(2 * ch * blk_step);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+#pragma unroll
+      for (int tx = 0; tx < MTX; ++tx)
+        tc::umma_bf16(acc0 + tx * spacing, da + (uint64_t)(tx * tx_step + 2u * k), db + 2u * k, idesc2, (ch | k) != 0 ? 1u : first);
+    }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+#pragma unroll
+      for (int tx = 0; tx < MTX; ++tx)
+        tc::umma_bf16(acc0 + tx * spacing, da + (uint64_t)(lo_off + tx * tx_step + 2u * k), db + 2u * k, idesc1, 1u);
+    }
+  }
+}
+
 struct HaloCtl {
   uint64_t halo_full;
   uint64_t w_full[kMaxStages];
@@ -449,9 +501,12 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
   const int tile_y = t % P.tiles_y;
   const int n = t / P.tiles_y;
   const int x0 = tile_x * P.TW, y0 = tile_y * P.TH;
-  const int num_kb = P.taps_h * P.taps_w * nchunks;
+  const int num_kb = P.taps_h * P.taps_w * P.kcb;                      // PHYSICAL weight k-blocks: each is streamed once per tile
   const int num_stages_total = (num_kb + P.kb_per_stage - 1) / P.kb_per_stage;
   const int MT = P.mtx * P.mty;
+  // Every CTA streams the same weights: started together they all hit the same L2 lines at the same time (d4 bf16x3: 1.0 TB/s
+  // L2->SMEM, 562 us).  Each CTA therefore starts the (commutative) K loop at its own ring stage.
+  const int rot = P.split ? (int)((blockIdx.x * 11u + blockIdx.y * 5u) % (unsigned)num_stages_total) : 0;
 
   const int tr = P.trace;
   if (threadIdx.x == 0) {
@@ -473,8 +528,9 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
     tc::mbar_init(&ctl->tmem_full, 1);
     tc::fence_barrier_init();
   }
+  const int acc_cols1 = P.nstack2 ? 2 * P.tile_cols : P.tile_cols;     // TMEM columns per accumulator ([main | correction] when N-stacked)
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(MT * P.tile_cols)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(MT * acc_cols1)) tmem_cols <<= 1;
   if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
@@ -489,28 +545,35 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
         for (int c = 0; c < nphys; ++c)    // physical chunks: the hi plane's chunks, then the lo plane's
           tc::tma_load_4d(halo + (size_t)(p * nphys + c) * P.chunk_bytes, c < P.kc ? &P.map_a : &P.map_a_lo, &ctl->halo_full,
                           (c < P.kc ? c : c - P.kc) * P.bk, sx * x0 - P.pad_l + p, sy * y0 - P.pad_t, n);
+      const int w_stages = P.w_stages, kb_per_stage = P.kb_per_stage, w_stage_bytes = P.w_stage_bytes, bk = P.bk, col0 = n_tile * P.tile_cols;
+      const CUtensorMap* map_b = &P.map_b;     // (registers: the TMA asm statements clobber memory)
+      const int box3 = P.w_box3;
       for (int st = 0; st < num_stages_total; ++st) {
-        const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
+        const int slot = st % w_stages, phase = (st / w_stages) & 1;
         tc::mbar_wait(&ctl->w_empty[slot], phase ^ 1);
-        const int kb0 = st * P.kb_per_stage;
-        const int nkb = min(P.kb_per_stage, num_kb - kb0);
+        const int se = st + rot < num_stages_total ? st + rot : st + rot - num_stages_total;
+        const int kb0 = se * kb_per_stage;
+        const int nkb = min(kb_per_stage, num_kb - kb0);
         tc::mbar_expect_tx(&ctl->w_full[slot], (uint32_t)(nkb * kb_bytes));
-        for (int j = 0; j < nkb; ++j) {
-          const int kbl = kb0 + j, tapl = kbl / nchunks, cl = kbl - tapl * nchunks;     // logical k-block -> physical weight k-block
-          const int bp = cl < P.b_fold ? cl : cl - P.b_sub;
-          tc::tma_load_2d(wring + (size_t)slot * P.w_stage_bytes + (size_t)j * kb_bytes, &P.map_b, &ctl->w_full[slot],
-                          (tapl * P.kcb + bp) * P.bk, n_tile * P.tile_cols);
-        }
+        if (box3) tc::tma_load_3d(wring + (size_t)slot * w_stage_bytes, map_b, &ctl->w_full[slot], 0, col0, kb0);   // the whole stage in one box
+        else
+          for (int j = 0; j < nkb; ++j)
+            tc::tma_load_2d(wring + (size_t)slot * w_stage_bytes + (size_t)j * kb_bytes, map_b, &ctl->w_full[slot], (kb0 + j) * bk, col0);
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
+      // every launch parameter the loop needs lives in a register: each tcgen05.mma carries a "memory" clobber, so a field read
+      // through `P` inside the loop is re-loaded (long-scoreboard stall) after every MMA - 148 cycles per MMA on d4 bf16x3
+      const int tile_n = P.tile_cols, bk = P.bk, TWp = P.TWp, taps_w = P.taps_w, mtx = P.mtx, mty = P.mty, kcb = P.kcb, kc = P.kc;
+      const int split = P.split, nstack2 = P.nstack2, kb_per_stage = P.kb_per_stage, w_stages = P.w_stages;
+      const uint32_t chunk_bytes = (uint32_t)P.chunk_bytes, w_stage_bytes = (uint32_t)P.w_stage_bytes;
+      const uint32_t idesc1 = tc::make_idesc_bf16(128, tile_n, 0, 0), idesc2 = tc::make_idesc_bf16(128, 2 * tile_n, 0, 0);
       const uint32_t lt = tc::layout_type_for(P.swizzle);
-      const uint32_t pix = (uint32_t)P.bk * 2u;              // bytes per pixel inside a chunk
-      const uint32_t a_sbo = (uint32_t)(sy * P.TWp) * pix;   // next row group = next output row = sy input rows
+      const uint32_t pix = (uint32_t)bk * 2u;                // bytes per pixel inside a chunk
+      const uint32_t a_sbo = (uint32_t)(sy * TWp) * pix;     // next row group = next output row = sy input rows
       const uint32_t b_sbo = 8u * pix;                       // weights: dense [tile_cols][bk]
-      const uint32_t halo_addr = tc::smem_u32(halo);
+      const uint32_t halo_addr = tc::smem_u32(halo), wring_addr = tc::smem_u32(wring);
       trace_mark(tr, 2);
       tc::mbar_wait(&ctl->halo_full, 0);
       tc::tc_fence_after();
@@ -518,44 +581,74 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
       // Descriptors differ only in their 14-bit start-address field (bits 0-13, units of 16 B): build one template per
       // operand and add offsets, so the single issuing thread spends a handful of instructions per MMA.
       const uint64_t a_tmpl = tc::make_smem_desc(0, 16, a_sbo, lt), b_tmpl = tc::make_smem_desc(0, 16, b_sbo, lt);
-      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * P.TWp) * pix) >> 4;
-      const uint32_t tile_cols = (uint32_t)P.tile_cols;
-      const int ksteps = P.bk / 16;
-      int kb = 0;
+      const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * TWp) * pix) >> 4;
+      const uint32_t tile_cols = (uint32_t)acc_cols1;      // accumulator spacing in TMEM
+      const int ksteps = bk / 16;
+      const int kb_inc = nstack2 ? 2 : 1;
+      const uint32_t kb_step = (uint32_t)(kb_inc * kb_bytes) >> 4;
+      const bool tap_unrolled = nstack2 && sx == 1 && mty == 1 && ksteps == 4 && (kb_per_stage % kcb) == 0 && (kc == 1 || kc == 2) &&
+                                (mtx == 1 || mtx == 2 || mtx == 4) && !(P.trace & 2);
+      const int taps_per_stage = kb_per_stage / kcb;
+      uint32_t first = 0u;                  // 0 for the very first MMA group of the tile (overwrites the accumulators)
       for (int st = 0; st < num_stages_total; ++st) {
-        const int slot = st % P.w_stages, phase = (st / P.w_stages) & 1;
+        const int slot = st % w_stages, phase = (st / w_stages) & 1;
         tc::mbar_wait(&ctl->w_full[slot], phase);
         tc::tc_fence_after();
-        const uint32_t wbase = tc::smem_u32(wring + (size_t)slot * P.w_stage_bytes);
-        const int kb_end = min(num_kb, kb + P.kb_per_stage);
-        uint32_t b_addr = wbase >> 4;
-        int tap = kb / nchunks, chunk = kb - tap * nchunks;
-        int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
-        for (; kb < kb_end; ++kb, b_addr += (uint32_t)kb_bytes >> 4) {
+        const int se = st + rot < num_stages_total ? st + rot : st + rot - num_stages_total;
+        int kb = se * kb_per_stage;
+        const int kb_end = min(num_kb, kb + kb_per_stage);
+        uint32_t b_addr = (wring_addr + (uint32_t)slot * w_stage_bytes) >> 4;
+        int tap = kb / kcb, jj = kb - tap * kcb;                        // physical weight block jj of filter tap (ta, tb)
+        int ta = tap / taps_w, tb = tap - ta * taps_w;
+        if (tap_unrolled)              // one stage = a whole number of taps (the planner made kb_per_stage a multiple of kcb)
+         for (int tt = 0; tt < taps_per_stage; ++tt) {
+          const uint64_t da_hi = a_tmpl + ((halo_addr + (uint32_t)(ta * TWp + tb) * pix) >> 4);
+          const uint32_t cstep = chunk_bytes >> 4, lo_off = (uint32_t)kc * cstep, bstep = (uint32_t)kb_bytes >> 4;
+          const uint64_t db0 = b_tmpl + b_addr + (uint32_t)(tt * kcb) * bstep;
+          if (kc == 1) {
+            if (mtx == 2) halo_issue_tap_pairs<4, 2, 1>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+            else if (mtx == 1) halo_issue_tap_pairs<4, 1, 1>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+            else halo_issue_tap_pairs<4, 4, 1>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+          } else {
+            if (mtx == 2) halo_issue_tap_pairs<4, 2, 2>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+            else if (mtx == 1) halo_issue_tap_pairs<4, 1, 2>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+            else halo_issue_tap_pairs<4, 4, 2>(da_hi, db0, tmem_base, tile_cols, idesc1, idesc2, tx_step, cstep, lo_off, bstep, first);
+          }
+          first = 1u;
+          kb = kb_end;
+          if (++tb == taps_w) { tb = 0; ++ta; }
+         }
+        for (; kb < kb_end; kb += kb_inc, b_addr += kb_step) {
+         int a0, a1;
+         const int na = phys_block_chunks(split, kc, jj, a0, a1);
+         // N-stacked pair: blocks (W_hi(ch), W_lo(ch)) are adjacent in the ring = ONE B operand of 2N rows:
+         //   q = 0: A_hi x [W_hi ; W_lo] -> columns [main | correction],  q = 1: A_lo x W_hi -> main
+         for (int q = 0; q < na; ++q, first = 1u) {
+          const uint32_t idesc = (nstack2 && q == 0) ? idesc2 : idesc1;
           // filter column tb = sx * b' + p: parity plane p, shifted by b' plane columns
-          const int ap = chunk % P.a_wrap;     // physical halo chunk of this logical chunk
-          const uint32_t a_tap = sx == 1 ? (halo_addr + (uint32_t)ap * (uint32_t)P.chunk_bytes + (uint32_t)(ta * P.TWp + tb) * pix) >> 4
-                                         : (halo_addr + (uint32_t)((tb % sx) * nphys + ap) * (uint32_t)P.chunk_bytes +
-                                            (uint32_t)(ta * P.TWp + tb / sx) * pix) >> 4;
+          const int ap = q ? a1 : a0;          // physical halo chunk multiplied with this weight block
+          const uint32_t a_tap = sx == 1 ? (halo_addr + (uint32_t)ap * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
+                                         : (halo_addr + (uint32_t)((tb % sx) * nphys + ap) * chunk_bytes + (uint32_t)(ta * TWp + tb / sx) * pix) >> 4;
           const uint64_t db = b_tmpl + b_addr;
-          const uint32_t first = kb != 0;
-          switch (P.mtx) {
-            case 1: halo_issue_kb<1>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
-            case 2: halo_issue_kb<2>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
-            case 4: halo_issue_kb<4>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
-            case 8: halo_issue_kb<8>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, P.mty, ksteps, ty_step, tx_step, first); break;
+          switch (mtx) {
+            case 1: halo_issue_kb<1>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            case 2: halo_issue_kb<2>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            case 4: halo_issue_kb<4>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
+            case 8: halo_issue_kb<8>(a_tmpl + a_tap, db, tmem_base, tile_cols, idesc, mty, ksteps, ty_step, tx_step, first); break;
             default:
               for (int k = 0; k < ksteps; ++k) {
                 uint32_t a_row = a_tap + 2u * k, acc = tmem_base;
                 const uint64_t dbk = db + 2u * k;
                 const uint32_t accum = k ? 1u : first;
-                for (int ty = 0; ty < P.mty; ++ty, a_row += ty_step) {
+                for (int ty = 0; ty < mty; ++ty, a_row += ty_step) {
                   uint64_t da = a_tmpl + a_row;
-                  for (int tx = 0; tx < P.mtx; ++tx, da += tx_step, acc += tile_cols) tc::umma_bf16(acc, da, dbk, idesc, accum);
+                  for (int tx = 0; tx < mtx; ++tx, da += tx_step, acc += tile_cols) tc::umma_bf16(acc, da, dbk, idesc, accum);
                 }
               }
           }
-          if (++chunk == nchunks) { chunk = 0; if (++tb == P.taps_w) { tb = 0; ++ta; } }
+         }
+         jj += kb_inc;
+         if (jj >= kcb) { jj = 0; if (++tb == taps_w) { tb = 0; ++ta; } }
         }
         tc::umma_commit(&ctl->w_empty[slot]);
       }
@@ -569,7 +662,7 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
     const int y = y0 + (row >> 3), x = x0 + (row & 7);             // accumulator (0,0): row group = image row, 8 pixels wide
     const long long opix0 = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
     const long long step_tx = 8LL * P.osx, step_ty = 16LL * P.osy * P.OW;
-    const int mtx = P.mtx, n_acc = MT, acc_stride = P.tile_cols, col_base = n_tile * P.tile_cols;
+    const int mtx = P.mtx, n_acc = MT, acc_stride = acc_cols1, col_base = n_tile * P.tile_cols;
     tc::mbar_wait(&ctl->tmem_full, 0);
     tc::tc_fence_after();
     if (threadIdx.x == 64) trace_mark(tr, 5);
@@ -720,7 +813,7 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
       const uint32_t tx_step = (8u * pix) >> 4, ty_step = (16u * (uint32_t)(sy * P.TWp) * pix) >> 4;
       const uint32_t tile_cols = (uint32_t)P.tile_cols, chunk_bytes = (uint32_t)P.chunk_bytes;
       const int ksteps = P.bk / 16, mtx = P.mtx, mty = P.mty, taps_w = P.taps_w, TWp = P.TWp;
-      const int a_wrap = P.a_wrap, b_fold = P.b_fold, b_sub = P.b_sub, kcb = P.kcb;
+      const int split_kind = P.split, kc_phys = P.kc, kcb = P.kcb;
       const uint32_t halo_addr = tc::smem_u32(halo), w_addr = tc::smem_u32(wsm) >> 4, kb_step = (uint32_t)kb_bytes >> 4;
       const bool env_shape_off = (P.trace & 2) != 0;      // SV_HALO_TRACE=2: generic issue loop (A/B)
       // unrolled issue sequences: 1 = 6x6 taps, K 16, 4 accumulators (d5 dgrad); 2 = 6x3 pair taps (first layer, 64x64 images);
@@ -759,7 +852,8 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
           else pc_issue_tile<6, 6, 2, 2, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
         } else
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int ap = chunk % a_wrap, bp = chunk < b_fold ? chunk : chunk - b_sub;   // logical chunk -> physical halo chunk / weight k-block
+          int ap, bp;                                          // logical chunk -> physical halo chunk / weight k-block
+          logical_chunk(split_kind, kc_phys, chunk, ap, bp);
           b_addr = w_addr + (uint32_t)((ta * taps_w + tb) * kcb + bp) * kb_step;
           const uint32_t a_tap = sx == 1 ? (h_addr + (uint32_t)ap * chunk_bytes + (uint32_t)(ta * TWp + tb) * pix) >> 4
                                          : (h_addr + (uint32_t)((tb % sx) * nphys + ap) * chunk_bytes + (uint32_t)(ta * TWp + tb / sx) * pix) >> 4;
@@ -1580,10 +1674,11 @@ struct PackJob {
   int nparts, part_n[3];
   long long part_w[3], part_b[3];
   int rows_pad, taps_h, taps_w, k_pad;   // dst = [rows_pad][taps_h*taps_w][k_pad]
-  // kind 0: one k-block row = [nsec sections][ppx pixels][cpp channels] (k_pad = nsec * ppx * cpp); k-block tap (a, b') covers the
-  // filter columns b = b' * ppx + px.  ppx = 1: one pixel per tap; 2: the pixel-pair views; 8: the first layer's window view.
-  // nsec = 2 (bf16x3): section 0 = bf16(W) = W_hi, section 1 = bf16(W - W_hi) = W_lo.  first_cat (first layer, bf16x3): the staged
-  // pixel holds [x_hi(3) x_lo(3) 0 0], so section 0 = [W_hi W_hi 0 0] (x_hi*W_hi + x_lo*W_hi) and section 1 = [W_lo 0 0 0].
+  // kind 0: the K axis of a tap (a, b') is a sequence of k-blocks of ppx pixels x cpp channels, [channel chunk][section]:
+  // k_pad = chunks * nsec * ppx * cpp; tap (a, b') covers the filter columns b = b' * ppx + px.  ppx = 1: one pixel per tap;
+  // 2: the pixel-pair views; 8: the first layer's window view.  nsec = 2 (bf16x3): section 0 = bf16(W) = W_hi, section 1 =
+  // bf16(W - W_hi) = W_lo.  first_cat (first layer, bf16x3): the staged pixel holds [x_hi(3) x_lo(3) 0 0], so section 0 =
+  // [W_hi W_hi 0 0] (x_hi*W_hi + x_lo*W_hi) and section 1 = [W_lo 0 0 0].
   int ppx, cpp, nsec, first_cat;
   int stride, rh, rw;       // dgrad: kh = stride*(taps_h-1-a) + rh  (stride 1: rh = 0)
   void* dst;
@@ -1655,12 +1750,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     int j = 0, lc = co;
     while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
     const float* src = params + J.part_w[j] + lc;
-    const int sec_len = J.ppx * J.cpp;
+    const int blk_len = J.ppx * J.cpp;                // one k-block: ppx pixels x cpp channels
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = tk * 32 + ty + 8 * i;
-      const int sec = kk / sec_len, rem = kk - sec * sec_len;
-      const int px = rem / J.cpp, c = rem - px * J.cpp;
+      const int blk = kk / blk_len, rem = kk - blk * blk_len;      // k-block of the tap: channel chunk blk / nsec, section blk % nsec
+      const int sec = blk % J.nsec, chunk = blk / J.nsec;
+      const int px = rem / J.cpp, c = chunk * J.cpp + (rem - px * J.cpp);
       const int b = bq * J.ppx + px;
       int ci = c, plane = sec;                       // plane: 0 = hi, 1 = lo, -1 = zero
       if (J.first_cat) {
@@ -1808,6 +1904,26 @@ const char* make_w_map(CUtensorMap* m, const void* base, int rows, long long k_t
   return nullptr;
 }
 
+// packed weights seen as [rows][blocks][bk]: box = {bk, tile_rows, nblk} = `nblk` consecutive k-blocks of `tile_rows` rows in ONE TMA
+// operation, landing block-major in shared memory (exactly the ring layout of halo_conv_kernel).  The TMA unit works through small
+// boxes one after the other (~700 cycles per 4 KB box of 32 rows: 6 B/clk per SM, phase trace of d4 bf16x3); large boxes stream.
+const char* make_w_map3(CUtensorMap* m, const void* base, int rows, long long k_total, int bk, int tile_rows, int nblk, int swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)rows, (cuuint64_t)(k_total / bk)};
+  cuuint64_t strides[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)bk * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)tile_rows, (cuuint32_t)nblk};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(weights3) failed: %d (rows %d k %lld bk %d tile %d x %d)", (int)r, rows,
+             k_total, bk, tile_rows, nblk);
+    return g_tc_error;
+  }
+  return nullptr;
+}
+
 // first-layer input as overlapping 8-pixel windows: element (k, wo, y, n) = xp[n][y][2*wo + k/8][k%8]
 const char* make_window_map(CUtensorMap* m, const void* xp, int N, int H, int W, int Wo, int tw, int th, int tn) {
   PFN_encodeTiled enc = get_encode();
@@ -1875,9 +1991,9 @@ bool tile_grid(TcLaunch& L, int GH, int GW, int n_img) {
 int env_int(const char* name, int dflt);
 // logical / physical chunk bookkeeping of a launch (TcLaunch::split: 0 plain, 1 bf16 pairs, 2 first layer with in-pixel pairs)
 void set_chunks(TcLaunch& L) {
-  if (L.split == 1) { L.kcl = 3 * L.kc; L.kca = L.a_wrap = 2 * L.kc; L.kcb = 2 * L.kc; L.b_fold = L.kc; L.b_sub = L.kc; }
-  else if (L.split == 2) { L.kcl = 2; L.kca = L.a_wrap = 1; L.kcb = 2; L.b_fold = 2; L.b_sub = 0; }      // (kc == 1)
-  else { L.kcl = L.kca = L.a_wrap = L.kcb = L.b_fold = L.kc; L.b_sub = 0; }
+  if (L.split == 1) { L.kcl = 3 * L.kc; L.kca = 2 * L.kc; L.kcb = 2 * L.kc; }
+  else if (L.split == 2) { L.kcl = 2; L.kca = 1; L.kcb = 2; }      // (kc == 1)
+  else { L.kcl = L.kca = L.kcb = L.kc; }
 }
 void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concurrent: launches of this shape sharing the GPU
   set_chunks(L);
@@ -1935,6 +2051,7 @@ size_t split_k_bytes(const TcLaunch& L) {
 void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bool force = false, size_t max_halo_bytes = 0,
               int tmem_limit = 512) {
   L.halo = 0;
+  L.nstack2 = 0;
   L.halo_sx = 1; L.halo_sy = 1;
   if (env_int("SV_NO_HALO", 0)) return;
   if ((sx == 1 && sy == 1 && L.a_stride != 1) || (GH % 16) || (GW % 8) || L.taps_h * L.taps_w < 2) return;
@@ -1947,11 +2064,15 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
   set_chunks(L);
   const int pix = L.bk * 2, nch = L.kca;                 // physical chunks held by the halo
   const int kb_bytes = L.tile_cols * L.bk * 2;
-  const int num_kb = L.taps_h * L.taps_w * L.kcl;        // (logical) weight k-blocks streamed per tile
+  const int num_kb = L.taps_h * L.taps_w * L.kcb;        // physical weight k-blocks, each streamed once per tile
   const double w_total = (double)num_kb * kb_bytes;
   int KB = 8192 / kb_bytes;
   if (KB < 1) KB = 1;
   if (KB > num_kb) KB = num_kb;
+  // bf16x3: one CTA per SM anyway (two halo planes), and the weight stream is the bottleneck (latency-bound with a 24 KB ring:
+  // d4 562 us) -> the ring takes all the shared memory the halo leaves, in up to kMaxStages stages
+  const bool deep = L.split != 0;
+  const size_t smem_cap = deep ? 226 * 1024 : 200 * 1024;
   int best_tw = 0, best_th = 0, best_stages = 0;
   double best_cost = 1e30;
   const int force_tw = env_int("SV_HALO_TW", 0), force_th = env_int("SV_HALO_TH", 0);
@@ -1970,7 +2091,8 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
       if (max_halo_bytes && chunk * nch * sx > max_halo_bytes) continue;
       for (int stages = 3; stages >= 2; --stages) {
         const size_t smem = chunk * nch * sx + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
-        if (smem > 200 * 1024) continue;
+        if (smem > smem_cap) continue;
+        if (deep && chunk * nch * sx + 64 * 1024 > smem_cap) continue;         // leave >= 64 KB for the weight ring
         int tmem_cols = 32;
         while (tmem_cols < MT * L.tile_cols) tmem_cols <<= 1;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -1992,6 +2114,36 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
   L.mtx = best_tw / 8; L.mty = best_th / 16;
   L.chunk_bytes = (int)(((size_t)L.THp * L.TWp * pix + 1023) / 1024 * 1024);
   L.kb_per_stage = KB; L.w_stages = best_stages; L.w_stage_bytes = KB * kb_bytes;
+  if (deep) {     // widen / deepen the ring into the free shared memory: <= kMaxStages stages of an even number of k-blocks
+    const size_t free_bytes = smem_cap - ((size_t)L.chunk_bytes * nch * sx + sizeof(HaloCtl) + 1024);
+    int total_kb = (int)(free_bytes / kb_bytes);
+    if (total_kb > num_kb) total_kb = num_kb;
+    int st = kMaxStages, per = total_kb / st;
+    while (st > 2 && per < 2) { --st; per = total_kb / st; }
+    if (per > 1) per -= per & 1;
+    if (per >= 1) { L.kb_per_stage = per; L.w_stages = st; L.w_stage_bytes = per * kb_bytes; }
+  }
+  // N-stacked weight pairs (one MMA of 2N columns for A_hi x [W_hi ; W_lo]): two MMAs per k-step instead of three where the MMA rate
+  // is bound by the A-operand read (N <= 64)
+  L.nstack2 = (L.split == 1 && (L.kb_per_stage % 2) == 0 && 2 * L.tile_cols <= 256 && 2 * (best_tw / 8) * (best_th / 16) * L.tile_cols <= 512 &&
+               env_int("SV_NSTACK2", 1)) ? 1 : 0;
+  L.w_box3 = 0;
+  if (L.nstack2) {
+    // one ring stage = a whole number of filter taps ([W_hi(ch) W_lo(ch)] x kc each; the kernel's unrolled per-tap issue sequence),
+    // loaded by ONE 3-D TMA box: ~24 KB stages, >= 3 of them
+    const size_t free_bytes = smem_cap - ((size_t)L.chunk_bytes * nch * sx + sizeof(HaloCtl) + 1024);
+    const size_t tap_bytes = (size_t)L.kcb * kb_bytes;
+    const int taps = L.taps_h * L.taps_w;
+    int tps = 1;
+    for (int c = 1; c <= taps; ++c)
+      if (taps % c == 0 && c * tap_bytes <= 24 * 1024 && free_bytes / (c * tap_bytes) >= 3 && c * L.kcb <= 256) tps = c;
+    int st = (int)(free_bytes / (tps * tap_bytes));
+    if (st > kMaxStages) st = kMaxStages;
+    if (st >= 2) {
+      L.kb_per_stage = tps * L.kcb; L.w_stages = st; L.w_stage_bytes = (int)(tps * tap_bytes);
+      L.w_box3 = env_int("SV_W_BOX3", 1);
+    }
+  }
   L.tiles_x = GW / best_tw; L.tiles_y = GH / best_th;
   L.n_img = n_img;
   L.smem_bytes = (size_t)L.chunk_bytes * nch * sx + (size_t)L.w_stages * L.w_stage_bytes + sizeof(HaloCtl) + 1024;
@@ -2020,6 +2172,8 @@ void plan_persist(TcLaunch& L, int n_classes) {
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   L.persist = 1; L.p_stages = nst; L.p_wbytes = (int)w_bytes; L.p_grid = grid; L.p_ntile = 0;
+  L.nstack2 = 0;                         // (the persistent kernel issues the three products separately)
+  L.w_box3 = 0;
   L.p_smem = w_bytes + (size_t)nst * stage_bytes + sizeof(PcCtl) + 1024;
 }
 
@@ -2344,6 +2498,15 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
               plan_persist(Q, split);
               if (Q.persist) { L = Q; t.fwd_pair = pair_ok; if (pair_ok) t.ci_pad = 2 * cpad; break; }
             }
+            // bf16x3: the pair's weights (2 sections) never stay resident beside the halo pairs; the one-tile-per-CTA halo kernel streams
+            // them instead, still reading the input once per tile (the per-tap kernel re-reads both planes per tap: e2 forward 86 us)
+            if (split_fwd && !L.persist && pair_ok && t.n_pad_fwd <= 128) {
+              TcLaunch Q = L;
+              Q.taps_w = g.kw / 2; Q.pad_l = g.pl / 2; Q.bk = 2 * L.bk; Q.swizzle = 2 * L.swizzle;
+              finish_launch(Q, t.n_pad_fwd);
+              try_halo(Q, g.Ho, g.Wo, g.B, 1, 2, true);
+              if (Q.halo) { L = Q; t.fwd_pair = true; t.ci_pad = 2 * cpad; }
+            }
           }
         }
         if (!split_fwd && g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
@@ -2513,7 +2676,9 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       e = make_a(&L.map_a_lo, in_lo);
       if (e) return e;
     }
-    e = make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * L.kcb * L.bk, L.bk, L.tile_cols, L.swizzle);
+    e = L.w_box3 ? make_w_map3(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * L.kcb * L.bk, L.bk, L.tile_cols,
+                               L.kb_per_stage, L.swizzle)
+                 : make_w_map(&L.map_b, ws + t.w_fwd_off, t.n_pad_fwd, (long long)L.taps_h * L.taps_w * L.kcb * L.bk, L.bk, L.tile_cols, L.swizzle);
     if (e) return e;
     L.bias = (const float*)(ws + t.bias_off);
     L.out = out;
@@ -2565,7 +2730,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
     if (cudaFuncSetAttribute(igemm4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
-  if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(halo4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(pconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (env_int("SV_TC_VERBOSE", 0)) {
@@ -2652,10 +2817,10 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
       J.kind = 0; J.rows_pad = t.n_pad_fwd; J.taps_h = L.taps_h; J.taps_w = L.taps_w;
       // pixels per k-block: 8 for the first layer's window view (one k-block per filter row), 2 for the pixel-pair views
       J.ppx = (t.first && !t.first_pair) ? 8 : (t.first_pair || t.fwd_pair) ? 2 : 1;
-      J.cpp = (L.kc * L.bk) / J.ppx;                  // channels per pixel slot of one plane
-      J.nsec = L.kcb / L.kc;                          // [W_hi | W_lo] sections (bf16x3) or one
+      J.cpp = L.bk / J.ppx;                           // channels per pixel slot of one k-block
+      J.nsec = L.kcb / L.kc;                          // [W_hi | W_lo] sections per channel chunk (bf16x3) or one
       J.first_cat = L.split == 2;
-      J.k_pad = J.nsec * J.ppx * J.cpp;
+      J.k_pad = L.kcb * L.bk;
       J.dst = t.ws + t.w_fwd_off;
       J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * J.k_pad;
       push(J);

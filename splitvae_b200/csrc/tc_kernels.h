@@ -17,12 +17,13 @@ struct TcLaunch {
   int taps_h, taps_w, pad_t, pad_l, a_stride;   // A coordinate of (out y, tap a) = y*a_stride + a - pad_t
   int kc;                                       // channel chunks per tap (c_pad / bk)
   // bf16x3 forward (operands are bf16 pairs hi + lo, product = hi*hi + lo*hi + hi*lo): per tap the K loop runs over `kcl` LOGICAL
-  // chunks that address `kca` physical A chunks (hi chunks then lo chunks, c -> c % a_wrap) and `kcb` physical weight
-  // k-blocks ([W_hi | W_lo] per tap, c -> c < b_fold ? c : c - b_sub).  Plain launches: kcl = kca = kcb = a_wrap = b_fold = kc.
-  //   split, kc chunks:   logical (hi,Whi)*kc (lo,Whi)*kc (hi,Wlo)*kc    -> kcl 3kc, kca 2kc, a_wrap 2kc, kcb 2kc, b_fold kc, b_sub kc
-  //   split, first layer: the 8-channel staged pixel holds [hi(3) lo(3) 0 0]; k-block 0 = [Whi Whi 0 0], k-block 1 = [Wlo 0 0 0]
-  //                                                                       -> kcl 2, kca 1, a_wrap 1, kcb 2, b_fold 2, b_sub 0
-  int split, kcl, kca, a_wrap, kcb, b_fold, b_sub;
+  // chunks that address `kca` physical A chunks (the hi plane's chunks, then the lo plane's) and `kcb` physical weight k-blocks
+  // ([W_hi(ch) W_lo(ch)] per channel chunk); the mapping is logical_chunk() / phys_block_chunks() in tc_kernels.cu.
+  //   split 0: plain, kcl = kca = kcb = kc;   split 1: kcl 3kc, kca 2kc, kcb 2kc;
+  //   split 2 (first layer): the 8-channel staged pixel holds [hi(3) lo(3) 0 0]; k-block 0 = [Whi Whi 0 0], 1 = [Wlo 0 0 0]: kcl 2, kca 1, kcb 2
+  int split, kcl, kca, kcb;
+  int w_box3;                                   // halo kernel: map_b is the 3-D [bk][rows][blocks] view, one TMA box per ring stage
+  int nstack2;                                  // halo kernel, split 1: A_hi x [W_hi ; W_lo] as ONE MMA of 2N columns (accumulator = [main | correction])
   void* out_lo;                                 // lo plane of a bf16 output (NULL: single bf16 / fp32 output)
   int bk, swizzle;                              // K elements per stage, swizzle bytes (= 2*bk)
   int tile_n_img, tile_h, tile_w;               // M tile = tile_n_img x tile_h x tile_w = 128 output pixels
