@@ -34,7 +34,9 @@ enum {
   SV_ERR_NOT_IMPLEMENTED = 4
 };
 
-enum { SV_MODEL_LGVAE = 0, SV_MODEL_LGGMVAE = 1 };      /* vae/main.py:63-69  --model */
+enum { SV_MODEL_LGVAE = 0, SV_MODEL_LGGMVAE = 1,        /* vae/main.py:63-69  --model lgvae | lggmvae */
+       SV_MODEL_GMVAE = 2 };                            /* vae/main.py:70-73  --model gmvae: gm encoder + ONE decoder fed by z_x (vae/model.py:277-299);
+                                                           outputs / scalars of the x_hat path are not available (sv_output_ptr fails for them) */
 enum { SV_PRECISION_BF16_TC = 0,   /* single-bf16 operands on tcgen05 tensor cores, fp32 accumulate: fastest; gradients 5-10 % from
                                       fp32 (ReLU masks of near-zero units flip under 2^-9 forward roundings) */
        SV_PRECISION_FP32_REF = 1,  /* fp32 SIMT reference kernels (debug / tight parity) */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsplitvae.so")
 
 SV_OK = 0
-SV_MODEL = {"lgvae": 0, "lggmvae": 1}
+SV_MODEL = {"lgvae": 0, "lggmvae": 1, "gmvae": 2}
 SV_PRECISION = {"bf16": 0, "fp32": 1, "bf16x3": 2}
 SV_FLAG_PLAN_ONLY = 1
 SV_FLAG_NO_TC = 2

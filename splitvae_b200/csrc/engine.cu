@@ -66,7 +66,7 @@ struct sv_handle {
   size_t ws_bytes = 0;
   std::vector<Layer> layers;
   ConvEnc enc_x{}, enc_xh{};
-  GmEnc gm{};
+  GmEnc gm_enc{};
   Decoder dec_x{}, dec_xh{};
   int ZCAT = -1, EPS_G = -1, EPS_L = -1, Z_G = -1, Z_L = -1, ZM_G = -1, ZS_G = -1, ZM_L = -1, ZS_L = -1;
   int ZPM_OUT = -1, ZPS_OUT = -1, SCALARS = -1, PARTIALS = -1, KLPART = -1, COLSUM = -1, ADAM = -1, TCWS = -1;
@@ -90,6 +90,8 @@ struct sv_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int COLSUM2 = -1;
   bool two_streams = true;
+  bool gm = false;            // gmvae-type encoder_x (lggmvae, gmvae)
+  bool has_local = true;      // the x_hat encoder / decoder pair exists (false: plain GMVAE, vae/model.py:277-299)
   // weight gradients run on one auxiliary stream per branch stream (dgrad chain = critical path, wgrad + reduce fill the gaps)
   // (SV_WGRAD_STREAMS = n streams per branch, used round-robin by consecutive layers; 0 = none.  Two per branch let wgrad(L-1) start
   // while wgrad(L) and its split-K reduce are still queued: on one in-order stream the encoders' last wgrads formed a serial tail)
@@ -298,10 +300,10 @@ std::vector<int> branch_layers(const sv_handle* h, int which) {
   auto dec = [](const Decoder& d) { return std::vector<int>{d.d5, d.d4, d.d3, d.d2, d.d1}; };
   auto enc = [](const ConvEnc& e) { return std::vector<int>{e.heads, e.e3, e.e2, e.e1}; };
   if (which == 0) return dec(h->dec_x);
-  if (which == 1) return dec(h->dec_xh);
-  if (which == 3) return enc(h->enc_xh);
-  if (h->cfg.model == SV_MODEL_LGGMVAE) {
-    const GmEnc& e = h->gm;
+  if (which == 1) return h->has_local ? dec(h->dec_xh) : std::vector<int>{};
+  if (which == 3) return h->has_local ? enc(h->enc_xh) : std::vector<int>{};
+  if (h->gm) {
+    const GmEnc& e = h->gm_enc;
     return {e.zheads, e.yheads, e.ydense, e.yb2, e.yb0e1, e.h3, e.h2, e.h1};
   }
   return enc(h->enc_x);
@@ -319,9 +321,9 @@ std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, bool with_ptrs) {
 
 LatentBufs latent_bufs(sv_handle* h) {
   LatentBufs L{};
-  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
-  L.heads_g = (const float*)bp(h, gm ? h->gm.HEADS : h->enc_x.HEADS);
-  L.heads_l = (const float*)bp(h, h->enc_xh.HEADS);
+  const bool gm = h->gm;
+  L.heads_g = (const float*)bp(h, gm ? h->gm_enc.HEADS : h->enc_x.HEADS);
+  L.heads_l = h->has_local ? (const float*)bp(h, h->enc_xh.HEADS) : nullptr;
   L.eps_g = (float*)bp(h, h->EPS_G); L.eps_l = (float*)bp(h, h->EPS_L);
   L.z_g = (float*)bp(h, h->Z_G); L.z_l = (float*)bp(h, h->Z_L);
   L.zm_g = (float*)bp(h, h->ZM_G); L.zs_g = (float*)bp(h, h->ZS_G);
@@ -329,10 +331,10 @@ LatentBufs latent_bufs(sv_handle* h) {
   L.zcat = bp(h, h->ZCAT);
   L.zcat_lo = (bf16*)bp(h, lo_buf(h, h->ZCAT));
   L.dzcat = bp(h, h->dec_x.dz);
-  L.dzl2 = bp(h, h->dec_xh.dz);
-  L.dheads_g = bp(h, gm ? h->gm.dHEADS : h->enc_x.dHEADS);
-  L.dheads_l = bp(h, h->enc_xh.dHEADS);
-  L.yheads = gm ? (const float*)bp(h, h->gm.YHEADS) : nullptr;
+  L.dzl2 = h->has_local ? bp(h, h->dec_xh.dz) : nullptr;
+  L.dheads_g = bp(h, gm ? h->gm_enc.dHEADS : h->enc_x.dHEADS);
+  L.dheads_l = h->has_local ? bp(h, h->enc_xh.dHEADS) : nullptr;
+  L.yheads = gm ? (const float*)bp(h, h->gm_enc.YHEADS) : nullptr;
   return L;
 }
 
@@ -396,7 +398,7 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
 }
 
 void branch_bias_grads(sv_handle* h, int which, cudaStream_t s) {
-  if (h->cs_on) h->launches += colsum_table_run(h->cs[which], h->grads, s);
+  if (h->cs_on && h->cs[which]) h->launches += colsum_table_run(h->cs[which], h->grads, s);
   join_wgrad_stream(h, s);
 }
 
@@ -414,7 +416,7 @@ void conv_encoder_bwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaS
 }
 
 void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStream_t s) {
-  const GmEnc& e = h->gm;
+  const GmEnc& e = h->gm_enc;
   layer_fwd(h, e.h1, inputs, s);
   layer_fwd(h, e.h2, nullptr, s);
   layer_fwd(h, e.h3, nullptr, s);
@@ -430,7 +432,7 @@ void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStrea
 }
 
 void gm_encoder_bwd(sv_handle* h, const float* inputs, cudaStream_t s) {
-  const GmEnc& e = h->gm;
+  const GmEnc& e = h->gm_enc;
   const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
   layer_bwd(h, e.zheads, nullptr, s);
   gm_glue_a(bp(h, e.dHSUM), bp(h, e.YB0E1), (const float*)bp(h, e.YHEADS), (const float*)bp(h, h->ZM_G),
@@ -481,11 +483,12 @@ __global__ void pack_z_kernel(const float* __restrict__ zg, const float* __restr
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 128) return;
   const int b = idx >> 7, d = idx & 127;
-  if (dt == DT_F32) { ((float*)zcat)[b * 256 + d] = zg[idx]; ((float*)zcat)[b * 256 + 128 + d] = zl[idx]; }
-  else { ((bf16*)zcat)[b * 256 + d] = __float2bfloat16_rn(zg[idx]); ((bf16*)zcat)[b * 256 + 128 + d] = __float2bfloat16_rn(zl[idx]); }
+  const float g = zg[idx], l = zl ? zl[idx] : 0.f;           // (zl == NULL: plain GMVAE, one latent)
+  if (dt == DT_F32) { ((float*)zcat)[b * 256 + d] = g; ((float*)zcat)[b * 256 + 128 + d] = l; }
+  else { ((bf16*)zcat)[b * 256 + d] = __float2bfloat16_rn(g); ((bf16*)zcat)[b * 256 + 128 + d] = __float2bfloat16_rn(l); }
   if (zcat_lo) {
-    zcat_lo[b * 256 + d] = __float2bfloat16_rn(zg[idx] - round_bf16(zg[idx]));
-    zcat_lo[b * 256 + 128 + d] = __float2bfloat16_rn(zl[idx] - round_bf16(zl[idx]));
+    zcat_lo[b * 256 + d] = __float2bfloat16_rn(g - round_bf16(g));
+    zcat_lo[b * 256 + 128 + d] = __float2bfloat16_rn(l - round_bf16(l));
   }
 }
 __global__ void pack_y_kernel(const float* __restrict__ y, void* yt, bf16* yt_lo, int dt, int B, int K) {
@@ -552,14 +555,14 @@ const char* sv_last_error(const sv_handle* h) { return h ? h->err : g_create_err
 sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   if (!cfg || !out) return fail(nullptr, SV_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->model != SV_MODEL_LGVAE && cfg->model != SV_MODEL_LGGMVAE)
+  if (cfg->model != SV_MODEL_LGVAE && cfg->model != SV_MODEL_LGGMVAE && cfg->model != SV_MODEL_GMVAE)
     return fail(nullptr, SV_ERR_INVALID, "unknown model %d", cfg->model);
   if (cfg->height < 16 || cfg->width < 16 || cfg->height % 16 || cfg->width % 16 || cfg->height > 256 || cfg->width > 256)
     return fail(nullptr, SV_ERR_INVALID, "image size %dx%d unsupported (multiples of 16 in [16,256])", cfg->height, cfg->width);
   if (cfg->batch < 1 || cfg->batch > 65536) return fail(nullptr, SV_ERR_INVALID, "batch %d unsupported", cfg->batch);
   if (cfg->global_latent_dims != 128 || cfg->local_latent_dims != 128)
     return fail(nullptr, SV_ERR_INVALID, "latent dims must be 128/128 (got %d/%d)", cfg->global_latent_dims, cfg->local_latent_dims);
-  if (cfg->model == SV_MODEL_LGGMVAE && (cfg->y_size < 2 || cfg->y_size > 32))
+  if (cfg->model != SV_MODEL_LGVAE && (cfg->y_size < 2 || cfg->y_size > 32))
     return fail(nullptr, SV_ERR_INVALID, "y_size %d unsupported (2..32)", cfg->y_size);
   if (cfg->world_size < 1) return fail(nullptr, SV_ERR_INVALID, "world_size must be >= 1");
   if (cfg->precision != SV_PRECISION_BF16_TC && cfg->precision != SV_PRECISION_FP32_REF && cfg->precision != SV_PRECISION_BF16X3)
@@ -585,7 +588,9 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
   h->use_tc = (cfg->precision == SV_PRECISION_BF16_TC && !(cfg->flags & SV_FLAG_NO_TC)) || h->split;
   h->B = cfg->batch; h->H = cfg->height; h->W = cfg->width;
   h->F = ((cfg->height / 8) * cfg->width) / 8 * 128;  // vae/model.py:152 precedence
-  h->K = cfg->model == SV_MODEL_LGGMVAE ? cfg->y_size : 0;
+  h->gm = cfg->model != SV_MODEL_LGVAE;
+  h->has_local = cfg->model != SV_MODEL_GMVAE;
+  h->K = h->gm ? cfg->y_size : 0;
   h->seed = 0x5EEDull + 0x9E3779B97F4A7C15ull * (unsigned long long)(unsigned)(cfg->flags >> 8);
   const int B = h->B;
   const int dout_ld = h->act_dt == DT_F32 ? 6 : 16;
@@ -607,23 +612,24 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 
   // Keras variable order: encoder_x, encoder_x_hat, decoder_x, decoder_x_hat (model.py:182-186, 230-234)
   if (cfg->model == SV_MODEL_LGVAE) h->enc_x = build_conv_encoder(h, "encoder_x", 0);
-  else h->gm = build_gm_encoder(h, "encoder_x");
-  h->enc_xh = build_conv_encoder(h, "encoder_x_hat", 3);
+  else h->gm_enc = build_gm_encoder(h, "encoder_x");
+  if (h->has_local) h->enc_xh = build_conv_encoder(h, "encoder_x_hat", 3);
   h->seg_split = h->arena_floats;
-  h->dec_x = build_decoder(h, "decoder_x", 256, 0, dzcat, 256, dout_ld);
-  h->dec_xh = build_decoder(h, "decoder_x_hat", 128, 128, dzl2, 128, dout_ld);
+  // (plain GMVAE: ONE decoder whose d1 reads z_x = columns 0..127 of the [B,256] latent buffer, vae/model.py:286,295)
+  h->dec_x = build_decoder(h, "decoder_x", h->has_local ? 256 : 128, 0, dzcat, 256, dout_ld);
+  if (h->has_local) h->dec_xh = build_decoder(h, "decoder_x_hat", 128, 128, dzl2, 128, dout_ld);
 
   if (h->act_dt == DT_BF16 && !getenv("SV_NO_MULTI_COLSUM")) {
     bool ok = true;
     for (int b = 0; b < 4 && ok; ++b) {
       const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
-      ok = colsum_multi_supported(sp.data(), (int)sp.size());
+      ok = sp.empty() || colsum_multi_supported(sp.data(), (int)sp.size());
     }
     if (ok) {
       h->cs_on = true;
       for (int b = 0; b < 4; ++b) {
         const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
-        h->CSP[b] = f32_buf(h, colsum_table_partial_floats(sp.data(), (int)sp.size()) + 64);
+        if (!sp.empty()) h->CSP[b] = f32_buf(h, colsum_table_partial_floats(sp.data(), (int)sp.size()) + 64);
       }
     }
   }
@@ -631,7 +637,7 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
     h->lo_of.resize(h->bufs.size(), -1);
     for (size_t li = 0; li < h->layers.size(); ++li) {
       Layer& L = h->layers[li];
-      L.split_fwd = (int)li != h->dec_x.d5 && (int)li != h->dec_xh.d5;
+      L.split_fwd = (int)li != h->dec_x.d5 && !(h->has_local && (int)li == h->dec_xh.d5);
       if (L.split_fwd) { L.in_lo = lo_buf(h, L.in); L.out_lo = lo_buf(h, L.out); }
     }
   }
@@ -733,6 +739,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (h->cs_on) {
     for (int b = 0; b < 4; ++b) {
       const std::vector<ColsumSpec> sp = branch_specs(h, b, true);
+      if (sp.empty()) continue;
       const char* cerr = nullptr;
       colsum_table_destroy(h->cs[b]);
       h->cs[b] = colsum_table_create(sp.data(), (int)sp.size(), (float*)bp(h, h->CSP[b]), &cerr);
@@ -785,21 +792,19 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   REQUIRE_BOUND(h);
   if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  const bool gm = h->gm, loc = h->has_local;
   stage_first_inputs(h, inputs, s);
-  cudaStream_t s2 = fork_side(h, s);
+  cudaStream_t s2 = loc ? fork_side(h, s) : s;
   if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
-  conv_encoder_fwd(h, h->enc_xh, inputs, s2);
-  join_side(h, s);
+  if (loc) { conv_encoder_fwd(h, h->enc_xh, inputs, s2); join_side(h, s); }
   reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), (float*)bp(h, h->KLPART), s);
   h->launches += 1;
-  s2 = fork_side(h, s);
+  s2 = loc ? fork_side(h, s) : s;
   decoder_fwd(h, h->dec_x, s);
-  decoder_fwd(h, h->dec_xh, s2);
-  join_side(h, s);
+  if (loc) { decoder_fwd(h, h->dec_xh, s2); join_side(h, s); }
   if (gm && prior_copies) {  // contiguous z_prior_mean / z_prior_sig for the reference's output tuple
-    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
-    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
+    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
+    copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
     h->launches += 2;
   }
   return check_launch(h, "sv_forward");
@@ -813,13 +818,13 @@ sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
   REQUIRE_BOUND(h);
   if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  const bool gm = h->gm, loc = h->has_local;
   const long long npix = (long long)h->B * h->H * h->W;
   const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
-  pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), (const float*)bp(h, h->dec_xh.OUT), bp(h, h->dec_x.dOUT),
-             bp(h, h->dec_xh.dOUT), h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
+  pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), loc ? (const float*)bp(h, h->dec_xh.OUT) : nullptr, bp(h, h->dec_x.dOUT),
+             loc ? bp(h, h->dec_xh.dOUT) : nullptr, h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
              (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s);
-  loss_scalars((const float*)bp(h, h->KLPART), reparam_blocks(h->B), gm ? (const float*)bp(h, h->gm.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
+  loss_scalars((const float*)bp(h, h->KLPART), reparam_blocks(h->B), gm ? (const float*)bp(h, h->gm_enc.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
                (const float*)bp(h, h->PARTIALS), pixel_loss_blocks(npix), (float*)bp(h, h->SCALARS), s);
   h->launches += 2;
   h->last_inputs = inputs;
@@ -839,25 +844,30 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
   const float* inputs = h->last_inputs;
+  const bool loc = h->has_local;
   if (seg == 0) {
-    cudaStream_t s2 = fork_side(h, s);
+    cudaStream_t s2 = loc ? fork_side(h, s) : s;
     decoder_bwd(h, h->dec_x, s);
     branch_bias_grads(h, 0, s);
-    decoder_bwd(h, h->dec_xh, s2);
-    branch_bias_grads(h, 1, s2);
-    join_side(h, s);
+    if (loc) {
+      decoder_bwd(h, h->dec_xh, s2);
+      branch_bias_grads(h, 1, s2);
+      join_side(h, s);
+    }
   } else if (seg == 1) {
     if (!inputs) return fail(h, SV_ERR_STATE, "sv_loss_fwd_bwd must precede sv_backward_segment");
-    const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+    const bool gm = h->gm;
     const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
     latent_bwd(latent_bufs(h), h->B, h->act_dt, gm, h->cfg.beta, inv_batch, s);
     h->launches += 1;
-    cudaStream_t s2 = fork_side(h, s);
-    conv_encoder_bwd(h, h->enc_xh, inputs, s2);
-    branch_bias_grads(h, 3, s2);
+    cudaStream_t s2 = loc ? fork_side(h, s) : s;
+    if (loc) {
+      conv_encoder_bwd(h, h->enc_xh, inputs, s2);
+      branch_bias_grads(h, 3, s2);
+    }
     if (gm) gm_encoder_bwd(h, inputs, s); else conv_encoder_bwd(h, h->enc_x, inputs, s);
     branch_bias_grads(h, 2, s);
-    join_side(h, s);
+    if (loc) join_side(h, s);
   } else {
     return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
   }
@@ -870,7 +880,7 @@ sv_status sv_adam_segment(sv_handle* h, int32_t seg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   AdamState* st = (AdamState*)bp(h, h->ADAM);
   if (seg == 0) {
-    adam_prepare(st, h->cfg.learning_rate, h->cfg.model == SV_MODEL_LGGMVAE, s);
+    adam_prepare(st, h->cfg.learning_rate, h->gm, s);     // staircase schedule for both GM models (vae/main.py:66-72)
     h->launches += 1;
   }
   const long long off = seg == 0 ? h->seg_split : 0, cnt = seg == 0 ? h->arena_floats - h->seg_split : h->seg_split;
@@ -907,21 +917,21 @@ sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t*
   sv_handle* h = const_cast<sv_handle*>(hc);
   if (!h || !ptr || !count) return SV_ERR_INVALID;
   if (!h->bound) return fail(h, SV_ERR_STATE, "sv_bind has not been called");
-  const bool gm = h->cfg.model == SV_MODEL_LGGMVAE;
+  const bool gm = h->gm, loc = h->has_local;
   const long long B = h->B;
   int id = -1;
   long long n = 0;
   switch (which) {
     case SV_OUT_DEC_X: id = h->dec_x.OUT; n = B * h->H * h->W * 6; break;
-    case SV_OUT_DEC_X_HAT: id = h->dec_xh.OUT; n = B * h->H * h->W * 6; break;
+    case SV_OUT_DEC_X_HAT: if (loc) { id = h->dec_xh.OUT; n = B * h->H * h->W * 6; } break;
     case SV_OUT_Z_X: id = h->Z_G; n = B * 128; break;
     case SV_OUT_Z_MEAN_X: id = h->ZM_G; n = B * 128; break;
     case SV_OUT_Z_SIG_X: id = h->ZS_G; n = B * 128; break;
-    case SV_OUT_Z_X_HAT: id = h->Z_L; n = B * 128; break;
-    case SV_OUT_Z_MEAN_X_HAT: id = h->ZM_L; n = B * 128; break;
-    case SV_OUT_Z_SIG_X_HAT: id = h->ZS_L; n = B * 128; break;
-    case SV_OUT_Y: if (gm) { id = h->gm.Y; n = B * 32; } break;
-    case SV_OUT_Y_LOGITS: if (gm) { id = h->gm.LOGITS; n = B * 32; } break;
+    case SV_OUT_Z_X_HAT: if (loc) { id = h->Z_L; n = B * 128; } break;
+    case SV_OUT_Z_MEAN_X_HAT: if (loc) { id = h->ZM_L; n = B * 128; } break;
+    case SV_OUT_Z_SIG_X_HAT: if (loc) { id = h->ZS_L; n = B * 128; } break;
+    case SV_OUT_Y: if (gm) { id = h->gm_enc.Y; n = B * 32; } break;
+    case SV_OUT_Y_LOGITS: if (gm) { id = h->gm_enc.LOGITS; n = B * 32; } break;
     case SV_OUT_Z_PRIOR_MEAN: if (gm) { id = h->ZPM_OUT; n = B * 128; } break;
     case SV_OUT_Z_PRIOR_SIG: if (gm) { id = h->ZPS_OUT; n = B * 128; } break;
     case SV_OUT_SCALARS: id = h->SCALARS; n = SV_SCALAR_COUNT; break;
@@ -935,26 +945,28 @@ sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t*
 
 sv_status sv_decode(sv_handle* h, const float* z_x, const float* z_x_hat, void* stream) {
   REQUIRE_BOUND(h);
-  if (!z_x || !z_x_hat) return fail(h, SV_ERR_INVALID, "null latent");
+  if (!z_x || (!z_x_hat && h->has_local)) return fail(h, SV_ERR_INVALID, "null latent");
   cudaStream_t s = (cudaStream_t)stream;
   pack_z_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>(z_x, z_x_hat, bp(h, h->ZCAT), (bf16*)bp(h, lo_buf(h, h->ZCAT)), h->act_dt, h->B);
   h->launches += 1;
-  cudaStream_t s2 = fork_side(h, s);
-  decoder_fwd(h, h->dec_x, s);
-  decoder_fwd(h, h->dec_xh, s2);
-  join_side(h, s);
+  if (h->has_local) {
+    cudaStream_t s2 = fork_side(h, s);
+    decoder_fwd(h, h->dec_x, s);
+    decoder_fwd(h, h->dec_xh, s2);
+    join_side(h, s);
+  } else decoder_fwd(h, h->dec_x, s);
   return check_launch(h, "sv_decode");
 }
 
 sv_status sv_encode_y(sv_handle* h, const float* y, void* stream) {
   REQUIRE_BOUND(h);
-  if (h->cfg.model != SV_MODEL_LGGMVAE) return fail(h, SV_ERR_INVALID, "encode_y needs the lggmvae model");
+  if (!h->gm) return fail(h, SV_ERR_INVALID, "encode_y needs a gmvae-type encoder (lggmvae / gmvae)");
   if (!y) return fail(h, SV_ERR_INVALID, "null y");
   cudaStream_t s = (cudaStream_t)stream;
-  pack_y_kernel<<<(h->B * 32 + 255) / 256, 256, 0, s>>>(y, bp(h, h->gm.YT), (bf16*)bp(h, lo_buf(h, h->gm.YT)), h->act_dt, h->B, h->K);
-  layer_fwd(h, h->gm.yheads, nullptr, s);
-  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
-  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
+  pack_y_kernel<<<(h->B * 32 + 255) / 256, 256, 0, s>>>(y, bp(h, h->gm_enc.YT), (bf16*)bp(h, lo_buf(h, h->gm_enc.YT)), h->act_dt, h->B, h->K);
+  layer_fwd(h, h->gm_enc.yheads, nullptr, s);
+  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
+  copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
   h->launches += 3;
   return check_launch(h, "sv_encode_y");
 }

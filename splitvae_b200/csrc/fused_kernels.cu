@@ -56,8 +56,10 @@ __global__ void __launch_bounds__(256) reparam_kernel(LatentBufs L, int B, const
     eg = ueg ? ueg[idx] : normal_from(r.x, r.y);
     el = uel ? uel[idx] : normal_from(r.z, r.w);
   }
+  const bool has_l = L.heads_l != nullptr;        // (plain GMVAE: no x_hat encoder; z_l = 0, sigma_l = 1 -> KL_l = 0)
   const float mg = L.heads_g[b * 256 + d], sg = L.heads_g[b * 256 + 128 + d];
-  const float ml = L.heads_l[b * 256 + d], sl = L.heads_l[b * 256 + 128 + d];
+  const float ml = has_l ? L.heads_l[b * 256 + d] : 0.f, sl = has_l ? L.heads_l[b * 256 + 128 + d] : 1.f;
+  if (!has_l) el = 0.f;
   const float zg = mg + sg * eg, zl = ml + sl * el;  // vae/model.py:13
   L.eps_g[idx] = eg; L.eps_l[idx] = el;
   L.z_g[idx] = zg; L.z_l[idx] = zl;
@@ -110,7 +112,8 @@ __global__ void latent_bwd_kernel(LatentBufs L, int B, int gm, float beta, float
   if (idx >= B * 128) return;
   const int b = idx >> 7, d = idx & 127;
   const float dzg = to_f32(ld_as<T>(L.dzcat, b * 256 + d));
-  const float dzl = to_f32(ld_as<T>(L.dzcat, b * 256 + 128 + d)) + to_f32(ld_as<T>(L.dzl2, idx));
+  const bool has_l = L.dheads_l != nullptr;
+  const float dzl = has_l ? to_f32(ld_as<T>(L.dzcat, b * 256 + 128 + d)) + to_f32(ld_as<T>(L.dzl2, idx)) : 0.f;
   const float mg = L.zm_g[idx], sg = L.zs_g[idx], ml = L.zm_l[idx], sl = L.zs_l[idx];
   const float k = beta * inv_batch;
   float dmg, dsg;
@@ -127,8 +130,10 @@ __global__ void latent_bwd_kernel(LatentBufs L, int B, int gm, float beta, float
   const float dsl = dzl * L.eps_l[idx] + k * (sl - 1.f / sl);
   ((T*)L.dheads_g)[b * 256 + d] = from_f32<T>(dmg);
   ((T*)L.dheads_g)[b * 256 + 128 + d] = from_f32<T>(dsg * (1.f - expf(-sg)));
-  ((T*)L.dheads_l)[b * 256 + d] = from_f32<T>(dml);
-  ((T*)L.dheads_l)[b * 256 + 128 + d] = from_f32<T>(dsl * (1.f - expf(-sl)));
+  if (has_l) {
+    ((T*)L.dheads_l)[b * 256 + d] = from_f32<T>(dml);
+    ((T*)L.dheads_l)[b * 256 + 128 + d] = from_f32<T>(dsl * (1.f - expf(-sl)));
+  }
 }
 
 void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s) {
@@ -364,12 +369,13 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
     float in[12], ox[12], oh[12];
     const float4* ip = reinterpret_cast<const float4*>(inputs + pr * 12);
     const float4* xp = reinterpret_cast<const float4*>(dec_x + pr * 12);
+    const bool two = dec_xh != nullptr;          // (plain GMVAE: one decoder, one likelihood term)
     const float4* hp = reinterpret_cast<const float4*>(dec_xh + pr * 12);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       reinterpret_cast<float4*>(in)[i] = __ldg(ip + i);
       reinterpret_cast<float4*>(ox)[i] = __ldg(xp + i);
-      reinterpret_cast<float4*>(oh)[i] = __ldg(hp + i);
+      reinterpret_cast<float4*>(oh)[i] = two ? __ldg(hp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
@@ -379,11 +385,13 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
         float gm_, gl_;
         sum_x += dll_elem<FAST>(in[px * 6 + c], ox[px * 6 + c], ox[px * 6 + 3 + c], gm_, gl_);
         gx[c] = gm_ * grad_scale; gx[3 + c] = gl_ * grad_scale;
-        sum_xh += dll_elem<FAST>(in[px * 6 + 3 + c], oh[px * 6 + c], oh[px * 6 + 3 + c], gm_, gl_);
-        gh[c] = gm_ * grad_scale; gh[3 + c] = gl_ * grad_scale;
+        if (two) {
+          sum_xh += dll_elem<FAST>(in[px * 6 + 3 + c], oh[px * 6 + c], oh[px * 6 + 3 + c], gm_, gl_);
+          gh[c] = gm_ * grad_scale; gh[3 + c] = gl_ * grad_scale;
+        }
       }
       store_dout<T, LD>(dout_x + (pr * 2 + px) * LD, gx);
-      store_dout<T, LD>(dout_xh + (pr * 2 + px) * LD, gh);
+      if (two) store_dout<T, LD>(dout_xh + (pr * 2 + px) * LD, gh);
     }
   }
   // deterministic block reduction

@@ -703,7 +703,9 @@ struct PcCtl {
 // MMAs of one tile, fully unrolled for the shapes of this model family (one channel chunk, unit column stride, one accumulator
 // row): KH x KW taps x KS k-steps x MTX accumulators.  The single issuing thread must spend only a few instructions per
 // tcgen05.mma - the generic nest costs ~60 per k-block and capped d5 dgrad at 85 cycles per MMA (44 is the pipe's own rate).
-template <int KH, int KW, int KS, int MTX, int SX = 1>
+// NB: weight k-blocks per tap that multiply the SAME A operand (2 for the bf16x3 first layer: [Whi Whi 0 0] and [Wlo 0 0 0] against
+// the staged pixel [x_hi x_lo 0 0])
+template <int KH, int KW, int KS, int MTX, int SX = 1, int NB = 1>
 __device__ __forceinline__ void pc_issue_tile(uint64_t da0, uint64_t db0, uint32_t acc, uint32_t tile_cols, uint32_t idesc, uint32_t row_step,
                                               uint32_t pix_step, uint32_t kb_step, uint32_t tx_step, uint32_t plane_step = 0) {
 #pragma unroll
@@ -712,12 +714,15 @@ __device__ __forceinline__ void pc_issue_tile(uint64_t da0, uint64_t db0, uint32
     for (int b = 0; b < KW; ++b) {
       // (SX parity planes: filter column b lives in plane b % SX, shifted by b / SX plane columns)
       const uint64_t da = da0 + (uint64_t)(a * row_step + (b / SX) * pix_step + (b % SX) * plane_step);
-      const uint64_t db = db0 + (uint64_t)((a * KW + b) * kb_step);
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
+      for (int j = 0; j < NB; ++j) {
+        const uint64_t db = db0 + (uint64_t)(((a * KW + b) * NB + j) * kb_step);
 #pragma unroll
-        for (int tx = 0; tx < MTX; ++tx)
-          tc::umma_bf16(acc + tx * tile_cols, da + (uint64_t)(tx * tx_step + 2u * k), db + 2u * k, idesc, (a | b | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < KS; ++k) {
+#pragma unroll
+          for (int tx = 0; tx < MTX; ++tx)
+            tc::umma_bf16(acc + tx * tile_cols, da + (uint64_t)(tx * tx_step + 2u * k), db + 2u * k, idesc, (a | b | j | k) != 0 ? 1u : 0u);
+        }
       }
     }
   }
@@ -819,7 +824,10 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
       // unrolled issue sequences: 1 = 6x6 taps, K 16, 4 accumulators (d5 dgrad); 2 = 6x3 pair taps (first layer, 64x64 images);
       // 3 = 3x3 taps, K 64, 2 accumulators (e2 dgrad classes); 4 = first layer, 32x32 images
       // 5 / 6 = 6x6 stride-2 forward over two parity planes, K 32, one / two accumulators (e2 forward)
-      const int shape = (nchunks != 1 || mty != 1 || env_shape_off) ? 0
+      // 8 / 9 = shapes 2 / 4 of the bf16x3 first layer: two weight k-blocks per pair tap against the same staged pixel pair
+      const int shape = (P.split == 2 && nphys == 1 && mty == 1 && sx == 1 && !env_shape_off && P.taps_h == 6 && taps_w == 3 && ksteps == 1 &&
+                         (mtx == 4 || mtx == 2)) ? (mtx == 4 ? 8 : 9)
+                        : (nchunks != 1 || mty != 1 || env_shape_off) ? 0
                         : sx == 2 ? ((P.taps_h == 6 && taps_w == 6 && ksteps == 2 && mtx == 1) ? 5
                                      : (P.taps_h == 6 && taps_w == 6 && ksteps == 2 && mtx == 2) ? 6 : 0)
                         : sx != 1 ? 0
@@ -848,6 +856,8 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
           else if (shape == 3) pc_issue_tile<3, 3, 4, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
           else if (shape == 4) pc_issue_tile<6, 3, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
           else if (shape == 7) pc_issue_tile<6, 3, 4, 1>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 8) pc_issue_tile<6, 3, 1, 4, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
+          else if (shape == 9) pc_issue_tile<6, 3, 1, 2, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step);
           else if (shape == 5) pc_issue_tile<6, 6, 2, 1, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
           else pc_issue_tile<6, 6, 2, 2, 2>(da0, db0, acc, tile_cols, idesc, row_step, pix_step, kb_step, tx_step, chunk_bytes >> 4);
         } else

@@ -173,8 +173,11 @@ class Engine:
     def scalars(self):
         """dict of the step's loss terms (vae/trainer.py:127-135, 153-164); synchronises."""
         s = self.output("scalars").cpu().tolist()
-        names = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "y_kl" if self.model == "lggmvae" else "total_kl", "total"]
-        return dict(zip(names, s[:6]))
+        names = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "y_kl" if self.model != "lgvae" else "total_kl", "total"]
+        d = dict(zip(names, s[:6]))
+        if self.model == "gmvae":          # one decoder, one Gaussian KL (vae/trainer.py:181-187)
+            d.pop("recon_x_hat"), d.pop("kl_x_hat")
+        return d
 
     @property
     def iterations(self):

@@ -52,7 +52,7 @@ def main(argv=None):
     print('Config:', config)
     from . import data, trainer
     from .augmentation import Augmentator
-    from .model import LGGMVae, LGVae
+    from .model import GMVae, LGGMVae, LGVae
     augmentor = Augmentator(type=config.augmentation, size=config.patch_size)
     real = bool(config.data_root)
     train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=real and config.label,
@@ -70,8 +70,13 @@ def main(argv=None):
         optimizer = trainer.Adam(learning_rate=lr_schedule)
         model = LGGMVae(global_latent_dims=config.global_latent_dims, local_latent_dims=config.local_latent_dims,
                         image_shape=input_shape, y_size=config.y_size, tau=config.tau, precision=config.precision)
+    elif config.model == 'gmvae':                  # vae/main.py:70-73
+        lr_schedule = trainer.ExponentialDecay(config.learning_rate, decay_steps=1000000, decay_rate=0.4, staircase=True)
+        optimizer = trainer.Adam(learning_rate=lr_schedule)
+        model = GMVae(global_latent_dims=config.global_latent_dims, image_shape=input_shape, y_size=config.y_size, tau=config.tau,
+                      precision=config.precision)
     else:
-        raise NotImplementedError("--model %s is outside the hot path of this build (lgvae | lggmvae)" % config.model)
+        raise NotImplementedError("--model %s: expected lgvae | lggmvae | gmvae" % config.model)
     print('Training local-global autoencoder')
     history = trainer.train_local_global_autoencoder(model, optimizer, config.dataset, train_dataset, test_dataset, config=config)
     if config.save_weights:                       # vae/trainer.py:421

@@ -36,7 +36,7 @@ class _SplitModel:
         kw = dict(self._engine_kwargs)
         kw.update(overrides)
         H, W = int(self.image_shape[1]), int(self.image_shape[2])
-        if self.global_latent_dims != 128 or self.local_latent_dims != 128:
+        if self.global_latent_dims != 128 or (self.local_latent_dims or 128) != 128:
             raise NotImplementedError("libsplitvae supports the reference default latent sizes (128/128) only")
         params = None
         if self.engine is not None:
@@ -147,6 +147,49 @@ class _SplitModel:
         if rescale:
             return torch.clip((x_mean + 1) * 0.5, 0., 1.), torch.clip((x_hat_mean + 1) * 0.5, 0., 1.)
         return x_mean, x_hat_mean
+
+
+class GMVae(_SplitModel):
+    """Plain GMVAE, vae/model.py:277-320: gmvae encoder on x + ONE decoder fed by z_x.  Constructor signature of the reference
+    (no local latent): GMVae(global_latent_dims, image_shape, y_size, tau)."""
+    _kind = "gmvae"
+
+    def __init__(self, global_latent_dims, image_shape, y_size, tau, variational=True, type="conv", **kw):
+        super().__init__(global_latent_dims, 128, image_shape, y_size=y_size, tau=tau, variational=variational, **kw)
+        self.local_latent_dims = None
+
+    def __call__(self, inputs, training=False, eps_g=None, u=None):
+        """vae/model.py:288-299: 9-tuple (x_mean, x_log_scale, z_x, z_mean_x, z_sig_x, y, y_logits, z_prior_mean, z_prior_sig)."""
+        e = self._ensure(inputs.shape[0])
+        e.forward(inputs, eps_g, None, u)
+        dx = e.output("dec_x")
+        o = e.output
+        return (dx[..., :3], dx[..., 3:], o("z_x"), o("z_mean_x"), o("z_sig_x"), o("y"), o("y_logits"), o("z_prior_mean"), o("z_prior_sig"))
+
+    def encode(self, inputs, eps_g=None, u=None):
+        """vae/model.py:301-305: the sampled z_x."""
+        e = self._ensure(inputs.shape[0])
+        e.forward(inputs, eps_g, None, u)
+        return e.output("z_x")
+
+    def decode(self, z_x, rescale=True):
+        """vae/model.py:307-312."""
+        e = self._ensure(z_x.shape[0])
+        e.decode(z_x.contiguous().float(), None)
+        x_mean = e.output("dec_x")[..., :3]
+        return torch.clip((x_mean + 1) * 0.5, 0., 1.) if rescale else x_mean
+
+    def encode_y(self, y, rescale=True):
+        """vae/model.py:314-316."""
+        e = self._ensure(y.shape[0])
+        e.encode_y(y.contiguous().float())
+        return e.output("z_prior_mean"), e.output("z_prior_sig")
+
+    def get_y(self, x, u=None):
+        """vae/model.py:318-320 (6-channel batch, channels 0-2 used)."""
+        e = self._ensure(x.shape[0])
+        e.forward(x, None, None, u)
+        return e.output("y"), e.output("y_logits")
 
 
 class LGVae(_SplitModel):

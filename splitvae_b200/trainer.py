@@ -18,7 +18,7 @@ import time
 import torch
 
 from . import _lib
-from .model import LGGMVae, LGVae
+from .model import GMVae, LGGMVae, LGVae
 from .parallel import BucketReducer, mean_scalars
 
 
@@ -87,7 +87,7 @@ class StepRunner:
         self.explicit_noise = explicit_noise
         self.eps_g = torch.zeros(B, 128, device=dev) if explicit_noise else None
         self.eps_l = torch.zeros(B, 128, device=dev) if explicit_noise else None
-        self.u = torch.full((B, engine.y_size), 0.5, device=dev) if explicit_noise and engine.model == "lggmvae" else None
+        self.u = torch.full((B, engine.y_size), 0.5, device=dev) if explicit_noise and engine.model != "lgvae" else None
 
     def _issue(self):
         e = self.e
@@ -139,8 +139,11 @@ class StepRunner:
     def scalars(self):
         s = self.e.output("scalars")[:6]
         s = mean_scalars(s, self.group).cpu().tolist()
-        names = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "y_kl" if self.e.model == "lggmvae" else "total_kl", "total"]
-        return dict(zip(names, s))
+        names = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "y_kl" if self.e.model != "lgvae" else "total_kl", "total"]
+        d = dict(zip(names, s))
+        if self.e.model == "gmvae":
+            d.pop("recon_x_hat"), d.pop("kl_x_hat")
+        return d
 
 
 def linear_assignment(labels, pred):
@@ -219,8 +222,9 @@ def make_metrics():
 def _update_metrics(metrics, split, sc, gm):
     metrics[f"x_recon_{split}_loss"](sc["recon_x"])
     metrics[f"x_kl_{split}_loss"](sc["kl_x"])
-    metrics[f"x_hat_recon_{split}_loss"](sc["recon_x_hat"])
-    metrics[f"x_hat_kl_{split}_loss"](sc["kl_x_hat"])
+    if "recon_x_hat" in sc:                 # (plain GMVAE updates x_recon / x_kl / y_kl only, vae/trainer.py:193-195)
+        metrics[f"x_hat_recon_{split}_loss"](sc["recon_x_hat"])
+        metrics[f"x_hat_kl_{split}_loss"](sc["kl_x_hat"])
     if gm:
         metrics[f"y_kl_{split}_loss"](sc["y_kl"])
     else:
@@ -265,8 +269,20 @@ def test_step_lg_gm_vae(model, images, labels=None, config=None, metrics=None, e
             o("z_mean_x_hat"), o("z_sig_x_hat"), o("y"), o("y_logits"), o("z_prior_mean"), o("z_prior_sig"))
 
 
+def test_step_gm_vae(model, images, labels=None, config=None, metrics=None, eps_g=None, u=None):
+    """vae/trainer.py:276-292: updates x_recon / x_kl / y_kl test metrics and returns the model's 9-tuple."""
+    sc, e = _test_step(model, images, config, eps_g, None, u)
+    if metrics is not None:
+        _update_metrics(metrics, "test", sc, gm=True)
+    o = e.output
+    dx = o("dec_x")
+    test_step_gm_vae.last_scalars = sc
+    return (dx[..., :3], dx[..., 3:], o("z_x"), o("z_mean_x"), o("z_sig_x"), o("y"), o("y_logits"), o("z_prior_mean"), o("z_prior_sig"))
+
+
 test_step_lg_vae.__test__ = False       # not pytest tests, whatever their names
 test_step_lg_gm_vae.__test__ = False
+test_step_gm_vae.__test__ = False
 
 REPORT_TEMPLATE = ('Training step {}\n'
                    '            X Recon Loss: {:.4f}, X KLD loss: {:.4f}, Total X loss: {:.4f} \n'
@@ -331,19 +347,26 @@ def train_step_lg_gm_vae(model, images, optimizer, config=None):
     _runner_for(model, images, optimizer, config).step(images)
 
 
+def train_step_gm_vae(model, images, optimizer, config=None):
+    """vae/trainer.py:175-195: recon_x + beta * KL(q(z|x) || p(z|y)) + alpha * KL(q(y|x) || U)."""
+    _runner_for(model, images, optimizer, config).step(images)
+
+
 def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, test_dataset, config):
     """Train loop of vae/trainer.py:72 (hot loop 305-311, stop 417-419).  `train_dataset` yields
     [B,H,W,6] float32 batches (or (images, labels) when config.label).  Every `report_every` steps the
     running means of the step scalars are printed (the reference prints them from its test loop
     every 10 000 steps, trainer.py:354-382; evaluation itself is out of scope)."""
-    if isinstance(model, LGVae):
-        train_step = train_step_lg_vae
+    if isinstance(model, LGVae):                       # vae/trainer.py:294-302
+        train_step, test_step = train_step_lg_vae, test_step_lg_vae
     elif isinstance(model, LGGMVae):
-        train_step = train_step_lg_gm_vae
+        train_step, test_step = train_step_lg_gm_vae, test_step_lg_gm_vae
+    elif isinstance(model, GMVae):
+        train_step, test_step = train_step_gm_vae, test_step_gm_vae
     else:
         raise NotImplementedError(type(model).__name__)
-    gm = isinstance(model, LGGMVae)
-    test_step = test_step_lg_gm_vae if gm else test_step_lg_vae
+    gm = isinstance(model, (LGGMVae, GMVae))
+    y_logits_index = 11 if isinstance(model, LGGMVae) else 6
     report_every = int(config.get("report_every", 10000) or 10000)
     metrics = make_metrics()
     start = time.time()
@@ -371,7 +394,7 @@ def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, tes
                     outs = test_step(model, test_images, config=config, metrics=metrics)
                     if config.get("label") and gm:            # trainer.py:323-328: labels and y_logits of the whole test set
                         all_labels.append(test_data[1].detach().cpu())
-                        all_pred.append(outs[11].detach().cpu().clone())
+                        all_pred.append(outs[y_logits_index].detach().cpu().clone())
                 if all_labels:                                # trainer.py:345-349: majority-vote cluster accuracy
                     labels = torch.cat(all_labels)
                     cluster_acc(labels, linear_assignment(labels, torch.cat(all_pred)))

@@ -32,7 +32,7 @@ def to_dev(a):
 def run_engine_step(e, batch, model, adam=True):
     x = to_dev(batch["inputs"])
     eg, el = to_dev(batch["eps_g"]), to_dev(batch["eps_l"])
-    u = to_dev(batch["u"]) if model == "lggmvae" else None
+    u = to_dev(batch["u"]) if model != "lgvae" else None
     e.forward(x, eg, el, u)
     e.loss_fwd_bwd(x)
     for s in range(len(e.segments)):

@@ -69,3 +69,44 @@ def test_model_classes_match_the_reference_model(kind):
         _close(y, G["api"]["get_y"][0], "get_y()[y]")
         _close(y_logits, G["api"]["get_y"][1], "get_y()[y_logits]")
         assert m.y_size == 30
+
+
+def test_gmvae_class_matches_the_reference_model():
+    """--model gmvae (vae/model.py:277-320): 9-tuple order of `model(inputs)`, encode -> z_x, decode(z_x, rescale), encode_y, get_y,
+    against the vectors of the reference's own GMVae class (tests/golden/reference_model_gmvae.json)."""
+    from splitvae_b200.model import GMVae
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_model_gmvae.json")) as f:
+        G = json.load(f)
+    c = G["case"]
+    H, B = c["H"], c["B"]
+    params = O.init_params("gmvae", H, H, seed=5 + c["seed_base"])
+    b = O.synthetic_batch(B, H, c["patch"], seed_base=c["seed_base"])
+    m = GMVae(128, [-1, H, H, 3], 30, 0.4, precision="fp32")
+    assert (m.global_latent_dims, m.image_shape, m.y_size) == (128, [-1, H, H, 3], 30)
+    m.set_weights_by_name(params)
+    x, eg, u = to_dev(b["inputs"]), to_dev(b["eps_g"]), to_dev(b["u"])
+    tup = m(x, training=True, eps_g=eg, u=u)
+    torch.cuda.synchronize()
+    assert len(tup) == len(G["output_order"]) == 9
+    for t, name in zip(tup, G["output_order"]):
+        _close(t, G["outputs"][name], f"call[{name}]")
+    api = G.get("api", {})
+    if "encode" in api:
+        _close(m.encode(x, eg, u).clone(), api["encode"][0] if isinstance(api["encode"], list) else api["encode"], "encode[z_x]")
+    z = 0.5 * eg
+    rec = m.decode(z)
+    assert tuple(rec.shape) == (B, H, H, 3) and float(rec.min()) >= 0.0 and float(rec.max()) <= 1.0
+    raw = m.decode(z, rescale=False).clone()
+    assert torch.allclose(torch.clip((raw + 1) * 0.5, 0., 1.), m.decode(z), atol=1e-6)
+    P = O.to_torch(params, torch.float64, requires_grad=False)       # decode / encode_y against the oracle's restatement
+    ref_mean, _ = O.decoder(P, "decoder_x", z.double().cpu(), H, H)
+    assert float((raw.double().cpu() - ref_mean).norm() / ref_mean.norm()) < 1e-4
+    y_in = torch.softmax(torch.log(u.double()), dim=1).float().contiguous()
+    zpm, zps = m.encode_y(y_in)
+    yd = y_in.double().cpu()
+    ref_pm = yd @ P["encoder_x.z_prior_mean.kernel"] + P["encoder_x.z_prior_mean.bias"]
+    ref_ps = torch.nn.functional.softplus(yd @ P["encoder_x.z_prior_sig.kernel"] + P["encoder_x.z_prior_sig.bias"])
+    assert float((zpm.double().cpu() - ref_pm).norm() / ref_pm.norm()) < 1e-4 and float((zps.double().cpu() - ref_ps).norm() / ref_ps.norm()) < 1e-4
+    y, y_logits = m.get_y(x, u=u)
+    _close(y, G["outputs"]["y"], "get_y()[y]")
+    _close(y_logits, G["outputs"]["y_logits"], "get_y()[y_logits]")
