@@ -131,18 +131,22 @@ sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs_dev, void* stream);
 
 /* tape.gradient (vae/trainer.py:137,166), split into segments so the host can overlap a
  * gradient all-reduce with the remaining backward work.  Segment s finishes the gradients of
- * the contiguous arena range returned by sv_segment_range. Segments must run in order 0..n-1. */
+ * the arena ranges returned by sv_segment_range. Segments must run in order 0..n-1. */
 int32_t sv_num_segments(const sv_handle* h);
-sv_status sv_segment_range(const sv_handle* h, int32_t segment, int64_t* offset_floats, int64_t* count_floats);
+/* Segment s owns sv_segment_num_ranges(h, s) contiguous arena ranges (its layers' variables; one or two: the two encoders are not
+ * adjacent in the Keras variable order).  Segments in backward order: 0 = the decoders, 1 = the encoders' last layers (dense heads and
+ * the last conv), 2 = the encoders' first convs. */
+int32_t sv_segment_num_ranges(const sv_handle* h, int32_t segment);
+sv_status sv_segment_range(const sv_handle* h, int32_t segment, int32_t range_index, int64_t* offset_floats, int64_t* count_floats);
 sv_status sv_backward_segment(sv_handle* h, int32_t segment, void* stream);
 
 /* optimizer.apply_gradients (vae/trainer.py:138,167): multi-tensor Keras-Adam over the arena,
  * step counter and (lggmvae) staircase LR schedule kept on the device (vae/main.py:65-68). */
 sv_status sv_adam_step(sv_handle* h, void* stream);
-/* The same update restricted to one backward segment's arena range (segment 0 also advances the step counter / bias-corrected
- * step size, so segments must be applied in order 0..n-1, each exactly once per step).  Lets the host update the decoders
- * (segment 0: its gradients are final - and all-reduced - first) while the encoders' backward pass is still running.
- * sv_adam_step == sv_adam_segment(0) ; sv_adam_segment(1). */
+/* The same update restricted to one backward segment's arena ranges (segment 0 also advances the step counter / bias-corrected
+ * step size, so segments must be applied in order 0..n-1, each exactly once per step).  Lets the host update segment k
+ * (its gradients are final - and all-reduced - first) while the backward pass of segment k+1 is still running.
+ * sv_adam_step == sv_adam_segment(0) ; ... ; sv_adam_segment(n-1). */
 sv_status sv_adam_segment(sv_handle* h, int32_t segment, void* stream);
 
 /* Whole train_step_* (vae/trainer.py:120-144 / 146-173) = forward + loss + all segments + Adam. */

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -81,7 +82,12 @@ struct sv_handle {
   const float* last_inputs = nullptr;  // inputs of the step in flight (first-layer wgrad reads them)
   unsigned long long seed = 0x5EEDull;
   TcPackTable* pack = nullptr;
-  TcPackTable* pack_seg[2] = {nullptr, nullptr};   // the same jobs split by backward segment (0: decoders, 1: encoders)
+  // Backward / optimizer SEGMENTS (gradient buckets of the data-parallel all-reduce, in the order their gradients become final):
+  //   0 decoders   1 encoder tops (heads, e3 | the GM dense stack, h_block.2)   2 encoder bottoms (e2, e1 | h_block.1, h_block.0)
+  // Each owns its layers' arena ranges (<= one contiguous range per encoder) and a re-pack table of its layers' operand copies.
+  static constexpr int kSegs = 3;
+  std::vector<std::pair<long long, long long>> seg_ranges[kSegs];
+  TcPackTable* pack_seg[kSegs] = {nullptr, nullptr, nullptr};
   cudaStream_t opt = nullptr;                      // optimizer stream: Adam + re-pack of segment 0 overlap the encoders' backward
   cudaEvent_t ev_opt_fork = nullptr, ev_opt_join = nullptr;
   // the x / x_hat encoders and the two decoders are independent: they run on two streams (fork/join with events, which
@@ -101,8 +107,10 @@ struct sv_handle {
   bool wgrad_streams = false;
   // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
   bool cs_on = false;
-  int CSP[4] = {-1, -1, -1, -1};
-  ColsumTable* cs[4] = {nullptr, nullptr, nullptr, nullptr};
+  // (encoders: part 0 = the layers of segment 1, part 1 = segment 2; decoders: part 0 only)
+  int CSP[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
+  ColsumTable* cs[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  cudaEvent_t ev_opt_fork2 = nullptr;
 };
 
 namespace {
@@ -296,21 +304,33 @@ Decoder build_decoder(sv_handle* h, const char* prefix, int L, int zcoff, int dz
 
 void* bp(sv_handle* h, int id) { return id < 0 ? nullptr : (void*)(h->ws + h->bufs[id].off); }
 
-std::vector<int> branch_layers(const sv_handle* h, int which) {
-  auto dec = [](const Decoder& d) { return std::vector<int>{d.d5, d.d4, d.d3, d.d2, d.d1}; };
-  auto enc = [](const ConvEnc& e) { return std::vector<int>{e.heads, e.e3, e.e2, e.e1}; };
+// layers of backward branch `which` (0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat) in backward order;
+// part 0 / 1 = the encoder layers of segment 1 / 2 (decoders: everything is part 0), part -1 = all
+std::vector<int> branch_layers(const sv_handle* h, int which, int part) {
+  auto dec = [&](const Decoder& d) { return part == 1 ? std::vector<int>{} : std::vector<int>{d.d5, d.d4, d.d3, d.d2, d.d1}; };
+  auto enc = [&](const ConvEnc& e) {
+    return part == 0 ? std::vector<int>{e.heads, e.e3} : part == 1 ? std::vector<int>{e.e2, e.e1} : std::vector<int>{e.heads, e.e3, e.e2, e.e1};
+  };
   if (which == 0) return dec(h->dec_x);
   if (which == 1) return h->has_local ? dec(h->dec_xh) : std::vector<int>{};
   if (which == 3) return h->has_local ? enc(h->enc_xh) : std::vector<int>{};
   if (h->gm) {
     const GmEnc& e = h->gm_enc;
+    if (part == 0) return {e.zheads, e.yheads, e.ydense, e.yb2, e.yb0e1, e.h3};
+    if (part == 1) return {e.h2, e.h1};
     return {e.zheads, e.yheads, e.ydense, e.yb2, e.yb0e1, e.h3, e.h2, e.h1};
   }
   return enc(h->enc_x);
 }
-std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, bool with_ptrs) {
+std::vector<int> segment_layers(const sv_handle* h, int seg) {
+  std::vector<int> v;
+  for (int b = seg == 0 ? 0 : 2; b < (seg == 0 ? 2 : 4); ++b)
+    for (int li : branch_layers(h, b, seg == 0 ? 0 : seg - 1)) v.push_back(li);
+  return v;
+}
+std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, int part, bool with_ptrs) {
   std::vector<ColsumSpec> v;
-  for (int li : branch_layers(h, which)) {
+  for (int li : branch_layers(h, which, part)) {
     ColsumSpec sp{};
     sp.g = h->layers[li].g;
     sp.dout = with_ptrs ? bp(h, h->layers[li].dout) : nullptr;
@@ -397,8 +417,8 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
   }
 }
 
-void branch_bias_grads(sv_handle* h, int which, cudaStream_t s) {
-  if (h->cs_on && h->cs[which]) h->launches += colsum_table_run(h->cs[which], h->grads, s);
+void branch_bias_grads(sv_handle* h, int which, int part, cudaStream_t s) {
+  if (h->cs_on && h->cs[which][part]) h->launches += colsum_table_run(h->cs[which][part], h->grads, s);
   join_wgrad_stream(h, s);
 }
 
@@ -408,11 +428,14 @@ void conv_encoder_fwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaS
   layer_fwd(h, e.e3, nullptr, s);
   layer_fwd(h, e.heads, nullptr, s);
 }
-void conv_encoder_bwd(sv_handle* h, const ConvEnc& e, const float* inputs, cudaStream_t s) {
-  layer_bwd(h, e.heads, nullptr, s);
-  layer_bwd(h, e.e3, nullptr, s);
-  layer_bwd(h, e.e2, nullptr, s);
-  layer_bwd(h, e.e1, inputs, s);
+void conv_encoder_bwd(sv_handle* h, const ConvEnc& e, const float* inputs, int part, cudaStream_t s) {
+  if (part == 0) {
+    layer_bwd(h, e.heads, nullptr, s);
+    layer_bwd(h, e.e3, nullptr, s);
+  } else {
+    layer_bwd(h, e.e2, nullptr, s);
+    layer_bwd(h, e.e1, inputs, s);
+  }
 }
 
 void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStream_t s) {
@@ -431,9 +454,14 @@ void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStrea
   h->launches += 2;
 }
 
-void gm_encoder_bwd(sv_handle* h, const float* inputs, cudaStream_t s) {
+void gm_encoder_bwd(sv_handle* h, const float* inputs, int part, cudaStream_t s) {
   const GmEnc& e = h->gm_enc;
   const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
+  if (part == 1) {
+    layer_bwd(h, e.h2, nullptr, s);
+    layer_bwd(h, e.h1, inputs, s);
+    return;
+  }
   layer_bwd(h, e.zheads, nullptr, s);
   gm_glue_a(bp(h, e.dHSUM), bp(h, e.YB0E1), (const float*)bp(h, e.YHEADS), (const float*)bp(h, h->ZM_G),
             (const float*)bp(h, h->ZS_G), bp(h, e.dYB0E1), bp(h, e.dYHEADS), h->act_dt, h->B, h->cfg.beta, inv_batch, s);
@@ -444,8 +472,6 @@ void gm_encoder_bwd(sv_handle* h, const float* inputs, cudaStream_t s) {
   layer_bwd(h, e.yb2, nullptr, s);   // writes columns 0..1023 of dYB0E1; glue A wrote 1024..1535
   layer_bwd(h, e.yb0e1, nullptr, s);
   layer_bwd(h, e.h3, nullptr, s);
-  layer_bwd(h, e.h2, nullptr, s);
-  layer_bwd(h, e.h1, inputs, s);
   h->launches += 2;
 }
 
@@ -621,16 +647,35 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 
   if (h->act_dt == DT_BF16 && !getenv("SV_NO_MULTI_COLSUM")) {
     bool ok = true;
-    for (int b = 0; b < 4 && ok; ++b) {
-      const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
-      ok = sp.empty() || colsum_multi_supported(sp.data(), (int)sp.size());
-    }
+    for (int b = 0; b < 4 && ok; ++b)
+      for (int part = 0; part < 2 && ok; ++part) {
+        const std::vector<ColsumSpec> sp = branch_specs(h, b, part, false);
+        ok = sp.empty() || colsum_multi_supported(sp.data(), (int)sp.size());
+      }
     if (ok) {
       h->cs_on = true;
-      for (int b = 0; b < 4; ++b) {
-        const std::vector<ColsumSpec> sp = branch_specs(h, b, false);
-        if (!sp.empty()) h->CSP[b] = f32_buf(h, colsum_table_partial_floats(sp.data(), (int)sp.size()) + 64);
+      for (int b = 0; b < 4; ++b)
+        for (int part = 0; part < 2; ++part) {
+          const std::vector<ColsumSpec> sp = branch_specs(h, b, part, false);
+          if (!sp.empty()) h->CSP[b][part] = f32_buf(h, colsum_table_partial_floats(sp.data(), (int)sp.size()) + 64);
+        }
+    }
+  }
+  for (int seg = 0; seg < sv_handle::kSegs; ++seg) {     // arena ranges of each segment: its layers' variables, adjacent slots merged
+    std::vector<std::pair<long long, long long>> r;
+    auto slot = [](long long n) { return (n + 63) / 64 * 64; };
+    for (int li : segment_layers(h, seg)) {
+      const ConvGeom& g = h->layers[li].g;
+      for (int j = 0; j < g.nparts; ++j) {
+        r.push_back({g.part_w[j], slot((long long)g.kh * g.kw * g.Ci * g.part_n[j])});
+        r.push_back({g.part_b[j], slot(g.part_n[j])});
       }
+    }
+    std::sort(r.begin(), r.end());
+    for (const auto& x : r) {
+      auto& out = h->seg_ranges[seg];
+      if (!out.empty() && out.back().first + out.back().second == x.first) out.back().second += x.second;
+      else out.push_back(x);
     }
   }
   if (h->split) {     // every forward product but the decoders' last layer multiplies bf16 pairs
@@ -666,11 +711,13 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 sv_status sv_destroy(sv_handle* h) {
   if (h) {
     tc_pack_table_destroy(h->pack);
-    for (int seg = 0; seg < 2; ++seg) tc_pack_table_destroy(h->pack_seg[seg]);
+    for (int seg = 0; seg < sv_handle::kSegs; ++seg) tc_pack_table_destroy(h->pack_seg[seg]);
+    if (h->ev_opt_fork2) cudaEventDestroy(h->ev_opt_fork2);
     if (h->ev_opt_fork) cudaEventDestroy(h->ev_opt_fork);
     if (h->ev_opt_join) cudaEventDestroy(h->ev_opt_join);
     if (h->opt) cudaStreamDestroy(h->opt);
-    for (int b = 0; b < 4; ++b) colsum_table_destroy(h->cs[b]);
+    for (int b = 0; b < 4; ++b)
+      for (int part = 0; part < 2; ++part) colsum_table_destroy(h->cs[b][part]);
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < 2; ++j) {
         if (h->ev_aux[k][j]) cudaEventDestroy(h->ev_aux[k][j]);
@@ -726,25 +773,25 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     tc_pack_table_destroy(h->pack);
     h->pack = tc_pack_table_create(tl.data(), tg.data(), (int)tl.size(), &perr);
     if (!h->pack) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
-    for (int seg = 0; seg < 2; ++seg) {
+    for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
       std::vector<TcLayer*> sl;
       std::vector<const ConvGeom*> sg;
-      for (auto& L : h->layers)
-        if ((L.g.part_w[0] >= h->seg_split) == (seg == 0)) { sl.push_back(&L.tc); sg.push_back(&L.g); }
+      for (int li : segment_layers(h, seg)) { sl.push_back(&h->layers[li].tc); sg.push_back(&h->layers[li].g); }
       tc_pack_table_destroy(h->pack_seg[seg]);
       h->pack_seg[seg] = tc_pack_table_create(sl.data(), sg.data(), (int)sl.size(), &perr);
       if (!h->pack_seg[seg]) return fail(h, SV_ERR_DEVICE, "tensor-core pack table: %s", perr ? perr : "?");
     }
   }
   if (h->cs_on) {
-    for (int b = 0; b < 4; ++b) {
-      const std::vector<ColsumSpec> sp = branch_specs(h, b, true);
-      if (sp.empty()) continue;
-      const char* cerr = nullptr;
-      colsum_table_destroy(h->cs[b]);
-      h->cs[b] = colsum_table_create(sp.data(), (int)sp.size(), (float*)bp(h, h->CSP[b]), &cerr);
-      if (!h->cs[b]) return fail(h, SV_ERR_DEVICE, "bias-gradient table: %s", cerr ? cerr : "?");
-    }
+    for (int b = 0; b < 4; ++b)
+      for (int part = 0; part < 2; ++part) {
+        const std::vector<ColsumSpec> sp = branch_specs(h, b, part, true);
+        if (sp.empty()) continue;
+        const char* cerr = nullptr;
+        colsum_table_destroy(h->cs[b][part]);
+        h->cs[b][part] = colsum_table_create(sp.data(), (int)sp.size(), (float*)bp(h, h->CSP[b][part]), &cerr);
+        if (!h->cs[b][part]) return fail(h, SV_ERR_DEVICE, "bias-gradient table: %s", cerr ? cerr : "?");
+      }
   }
   if (!h->side) {
     const char* one = getenv("SV_ONE_STREAM");
@@ -760,6 +807,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     if (!(off && *off == '0') &&
         (cudaStreamCreateWithFlags(&h->opt, cudaStreamNonBlocking) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_fork, cudaEventDisableTiming) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_opt_fork2, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "optimizer stream / event creation failed");
   }
@@ -831,12 +879,16 @@ sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
   return check_launch(h, "sv_loss_fwd_bwd");
 }
 
-int32_t sv_num_segments(const sv_handle* h) { return h ? 2 : 0; }
+int32_t sv_num_segments(const sv_handle* h) { return h ? sv_handle::kSegs : 0; }
 
-sv_status sv_segment_range(const sv_handle* h, int32_t seg, int64_t* off, int64_t* cnt) {
-  if (!h || !off || !cnt || seg < 0 || seg > 1) return SV_ERR_INVALID;
-  if (seg == 0) { *off = h->seg_split; *cnt = h->arena_floats - h->seg_split; }
-  else { *off = 0; *cnt = h->seg_split; }
+int32_t sv_segment_num_ranges(const sv_handle* h, int32_t seg) {
+  return (h && seg >= 0 && seg < sv_handle::kSegs) ? (int32_t)h->seg_ranges[seg].size() : 0;
+}
+
+sv_status sv_segment_range(const sv_handle* h, int32_t seg, int32_t index, int64_t* off, int64_t* cnt) {
+  if (!h || !off || !cnt || seg < 0 || seg >= sv_handle::kSegs || index < 0 || index >= (int32_t)h->seg_ranges[seg].size()) return SV_ERR_INVALID;
+  *off = h->seg_ranges[seg][index].first;
+  *cnt = h->seg_ranges[seg][index].second;
   return SV_OK;
 }
 
@@ -848,25 +900,28 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
   if (seg == 0) {
     cudaStream_t s2 = loc ? fork_side(h, s) : s;
     decoder_bwd(h, h->dec_x, s);
-    branch_bias_grads(h, 0, s);
+    branch_bias_grads(h, 0, 0, s);
     if (loc) {
       decoder_bwd(h, h->dec_xh, s2);
-      branch_bias_grads(h, 1, s2);
+      branch_bias_grads(h, 1, 0, s2);
       join_side(h, s);
     }
-  } else if (seg == 1) {
+  } else if (seg == 1 || seg == 2) {
     if (!inputs) return fail(h, SV_ERR_STATE, "sv_loss_fwd_bwd must precede sv_backward_segment");
     const bool gm = h->gm;
-    const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
-    latent_bwd(latent_bufs(h), h->B, h->act_dt, gm, h->cfg.beta, inv_batch, s);
-    h->launches += 1;
+    const int part = seg - 1;          // 0: heads .. e3 (gradients final first), 1: e2, e1
+    if (part == 0) {
+      const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
+      latent_bwd(latent_bufs(h), h->B, h->act_dt, gm, h->cfg.beta, inv_batch, s);
+      h->launches += 1;
+    }
     cudaStream_t s2 = loc ? fork_side(h, s) : s;
     if (loc) {
-      conv_encoder_bwd(h, h->enc_xh, inputs, s2);
-      branch_bias_grads(h, 3, s2);
+      conv_encoder_bwd(h, h->enc_xh, inputs, part, s2);
+      branch_bias_grads(h, 3, part, s2);
     }
-    if (gm) gm_encoder_bwd(h, inputs, s); else conv_encoder_bwd(h, h->enc_x, inputs, s);
-    branch_bias_grads(h, 2, s);
+    if (gm) gm_encoder_bwd(h, inputs, part, s); else conv_encoder_bwd(h, h->enc_x, inputs, part, s);
+    branch_bias_grads(h, 2, part, s);
     if (loc) join_side(h, s);
   } else {
     return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
@@ -876,41 +931,50 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
 
 sv_status sv_adam_segment(sv_handle* h, int32_t seg, void* stream) {
   REQUIRE_BOUND(h);
-  if (seg < 0 || seg > 1) return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
+  if (seg < 0 || seg >= sv_handle::kSegs) return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
   cudaStream_t s = (cudaStream_t)stream;
   AdamState* st = (AdamState*)bp(h, h->ADAM);
   if (seg == 0) {
     adam_prepare(st, h->cfg.learning_rate, h->gm, s);     // staircase schedule for both GM models (vae/main.py:66-72)
     h->launches += 1;
   }
-  const long long off = seg == 0 ? h->seg_split : 0, cnt = seg == 0 ? h->arena_floats - h->seg_split : h->seg_split;
-  adam_apply(h->params + off, h->grads + off, h->adam_m + off, h->adam_v + off, cnt, st, 0.f, s);
-  h->launches += 1;
+  for (const auto& r : h->seg_ranges[seg]) {
+    adam_apply(h->params + r.first, h->grads + r.first, h->adam_m + r.first, h->adam_v + r.first, r.second, st, 0.f, s);
+    h->launches += 1;
+  }
   if (h->use_tc) h->launches += tc_repack_all(h->pack_seg[seg], h->params, s);
   return check_launch(h, "sv_adam_segment");
 }
 
 sv_status sv_adam_step(sv_handle* h, void* stream) {
-  sv_status st = sv_adam_segment(h, 0, stream);
-  if (st) return st;
-  return sv_adam_segment(h, 1, stream);
+  for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
+    const sv_status st = sv_adam_segment(h, seg, stream);
+    if (st) return st;
+  }
+  return SV_OK;
 }
 
 sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u, void* stream) {
   sv_status st = forward_impl(h, inputs, eps_g, eps_l, u, stream, false);
   if (st) return st;
   if ((st = sv_loss_fwd_bwd(h, inputs, stream))) return st;
-  if ((st = sv_backward_segment(h, 0, stream))) return st;
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->opt) {   // decoders: gradients final -> Adam + re-pack on the optimizer stream while the encoders' backward runs
-    cudaEventRecord(h->ev_opt_fork, s);
-    cudaStreamWaitEvent(h->opt, h->ev_opt_fork, 0);
-    if ((st = sv_adam_segment(h, 0, h->opt))) return st;
-    cudaEventRecord(h->ev_opt_join, h->opt);
-  } else if ((st = sv_adam_segment(h, 0, stream))) return st;
-  if ((st = sv_backward_segment(h, 1, stream))) return st;
-  if (h->opt) cudaStreamWaitEvent(s, h->ev_opt_join, 0);
-  return sv_adam_segment(h, 1, stream);
+  // segment k's gradients are final after its backward: Adam + re-pack of segment k run on the optimizer stream while the
+  // backward of segment k+1 runs; only the last (smallest) segment's update is exposed
+  for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
+    if ((st = sv_backward_segment(h, seg, stream))) return st;
+    if (h->opt && seg + 1 < sv_handle::kSegs) {
+      cudaEvent_t ev = seg == 0 ? h->ev_opt_fork : h->ev_opt_fork2;
+      cudaEventRecord(ev, s);
+      cudaStreamWaitEvent(h->opt, ev, 0);
+      if ((st = sv_adam_segment(h, seg, h->opt))) return st;
+      if (seg + 2 == sv_handle::kSegs) cudaEventRecord(h->ev_opt_join, h->opt);
+    } else {
+      if (h->opt) cudaStreamWaitEvent(s, h->ev_opt_join, 0);
+      if ((st = sv_adam_segment(h, seg, stream))) return st;
+    }
+  }
+  return SV_OK;
 }
 
 sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t* count) {

@@ -62,11 +62,14 @@ class Engine:
         check(self.lib.sv_bind(self.h, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
                                _ptr(self._ws), self.workspace_bytes), self.h, "sv_bind")
         self._outs = {}
-        self.segments = []
+        self.segments = []        # per backward segment: its arena ranges [(offset, count), ...] (gradient buckets, in backward order)
         off64, cnt64 = C.c_int64(), C.c_int64()
         for s in range(self.lib.sv_num_segments(self.h)):
-            check(self.lib.sv_segment_range(self.h, s, C.byref(off64), C.byref(cnt64)), self.h, "sv_segment_range")
-            self.segments.append((int(off64.value), int(cnt64.value)))
+            ranges = []
+            for i in range(self.lib.sv_segment_num_ranges(self.h, s)):
+                check(self.lib.sv_segment_range(self.h, s, i, C.byref(off64), C.byref(cnt64)), self.h, "sv_segment_range")
+                ranges.append((int(off64.value), int(cnt64.value)))
+            self.segments.append(ranges)
 
     def __del__(self):
         try:
@@ -132,6 +135,10 @@ class Engine:
 
     def adam_step(self):
         check(self.lib.sv_adam_step(self.h, _stream()), self.h, "sv_adam_step")
+
+    def adam_segment(self, seg):
+        """Adam + operand re-pack of one backward segment (in order 0..n-1, once per step each), on the current stream."""
+        check(self.lib.sv_adam_segment(self.h, seg, _stream()), self.h, "sv_adam_segment")
 
     def train_step(self, inputs, eps_g=None, eps_l=None, u=None):
         self._check_inputs(inputs)

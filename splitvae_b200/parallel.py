@@ -41,20 +41,27 @@ def shard_range(global_batch: int, world: int, rank: int):
 
 
 class BucketReducer:
-    """SUM all-reduce of contiguous ranges ("buckets") of one flat tensor, asynchronously."""
+    """SUM all-reduce of "buckets" of one flat tensor, asynchronously.  A bucket = one backward segment = a few contiguous ranges
+    (the arena keeps the Keras variable order, so the two encoders' layers of one segment are two ranges)."""
 
     def __init__(self, flat: torch.Tensor, segments, group=None):
         self.flat = flat
-        self.segments = [(int(o), int(c)) for o, c in segments]
+        self.segments = []
+        for seg in segments:
+            ranges = [seg] if seg and isinstance(seg[0], int) else list(seg)
+            self.segments.append([(int(o), int(c)) for o, c in ranges])
         self.group = group
         self._work = []
         self.enabled = dist.is_initialized() and dist.get_world_size(group) > 1
 
     def reduce(self, seg: int):
+        """Issues the all-reduce of bucket `seg` behind the work queued so far on the current stream; returns its work handles."""
         if not self.enabled:
-            return
-        off, cnt = self.segments[seg]
-        self._work.append(dist.all_reduce(self.flat[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return []
+        works = [dist.all_reduce(self.flat[off:off + cnt], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                 for off, cnt in self.segments[seg]]
+        self._work.extend(works)
+        return works
 
     def wait_all(self):
         for w in self._work:

@@ -81,6 +81,7 @@ class StepRunner:
         self.reducer = BucketReducer(engine.grads, engine.segments, group)
         self.use_graph = use_graph
         self.graph = None
+        self.opt_stream = None
         dev = engine.device
         B = engine.B
         self.inputs = torch.zeros(B, engine.H, engine.W, 6, dtype=torch.float32, device=dev)
@@ -90,17 +91,35 @@ class StepRunner:
         self.u = torch.full((B, engine.y_size), 0.5, device=dev) if explicit_noise and engine.model != "lgvae" else None
 
     def _issue(self):
+        """One train step.  Data parallel: the gradients of backward segment k are final - decoders, then the encoders' last layers,
+        then their first convs - so bucket k is all-reduced while segment k+1 runs, and its Adam update + operand re-pack follow on
+        an optimizer stream as soon as the reduction lands.  Only the last (smallest) bucket and its update are exposed."""
         e = self.e
         if not self.reducer.enabled:
             e.train_step(self.inputs, self.eps_g, self.eps_l, self.u)
             return
+        main = torch.cuda.current_stream()
+        if self.opt_stream is None:
+            self.opt_stream = torch.cuda.Stream()
+        opt = self.opt_stream
         e.forward(self.inputs, self.eps_g, self.eps_l, self.u)
         e.loss_fwd_bwd(self.inputs)
-        for s in range(len(e.segments)):
+        nseg = len(e.segments)
+        for s in range(nseg):
             e.backward_segment(s)
-            self.reducer.reduce(s)      # all-reduce of this bucket overlaps the next segment
-        self.reducer.wait_all()
-        e.adam_step()
+            works = self.reducer.reduce(s)          # behind segment s on NCCL's stream
+            if s + 1 < nseg:
+                opt.wait_stream(main)               # (joins the optimizer stream into the capture)
+                with torch.cuda.stream(opt):
+                    for w in works:
+                        w.wait()                    # the optimizer stream waits for the reduction, the main stream does not
+                    e.adam_segment(s)
+            else:
+                for w in works:
+                    w.wait()
+                main.wait_stream(opt)
+                e.adam_segment(s)
+        self.reducer._work = []
 
     def capture(self, warmup=2):
         side = torch.cuda.Stream()

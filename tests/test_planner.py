@@ -61,3 +61,32 @@ def test_c2_layer_to_kernel_map_bf16x3():
     info = {L.name.decode(): L for L in e.debug_layers()}
     assert all(L.split_fwd == (0 if n.endswith(".d5") else 1) for n, L in info.items())
     assert e.workspace_bytes < 4 << 30
+
+
+@pytest.mark.parametrize("model,H", [("lgvae", 64), ("lggmvae", 32), ("gmvae", 32)])
+def test_backward_segments_partition_the_arena(model, H):
+    """The gradient buckets (sv_segment_range): three segments in backward order whose ranges are disjoint and together hold every
+    variable exactly once - the data-parallel all-reduce and the per-segment Adam both rely on it."""
+    e = Engine(model=model, height=H, width=H, batch=8, plan_only=True)
+    import ctypes as C
+    lib, off, cnt = e.lib, C.c_int64(), C.c_int64()
+    segs = []
+    for s in range(lib.sv_num_segments(e.h)):
+        r = []
+        for i in range(lib.sv_segment_num_ranges(e.h, s)):
+            assert lib.sv_segment_range(e.h, s, i, C.byref(off), C.byref(cnt)) == 0
+            r.append((off.value, cnt.value))
+        segs.append(r)
+    assert len(segs) == 3 and all(1 <= len(r) <= 2 for r in segs)
+    flat = sorted(x for r in segs for x in r)
+    assert all(a[0] + a[1] <= b[0] for a, b in zip(flat, flat[1:]))                 # disjoint
+    assert sum(c for _, c in flat) == e.arena_floats                                # nothing left out
+    owner = lambda o: next(i for i, r in enumerate(segs) if any(a <= o < a + c for a, c in r))
+    for name, shape, o, c in e.table:
+        seg = owner(o)
+        if name.startswith("decoder"):
+            assert seg == 0, name
+        elif any(k in name for k in (".e1.", ".e2.", "h_block.0", "h_block.1")) and not (model != "lgvae" and name.startswith("encoder_x.e1")):
+            assert seg == 2, name
+        else:
+            assert seg == 1, name
