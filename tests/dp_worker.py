@@ -77,7 +77,9 @@ def main():
             if np.linalg.norm(dr) < 1e-9:
                 continue
             wd = max(wd, float(np.linalg.norm((new_params[k] - params[k]) - dr) / np.linalg.norm(dr)))
-        if wd > (0.02 if prec == "fp32" else 0.1):
+        # (bf16x3: at step 1 Adam's update is -lr * sign(g) per element, so the ~0.5 % gradient error flips the sign of the elements
+        #  with |g| below it: a few percent of them, each contributing 2 * lr)
+        if wd > (0.02 if prec == "fp32" else 0.5):
             ok = False
             msgs.append(f"Adam displacement rel-L2 {wd:.3e}")
         print(json.dumps({"ok": ok, "world": world, "model": model, "H": H, "per_gpu_batch": b, "precision": prec, "iterations": e.iterations,
