@@ -88,7 +88,9 @@ enum {
   SV_OUT_Z_PRIOR_MEAN = 10,
   SV_OUT_Z_PRIOR_SIG = 11,
   SV_OUT_SCALARS = 12,     /* float[8]: see SV_SCALAR_* */
-  SV_OUT_COUNT = 13
+  SV_OUT_SCALAR_SUMS = 13, /* float[16]: running sums of SV_SCALAR_* [0..5] over every sv_loss_fwd_bwd since the caller last zeroed them,
+                              [8] = number of passes (the reference's Keras Mean metrics, vae/trainer.py:140-144); caller may memset */
+  SV_OUT_COUNT = 14
 };
 enum { SV_SCALAR_RECON_X = 0, SV_SCALAR_RECON_X_HAT = 1, SV_SCALAR_KL_X = 2, SV_SCALAR_KL_X_HAT = 3,
        SV_SCALAR_TOTAL_KL = 4, /* lgvae: beta*(kl_x+kl_x_hat) (trainer.py:130); lggmvae: y_kl (trainer.py:161) */
@@ -163,9 +165,10 @@ sv_status sv_decode(sv_handle* h, const float* z_x_dev, const float* z_x_hat_dev
 /* Encoder.encode_y (vae/model.py:137-140): prior heads on y [B,y_size] -> SV_OUT_Z_PRIOR_*. */
 sv_status sv_encode_y(sv_handle* h, const float* y_dev, void* stream);
 
-/* Optimizer iteration counter (optimizer.iterations), device-resident; get/set are synchronous. */
-sv_status sv_get_iterations(sv_handle* h, int64_t* iterations);
-sv_status sv_set_iterations(sv_handle* h, int64_t iterations);
+/* Optimizer iteration counter (optimizer.iterations), device-resident.  get / set are ordered on `stream` and return once it has
+ * drained (they synchronise that stream, nothing else). */
+sv_status sv_get_iterations(sv_handle* h, int64_t* iterations, void* stream);
+sv_status sv_set_iterations(sv_handle* h, int64_t iterations, void* stream);
 
 /* Number of kernels this library launched since creation (for bench.py's gpu_launches). */
 int64_t sv_launch_count(const sv_handle* h);

@@ -16,7 +16,7 @@ SV_FLAG_PLAN_ONLY = 1
 SV_FLAG_NO_TC = 2
 
 OUT_NAMES = ["dec_x", "dec_x_hat", "z_x", "z_mean_x", "z_sig_x", "z_x_hat", "z_mean_x_hat", "z_sig_x_hat",
-             "y", "y_logits", "z_prior_mean", "z_prior_sig", "scalars"]
+             "y", "y_logits", "z_prior_mean", "z_prior_sig", "scalars", "scalar_sums"]
 SCALAR_NAMES = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "total_kl_or_y_kl", "total"]
 
 # every symbol include/splitvae.h declares (checked by tests/test_abi.py)
@@ -96,8 +96,8 @@ def load():
     lib.sv_output_ptr.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
     lib.sv_decode.argtypes = [vp, vp, vp, vp]
     lib.sv_encode_y.argtypes = [vp, vp, vp]
-    lib.sv_get_iterations.argtypes = [vp, C.POINTER(i64)]
-    lib.sv_set_iterations.argtypes = [vp, i64]
+    lib.sv_get_iterations.argtypes = [vp, C.POINTER(i64), vp]
+    lib.sv_set_iterations.argtypes = [vp, i64, vp]
     lib.sv_launch_count.argtypes = [vp]
     lib.sv_launch_count.restype = i64
     lib.sv_discretised_logistic_loss.argtypes = [vp, vp, vp, vp, i64, vp]

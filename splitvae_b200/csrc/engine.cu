@@ -339,6 +339,8 @@ std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, int part, bool wit
   return v;
 }
 
+unsigned long long* noise_counter(sv_handle* h) { return (unsigned long long*)((char*)bp(h, h->ADAM) + 64); }
+
 LatentBufs latent_bufs(sv_handle* h) {
   LatentBufs L{};
   const bool gm = h->gm;
@@ -447,7 +449,7 @@ void gm_encoder_fwd(sv_handle* h, const float* inputs, const float* u, cudaStrea
   layer_fwd(h, e.yb2, nullptr, s);
   layer_fwd(h, e.ydense, nullptr, s);
   gumbel_fwd((const float*)bp(h, e.LOGITS), u, (float*)bp(h, e.U), (float*)bp(h, e.Y), bp(h, e.YT), bp(h, lo_buf(h, e.YT)), h->act_dt, h->B,
-             h->K, h->cfg.tau, h->seed, (const unsigned long long*)bp(h, h->ADAM), s);
+             h->K, h->cfg.tau, h->seed, noise_counter(h), s);
   layer_fwd(h, e.yheads, nullptr, s);
   gm_add(bp(h, e.YB0E1), bp(h, lo_buf(h, e.YB0E1)), (const float*)bp(h, e.YHEADS), bp(h, e.HSUM), bp(h, lo_buf(h, e.HSUM)), h->act_dt, h->B, s);
   layer_fwd(h, e.zheads, nullptr, s);
@@ -525,6 +527,10 @@ __global__ void pack_y_kernel(const float* __restrict__ y, void* yt, bf16* yt_lo
   if (dt == DT_F32) ((float*)yt)[idx] = v; else ((bf16*)yt)[idx] = __float2bfloat16_rn(v);
   if (yt_lo) yt_lo[idx] = __float2bfloat16_rn(v - round_bf16(v));
 }
+// The Philox counter of the in-kernel noise (Sampling eps, gumbel u): its own device-side word, bumped once per forward pass, so
+// forward-only engines (evaluation, model(x), encode, get_y) draw fresh noise on every call like tf.random does - the optimizer's
+// iteration count, which only training advances, used to serve as the counter.
+__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
 __global__ void copy_cols_kernel(const float* __restrict__ src, int ld, int coff, float* __restrict__ dst, int B, int n) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * n) return;
@@ -845,11 +851,13 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   cudaStream_t s2 = loc ? fork_side(h, s) : s;
   if (gm) gm_encoder_fwd(h, inputs, u, s); else conv_encoder_fwd(h, h->enc_x, inputs, s);
   if (loc) { conv_encoder_fwd(h, h->enc_xh, inputs, s2); join_side(h, s); }
-  reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, (const unsigned long long*)bp(h, h->ADAM), (float*)bp(h, h->KLPART), s);
+  reparam(latent_bufs(h), h->B, h->act_dt, eps_g, eps_l, h->seed, noise_counter(h), (float*)bp(h, h->KLPART), s);
   h->launches += 1;
   s2 = loc ? fork_side(h, s) : s;
   decoder_fwd(h, h->dec_x, s);
   if (loc) { decoder_fwd(h, h->dec_xh, s2); join_side(h, s); }
+  bump_counter_kernel<<<1, 1, 0, s>>>(noise_counter(h));
+  h->launches += 1;
   if (gm && prior_copies) {  // contiguous z_prior_mean / z_prior_sig for the reference's output tuple
     copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);
     copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 640, (float*)bp(h, h->ZPS_OUT), h->B, 128);
@@ -999,10 +1007,12 @@ sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t*
     case SV_OUT_Z_PRIOR_MEAN: if (gm) { id = h->ZPM_OUT; n = B * 128; } break;
     case SV_OUT_Z_PRIOR_SIG: if (gm) { id = h->ZPS_OUT; n = B * 128; } break;
     case SV_OUT_SCALARS: id = h->SCALARS; n = SV_SCALAR_COUNT; break;
+    case SV_OUT_SCALAR_SUMS: id = h->SCALARS; n = 16; break;          // (offset applied below)
     default: break;
   }
   if (id < 0) return fail(h, SV_ERR_INVALID, "output %d not available for this model", which);
   *ptr = bp(h, id);
+  if (which == SV_OUT_SCALAR_SUMS) *ptr = (float*)*ptr + 8;
   *count = n;
   return SV_OK;
 }
@@ -1035,19 +1045,25 @@ sv_status sv_encode_y(sv_handle* h, const float* y, void* stream) {
   return check_launch(h, "sv_encode_y");
 }
 
-sv_status sv_get_iterations(sv_handle* h, int64_t* it) {
+// Both are ordered on the caller's stream (the legacy default stream is not ordered against non-blocking streams) and return after
+// that stream has drained: a read sees every step queued before it, a write cannot race an in-flight adam_prepare.
+sv_status sv_get_iterations(sv_handle* h, int64_t* it, void* stream) {
   REQUIRE_BOUND(h);
   if (!it) return SV_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
   unsigned long long v = 0;
-  if (cudaMemcpy(&v, bp(h, h->ADAM), 8, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, SV_ERR_DEVICE, "memcpy failed");
+  if (cudaMemcpyAsync(&v, bp(h, h->ADAM), 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(h, SV_ERR_DEVICE, "memcpy failed");
   *it = (int64_t)v;
   return SV_OK;
 }
 
-sv_status sv_set_iterations(sv_handle* h, int64_t it) {
+sv_status sv_set_iterations(sv_handle* h, int64_t it, void* stream) {
   REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
   unsigned long long v = (unsigned long long)it;
-  if (cudaMemcpy(bp(h, h->ADAM), &v, 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail(h, SV_ERR_DEVICE, "memcpy failed");
+  if (cudaMemcpyAsync(bp(h, h->ADAM), &v, 8, cudaMemcpyHostToDevice, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(h, SV_ERR_DEVICE, "memcpy failed");
   return SV_OK;
 }
 

@@ -483,6 +483,11 @@ __global__ void __launch_bounds__(1024) loss_scalars_kernel(const float* __restr
     scalars[5] = (float)(t[3] + t[4] + klsum + (gm ? alpha * t[2] : 0.0));
     scalars[6] = 0.f;
     scalars[7] = 0.f;
+    // running sums of the six terms + the number of passes (Keras Mean metrics, vae/trainer.py:140-144, 169-173: updated EVERY step
+    // inside the step; the host reads and clears them at report time - no per-step synchronisation)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) scalars[8 + q] += scalars[q];
+    scalars[16] += 1.f;
   }
 }
 

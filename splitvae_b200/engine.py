@@ -172,7 +172,7 @@ class Engine:
             t = t.view(B, self.H, self.W, 6)
         elif name in ("y", "y_logits"):
             t = t.view(B, 32)[:, :self.y_size]
-        elif name != "scalars":
+        elif name not in ("scalars", "scalar_sums"):
             t = t.view(B, 128)
         self._outs[name] = t
         return t
@@ -186,15 +186,29 @@ class Engine:
             d.pop("recon_x_hat"), d.pop("kl_x_hat")
         return d
 
+    def metric_means(self, reset=True):
+        """Means of the loss terms over every loss pass since the last reset (the reference's Keras Mean metrics, accumulated on the
+        device inside the step; vae/trainer.py:140-144) and the number of passes; synchronises."""
+        sums = self.output("scalar_sums")
+        host = sums.cpu().tolist()
+        if reset:
+            sums.zero_()
+        n = host[8]
+        names = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "y_kl" if self.model != "lgvae" else "total_kl", "total"]
+        d = {k: (v / n if n else 0.0) for k, v in zip(names, host[:6])}
+        if self.model == "gmvae":
+            d.pop("recon_x_hat"), d.pop("kl_x_hat")
+        return d, int(n)
+
     @property
     def iterations(self):
         v = C.c_int64()
-        check(self.lib.sv_get_iterations(self.h, C.byref(v)), self.h, "sv_get_iterations")
+        check(self.lib.sv_get_iterations(self.h, C.byref(v), _stream()), self.h, "sv_get_iterations")
         return int(v.value)
 
     @iterations.setter
     def iterations(self, v):
-        check(self.lib.sv_set_iterations(self.h, int(v)), self.h, "sv_set_iterations")
+        check(self.lib.sv_set_iterations(self.h, int(v), _stream()), self.h, "sv_set_iterations")
 
     @property
     def launch_count(self):

@@ -12,6 +12,65 @@ import torch
 from .engine import Engine
 
 
+def keras_weight_names(kind):
+    """Attribute-path variable name of this build -> the name Keras gives the same variable in the reference's `save_weights` HDF5
+    file (group = the sub-model layer, dataset = `<model>/<layer>/<sublayer>/<kernel|bias>:0`).  DERIVED from Keras' auto-naming rules
+    (snake-cased class names, one global counter per layer class, creation order = vae/model.py:34-79,152-156,182-186,230-234,284-285)
+    because TensorFlow cannot be installed here to read a real file; scripts/convert_checkpoint.py uses it on a machine with h5py."""
+    model_name = {"lgvae": "lg_vae", "lggmvae": "lggm_vae", "gmvae": "gm_vae"}[kind]
+    counters = {}
+
+    def auto(cls):
+        n = counters.get(cls, 0)
+        counters[cls] = n + 1
+        return cls if n == 0 else f"{cls}_{n}"
+
+    names = {}
+
+    def conv_encoder(attr):
+        layer = auto("encoder")
+        for v in ("e1", "e2", "e3"):
+            names[f"{attr}.{v}"] = f"{model_name}/{layer}/{auto('conv2d')}"
+        for v in ("e4_mean", "e4_sd"):
+            names[f"{attr}.{v}"] = f"{model_name}/{layer}/{auto('dense')}"
+
+    def gm_encoder(attr):
+        layer = auto("encoder")
+        seq = auto("sequential")
+        for i in range(3):
+            names[f"{attr}.h_block.{i}"] = f"{model_name}/{layer}/{seq}/{auto('conv2d')}"
+        seq = auto("sequential")
+        names[f"{attr}.y_block.0"] = f"{model_name}/{layer}/{seq}/{auto('dense')}"
+        names[f"{attr}.y_block.2"] = f"{model_name}/{layer}/{seq}/{auto('dense')}"
+        names[f"{attr}.y_dense"] = f"{model_name}/{layer}/y_dense"
+        names[f"{attr}.h_top_dense"] = f"{model_name}/{layer}/{auto('dense')}"
+        names[f"{attr}.z_prior_mean"] = f"{model_name}/{layer}/z_prior_mean"
+        names[f"{attr}.z_prior_sig"] = f"{model_name}/{layer}/z_prior_sig"
+        for v in ("e1", "z_mean", "z_sig"):
+            names[f"{attr}.{v}"] = f"{model_name}/{layer}/{auto('dense')}"
+
+    def decoder(attr):
+        layer = auto("decoder")
+        names[f"{attr}.d1"] = f"{model_name}/{layer}/{auto('dense')}"
+        for v in ("d2", "d3", "d4", "d5"):
+            names[f"{attr}.{v}"] = f"{model_name}/{layer}/{auto('conv2d')}"
+
+    if kind == "lgvae":
+        conv_encoder("encoder_x")
+    else:
+        gm_encoder("encoder_x")
+    if kind != "gmvae":
+        conv_encoder("encoder_x_hat")
+    decoder("decoder_x")
+    if kind != "gmvae":
+        decoder("decoder_x_hat")
+    out = {}
+    for k, v in names.items():
+        out[k + ".kernel"] = v + "/kernel:0"
+        out[k + ".bias"] = v + "/bias:0"
+    return out
+
+
 class _SplitModel:
     _kind = None
 
@@ -30,6 +89,7 @@ class _SplitModel:
         self.engine = None
         self._eval_engines = {}
         self._pending_params = None
+        self._pending_optimizer = None      # (adam_m, adam_v, iterations) of a checkpoint loaded before the engine exists
 
     # -- engine management -------------------------------------------------------------------
     def build(self, batch_size, **overrides):
@@ -38,23 +98,35 @@ class _SplitModel:
         H, W = int(self.image_shape[1]), int(self.image_shape[2])
         if self.global_latent_dims != 128 or (self.local_latent_dims or 128) != 128:
             raise NotImplementedError("libsplitvae supports the reference default latent sizes (128/128) only")
-        params = None
-        if self.engine is not None:
-            params = self.engine.get_params()
+        old = self.engine
         self.engine = Engine(model=self._kind, height=H, width=W, batch=int(batch_size), y_size=self.y_size or 30,
                              tau=self.tau or 0.4, precision=self.precision, **kw)
-        if params is not None:
-            self.engine.load_params(params)
+        e = self.engine
+        if old is not None:        # a new TRAINING engine (another batch size / loss weights): the whole optimizer state moves over
+            torch.cuda.synchronize()
+            e.params.copy_(old.params); e.adam_m.copy_(old.adam_m); e.adam_v.copy_(old.adam_v)
+            e.params_updated()
+            e.iterations = old.iterations
         elif self._pending_params is not None:
-            self.engine.load_params(self._pending_params)
+            e.load_params(self._pending_params)
+            if self._pending_optimizer is not None:
+                self._apply_optimizer_state(*self._pending_optimizer)
+                self._pending_optimizer = None
         else:
-            self.engine.init_params(seed=kw.get("rng_stream", 0) * 0 + 5)
-        return self.engine
+            e.init_params(seed=5)
+        self._eval_engines = {}
+        return e
 
     def _ensure(self, batch_size):
-        if self.engine is None or self.engine.B != int(batch_size):
-            self.build(batch_size)
-        return self.engine
+        """Engine for a forward-only call (model(x), encode, decode, encode_y, get_y).  The training engine serves its own batch size;
+        any other batch size gets a separate forward engine fed with the current weights - the training engine, its Adam state,
+        iteration count and captured graph are never replaced by such a call (the reference calls model(tf.zeros([8, ...])) before
+        training and the visualiser decodes other batch sizes mid-training)."""
+        if self.engine is None:
+            return self.build(batch_size)
+        if self.engine.B == int(batch_size):
+            return self.engine
+        return self.eval_engine(batch_size)
 
     def configure(self, **kw):
         """Loss weights / optimizer settings that live in the reference's `config` and optimizer objects."""
@@ -65,30 +137,43 @@ class _SplitModel:
         VALUES (copied device to device before every evaluation pass): rebuilding the training engine for a different
         batch would drop its Adam state and captured graph."""
         b = int(batch_size)
-        if self.engine is not None and self.engine.B == b and not self._eval_engines:
+        if self.engine is not None and self.engine.B == b:
             return self.engine
         ev = self._eval_engines.get(b)
         if ev is None:
             kw = dict(self._engine_kwargs)
+            kw["rng_stream"] = (int(kw.get("rng_stream", 0)) ^ 0x400000) + len(self._eval_engines)     # its own noise stream
             H, W = int(self.image_shape[1]), int(self.image_shape[2])
             ev = Engine(model=self._kind, height=H, width=W, batch=b, y_size=self.y_size or 30, tau=self.tau or 0.4,
                         precision=self.precision, **kw)
+            ev._synced = None
             self._eval_engines[b] = ev
-        if self.engine is not None:
-            ev.params.copy_(self.engine.params)
-        elif self._pending_params is not None:
-            ev.load_params(self._pending_params)
-        ev.params_updated()
+        # copy + re-pack the weights once per training iteration, not once per evaluation batch (~400 batches per SVHN pass)
+        stamp = (id(self.engine), self.engine.iterations, self._weights_version) if self.engine is not None else ("pending", self._weights_version)
+        if ev._synced != stamp:
+            if self.engine is not None:
+                ev.params.copy_(self.engine.params)
+                ev.params_updated()
+            elif self._pending_params is not None:
+                ev.load_params(self._pending_params)
+            ev._synced = stamp
         return ev
+
+    _weights_version = 0
 
     # -- checkpoints (vae/trainer.py:421 model.save_weights; Keras variable names and layouts) ----
     def save_weights(self, path, include_optimizer=False):
         """The reference writes Keras HDF5 (`model.save_weights('models/<run>.h5')`); h5py is not part of this image, so the
-        same variables (Keras names, conv HWIO / dense [in,out] layouts) go into a NumPy `.npz`.  With include_optimizer the
-        Adam moments and the iteration counter are stored too (the reference cannot resume; this build can)."""
+        same variables in Keras LAYOUTS (conv HWIO, dense [in,out], bias [out]) go into a NumPy `.npz` keyed by this build's
+        attribute-path names (`encoder_x.e1.kernel`, ...); the entry `keras_names` maps each key to the variable's name in a Keras
+        HDF5 file (see keras_weight_names), which scripts/convert_checkpoint.py uses to convert `.npz` <-> `.h5` where h5py exists.
+        With include_optimizer the Adam moments and the iteration counter are stored too (the reference cannot resume; this can)."""
+        import json
+
         import numpy as np
         e = self.engine
         blob = {name: a for name, a in e.get_params().items()}
+        blob["keras_names"] = np.asarray(json.dumps(keras_weight_names(self._kind)))
         if include_optimizer:
             for name, a in e._export(e.adam_m).items():
                 blob["adam_m/" + name] = a
@@ -104,21 +189,33 @@ class _SplitModel:
         import numpy as np
         with np.load(path) as z:
             blob = {k: z[k] for k in z.files}
-        named = {k: v for k, v in blob.items() if "/" not in k}
+        named = {k: v for k, v in blob.items() if "/" not in k and k != "keras_names"}
         self.set_weights_by_name(named)
-        if self.engine is not None and "optimizer/iterations" in blob:
-            e = self.engine
-            for arena, prefix in ((e.adam_m, "adam_m/"), (e.adam_v, "adam_v/")):
-                host = arena.cpu()
-                for name, shape, off, cnt in e.table:
-                    host[off:off + cnt] = torch.from_numpy(np.asarray(blob[prefix + name], dtype=np.float32).reshape(-1))
-                arena.copy_(host)
-            e.iterations = int(blob["optimizer/iterations"])
+        if "optimizer/iterations" in blob:       # resume: the Adam moments and the step count (LR schedule, bias correction) come back too
+            missing = [p + k for p in ("adam_m/", "adam_v/") for k in named if p + k not in blob]
+            if missing:
+                raise KeyError(f"{path}: optimizer state incomplete, missing {missing[:3]} ...")
+            state = ({k: blob["adam_m/" + k] for k in named}, {k: blob["adam_v/" + k] for k in named}, int(blob["optimizer/iterations"]))
+            if self.engine is not None:
+                self._apply_optimizer_state(*state)
+            else:
+                self._pending_optimizer = state      # applied by build(), when the engine exists
 
     def set_weights_by_name(self, named):
         self._pending_params = named
+        self._weights_version += 1
         if self.engine is not None:
             self.engine.load_params(named)
+
+    def _apply_optimizer_state(self, adam_m, adam_v, iterations):
+        e = self.engine
+        import numpy as np
+        for arena, blob in ((e.adam_m, adam_m), (e.adam_v, adam_v)):
+            host = arena.cpu()
+            for name, shape, off, cnt in e.table:
+                host[off:off + cnt] = torch.from_numpy(np.asarray(blob[name], dtype=np.float32).reshape(-1))
+            arena.copy_(host)
+        e.iterations = int(iterations)
 
     def get_weights_by_name(self):
         return self.engine.get_params()
@@ -128,8 +225,7 @@ class _SplitModel:
         return list(self.engine.get_params().items())
 
     # -- reference API -----------------------------------------------------------------------
-    def _split_outputs(self):
-        e = self.engine
+    def _split_outputs(self, e):
         dx, dxh = e.output("dec_x"), e.output("dec_x_hat")
         return dx[..., :3], dx[..., 3:], dxh[..., :3], dxh[..., 3:]
 
@@ -143,7 +239,7 @@ class _SplitModel:
         """vae/model.py:211-218 / 259-266."""
         e = self._ensure(z_x.shape[0])
         e.decode(z_x.contiguous().float(), z_x_hat.contiguous().float())
-        x_mean, _, x_hat_mean, _ = self._split_outputs()
+        x_mean, _, x_hat_mean, _ = self._split_outputs(e)
         if rescale:
             return torch.clip((x_mean + 1) * 0.5, 0., 1.), torch.clip((x_hat_mean + 1) * 0.5, 0., 1.)
         return x_mean, x_hat_mean
@@ -205,7 +301,7 @@ class LGVae(_SplitModel):
         x_hat_log_scale, z_mean_x_hat, z_sig_x_hat)."""
         e = self._ensure(inputs.shape[0])
         e.forward(inputs, eps_g, eps_l, None)
-        x_mean, x_ls, xh_mean, xh_ls = self._split_outputs()
+        x_mean, x_ls, xh_mean, xh_ls = self._split_outputs(e)
         o = e.output
         return (x_mean, x_ls, o("z_x"), o("z_mean_x"), o("z_sig_x"), o("z_x_hat"), xh_mean, xh_ls,
                 o("z_mean_x_hat"), o("z_sig_x_hat"))
@@ -224,7 +320,7 @@ class LGGMVae(_SplitModel):
         accepted and, as in the reference (model.py:242), has no effect (all dropout inactive)."""
         e = self._ensure(inputs.shape[0])
         e.forward(inputs, eps_g, eps_l, u)
-        x_mean, x_ls, xh_mean, xh_ls = self._split_outputs()
+        x_mean, x_ls, xh_mean, xh_ls = self._split_outputs(e)
         o = e.output
         return (x_mean, x_ls, o("z_x"), o("z_mean_x"), o("z_sig_x"), o("z_x_hat"), xh_mean, xh_ls,
                 o("z_mean_x_hat"), o("z_sig_x_hat"), o("y"), o("y_logits"), o("z_prior_mean"), o("z_prior_sig"))

@@ -155,6 +155,16 @@ class StepRunner:
         else:
             self._issue()
 
+    def metric_means(self, reset=True):
+        """Means of the step's loss terms over every step since the last reset (accumulated on the device inside the step), averaged
+        over the data-parallel ranks, and the number of steps."""
+        d, n = self.e.metric_means(reset)
+        if self.reducer.enabled:
+            names = list(d)
+            v = mean_scalars(torch.tensor([d[k] for k in names], device=self.e.device, dtype=torch.float32), self.group).cpu().tolist()
+            d = dict(zip(names, v))
+        return d, n
+
     def scalars(self):
         s = self.e.output("scalars")[:6]
         s = mean_scalars(s, self.group).cpu().tolist()
@@ -217,9 +227,10 @@ class Mean:
         self.name = name
         self.total, self.count = 0.0, 0
 
-    def __call__(self, value):
-        self.total += float(value)
-        self.count += 1
+    def __call__(self, value, count=1):
+        """`count` > 1: `value` is already the mean of that many samples (device-side running sums read at report time)."""
+        self.total += float(value) * count
+        self.count += count
 
     update_state = __call__
 
@@ -238,16 +249,16 @@ def make_metrics():
     return {f"{n}_{split}_loss": Mean(f"{n}_{split}_loss") for split in ("train", "test") for n in METRIC_NAMES}
 
 
-def _update_metrics(metrics, split, sc, gm):
-    metrics[f"x_recon_{split}_loss"](sc["recon_x"])
-    metrics[f"x_kl_{split}_loss"](sc["kl_x"])
+def _update_metrics(metrics, split, sc, gm, count=1):
+    metrics[f"x_recon_{split}_loss"](sc["recon_x"], count)
+    metrics[f"x_kl_{split}_loss"](sc["kl_x"], count)
     if "recon_x_hat" in sc:                 # (plain GMVAE updates x_recon / x_kl / y_kl only, vae/trainer.py:193-195)
-        metrics[f"x_hat_recon_{split}_loss"](sc["recon_x_hat"])
-        metrics[f"x_hat_kl_{split}_loss"](sc["kl_x_hat"])
+        metrics[f"x_hat_recon_{split}_loss"](sc["recon_x_hat"], count)
+        metrics[f"x_hat_kl_{split}_loss"](sc["kl_x_hat"], count)
     if gm:
-        metrics[f"y_kl_{split}_loss"](sc["y_kl"])
+        metrics[f"y_kl_{split}_loss"](sc["y_kl"], count)
     else:
-        metrics[f"total_kl_{split}_loss"](sc["total_kl"])
+        metrics[f"total_kl_{split}_loss"](sc["total_kl"], count)
 
 
 def _test_step(model, images, config=None, eps_g=None, eps_l=None, u=None):
@@ -347,10 +358,14 @@ def _runner_for(model, images, optimizer, config=None):
         if config is not None:
             kw["beta"] = float(config.get("beta", 40.0))
             kw["alpha"] = float(config.get("alpha", 40.0) or 40.0)
+            if config.get("seed") is not None:      # per-run, per-rank Philox stream of the in-kernel noise (the reference never seeds)
+                import os
+                kw["rng_stream"] = (int(config.get("seed")) * 8191 + int(os.environ.get("RANK", "0")) + 1) & 0x3FFFFF
         if optimizer is not None:
             kw["learning_rate"] = optimizer.learning_rate
         model.configure(**kw)
-        model.build(images.shape[0])
+        model.build(images.shape[0])            # (keeps weights, Adam moments and the iteration count of a previous engine)
+        model.engine.output("scalar_sums").zero_()
         r = StepRunner(model.engine, use_graph=bool(config.get("use_graph", True)) if config is not None else True)
         _RUNNERS[key] = r
     return r
@@ -396,10 +411,12 @@ def train_local_global_autoencoder(model, optimizer, dataset, train_dataset, tes
             images = images.cuda(non_blocking=True)
         train_step(model, images, optimizer, config)
         if step % report_every == 0:
-            # (the reference updates its train metrics every step inside the tf.function; reading the device scalars every
-            # step would put a host synchronisation into the hot loop, so they are sampled at the report steps)
-            sc = _RUNNERS[id(model)].scalars()
-            _update_metrics(metrics, "train", sc, gm)
+            # the reference updates its Keras Mean train metrics every step inside the tf.function (trainer.py:140-144); here the
+            # step accumulates the running sums on the device and the host reads + clears them at the report steps only
+            runner = _RUNNERS[id(model)]
+            means, n_steps = runner.metric_means(reset=True)
+            _update_metrics(metrics, "train", means, gm, count=max(n_steps, 1))
+            sc = runner.scalars()
             history.append((step, sc))
             print("Training time: {:.2f}".format(time.time() - start))
             start = time.time()

@@ -112,3 +112,133 @@ def test_cli_trains_evaluates_and_saves(tmp_path, capsys):
     assert hist[-1][1]["total"] < hist[0][1]["total"]                # six Adam steps on a fixed synthetic pool reduce the loss
     with np.load(str(out) + ".npz") as z:
         assert "encoder_x.e1.kernel" in z.files or any(k.endswith("e1.kernel") for k in z.files)
+
+
+def test_forward_calls_with_other_batch_sizes_keep_the_training_state():
+    """the reference's own usage - model(tf.zeros([8, ...])) before training (vae/main.py:74), visualiser decodes of other
+    batch sizes mid-training - must not replace the training engine: Adam moments, iteration count (staircase LR, bias correction)
+    and the weights stay with it; the other batch size is served by a forward engine fed with the current weights."""
+    kind, H, B = "lgvae", 32, 4
+    params, batch = make_case(kind, H, B, 4, seed_base=43)
+    x, eg, el = to_dev(batch["inputs"]), to_dev(batch["eps_g"]), to_dev(batch["eps_l"])
+    m = _model(kind, H)
+    m.set_weights_by_name(params)
+    m.build(B)
+    train_engine = m.engine
+    for _ in range(3):
+        m.engine.train_step(x, eg, el, None)
+    torch.cuda.synchronize()
+    v_before, p_before = m.engine.adam_v.clone(), m.engine.params.clone()
+    out8 = m(torch.zeros(8, H, H, 6, device="cuda"))                 # batch 8 != training batch 4
+    zx, zxh = m.encode(torch.zeros(2, H, H, 6, device="cuda"))
+    rec = m.decode(torch.zeros(16, 128, device="cuda"), torch.zeros(16, 128, device="cuda"))
+    torch.cuda.synchronize()
+    assert out8[0].shape[0] == 8 and zx.shape[0] == 2 and rec[0].shape[0] == 16
+    assert m.engine is train_engine and m.engine.B == B and m.engine.iterations == 3
+    assert torch.equal(m.engine.adam_v, v_before) and torch.equal(m.engine.params, p_before)
+    # the forward engine saw the TRAINED weights: decode(0) equals the training engine's own decode of zeros at its batch size
+    mine = m.decode(torch.zeros(B, 128, device="cuda"), torch.zeros(B, 128, device="cuda"))[0][0].clone()
+    assert torch.allclose(rec[0][0], mine, atol=1e-6)
+    # an explicit rebuild for a new TRAINING batch carries the optimizer state over as well
+    m.build(8)
+    assert m.engine.iterations == 3 and m.engine.B == 8 and float(m.engine.adam_v.abs().sum()) == float(v_before.abs().sum())
+
+
+def test_in_kernel_noise_is_fresh_on_every_forward_call():
+    """forward-only calls draw new Philox noise each time (tf.random does); the counter is bumped on the device by every
+    forward pass, not only by optimizer steps, and evaluation engines use their own stream."""
+    kind, H, B = "lggmvae", 32, 4
+    params, batch = make_case(kind, H, B, 4, seed_base=44)
+    m = _model(kind, H)
+    m.set_weights_by_name(params)
+    x = to_dev(batch["inputs"])
+    z1 = m.encode(x)[0].clone()
+    y1 = m.get_y(x)[0].clone()
+    z2 = m.encode(x)[0].clone()
+    y2 = m.get_y(x)[0].clone()
+    assert not torch.equal(z1, z2) and not torch.equal(y1, y2)
+    ev = m.eval_engine(2 * B)
+    ev.forward(torch.cat([x, x]), None, None, None)
+    torch.cuda.synchronize()
+    assert not torch.equal(ev.output("z_x")[:B], z2)
+
+
+def test_checkpoint_loaded_before_the_engine_exists_restores_the_optimizer(tmp_path):
+    """load_weights on a freshly constructed model (no engine yet - the normal state) must not drop the Adam moments and
+    the iteration count silently: they are applied when the engine is built; a truncated checkpoint raises."""
+    kind, H, B = "lggmvae", 32, 4
+    params, batch = make_case(kind, H, B, 4, seed_base=45)
+    x, eg, el, u = to_dev(batch["inputs"]), to_dev(batch["eps_g"]), to_dev(batch["eps_l"]), to_dev(batch["u"])
+    a = _model(kind, H)
+    a.set_weights_by_name(params)
+    a.build(B)
+    for _ in range(2):
+        a.engine.train_step(x, eg, el, u)
+    path = a.save_weights(str(tmp_path / "ckpt"), include_optimizer=True)
+    a.engine.train_step(x, eg, el, u)
+    torch.cuda.synchronize()
+    b = _model(kind, H)
+    b.load_weights(path)                       # no engine yet
+    assert b.engine is None
+    b.build(B)
+    assert b.engine.iterations == 2
+    b.engine.train_step(x, eg, el, u)
+    torch.cuda.synchronize()
+    assert torch.equal(a.engine.params, b.engine.params) and torch.equal(a.engine.adam_m, b.engine.adam_m)
+    import json
+    with np.load(path) as z:
+        blob = {k: z[k] for k in z.files}
+    assert json.loads(str(blob["keras_names"]))["encoder_x.y_dense.kernel"] == "lggm_vae/encoder/y_dense/kernel:0"
+    del blob["adam_v/decoder_x.d1.kernel"]
+    np.savez(str(tmp_path / "broken.npz"), **blob)
+    with pytest.raises(KeyError):
+        _model(kind, H).load_weights(str(tmp_path / "broken.npz"))
+
+
+def test_staircase_learning_rate_step_at_one_million_iterations():
+    """ExponentialDecay(lr, 1e6, 0.4, staircase=True) on optimizer.iterations (vae/main.py:67-68): the device-side schedule
+    (adam_prepare) is exercised across the 1e6 boundary through sv_set_iterations and compared with the oracle's Keras Adam."""
+    kind, H, B, lr = "lggmvae", 32, 2, float(np.float32(1e-3))
+    params, batch = make_case(kind, H, B, 4, seed_base=46)
+    x, eg, el, u = to_dev(batch["inputs"]), to_dev(batch["eps_g"]), to_dev(batch["eps_l"]), to_dev(batch["u"])
+    from helpers import make_engine
+    disp = {}
+    for it0 in (999_999, 1_000_000, 2_000_000):
+        e = make_engine(kind, H, B, "fp32", 10.0, lr=lr)
+        e.load_params(params)
+        e.iterations = it0
+        e.train_step(x, eg, el, u)
+        torch.cuda.synchronize()
+        assert e.iterations == it0 + 1
+        st = O.TrainState(params)
+        st.iterations = it0
+        O.train_step(st, kind, batch["inputs"], batch["eps_g"], batch["eps_l"], batch["u"], beta=10.0, lr=lr)
+        mine = e.get_params()
+        k = "decoder_x.d3.kernel"
+        dm, dr = mine[k] - params[k], st.params[k] - params[k]
+        assert rel_l2(dm, dr) < 0.02, (it0, rel_l2(dm, dr))
+        disp[it0] = float(np.linalg.norm(dm))
+    assert abs(disp[1_000_000] / disp[999_999] - 0.4) < 0.01            # the step at 1e6 (0-based iteration count)
+    assert abs(disp[2_000_000] / disp[1_000_000] - 0.4) < 0.01
+
+
+def test_train_metrics_accumulate_on_the_device_every_step():
+    """The reference's Keras Mean metrics see EVERY train step (vae/trainer.py:140-144); here the step adds its scalars to running sums
+    on the device, read and cleared at report time."""
+    kind, H, B = "lgvae", 32, 4
+    params, batch = make_case(kind, H, B, 4, seed_base=47)
+    x, eg, el = to_dev(batch["inputs"]), to_dev(batch["eps_g"]), to_dev(batch["eps_l"])
+    from helpers import make_engine
+    e = make_engine(kind, H, B, "fp32", 5.0)
+    e.load_params(params)
+    e.output("scalar_sums").zero_()
+    per_step = []
+    for _ in range(4):
+        e.train_step(x, eg, el, None)
+        torch.cuda.synchronize()
+        per_step.append(e.scalars())
+    means, n = e.metric_means(reset=True)
+    assert n == 4
+    for k in means:
+        assert abs(means[k] - np.mean([s[k] for s in per_step])) <= 1e-5 * max(1.0, abs(means[k])), k
+    assert e.metric_means()[1] == 0

@@ -182,3 +182,24 @@ def test_svhn_mat_reader_host_side(tmp_path):
     assert len(nx) == 10                                 # svhn_no_extra
     with pytest.raises(FileNotFoundError):
         data.SvhnBatches(str(tmp_path / "missing"), "train", 4, None)
+
+
+def test_keras_weight_name_map_covers_every_variable():
+    """Checkpoint interop (vae/trainer.py:421): every variable of every model kind has a Keras HDF5 name, names are unique, layer counters
+    follow the creation order of vae/model.py (conv2d .. conv2d_13, dense .. dense_5 for LGVae)."""
+    from oracle import splitvae_oracle as O
+    from splitvae_b200.model import keras_weight_names
+    for kind, n in (("lgvae", 40), ("lggmvae", 54), ("gmvae", 34)):
+        names = keras_weight_names(kind)
+        ours = [f"{name}.{part}" for name, _, _, _ in O.layer_table(kind, 32, 32) for part in ("kernel", "bias")]
+        assert sorted(names) == sorted(ours) and len(names) == n
+        assert len(set(names.values())) == n
+    lg = keras_weight_names("lgvae")
+    assert lg["encoder_x.e1.kernel"] == "lg_vae/encoder/conv2d/kernel:0"
+    assert lg["encoder_x_hat.e4_sd.bias"] == "lg_vae/encoder_1/dense_3/bias:0"
+    assert lg["decoder_x.d1.kernel"] == "lg_vae/decoder/dense_4/kernel:0"
+    assert lg["decoder_x_hat.d5.kernel"] == "lg_vae/decoder_1/conv2d_13/kernel:0"
+    gm = keras_weight_names("lggmvae")
+    assert gm["encoder_x.y_dense.kernel"] == "lggm_vae/encoder/y_dense/kernel:0"
+    assert gm["encoder_x.z_sig.bias"] == "lggm_vae/encoder/dense_5/bias:0"
+    assert gm["encoder_x_hat.e1.kernel"] == "lggm_vae/encoder_1/conv2d_3/kernel:0"
