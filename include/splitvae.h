@@ -155,6 +155,15 @@ sv_status sv_adam_segment(sv_handle* h, int32_t segment, void* stream);
 sv_status sv_train_step(sv_handle* h, const float* inputs_dev, const float* eps_g_dev,
                         const float* eps_l_dev, const float* u_dev, void* stream);
 
+/* The whole train step as a CUDA graph owned by the handle, for hosts without a graph API of their own (the reference's step is
+ * one @tf.function graph execution, vae/trainer.py:120,146).  sv_capture_graph records ONE sv_train_step issued on `stream` (a
+ * non-default stream; nothing executes) with the given device pointers baked in: keep those buffers alive and refill them in
+ * place between replays; NULL noise pointers keep the in-kernel Philox draws, which advance on the device at every replay.
+ * sv_replay launches the captured step n_steps times on `stream`.  Re-capturing replaces the previous graph. */
+sv_status sv_capture_graph(sv_handle* h, const float* inputs_dev, const float* eps_g_dev, const float* eps_l_dev,
+                           const float* u_dev, void* stream);
+sv_status sv_replay(sv_handle* h, int32_t n_steps, void* stream);
+
 /* Device pointer of a named result (valid after sv_bind; contents after the producing call). */
 sv_status sv_output_ptr(const sv_handle* h, int32_t which, void** dev_ptr, int64_t* count_floats);
 
@@ -184,6 +193,16 @@ sv_status sv_adam_flat(float* p_dev, const float* g_dev, float* m_dev, float* v_
  * u8_dev [B,H,W,3], perm_dev [B,(H/p)*(W/p)] int32 -> inputs_dev [B,H,W,6] fp32. */
 sv_status sv_stage_scramble(const uint8_t* u8_dev, const int32_t* perm_dev, float* inputs_dev,
                             int32_t batch, int32_t height, int32_t width, int32_t patch, void* stream);
+
+/* CelebA preprocessing (vae/data.py:82-87: decode_jpeg -> resize_with_crop_or_pad(178,178) -> tf.image.resize([64,64]) -> /255*2-1)
+ * fused with the scramble: u8_dev [B,Hs,Ws,3] decoded images, centre crop [crop_y, crop_y+crop_h) x [crop_x, crop_x+crop_w), bilinear
+ * resize (half-pixel centres, no antialiasing) to height x width, perm_dev as above -> inputs_dev [B,height,width,6] fp32. */
+sv_status sv_stage_resize_scramble(const uint8_t* u8_dev, const int32_t* perm_dev, float* inputs_dev, int32_t batch, int32_t src_height,
+                                   int32_t src_width, int32_t crop_y, int32_t crop_x, int32_t crop_h, int32_t crop_w, int32_t height,
+                                   int32_t width, int32_t patch, void* stream);
+/* tf.random.shuffle of the patches (augmentation.py:49) on the device: perm_dev [B, n_patch] int32, one uniform permutation per image
+ * (n_patch <= 4096), Philox stream (seed, step). */
+sv_status sv_draw_permutations(int32_t* perm_dev, int32_t batch, int32_t n_patch, uint64_t seed, uint64_t step, void* stream);
 
 /* ---- test hooks: run ONE layer of the plan with the reference (SIMT) or the tensor-core kernel on the
  * handle's own buffers, so the parity tests can check each tcgen05 kernel against its reference. --------- */

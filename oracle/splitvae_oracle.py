@@ -416,6 +416,18 @@ def scramble(x_hwc, p, perm):
     return np.concatenate([x_hwc, x_aug], axis=2)
 
 
+def celeba_preprocess(u8_hwc, size=64, crop=178):
+    """vae/data.py:82-87 on one decoded image [Hs,Ws,3] uint8: tf.image.resize_with_crop_or_pad(image, 178, 178) (centre crop, offset
+    (Hs-178)//2 - zero padding when smaller is not needed for the 218x178 aligned CelebA files), tf.image.resize(image, [64, 64])
+    (TF2 default: bilinear, half-pixel centres, NO antialiasing == F.interpolate(align_corners=False, antialias=False)), /255*2-1."""
+    a = np.asarray(u8_hwc)
+    Hs, Ws = a.shape[:2]
+    cy, cx = (Hs - crop) // 2, (Ws - crop) // 2
+    t = torch.tensor(a[cy:cy + crop, cx:cx + crop].astype(np.float64)).permute(2, 0, 1)[None]
+    r = F.interpolate(t, size=(size, size), mode="bilinear", align_corners=False, antialias=False)[0].permute(1, 2, 0)
+    return (r / 255.0 * 2 - 1).numpy().astype(np.float32)
+
+
 def synthetic_batch(B, H, p, y_size=30, seed_base=0):
     """Inputs / noise of BASELINE.md section 5 (seeds 0..4 offset by seed_base)."""
     k = np.random.default_rng(seed_base + 0).integers(0, 256, size=(B, H, H, 3), dtype=np.uint8)

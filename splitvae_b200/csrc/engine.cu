@@ -111,6 +111,8 @@ struct sv_handle {
   int CSP[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
   ColsumTable* cs[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   cudaEvent_t ev_opt_fork2 = nullptr;
+  cudaGraph_t graph = nullptr;            // sv_capture_graph: one captured sv_train_step
+  cudaGraphExec_t graph_exec = nullptr;
 };
 
 namespace {
@@ -716,6 +718,8 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
 
 sv_status sv_destroy(sv_handle* h) {
   if (h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
     tc_pack_table_destroy(h->pack);
     for (int seg = 0; seg < sv_handle::kSegs; ++seg) tc_pack_table_destroy(h->pack_seg[seg]);
     if (h->ev_opt_fork2) cudaEventDestroy(h->ev_opt_fork2);
@@ -985,6 +989,43 @@ sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, c
   return SV_OK;
 }
 
+sv_status sv_capture_graph(sv_handle* h, const float* inputs, const float* eps_g, const float* eps_l, const float* u, void* stream) {
+  REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!s) return fail(h, SV_ERR_INVALID, "sv_capture_graph needs a non-default stream");
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, SV_ERR_DEVICE, "cudaStreamBeginCapture failed");
+  }
+  const long long before = h->launches;
+  const sv_status st = sv_train_step(h, inputs, eps_g, eps_l, u, stream);
+  h->launches = before;                                    // (capture records, nothing ran)
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(s, &g);
+  if (st != SV_OK) { if (g) cudaGraphDestroy(g); return st; }
+  if (ce != cudaSuccess || !g) { cudaGetLastError(); return fail(h, SV_ERR_DEVICE, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce)); }
+  h->graph = g;
+  if (cudaGraphInstantiate(&h->graph_exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, SV_ERR_DEVICE, "cudaGraphInstantiate failed");
+  }
+  return SV_OK;
+}
+
+sv_status sv_replay(sv_handle* h, int32_t n_steps, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!h->graph_exec) return fail(h, SV_ERR_STATE, "sv_capture_graph has not been called");
+  if (n_steps < 0) return fail(h, SV_ERR_INVALID, "n_steps < 0");
+  for (int i = 0; i < n_steps; ++i)
+    if (cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, SV_ERR_DEVICE, "cudaGraphLaunch failed");
+    }
+  return SV_OK;
+}
+
 sv_status sv_output_ptr(const sv_handle* hc, int32_t which, void** ptr, int64_t* count) {
   sv_handle* h = const_cast<sv_handle*>(hc);
   if (!h || !ptr || !count) return SV_ERR_INVALID;
@@ -1138,6 +1179,21 @@ int32_t sv_debug_halo_trace(uint64_t* out_host, int32_t max_ctas) {
 sv_status sv_stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int32_t B, int32_t H, int32_t W, int32_t p, void* stream) {
   if (!u8 || !perm || !inputs || B < 1 || p < 1 || H % p || W % p) return SV_ERR_INVALID;
   stage_scramble(u8, perm, inputs, B, H, W, p, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+sv_status sv_stage_resize_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int32_t B, int32_t Hs, int32_t Ws,
+                                   int32_t crop_y, int32_t crop_x, int32_t crop_h, int32_t crop_w, int32_t H, int32_t W, int32_t p, void* stream) {
+  if (!u8 || !perm || !inputs || B < 1 || p < 1 || H % p || W % p || crop_y < 0 || crop_x < 0 || crop_h < 1 || crop_w < 1 ||
+      crop_y + crop_h > Hs || crop_x + crop_w > Ws)
+    return SV_ERR_INVALID;
+  stage_resize_scramble(u8, perm, inputs, B, Hs, Ws, crop_y, crop_x, crop_h, crop_w, H, W, p, (cudaStream_t)stream);
+  return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
+}
+
+sv_status sv_draw_permutations(int32_t* perm, int32_t B, int32_t n_patch, uint64_t seed, uint64_t step, void* stream) {
+  if (!perm || B < 1 || n_patch < 1 || n_patch > 4096) return SV_ERR_INVALID;
+  draw_permutations(perm, B, n_patch, seed, step, (cudaStream_t)stream);
   return cudaPeekAtLastError() == cudaSuccess ? SV_OK : SV_ERR_DEVICE;
 }
 

@@ -564,6 +564,81 @@ __global__ void stage_scramble_kernel(const uint8_t* __restrict__ u8, const int3
     }
   }
 }
+// CelebA staging (vae/data.py:82-87 + augmentation.py:43-57 in one pass): centre crop of the decoded uint8 image
+// (tf.image.resize_with_crop_or_pad to 178x178), bilinear resize to H x W (tf.image.resize: half-pixel centres, no antialiasing, edge
+// clamp), /255*2-1, and the patch scramble - x_hat is the resized image sampled at the permuted patch's pixel.
+__device__ __forceinline__ void bilinear_rgb(const uint8_t* img, int Ws, int cy, int cx, int ch, int cw, float sy, float sx, int oy, int ox, float* out) {
+  const float fy = ((float)oy + 0.5f) * sy - 0.5f, fx = ((float)ox + 0.5f) * sx - 0.5f;
+  const float y0f = floorf(fy), x0f = floorf(fx);
+  const float wy = fy - y0f, wx = fx - x0f;
+  const int y0 = min(max((int)y0f, 0), ch - 1), y1 = min(max((int)y0f + 1, 0), ch - 1);
+  const int x0 = min(max((int)x0f, 0), cw - 1), x1 = min(max((int)x0f + 1, 0), cw - 1);
+  const uint8_t* r0 = img + ((size_t)(cy + y0) * Ws + cx) * 3;
+  const uint8_t* r1 = img + ((size_t)(cy + y1) * Ws + cx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float top = (float)r0[x0 * 3 + c] + ((float)r0[x1 * 3 + c] - (float)r0[x0 * 3 + c]) * wx;
+    const float bot = (float)r1[x0 * 3 + c] + ((float)r1[x1 * 3 + c] - (float)r1[x0 * 3 + c]) * wx;
+    out[c] = (top + (bot - top) * wy) / 255.f * 2.f - 1.f;         // vae/data.py:86
+  }
+}
+__global__ void stage_resize_scramble_kernel(const uint8_t* __restrict__ u8, const int32_t* __restrict__ perm, float* __restrict__ inputs,
+                                             int B, int Hs, int Ws, int cy, int cx, int ch, int cw, int H, int W, int p) {
+  const long long total = (long long)B * H * W;
+  const int G = W / p, npatch = (H / p) * G;
+  const float sy = (float)ch / (float)H, sx = (float)cw / (float)W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W), y = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
+    const int q = perm[(long long)b * npatch + (y / p) * G + (x / p)];
+    const int py = (q / G) * p + y % p, px = (q % G) * p + x % p;
+    const uint8_t* img = u8 + (size_t)b * Hs * Ws * 3;
+    float* o = inputs + idx * 6;
+    bilinear_rgb(img, Ws, cy, cx, ch, cw, sy, sx, y, x, o);
+    bilinear_rgb(img, Ws, cy, cx, ch, cw, sy, sx, py, px, o + 3);
+  }
+}
+void stage_resize_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int Hs, int Ws, int cy, int cx, int ch, int cw,
+                           int H, int W, int p, cudaStream_t s) {
+  const long long total = (long long)B * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_resize_scramble_kernel<<<(int)blocks, 256, 0, s>>>(u8, perm, inputs, B, Hs, Ws, cy, cx, ch, cw, H, W, p);
+}
+
+// One uniform random permutation of n patches per image (tf.random.shuffle, augmentation.py:49), drawn on the device: Philox keys,
+// bitonic sort of (key, index) in shared memory, one block per image.  n <= 4096 (64x64 image, patch_size 1).
+__global__ void __launch_bounds__(1024) draw_permutations_kernel(int32_t* __restrict__ perm, int n, int npow2, unsigned long long seed,
+                                                                 unsigned long long step) {
+  extern __shared__ unsigned long long keys[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    unsigned long long k = ~0ull;                       // padding sorts last
+    if (i < n) {
+      const U4 r = philox4x32(U4{(uint32_t)i, (uint32_t)b, (uint32_t)step, (uint32_t)(step >> 32)}, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x7065726Du);
+      k = ((unsigned long long)r.x << 32 | (unsigned long long)(r.y & 0xFFFFF000u)) | (unsigned long long)i;     // 52 random bits, index in the low 12
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= npow2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < npow2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = keys[lo], c = keys[hi];
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[(long long)b * n + i] = (int32_t)(keys[i] & 0xFFFull);
+}
+void draw_permutations(int32_t* perm, int B, int n, unsigned long long seed, unsigned long long step, cudaStream_t s) {
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  const int threads = npow2 / 2 < 32 ? 32 : npow2 / 2 > 1024 ? 1024 : npow2 / 2;
+  draw_permutations_kernel<<<B, threads, (size_t)npow2 * sizeof(unsigned long long), s>>>(perm, n, npow2, seed, step);
+}
+
 void stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int H, int W, int p, cudaStream_t s) {
   const long long total = (long long)B * H * W;
   long long blocks = (total + 255) / 256;

@@ -86,5 +86,10 @@ void adam_apply(float* p, const float* g, float* m, float* v, long long n, const
                 cudaStream_t s);
 
 void stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int H, int W, int p, cudaStream_t s);
+// CelebA: centre crop [cy, cy+ch) x [cx, cx+cw) of a [B,Hs,Ws,3] uint8 batch, bilinear resize to H x W, scaling and scramble in one pass
+void stage_resize_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int Hs, int Ws, int cy, int cx, int ch, int cw,
+                           int H, int W, int p, cudaStream_t s);
+// uniform patch permutations [B, n] (n <= 4096), Philox stream (seed, step)
+void draw_permutations(int32_t* perm, int B, int n, unsigned long long seed, unsigned long long step, cudaStream_t s);
 
 }  // namespace sv

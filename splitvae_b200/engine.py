@@ -144,6 +144,16 @@ class Engine:
         self._check_inputs(inputs)
         check(self.lib.sv_train_step(self.h, _ptr(inputs), _ptr(eps_g), _ptr(eps_l), _ptr(u), _stream()), self.h, "sv_train_step")
 
+    def capture_graph(self, inputs, eps_g=None, eps_l=None, u=None):
+        """Records one train step into the library's own CUDA graph (sv_capture_graph) on the current (non-default) stream; the
+        tensors are baked in by address: refill them in place between replays."""
+        self._check_inputs(inputs)
+        self._graph_refs = (inputs, eps_g, eps_l, u)
+        check(self.lib.sv_capture_graph(self.h, _ptr(inputs), _ptr(eps_g), _ptr(eps_l), _ptr(u), _stream()), self.h, "sv_capture_graph")
+
+    def replay(self, n_steps=1):
+        check(self.lib.sv_replay(self.h, int(n_steps), _stream()), self.h, "sv_replay")
+
     def decode(self, z_x, z_x_hat):
         check(self.lib.sv_decode(self.h, _ptr(z_x), _ptr(z_x_hat), _stream()), self.h, "sv_decode")
 

@@ -53,7 +53,7 @@ def main(argv=None):
     from . import data, trainer
     from .augmentation import Augmentator
     from .model import GMVae, LGGMVae, LGVae
-    augmentor = Augmentator(type=config.augmentation, size=config.patch_size)
+    augmentor = Augmentator(type=config.augmentation, size=config.patch_size, seed=config.seed)
     real = bool(config.data_root)
     train_dataset, test_dataset, input_shape = data.get_dataset(dataset=config.dataset, get_label=real and config.label,
                                                                 batch_size=config.batch_size, augmentor=augmentor,

@@ -135,3 +135,28 @@ def test_gradients_scale_exactly_with_world_size():
     _, gb = _step(b, x, eg, el, u)
     # the loss gradient enters the network scaled by 1/(B*world): a power of two, so every bf16 / fp32 rounding is unchanged
     assert torch.equal(ga, gb * 2)
+
+
+def test_c_abi_graph_capture_and_replay_equal_eager_steps():
+    """sv_capture_graph / sv_replay: a host without torch's graph API gets the captured step from the C-ABI.  Three
+    replays from the same state are bit-identical to three eager sv_train_step calls (explicit noise: both see the same epsilon)."""
+    model, H, B = "lgvae", 64, 32
+    x, eg, el, u = _inputs(model, H, B, seed=3)
+    e = make_engine(model, H, B, "bf16x3", 120.0)
+    e.init_params(seed=10)
+    p0 = e.params.clone()
+    for _ in range(3):
+        e.train_step(x, eg, el, u)
+    torch.cuda.synchronize()
+    eager = e.params.clone()
+    e.params.copy_(p0); e.adam_m.zero_(); e.adam_v.zero_(); e.iterations = 0
+    e.params_updated()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        e.capture_graph(x, eg, el, u)
+        assert e.iterations == 0 and torch.equal(e.params, p0)          # capture records, nothing ran
+        e.replay(3)
+    s.synchronize()
+    assert e.iterations == 3
+    assert torch.equal(e.params, eager)

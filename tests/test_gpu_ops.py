@@ -116,3 +116,62 @@ def test_stage_scramble_matches_the_reference_source_vectors():
         scale = lambda k: (np.asarray(k, np.float64).reshape(H, H, 3) / 255.0 * 2 - 1).astype(np.float32)   # vae/data.py:52
         assert np.array_equal(out[..., :3], scale(c["x"])), (H, p)
         assert np.array_equal(out[..., 3:], scale(c["x_hat"])), (H, p)
+
+
+def test_celeba_resize_scramble_kernel_matches_the_oracle():
+    """sv_stage_resize_scramble (vae/data.py:82-87 + augmentation.py:43-57 in one kernel) against the oracle's preprocess + scramble."""
+    from splitvae_b200.augmentation import Augmentator
+    rng = np.random.default_rng(11)
+    B, Hs, Ws, p = 3, 218, 178, 8
+    u8 = rng.integers(0, 256, size=(B, Hs, Ws, 3), dtype=np.uint8)
+    perms = np.stack([rng.permutation((64 // p) ** 2) for _ in range(B)]).astype(np.int32)
+    aug = Augmentator("scramble", p)
+    out = aug.scramble_resized(torch.from_numpy(u8).cuda(), 64, 64, perms=torch.from_numpy(perms).cuda()).cpu().numpy()
+    for b in range(B):
+        ref = O.scramble(O.celeba_preprocess(u8[b]), p, perms[b])
+        assert np.abs(out[b] - ref).max() < 2e-5, b
+
+
+def test_device_permutation_draw_is_uniform_and_reproducible():
+    """sv_draw_permutations (tf.random.shuffle of the patches, augmentation.py:49): every row is a permutation, rows differ, the same
+    (seed, step) reproduces, and the position of a given patch is uniform (chi-square over 4096 draws of 16 patches)."""
+    from splitvae_b200.augmentation import Augmentator
+    for H, p in ((32, 1), (64, 1), (64, 8), (32, 4)):
+        a = Augmentator("scramble", p, seed=5)
+        perm = a.draw_permutations(16, H, H).cpu().numpy()
+        n = (H // p) ** 2
+        assert perm.shape == (16, n) and (np.sort(perm, axis=1) == np.arange(n)).all()
+        assert len({r.tobytes() for r in perm}) == 16
+        b = Augmentator("scramble", p, seed=5)
+        assert (b.draw_permutations(16, H, H).cpu().numpy() == perm).all()
+        assert not (a.draw_permutations(16, H, H).cpu().numpy() == perm).all()       # the next draw differs
+    a = Augmentator("scramble", 8, seed=9)
+    pos = a.draw_permutations(4096, 32, 32).cpu().numpy()            # 16 patches
+    counts = np.stack([(pos == v).sum(axis=0) for v in range(16)])    # [value, position]
+    chi2 = ((counts - 256.0) ** 2 / 256.0).sum()                      # 225 degrees of freedom: mean 225, sd ~21
+    assert 120 < chi2 < 340, chi2
+
+
+def test_celeba_reader_end_to_end(tmp_path):
+    """data.CelebaBatches on a miniature img_align_celeba/ directory of JPEGs written here: test split = first tenth of the sorted
+    files, one decode pass cached as uint8, batches = the oracle's preprocess of the decoded pixels, scrambled."""
+    from PIL import Image
+    from splitvae_b200 import data
+    from splitvae_b200.augmentation import Augmentator
+    rng = np.random.default_rng(3)
+    d = tmp_path / "img_align_celeba"
+    d.mkdir()
+    smooth = lambda: np.clip(np.cumsum(np.cumsum(rng.normal(0, 2.0, (218, 178, 3)), axis=0), axis=1) * 0.05 + 128, 0, 255).astype(np.uint8)
+    for i in range(20):
+        Image.fromarray(smooth()).save(d / f"{i + 1:06d}.jpg", quality=95)
+    train, test, shape = data.get_dataset("celeba64", batch_size=4, augmentor=Augmentator("scramble", 8, seed=1), data_root=str(tmp_path))
+    assert shape == [-1, 64, 64, 3] and len(test) == 2 and len(train) == 18
+    batches = list(test)
+    assert len(batches) == 1 and tuple(batches[0].shape) == (2, 64, 64, 6)
+    decoded = np.asarray(Image.open(d / "000001.jpg").convert("RGB"))
+    ref = O.celeba_preprocess(decoded)
+    assert np.abs(batches[0][0, ..., :3].cpu().numpy() - ref).max() < 2e-5
+    it = iter(train)
+    seen = [next(it) for _ in range(6)]                              # repeats past one epoch (18 images, batch 4)
+    assert all(tuple(b.shape) == (4, 64, 64, 6) for b in seen)
+    assert float(seen[0].abs().max()) <= 1.0 + 1e-6

@@ -274,3 +274,20 @@ def test_scramble_matches_the_reference_source():
         assert out.shape == (H, H, 6)
         assert np.array_equal(out[..., :3], x)
         assert np.array_equal(out[..., 3:], np.asarray(c["x_hat"], np.float64).reshape(H, H, 3)), (H, p)
+
+
+def test_celeba_preprocess_known_answers():
+    """vae/data.py:82-87: centre crop 178, bilinear resize to 64 with half-pixel centres and no antialiasing, /255*2-1.  Bilinear
+    interpolation reproduces a linear ramp exactly at the half-pixel sample positions; a constant image stays constant."""
+    Hs, Ws = 218, 178
+    yy, xx = np.meshgrid(np.arange(Hs), np.arange(Ws), indexing="ij")
+    img = np.stack([yy, xx, np.full_like(yy, 77)], axis=2).astype(np.uint8)        # (values < 256: y up to 217, x up to 177)
+    out = O.celeba_preprocess(img)
+    assert out.shape == (64, 64, 3) and out.dtype == np.float32
+    s = 178 / 64.0
+    cy = (Hs - 178) // 2
+    for o in (0, 1, 31, 63):
+        src = (o + 0.5) * s - 0.5                                  # sample position inside the crop
+        assert abs(out[o, 5, 0] - ((cy + src) / 255.0 * 2 - 1)) < 1e-5            # row ramp (crop offset 20)
+        assert abs(out[5, o, 1] - (src / 255.0 * 2 - 1)) < 1e-5                   # column ramp (crop offset 0)
+    assert np.allclose(out[..., 2], 77 / 255.0 * 2 - 1, atol=1e-6)
