@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the secondary single-bf16 throughput measurement")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the short device-resident lines of the other BASELINE.json configs")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="data parallel through the bucketed NCCL all-reduce even when NVLS multicast is available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hang-dump", type=int, default=0, help="dump all Python stacks after this many seconds (debugging)")
     args = ap.parse_args()
@@ -198,10 +199,15 @@ def main():
     dev = torch.device("cuda", local_rank)
     K, Wm = args.steps, max(3, args.warmup)
 
+    nvls = None
+    if world > 1 and not args.nccl:
+        from splitvae_b200.parallel import NvlsArenas
+        if NvlsArenas.available():
+            nvls = NvlsArenas()
     e = Engine(model=model, height=H, width=H, batch=B, beta=beta, alpha=alpha, learning_rate=1e-4, world_size=world,
-               precision=args.precision, rng_stream=rank)
+               precision=args.precision, rng_stream=rank, arena_alloc=nvls.alloc if nvls else None)
     e.init_params(seed=5)  # same seed on every rank: replicated weights
-    runner = StepRunner(e, use_graph=not args.no_graph)
+    runner = StepRunner(e, use_graph=not args.no_graph, nvls=nvls)
     aug = Augmentator("scramble", patch)
 
     # synthetic data: a pool of pinned uint8 batches (distinct per rank) + per-image patch permutations
@@ -461,6 +467,8 @@ def main():
             "warmup": Wm, "ms_per_step": 1000.0 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": desc, "model": model, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none" if world == 1 else "fused NVLS multimem reduce-scatter + Adam(shard) + all-gather kernel" if nvls
+                                             else "bucketed NCCL all-reduce (3 buckets) overlapped with backward"),
                        "cuda_graph": not args.no_graph, "l2": "per-step working set (activations + weights + Adam state) exceeds the 126 MB L2; no flush between steps",
                        "noise": "in-kernel Philox", "precision": args.precision, "operands": OPERANDS[args.precision]},
             "e2e": {"value": total_images / t_e2e, "unit": "images/s", "h2d_bytes_per_step": int(dev_u8.numel() + dev_perm.numel() * 4),

@@ -151,6 +151,17 @@ sv_status sv_adam_step(sv_handle* h, void* stream);
  * sv_adam_step == sv_adam_segment(0) ; ... ; sv_adam_segment(n-1). */
 sv_status sv_adam_segment(sv_handle* h, int32_t segment, void* stream);
 
+/* Data parallel over NVLS (NVLink 5 / NVSwitch multicast): the gradient all-reduce FUSED with the optimizer.  mc_grads_dev / mc_params_dev
+ * are the MULTICAST addresses of symmetric allocations that back every rank's gradient / parameter arena (the arenas given to sv_bind
+ * must be those allocations).  One kernel per arena range of the segment: multimem.ld_reduce sums the ranks' gradients in the switch
+ * (reduce-scatter), this rank applies Keras Adam to its 1/world shard (its m / v shard only), multimem.st writes the new weights into
+ * every rank's arena (all-gather).  The caller provides the cross-rank ordering: a barrier after the segment's backward pass and
+ * before this call, another after it and before sv_repack_segment (the operand re-pack of the segment's layers) or any other read of
+ * the parameters.  Segment 0 advances the step counter; segments in order 0..n-1, once per step, on every rank. */
+sv_status sv_nvls_adam_segment(sv_handle* h, int32_t segment, const float* mc_grads_dev, float* mc_params_dev, int32_t rank,
+                               int32_t world, int32_t write_reduced_grads, void* stream);
+sv_status sv_repack_segment(sv_handle* h, int32_t segment, void* stream);
+
 /* Whole train_step_* (vae/trainer.py:120-144 / 146-173) = forward + loss + all segments + Adam. */
 sv_status sv_train_step(sv_handle* h, const float* inputs_dev, const float* eps_g_dev,
                         const float* eps_l_dev, const float* u_dev, void* stream);

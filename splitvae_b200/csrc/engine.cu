@@ -958,6 +958,33 @@ sv_status sv_adam_segment(sv_handle* h, int32_t seg, void* stream) {
   return check_launch(h, "sv_adam_segment");
 }
 
+sv_status sv_nvls_adam_segment(sv_handle* h, int32_t seg, const float* mc_grads, float* mc_params, int32_t rank, int32_t world,
+                               int32_t write_reduced_grads, void* stream) {
+  REQUIRE_BOUND(h);
+  if (seg < 0 || seg >= sv_handle::kSegs) return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
+  if (!mc_grads || !mc_params || world < 1 || rank < 0 || rank >= world) return fail(h, SV_ERR_INVALID, "bad multicast pointers / rank");
+  if (world != h->cfg.world_size) return fail(h, SV_ERR_INVALID, "world %d differs from the handle's world_size %d (gradient scale)", world, h->cfg.world_size);
+  cudaStream_t s = (cudaStream_t)stream;
+  AdamState* st = (AdamState*)bp(h, h->ADAM);
+  if (seg == 0) {
+    adam_prepare(st, h->cfg.learning_rate, h->gm, s);
+    h->launches += 1;
+  }
+  for (const auto& r : h->seg_ranges[seg]) {
+    nvls_adam(mc_grads, mc_params, h->params, h->adam_m, h->adam_v, write_reduced_grads ? const_cast<float*>(mc_grads) : nullptr, r.first, r.second,
+              rank, world, st, s);
+    h->launches += 1;
+  }
+  return check_launch(h, "sv_nvls_adam_segment");
+}
+
+sv_status sv_repack_segment(sv_handle* h, int32_t seg, void* stream) {
+  REQUIRE_BOUND(h);
+  if (seg < 0 || seg >= sv_handle::kSegs) return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
+  if (h->use_tc) h->launches += tc_repack_all(h->pack_seg[seg], h->params, (cudaStream_t)stream);
+  return check_launch(h, "sv_repack_segment");
+}
+
 sv_status sv_adam_step(sv_handle* h, void* stream) {
   for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
     const sv_status st = sv_adam_segment(h, seg, stream);

@@ -544,6 +544,70 @@ void adam_apply(float* p, const float* g, float* m, float* v, long long n, const
   adam_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, n, st, alpha_host);
 }
 
+// ------------------------------------------------------------------ data parallel: reduce-scatter + Adam(shard) + all-gather in ONE kernel
+// over NVLS multicast memory (NVLink 5 / NVSwitch).  Every rank's gradient arena and parameter arena are symmetric allocations mapped
+// behind one multicast address each: multimem.ld_reduce on the gradient multicast address returns the SUM over all ranks (the switch
+// reduces in flight = the reduce-scatter), the rank applies Keras Adam to ITS 1/world shard of the range (m, v live only for that
+// shard: 1/world of the optimizer traffic), and multimem.st on the parameter multicast address writes the new weights into every
+// rank's arena (the all-gather).  No NCCL kernel, no second pass over the gradients; a few small CTAs that co-reside with the
+// persistent convolution kernels instead of taking whole SMs.  The caller brackets the kernel with cross-rank barriers.
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int kNvlsUnroll = 4;      // independent multimem.ld_reduce round trips (SM -> switch -> every GPU -> SM, a few us) in flight per thread
+__global__ void __launch_bounds__(256) nvls_adam_kernel(const float* __restrict__ mc_grads, float* __restrict__ mc_params,
+                                                        const float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                                                        float* __restrict__ mc_grads_out, long long off, long long cnt, int rank, int world,
+                                                        const AdamState* __restrict__ st) {
+  const float alpha = st->alpha;
+  const long long n4 = cnt >> 2;                                   // (arena slots are multiples of 64 floats)
+  const long long per = (n4 + world - 1) / world;
+  const long long begin = (long long)rank * per, end = begin + per < n4 ? begin + per : n4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = begin + blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < end; i0 += stride * kNvlsUnroll) {
+    float4 g[kNvlsUnroll];
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < end) g[u] = multimem_ld_reduce_f32x4(mc_grads + off + 4 * i);      // sum over ranks, reduced by the switch
+    }
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= end) break;
+      const long long e = off + 4 * i;
+      float4 pp = *reinterpret_cast<const float4*>(params + e);
+      float4 mm = *reinterpret_cast<const float4*>(m + e), vv = *reinterpret_cast<const float4*>(v + e);
+      adam_one(pp.x, g[u].x, mm.x, vv.x, alpha);
+      adam_one(pp.y, g[u].y, mm.y, vv.y, alpha);
+      adam_one(pp.z, g[u].z, mm.z, vv.z, alpha);
+      adam_one(pp.w, g[u].w, mm.w, vv.w, alpha);
+      *reinterpret_cast<float4*>(m + e) = mm;
+      *reinterpret_cast<float4*>(v + e) = vv;
+      multimem_st_f32x4(mc_params + e, pp);                           // new weights into every rank's arena
+      if (mc_grads_out) multimem_st_f32x4(mc_grads_out + e, g[u]);    // (tests: leave the reduced gradient in every arena)
+    }
+  }
+}
+
+void nvls_adam(const float* mc_grads, float* mc_params, const float* params, float* m, float* v, float* mc_grads_out, long long off,
+               long long cnt, int rank, int world, const AdamState* st, cudaStream_t s) {
+  const long long per = ((cnt >> 2) + world - 1) / world;
+  // small CTAs (256 threads, ~32 registers, no shared memory) that co-reside with the persistent convolution kernels; enough of
+  // them to keep ~100 k vector loads in flight across the switch
+  long long blocks = (per + 256 * kNvlsUnroll - 1) / (256 * kNvlsUnroll);
+  if (blocks > 128) blocks = 128;
+  if (blocks < 1) blocks = 1;
+  nvls_adam_kernel<<<(int)blocks, 256, 0, s>>>(mc_grads, mc_params, params, m, v, mc_grads_out, off, cnt, rank, world, st);
+}
+
 // ------------------------------------------------------------------ scramble staging
 __global__ void stage_scramble_kernel(const uint8_t* __restrict__ u8, const int32_t* __restrict__ perm,
                                       float* __restrict__ inputs, int B, int H, int W, int p) {

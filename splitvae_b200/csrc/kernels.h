@@ -85,6 +85,10 @@ void adam_prepare(AdamState* st, float lr, int staircase, cudaStream_t s);
 void adam_apply(float* p, const float* g, float* m, float* v, long long n, const AdamState* st, float alpha_host,
                 cudaStream_t s);
 
+// fused reduce-scatter + Adam(shard) + all-gather over NVLS multicast addresses of the gradient / parameter arenas (see fused_kernels.cu)
+void nvls_adam(const float* mc_grads, float* mc_params, const float* params, float* m, float* v, float* mc_grads_out, long long off,
+               long long cnt, int rank, int world, const AdamState* st, cudaStream_t s);
+
 void stage_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int H, int W, int p, cudaStream_t s);
 // CelebA: centre crop [cy, cy+ch) x [cx, cx+cw) of a [B,Hs,Ws,3] uint8 batch, bilinear resize to H x W, scaling and scramble in one pass
 void stage_resize_scramble(const uint8_t* u8, const int32_t* perm, float* inputs, int B, int Hs, int Ws, int cy, int cx, int ch, int cw,

@@ -27,7 +27,7 @@ class Engine:
 
     def __init__(self, model="lgvae", height=32, width=32, batch=64, y_size=30, tau=0.4, beta=40.0, alpha=40.0,
                  learning_rate=1e-4, world_size=1, precision="bf16x3", device=None, rng_stream=0, no_tc=False,
-                 plan_only=False):
+                 plan_only=False, arena_alloc=None):
         self.lib = _lib.load()
         self.model, self.H, self.W, self.B = model, int(height), int(width), int(batch)
         self.y_size = int(y_size)
@@ -52,8 +52,11 @@ class Engine:
         if plan_only:
             return
         dev = self.device
-        self.params = torch.zeros(self.arena_floats, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros_like(self.params)
+        # arena_alloc(n_floats) -> zeroed fp32 CUDA tensor: lets the data-parallel host place the parameter and gradient arenas in
+        # symmetric (NVLS multicast) memory so the fused reduce-scatter + Adam + all-gather kernel can address every rank's copy
+        alloc = arena_alloc or (lambda n: torch.zeros(n, dtype=torch.float32, device=dev))
+        self.params = alloc(self.arena_floats)
+        self.grads = alloc(self.arena_floats)
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
         self.workspace = torch.zeros(self.workspace_bytes + 1024, dtype=torch.uint8, device=dev)
@@ -135,6 +138,14 @@ class Engine:
 
     def adam_step(self):
         check(self.lib.sv_adam_step(self.h, _stream()), self.h, "sv_adam_step")
+
+    def nvls_adam_segment(self, seg, mc_grads_ptr, mc_params_ptr, rank, world, write_reduced_grads=False):
+        """sv_nvls_adam_segment: in-switch gradient reduction + Adam on this rank's shard + multicast of the new weights."""
+        check(self.lib.sv_nvls_adam_segment(self.h, seg, C.c_void_p(mc_grads_ptr), C.c_void_p(mc_params_ptr), rank, world,
+                                            1 if write_reduced_grads else 0, _stream()), self.h, "sv_nvls_adam_segment")
+
+    def repack_segment(self, seg):
+        check(self.lib.sv_repack_segment(self.h, seg, _stream()), self.h, "sv_repack_segment")
 
     def adam_segment(self, seg):
         """Adam + operand re-pack of one backward segment (in order 0..n-1, once per step each), on the current stream."""

@@ -69,6 +69,53 @@ class BucketReducer:
         self._work = []
 
 
+class NvlsArenas:
+    """Symmetric (NVLS multicast) parameter and gradient arenas for the fused data-parallel optimizer (sv_nvls_adam_segment).
+
+    torch.distributed._symmetric_memory provides the plumbing only: identical allocations on every rank, the multicast address that
+    maps all of them (NVLink 5 / NVSwitch), and a device-side cross-rank barrier.  The reduction, the Adam update and the broadcast
+    are libsplitvae's kernel.  `available()` is False when the group has no multicast support (then the NCCL bucket path is used)."""
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.tensors, self.handles = [], []
+
+    @staticmethod
+    def available(group=None):
+        if os.environ.get("SV_NO_NVLS", "0") == "1" or not dist.is_initialized() or dist.get_world_size(group) < 2:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(1024, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+            h = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            return bool(h.has_multicast_support) and int(h.multicast_ptr) != 0
+        except Exception:
+            return False
+
+    def alloc(self, n_floats):
+        """Zeroed fp32 arena in symmetric memory (every rank must call this in the same order with the same size)."""
+        t = self.symm.empty(int(n_floats), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        t.zero_()
+        h = self.symm.rendezvous(t, self.group)
+        if not h.has_multicast_support or int(h.multicast_ptr) == 0:
+            raise RuntimeError("symmetric memory without multicast support")
+        self.tensors.append(t)
+        self.handles.append(h)
+        return t
+
+    def multicast_ptr(self, tensor):
+        i = next(k for k, t in enumerate(self.tensors) if t.data_ptr() == tensor.data_ptr())
+        h = self.handles[i]
+        return int(h.multicast_ptr) + int(getattr(h, "offset", 0) or 0)
+
+    def barrier(self, channel=0):
+        """Cross-rank barrier on the current stream (a small kernel over the signal pads; graph-capturable)."""
+        self.handles[0].barrier(channel=channel)
+
+
 def mean_scalars(values: torch.Tensor, group=None) -> torch.Tensor:
     """Average of per-rank loss scalars = the scalar of the global batch (equal shards)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -75,10 +75,14 @@ class StepRunner:
     all-reduce, Adam) is captured once into a CUDA graph and replayed; inputs/noise are staged into
     static device buffers before each replay."""
 
-    def __init__(self, engine, use_graph=True, group=None, explicit_noise=False):
+    def __init__(self, engine, use_graph=True, group=None, explicit_noise=False, nvls=None, write_reduced_grads=False):
         self.e = engine
         self.group = group
         self.reducer = BucketReducer(engine.grads, engine.segments, group)
+        # nvls: parallel.NvlsArenas whose alloc() backs engine.params / engine.grads -> the fused in-switch reduce + Adam + broadcast
+        # kernel replaces the NCCL all-reduce and the per-rank full-arena Adam
+        self.nvls = nvls
+        self.write_reduced_grads = write_reduced_grads
         self.use_graph = use_graph
         self.graph = None
         self.opt_stream = None
@@ -105,6 +109,19 @@ class StepRunner:
         e.forward(self.inputs, self.eps_g, self.eps_l, self.u)
         e.loss_fwd_bwd(self.inputs)
         nseg = len(e.segments)
+        if self.nvls is not None:
+            nv = self.nvls
+            mc_g, mc_p = nv.multicast_ptr(e.grads), nv.multicast_ptr(e.params)
+            for s in range(nseg):
+                e.backward_segment(s)
+                opt.wait_stream(main)
+                with torch.cuda.stream(opt):
+                    nv.barrier(2 * s)                       # every rank's gradients of segment s are written
+                    e.nvls_adam_segment(s, mc_g, mc_p, nv.rank, nv.world, self.write_reduced_grads)
+                    nv.barrier(2 * s + 1)                   # every shard of the new weights has landed in this rank's arena
+                    e.repack_segment(s)
+            main.wait_stream(opt)
+            return
         for s in range(nseg):
             e.backward_segment(s)
             works = self.reducer.reduce(s)          # behind segment s on NCCL's stream

@@ -21,6 +21,7 @@ import torch.distributed as dist
 
 def main():
     model, H, b, p, beta, prec = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5]), sys.argv[6]
+    path = sys.argv[7] if len(sys.argv) > 7 else "nccl"            # "nvls": the fused multimem reduce + Adam + broadcast kernel
     from oracle import splitvae_oracle as O
     from splitvae_b200.engine import Engine
     from splitvae_b200.parallel import init_from_env
@@ -32,9 +33,19 @@ def main():
     batch = O.synthetic_batch(world * b, H, p)
     sl = slice(rank * b, (rank + 1) * b)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    e = Engine(model=model, height=H, width=H, batch=b, beta=beta, alpha=40.0, learning_rate=lr, world_size=world, precision=prec)
+    nvls = None
+    if path == "nvls":
+        from splitvae_b200.parallel import NvlsArenas
+        if not NvlsArenas.available():
+            if rank == 0:
+                print(json.dumps({"ok": True, "skipped": "no NVLS multicast support on this box", "world": world, "iterations": 1, "messages": []}), flush=True)
+            dist.barrier()
+            os._exit(0)
+        nvls = NvlsArenas()
+    e = Engine(model=model, height=H, width=H, batch=b, beta=beta, alpha=40.0, learning_rate=lr, world_size=world, precision=prec,
+               arena_alloc=nvls.alloc if nvls else None)
     e.load_params(params)
-    runner = StepRunner(e, use_graph=True, explicit_noise=True)
+    runner = StepRunner(e, use_graph=True, explicit_noise=True, nvls=nvls, write_reduced_grads=True)
     u = dev(batch["u"][sl]) if model != "lgvae" else None
     runner.step(dev(batch["inputs"][sl]), dev(batch["eps_g"][sl]), dev(batch["eps_l"][sl]), u)
     torch.cuda.synchronize()
@@ -82,7 +93,7 @@ def main():
         if wd > (0.02 if prec == "fp32" else 0.5):
             ok = False
             msgs.append(f"Adam displacement rel-L2 {wd:.3e}")
-        print(json.dumps({"ok": ok, "world": world, "model": model, "H": H, "per_gpu_batch": b, "precision": prec, "iterations": e.iterations,
+        print(json.dumps({"ok": ok, "path": path, "world": world, "model": model, "H": H, "per_gpu_batch": b, "precision": prec, "iterations": e.iterations,
                           "worst_gradient": worst, "adam_displacement_rel": wd, "scalars": sc, "messages": msgs}), flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
