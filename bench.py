@@ -342,10 +342,14 @@ def main():
         others = {}
         for ow in ("c1", "c3", "c4"):
             om, oH, oB, op_, ob, oa, odesc = WORKLOADS[ow]
+            nvo = None
+            if nvls is not None:
+                from splitvae_b200.parallel import NvlsArenas
+                nvo = NvlsArenas()
             eo = Engine(model=om, height=oH, width=oH, batch=oB, beta=ob, alpha=oa, learning_rate=1e-4, world_size=world,
-                        precision=args.precision, rng_stream=rank)
+                        precision=args.precision, rng_stream=rank, arena_alloc=nvo.alloc if nvo else None)
             eo.init_params(seed=5)
-            ro = StepRunner(eo, use_graph=True)
+            ro = StepRunner(eo, use_graph=True, nvls=nvo)
             go = torch.Generator().manual_seed(2000 + rank)
             u8o = torch.randint(0, 256, (oB, oH, oH, 3), dtype=torch.uint8, generator=go).to(dev)
             Augmentator("scramble", op_, seed=rank).scramble(u8o, out=ro.inputs)
