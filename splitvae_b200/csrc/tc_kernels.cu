@@ -948,7 +948,9 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
   const int r = p / W, x = p - r * W;
   const int nchunk8 = nb >> 3;
   const int mb = P.mb;                          // 128-pixel blocks per tile (each R rows), one accumulator per block
-  const int acc1 = P.ng * P.ncols, acc_cols = mb * acc1;
+  const int acc1 = P.acc1, acc_cols = mb * acc1;
+  const int pair = P.pair, corr_off = P.n_total;      // pair mode: correction columns (hi * W_lo) sit n_total columns after the main ones
+  bf16* out_lo = (bf16*)P.out_lo;
   const int split = blockIdx.x % P.co_splits, cta = blockIdx.x / P.co_splits, ncta = gridDim.x / P.co_splits;
   const int cbase = split * nb;               // first output channel of this CTA's split
   const int my_last = cl + ((nchunk8 - 1 - cl) / lanes) * lanes;   // last block this warp reads (< 0: none)
@@ -984,6 +986,17 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
 #pragma unroll
       for (int b = 0; b < KW; ++b) tc::tmem_ld8(tacc + (uint32_t)(b * nb + cc * 8), v[b]);
       tc::tmem_ld_wait();
+      if (pair) {                                   // D = main + correction
+        uint32_t w[KW][8];
+#pragma unroll
+        for (int b = 0; b < KW; ++b) tc::tmem_ld8(tacc + (uint32_t)(corr_off + b * nb + cc * 8), w[b]);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int b = 0; b < KW; ++b) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[b][j] = __float_as_uint(__uint_as_float(v[b][j]) + __uint_as_float(w[b][j]));
+        }
+      }
       if (cc == my_last && mbi == mb - 1) {       // this warp is done with the accumulators: hand them back to the MMA warp
         tc::tc_fence_before();
         __syncwarp();
@@ -1059,6 +1072,19 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
           for (int j = 0; j < 8; ++j)
             if (c0 + j < n_valid) dst[j] = __float2bfloat16_rn(o[j]);
         }
+        if (out_lo) {                                 // output pair: lo = bf16(v - hi)
+          bf16* dl = out_lo + opix * out_ld + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] -= round_bf16(o[j]);
+          if ((out_ld & 7) == 0 && c0 + 8 <= n_valid) {
+            uint4 pk;
+            pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]); pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dl) = pk;
+          } else {
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < n_valid) dl[j] = __float2bfloat16_rn(o[j]);
+          }
+        }
       }
     }
     }
@@ -1089,17 +1115,22 @@ __device__ __forceinline__ void ns_epilogue(const TcNsConv& P, NsCtl* ctl, float
 #undef SV_NS_EPI_ARGS
 
 // MMAs of one tile, fully unrolled: KH filter rows x KS k-steps of 16 channels x NG column groups.
-template <int KH, int KS, int NG>
+// (NCH channel chunks per filter row: A chunk c sits chunk_step further, its weight k-block is (a * NCH + c); accum0 = 1: the first MMA
+//  accumulates too - the lo-plane pass of the pair mode)
+template <int KH, int KS, int NG, int NCH = 1>
 __device__ __forceinline__ void ns_issue_tile(uint64_t da0, uint64_t db0, uint32_t acc, uint32_t idesc, uint32_t row_step, uint32_t wk_step,
-                                              uint32_t grp_step, uint32_t ncols) {
+                                              uint32_t grp_step, uint32_t ncols, uint32_t accum0 = 0u, uint32_t chunk_step = 0u) {
 #pragma unroll
   for (int a = 0; a < KH; ++a) {
-    const uint64_t da_a = da0 + (uint64_t)(a * row_step), db_a = db0 + (uint64_t)(a * wk_step);
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
+    for (int c = 0; c < NCH; ++c) {
+      const uint64_t da_a = da0 + (uint64_t)(a * row_step + c * chunk_step), db_a = db0 + (uint64_t)((a * NCH + c) * wk_step);
 #pragma unroll
-      for (int g = 0; g < NG; ++g)
-        tc::umma_bf16(acc + g * ncols, da_a + 2u * k, db_a + (uint64_t)(g * grp_step) + 2u * k, idesc, (a | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < KS; ++k) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          tc::umma_bf16(acc + g * ncols, da_a + 2u * k, db_a + (uint64_t)(g * grp_step) + 2u * k, idesc, (a | c | k) != 0 ? 1u : accum0);
+      }
     }
   }
 }
@@ -1117,12 +1148,14 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&P.map_x);
     tc::prefetch_tmap(&P.map_w);
+    if (P.pair) tc::prefetch_tmap(&P.map_x_lo);
     tc::mbar_init(&ctl->w_full, 1);
     for (int i = 0; i < P.nstages; ++i) { tc::mbar_init(&ctl->halo_full[i], 1); tc::mbar_init(&ctl->halo_empty[i], 1); }
     for (int i = 0; i < P.groups; ++i) { tc::mbar_init(&ctl->acc_full[i], 1); tc::mbar_init(&ctl->acc_empty[i], 4 * P.lanes); }
     tc::fence_barrier_init();
   }
-  const int acc1 = P.ng * P.ncols, acc_cols = P.mb * acc1;
+  const int acc1 = P.acc1, acc_cols = P.mb * acc1;
+  const int pair = P.pair, wrows = pair ? 2 * P.n_total : P.n_total;      // rows of one weight k-block
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(P.groups * acc_cols)) tmem_cols <<= 1;
   if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
@@ -1135,18 +1168,21 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
     if (tc::elect_one()) {
       tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(P.num_kb * P.wk_bytes));
       for (int j = 0; j < P.num_kb; ++j)
-        for (int r0 = 0; r0 < P.n_total; r0 += P.n_box)
-          tc::tma_load_2d(wsm + (size_t)j * P.wk_bytes + (size_t)r0 * P.pixB, &P.map_w, &ctl->w_full, j * P.ck, split * P.n_total + r0);
+        for (int r0 = 0; r0 < wrows; r0 += P.n_box)
+          tc::tma_load_2d(wsm + (size_t)j * P.wk_bytes + (size_t)r0 * P.pixB, &P.map_w, &ctl->w_full, j * P.ck, split * wrows + r0);
       const uint32_t halo_tx = (uint32_t)(P.nchunks * P.halo_rows * P.W * P.pixB);
+      const int passes = pair ? 2 : 1;            // pair: the hi plane and the lo plane of a tile are two consecutive ring stages
       int i = 0;
-      for (int t = cta; t < P.tiles; t += ncta, ++i) {
-        const int st = i % P.nstages, ph = (i / P.nstages) & 1;
+      for (int t = cta; t < P.tiles; t += ncta) {
         const int n = t / P.tiles_per_img, y0 = (t - n * P.tiles_per_img) * P.R * P.mb;
-        tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
-        tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
-        for (int c = 0; c < P.nchunks; ++c)
-          tc::tma_load_4d(halo + (size_t)st * P.stage_bytes + (size_t)c * P.chunk_bytes, &P.map_x, &ctl->halo_full[st], c * P.ck, 0,
-                          y0 - P.pad_t, n);
+        for (int pl = 0; pl < passes; ++pl, ++i) {
+          const int st = i % P.nstages, ph = (i / P.nstages) & 1;
+          tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
+          tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
+          for (int c = 0; c < P.nchunks; ++c)
+            tc::tma_load_4d(halo + (size_t)st * P.stage_bytes + (size_t)c * P.chunk_bytes, pl ? &P.map_x_lo : &P.map_x, &ctl->halo_full[st],
+                            c * P.ck, 0, y0 - P.pad_t, n);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1166,13 +1202,18 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
       const int shape = nchunks != 1 || kh != 6 ? 0
                         : ng == 1 ? (ksteps == 4 ? 1 : ksteps == 2 ? 2 : ksteps == 1 ? 3 : 0)
                                   : ng == 2 ? (ksteps == 2 ? 4 : ksteps == 4 ? 5 : 0) : 0;
+      // pair mode: pass 0 = hi plane x the whole k-block (N = 2 * n_total: [main | correction]), pass 1 = lo plane x the W_hi rows
+      const uint32_t idesc_hi = tc::make_idesc_bf16(128, 2 * P.n_total, 0, 0);
+      const int passes = pair ? 2 : 1;
+      const int pshape = !pair ? 0 : (kh == 6 && nchunks == 1 && ksteps == 4) ? 1 : (kh == 4 && nchunks == 2 && ksteps == 4) ? 2 : 0;
       tc::mbar_wait(&ctl->w_full, 0);
-      int i = 0;
-      for (int t = cta; t < tiles; t += ncta, ++i) {
+      int i = 0, it = 0;                        // i: ring stage counter, it: tile counter
+      for (int t = cta; t < tiles; t += ncta, ++it) {
+        const int ab = it % groups, aph = (it / groups) & 1;
+        for (int pl = 0; pl < passes; ++pl, ++i) {
         const int st = i % nstages, ph = (i / nstages) & 1;
-        const int ab = i % groups, aph = (i / groups) & 1;
         tc::mbar_wait(&ctl->halo_full[st], ph);
-        tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
+        if (pl == 0) tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
         tc::tc_fence_after();
         for (int mbi = 0; mbi < mb; ++mbi) {    // block mbi of the tile: rows mbi*R .. of the shared halo, its own accumulator
         const uint32_t h_addr = halo_addr + (uint32_t)st * stage_step + (uint32_t)mbi * blk_step;
@@ -1181,6 +1222,22 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
         // fully unrolled issue sequences for the shapes of this model family (the single issuing thread must spend only a
         // few instructions per tcgen05.mma: the generic nest below costs ~75 and caps the tensor pipe at ~35 %)
         if (P.debug & 2) { }
+        else if (pair) {
+          const uint32_t id = pl ? idesc : idesc_hi, acc0 = pl ? 1u : 0u;
+          if (pshape == 1) ns_issue_tile<6, 4, 1>(da0, db0, acc, id, row_step, wk_step, grp_step, ncols, acc0);
+          else if (pshape == 2) ns_issue_tile<4, 4, 1, 2>(da0, db0, acc, id, row_step, wk_step, grp_step, ncols, acc0, chunk_step);
+          else {
+            uint32_t b_addr = w_addr, accum = acc0;
+            for (int a = 0; a < kh; ++a) {
+              uint32_t a_addr = h_addr + (uint32_t)a * row_step;
+              for (int c = 0; c < nchunks; ++c, a_addr += chunk_step, b_addr += wk_step)
+                for (int k = 0; k < ksteps; ++k) {
+                  tc::umma_bf16(acc, tmpl + a_addr + 2u * k, tmpl + b_addr + 2u * k, id, accum);
+                  accum = 1u;
+                }
+            }
+          }
+        }
         else if (shape == 1) ns_issue_tile<6, 4, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
         else if (shape == 2) ns_issue_tile<6, 2, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
         else if (shape == 3) ns_issue_tile<6, 1, 1>(da0, db0, acc, idesc, row_step, wk_step, grp_step, ncols);
@@ -1203,6 +1260,7 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
         }
         }
         tc::umma_commit(&ctl->halo_empty[st]);
+        }
         tc::umma_commit(&ctl->acc_full[ab]);
       }
     }
@@ -1809,14 +1867,19 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
       const int k_total = J.taps_h * J.k_pad;
       const int k = (int)(idx % k_total);
       int nrow = (int)(idx / k_total);
-      const int rows_per_split = J.taps_w * J.rows_pad;          // J.rows_pad = channels per filter column per split
+      const int nsec = J.kind == 4 && J.nsec == 2 ? 2 : 1;
+      const int rows_per_sec = J.taps_w * J.rows_pad;            // J.rows_pad = channels per filter column per split
+      const int rows_per_split = nsec * rows_per_sec;
       const int split = nrow / rows_per_split;
       nrow -= split * rows_per_split;
+      const int sec = nrow / rows_per_sec;                       // 0: W_hi rows, 1: W_lo rows (bf16x3 pair mode)
+      nrow -= sec * rows_per_sec;
       const int b = nrow / J.rows_pad, nn = split * J.rows_pad + (nrow - b * J.rows_pad);
       const int a = k / J.k_pad, c = k - a * J.k_pad;
       float v = 0.f;
       if (J.kind == 4) { if (nn < J.Co && c < J.Ci) v = master_w(J, params, a, b, c, nn); }            // fwd: n = co, k = ci
       else if (nn < J.Ci && c < J.Co) v = master_w(J, params, J.KH - 1 - a, J.KW - 1 - b, nn, c);      // dgrad: n = ci, k = co, flipped
+      if (sec) v -= round_bf16(v);
       ((bf16*)J.dst)[idx] = __float2bfloat16_rn(v);
       continue;
     }
@@ -2270,8 +2333,10 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
 
 // Plans the N-stacked persistent kernel for a stride-1 convolution C -> n_out over an H x W image (W in {16, 32, 64}).
 // Returns false when the layer is not eligible (then the per-tap / halo kernels are used).
-bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W, int n_img, int C, int n_out) {
+bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W, int n_img, int C, int n_out, bool pair = false) {
   if (env_int("SV_NO_NSCONV", 0)) return false;
+  if (pair && !env_int("SV_NS_PAIR", 1)) return false;
+  P.pair = pair ? 1 : 0;
   if (!(kw == 4 || kw == 6) || pad_l > 4 || kw - 1 - pad_l > 4) return false;
   if (!(W == 16 || W == 32 || W == 64)) return false;
   const int R = 128 / W;
@@ -2298,18 +2363,33 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   // (measured: the split costs more than it buys whenever the whole weight set fits beside two halo stages - d4 forward
   // 35.6 us unsplit vs 41.8 us split - so it is only used where the layer would otherwise not fit at all: d3)
   int co_splits = 1;
+  if (pair) {
+    // bf16x3: resident [W_hi-stack ; W_lo-stack] k-blocks (twice the bytes) beside >= 2 single-plane halo stages, and the hi pass is ONE
+    // MMA of 2 * kw * nb <= 256 columns: split the output channels over 2 / 4 CTA classes until both hold
+    mb = 1;
+    const int want = env_int("SV_NS_PAIR_SPLITS", 0);
+    for (co_splits = 1; co_splits <= 8; co_splits *= 2) {
+      if (nb_all % (8 * co_splits)) return false;
+      const int nbs = nb_all / co_splits;
+      if ((kw * nbs) % 16 || 2 * kw * nbs > 256) continue;
+      if (want && co_splits != want) continue;
+      if ((size_t)2 * kw * nbs * num_kb * pixB + 2 * (size_t)round_up((R + kh - 1) * W * pixB, 1024) * nchunks <= budget) break;
+    }
+    if (co_splits > 8) return false;
+  } else
   if ((size_t)kw * nb_all * num_kb * pixB + 2 * (size_t)stage_bytes > budget && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 &&
       !env_int("SV_NS_NOSPLIT", 0))
     co_splits = 2;
   // N wider than one MMA (d4 dgrad: 6 x 64 = 384 columns) leaves room for a single accumulator set in TMEM, so the MMAs and the
   // epilogue of a tile serialise; splitting the output channels over CTA pairs halves N and restores the double buffering
-  if (co_splits == 1 && kw * nb_all > 256 && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 && env_int("SV_NS_SPLIT_WIDE", 1))   // d4 dgrad 55 -> 45 us, 1.538 -> 1.514 ms/step
+  if (!pair && co_splits == 1 && kw * nb_all > 256 && (nb_all % 16) == 0 && ((kw * nb_all / 2) % 16) == 0 && env_int("SV_NS_SPLIT_WIDE", 1))   // d4 dgrad 55 -> 45 us, 1.538 -> 1.514 ms/step
     co_splits = 2;
   const int nb = nb_all / co_splits;
   const int n_total = kw * nb;
+  const int chunk_bytes_f = round_up((mb * R + kh - 1) * W * pixB, 1024), stage_bytes_f = chunk_bytes_f * nchunks;   // (pair mode forces mb = 1)
   int ng = 1;
   if (n_total > 256) {
-    if ((kw % 2) || n_total / 2 > 256 || (n_total / 2) % 16) return false;
+    if (pair || (kw % 2) || n_total / 2 > 256 || (n_total / 2) % 16) return false;
     ng = 2;
   }
   P.kh = kh; P.kw = kw; P.pad_t = pad_t; P.pad_l = pad_l;
@@ -2319,8 +2399,10 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   P.ck = ck; P.nchunks = nchunks; P.pixB = pixB;
   P.nb = nb; P.ng = ng; P.ncols = n_total / ng; P.n_total = n_total; P.co_splits = co_splits;
   // epilogue warp sets: `groups` accumulator buffers / tile round-robin, `lanes` warps per TMEM quarter splitting the 8-channel blocks
-  int groups = 512 / (n_total * mb);
+  P.acc1 = pair ? 2 * n_total : n_total;          // (ng * ncols == n_total)
+  int groups = 512 / (P.acc1 * mb);
   if (groups > kNsMaxGroups) groups = kNsMaxGroups;
+  if (groups < 1) return false;
   const int sets = kNsEpiWarps / 4;
   int lanes = sets / groups;
   if (lanes > nb / 8) lanes = nb / 8;
@@ -2331,21 +2413,21 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
   P.groups = groups; P.lanes = lanes;
   P.nacc = groups;
   P.halo_rows = mb * R + kh - 1;
-  P.chunk_bytes = chunk_bytes;
-  P.stage_bytes = stage_bytes;
+  P.chunk_bytes = chunk_bytes_f;
+  P.stage_bytes = stage_bytes_f;
   P.num_kb = num_kb;
-  P.wk_bytes = n_total * pixB;
-  if (P.wk_bytes % 1024) return false;            // every weight k-block starts on a swizzle-atom boundary
+  P.wk_bytes = (pair ? 2 : 1) * n_total * pixB;
+  if (P.wk_bytes % 1024 || (n_total * pixB) % 1024) return false;            // every weight k-block (and its W_lo half) starts on a swizzle-atom boundary
   P.w_bytes = round_up(P.num_kb * P.wk_bytes, 1024);
-  P.n_box = n_total <= 256 ? n_total : P.ncols;
+  P.n_box = pair ? 2 * n_total : n_total <= 256 ? n_total : P.ncols;
   P.xch_off = 256;                                // after NsCtl
-  if ((size_t)P.w_bytes + 2 * (size_t)stage_bytes > budget) return false;
-  int nst = (int)((budget - P.w_bytes) / stage_bytes);
+  if ((size_t)P.w_bytes + 2 * (size_t)stage_bytes_f > budget) return false;
+  int nst = (int)((budget - P.w_bytes) / stage_bytes_f);
   const int cap = env_int("SV_NS_STAGES", 6);
   if (nst > cap) nst = cap;
   if (nst > kNsMaxStages) nst = kNsMaxStages;
   P.nstages = nst;
-  P.smem_bytes = (size_t)P.w_bytes + (size_t)nst * stage_bytes + 256 + xch_bytes + 1024;
+  P.smem_bytes = (size_t)P.w_bytes + (size_t)nst * stage_bytes_f + 256 + xch_bytes + 1024;
   P.grid = 148;
   const int work = P.tiles * co_splits;
   if (work < P.grid) P.grid = work;
@@ -2519,8 +2601,9 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
             }
           }
         }
-        if (!split_fwd && g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff && g.Ho == g.Hi && g.Wo == g.Wi &&
-            plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co)) {
+        // (bf16x3: the pair mode of the N-stacked kernel, W <= 32 only - d3 / d4; the 64-wide cross-warp epilogue is not paired)
+        if ((!split_fwd || g.Wo <= 32) && g.stride == 1 && g.nparts == 1 && g.part_act[0] != ACT_SOFTPLUS && cpad <= g.in_ld - g.in_coff &&
+            g.Ho == g.Hi && g.Wo == g.Wi && plan_nsconv(t.ns_fwd, g.kh, g.kw, g.pt, g.pl, g.Ho, g.Wo, g.B, g.Ci, g.Co, split_fwd)) {
           TcNsConv& P = t.ns_fwd;
           P.n_valid = g.Co; P.out_ld = g.out_ld; P.out_f32 = out_dt == DT_F32; P.act = g.part_act[0]; P.mask_act = ACT_NONE;
           t.fwd_ns = true;
@@ -2705,8 +2788,15 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       const char* e = which ? make_act_map(&P.map_x, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, P.nchunks * P.ck, P.ck, P.W, P.halo_rows, 1, 1, P.pixB)
                             : make_act_map(&P.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, P.nchunks * P.ck, P.ck, P.W, P.halo_rows, 1, 1, P.pixB);
       if (e) return e;
-      e = make_w_map(&P.map_w, ws + (which ? t.w_nsd_off : t.w_nsf_off), P.co_splits * P.n_total, (long long)P.kh * P.nchunks * P.ck, P.ck, P.n_box, P.pixB);
+      if (P.pair) {
+        if (which || !in_lo) return "bf16x3 N-stacked forward needs the lo plane of the layer input";
+        e = make_act_map(&P.map_x_lo, in_lo, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, P.nchunks * P.ck, P.ck, P.W, P.halo_rows, 1, 1, P.pixB);
+        if (e) return e;
+      }
+      e = make_w_map(&P.map_w, ws + (which ? t.w_nsd_off : t.w_nsf_off), P.co_splits * (P.pair ? 2 : 1) * P.n_total, (long long)P.kh * P.nchunks * P.ck,
+                     P.ck, P.n_box, P.pixB);
       if (e) return e;
+      P.out_lo = (!which && P.pair) ? out_lo : nullptr;
       P.bias = which ? nullptr : (const float*)(ws + t.bias_off);
       P.out = which ? din : out;
       P.mask_src = which ? mask_src : nullptr;
@@ -2810,8 +2900,9 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     if (t.fwd_ns) {
       PackJob J = B;
       J.kind = 4; J.rows_pad = t.ns_fwd.nb; J.taps_h = g.kh; J.taps_w = g.kw; J.k_pad = t.ns_fwd.nchunks * t.ns_fwd.ck;
+      J.nsec = t.ns_fwd.pair ? 2 : 1;               // pair: rows [W_hi-stack ; W_lo-stack] per output-channel split
       J.dst = t.ws + t.w_nsf_off;
-      J.count = (long long)t.ns_fwd.co_splits * t.ns_fwd.n_total * g.kh * J.k_pad;
+      J.count = (long long)t.ns_fwd.co_splits * J.nsec * t.ns_fwd.n_total * g.kh * J.k_pad;
       push(J);
     }
     if (t.dgrad_ns) {

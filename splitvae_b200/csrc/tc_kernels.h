@@ -123,6 +123,13 @@ struct TcHaloWgrad {
 // double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
 struct TcNsConv {
   CUtensorMap map_x, map_w;
+  // bf16x3 forward ("pair" mode): the input is a bf16 pair (hi plane map_x, lo plane map_x_lo); every weight k-block holds the rows
+  // [W_hi-stack ; W_lo-stack] (2 * n_total rows).  A tile runs as two half-tile passes through the halo ring: the hi plane against the
+  // whole k-block (ONE MMA of 2 * n_total columns -> accumulator columns [main | correction]), then the lo plane against the W_hi rows
+  // (n_total columns -> main).  The epilogue adds main + correction and stores the output pair.
+  CUtensorMap map_x_lo;
+  int pair, acc1;                   // acc1: TMEM columns of one accumulator (pair: 2 * n_total, else ng * ncols)
+  void* out_lo;
   int kh, kw, pad_t, pad_l;
   int W, R, H, n_img;               // block = R rows x W pixels (R * W = 128)
   int mb;                           // blocks per tile (tile = mb * R rows sharing one halo; one accumulator per block)
