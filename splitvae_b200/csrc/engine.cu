@@ -803,11 +803,26 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
         if (!h->cs[b][part]) return fail(h, SV_ERR_DEVICE, "bias-gradient table: %s", cerr ? cerr : "?");
       }
   }
+  // Stream priorities (only the order in which PENDING blocks are dispatched; nothing is pre-empted): the forward / dgrad chain
+  // (caller's stream + side stream) goes first, the weight-gradient streams fill the SMs the chain leaves, and the optimizer stream
+  // (Adam + operand re-pack: thousands of short blocks that otherwise sit in front of the chain's next kernel) comes last.  The
+  // caller's stream keeps its own priority: trainer.StepRunner and bench.py capture on a highest-priority stream.
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  const char* pv = getenv("SV_STREAM_PRIO");
+  const bool use_prio = !(pv && *pv == '0');
+  // (-3 = the highest level torch.cuda.Stream(priority=...) hands out, so the caller's capture stream and the side stream are equals)
+  const int prio_side = use_prio ? (prio_greatest > -3 ? prio_greatest : -3) : 0;
+  int prio_aux = use_prio ? prio_side + 1 : 0;
+  if (const char* av = getenv("SV_AUX_PRIO")) if (*av) prio_aux = atoi(av);
+  if (prio_aux > prio_least) prio_aux = prio_least;
+  if (prio_aux < prio_greatest) prio_aux = prio_greatest;
+  const int prio_opt = prio_least;
   if (!h->side) {
     const char* one = getenv("SV_ONE_STREAM");
     h->two_streams = !(one && *one == '1');
     if (h->two_streams &&
-        (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_side) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "side stream / event creation failed");
@@ -815,7 +830,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (!h->opt) {
     const char* off = getenv("SV_OPT_STREAM");
     if (!(off && *off == '0') &&
-        (cudaStreamCreateWithFlags(&h->opt, cudaStreamNonBlocking) != cudaSuccess ||
+        (cudaStreamCreateWithPriority(&h->opt, cudaStreamNonBlocking, prio_opt) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_fork, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_fork2, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_join, cudaEventDisableTiming) != cudaSuccess))
@@ -828,7 +843,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     h->wgrad_streams = h->aux_n > 0;
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < h->aux_n; ++j)
-        if (cudaStreamCreateWithFlags(&h->aux[k][j], cudaStreamNonBlocking) != cudaSuccess ||
+        if (cudaStreamCreateWithPriority(&h->aux[k][j], cudaStreamNonBlocking, prio_aux) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_aux[k][j], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_aux_join[k][j], cudaEventDisableTiming) != cudaSuccess)
           return fail(h, SV_ERR_DEVICE, "auxiliary stream / event creation failed");

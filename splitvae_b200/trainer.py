@@ -154,7 +154,9 @@ class StepRunner:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on a highest-priority stream: the engine's side stream matches it, its weight-gradient streams sit one level
+        # below and its optimizer stream at the bottom (kernel nodes keep the priority of the stream they were captured on)
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=-3)):
             self._issue()
         # capture does not execute: state is untouched
 
