@@ -141,6 +141,12 @@ int32_t sv_num_segments(const sv_handle* h);
 int32_t sv_segment_num_ranges(const sv_handle* h, int32_t segment);
 sv_status sv_segment_range(const sv_handle* h, int32_t segment, int32_t range_index, int64_t* offset_floats, int64_t* count_floats);
 sv_status sv_backward_segment(sv_handle* h, int32_t segment, void* stream);
+/* The same work, but the segment's gradients are final on `done_stream` (the stream the host reduces / updates them on) instead of
+ * `stream`: the library's internal weight- and bias-gradient streams are joined into done_stream, so the backward chain of segment
+ * s+1 issued on `stream` starts while segment s's weight gradients are still running.  `stream` only carries the chain itself
+ * (activation gradients).  done_stream must already be ordered behind `stream` (and, under stream capture, part of the capture);
+ * done_stream == stream or NULL is sv_backward_segment.  The LAST segment must be issued with sv_backward_segment. */
+sv_status sv_backward_segment_deferred(sv_handle* h, int32_t segment, void* stream, void* done_stream);
 
 /* optimizer.apply_gradients (vae/trainer.py:138,167): multi-tensor Keras-Adam over the arena,
  * step counter and (lggmvae) staircase LR schedule kept on the device (vae/main.py:65-68). */

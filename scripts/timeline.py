@@ -15,17 +15,25 @@ from splitvae_b200.engine import Engine
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
+ap.add_argument("--graph", action="store_true", help="profile CUDA-graph replays of the captured step (trainer.StepRunner) instead of eager steps")
 args = ap.parse_args()
 model, H, B, patch, beta, alpha, desc = WORKLOADS[args.workload]
 e = Engine(model=model, height=H, width=H, batch=B, beta=beta, alpha=alpha)
 e.init_params(seed=5)
 x = torch.rand(B, H, H, 6, device="cuda") * 2 - 1
+if args.graph:
+    from splitvae_b200.trainer import StepRunner
+    runner = StepRunner(e, use_graph=True)
+    runner.inputs.copy_(x)
+    step = runner.step
+else:
+    step = lambda: e.train_step(x)
 for _ in range(3):
-    e.train_step(x)
+    step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
-        e.train_step(x)
+        step()
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "trace.json")
 prof.export_chrome_trace(path)

@@ -22,7 +22,7 @@ SCALAR_NAMES = ["recon_x", "recon_x_hat", "kl_x", "kl_x_hat", "total_kl_or_y_kl"
 # every symbol include/splitvae.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["sv_create", "sv_destroy", "sv_last_error", "sv_version", "sv_param_count", "sv_param_describe",
            "sv_arena_floats", "sv_workspace_bytes", "sv_bind", "sv_params_updated", "sv_forward", "sv_loss_fwd_bwd",
-           "sv_num_segments", "sv_segment_num_ranges", "sv_segment_range", "sv_backward_segment", "sv_adam_step", "sv_adam_segment", "sv_nvls_adam_segment", "sv_repack_segment", "sv_train_step",
+           "sv_num_segments", "sv_segment_num_ranges", "sv_segment_range", "sv_backward_segment", "sv_backward_segment_deferred", "sv_adam_step", "sv_adam_segment", "sv_nvls_adam_segment", "sv_repack_segment", "sv_train_step",
            "sv_capture_graph", "sv_replay", "sv_output_ptr", "sv_decode", "sv_encode_y", "sv_get_iterations", "sv_set_iterations", "sv_launch_count",
            "sv_discretised_logistic_loss", "sv_adam_flat", "sv_stage_scramble", "sv_stage_resize_scramble", "sv_draw_permutations", "sv_debug_layer_count",
            "sv_debug_layer_info", "sv_debug_run_layer", "sv_debug_halo_trace"]
@@ -90,6 +90,7 @@ def load():
     lib.sv_segment_num_ranges.argtypes = [vp, i32]
     lib.sv_segment_range.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     lib.sv_backward_segment.argtypes = [vp, i32, vp]
+    lib.sv_backward_segment_deferred.argtypes = [vp, i32, vp, vp]
     lib.sv_adam_step.argtypes = [vp, vp]
     lib.sv_adam_segment.argtypes = [vp, i32, vp]
     lib.sv_nvls_adam_segment.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp]

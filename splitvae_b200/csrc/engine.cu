@@ -104,18 +104,22 @@ struct sv_handle {
   cudaStream_t aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   cudaEvent_t ev_aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, ev_aux_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   int aux_n = 0, aux_rr[2] = {0, 0};
+  bool aux_dirty[2][2] = {{false, false}, {false, false}};   // forked since the last join
+  bool defer_join = false;                                    // inside sv_backward_segment_deferred
   bool wgrad_streams = false;
   // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
   bool cs_on = false;
   // (encoders: part 0 = the layers of segment 1, part 1 = segment 2; decoders: part 0 only)
   int CSP[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
   ColsumTable* cs[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  cudaEvent_t ev_opt_fork2 = nullptr;
+  cudaEvent_t ev_seg_done = nullptr;
   cudaGraph_t graph = nullptr;            // sv_capture_graph: one captured sv_train_step
   cudaGraphExec_t graph_exec = nullptr;
 };
 
 namespace {
+
+bool getenv_off(const char* name) { const char* v = getenv(name); return v && *v == '0'; }
 
 sv_status fail(sv_handle* h, sv_status code, const char* fmt, ...) {
   va_list ap;
@@ -382,6 +386,7 @@ cudaStream_t wgrad_stream(sv_handle* h, cudaStream_t s) {
   const int j = h->aux_rr[k]++ % h->aux_n;
   cudaEventRecord(h->ev_aux[k][j], s);
   cudaStreamWaitEvent(h->aux[k][j], h->ev_aux[k][j], 0);
+  h->aux_dirty[k][j] = true;
   return h->aux[k][j];
 }
 void join_wgrad_stream(sv_handle* h, cudaStream_t s) {
@@ -391,8 +396,25 @@ void join_wgrad_stream(sv_handle* h, cudaStream_t s) {
   for (int j = 0; j < used; ++j) {
     cudaEventRecord(h->ev_aux_join[k][j], h->aux[k][j]);
     cudaStreamWaitEvent(s, h->ev_aux_join[k][j], 0);
+    h->aux_dirty[k][j] = false;
   }
   h->aux_rr[k] = 0;
+}
+// Deferred mode (sv_backward_segment_deferred): the weight-gradient / bias-gradient streams of BOTH branches are joined into
+// `target` (the optimizer / reduction stream) instead of the chain's stream, so the dgrad chain of the next segment starts while
+// this segment's weight gradients are still running (they occupy 37 SMs each: the chain used to idle ~150 us behind them at
+// the decoder -> encoder boundary and ~60 us between the encoder halves).
+void join_all_wgrad_streams(sv_handle* h, cudaStream_t target) {
+  if (!h->wgrad_streams || !h->cs_on) return;
+  for (int k = 0; k < 2; ++k) {
+    for (int j = 0; j < h->aux_n; ++j)
+      if (h->aux_dirty[k][j]) {
+        cudaEventRecord(h->ev_aux_join[k][j], h->aux[k][j]);
+        cudaStreamWaitEvent(target, h->ev_aux_join[k][j], 0);
+        h->aux_dirty[k][j] = false;
+      }
+    h->aux_rr[k] = 0;
+  }
 }
 
 void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
@@ -422,6 +444,10 @@ void layer_bwd(sv_handle* h, int li, const float* ext_in, cudaStream_t s) {
 }
 
 void branch_bias_grads(sv_handle* h, int which, int part, cudaStream_t s) {
+  if (h->defer_join) {     // every dY of the branch is complete on s here: the column sums leave the chain too
+    if (h->cs_on && h->cs[which][part]) h->launches += colsum_table_run(h->cs[which][part], h->grads, wgrad_stream(h, s));
+    return;
+  }
   if (h->cs_on && h->cs[which][part]) h->launches += colsum_table_run(h->cs[which][part], h->grads, s);
   join_wgrad_stream(h, s);
 }
@@ -722,7 +748,7 @@ sv_status sv_destroy(sv_handle* h) {
     if (h->graph) cudaGraphDestroy(h->graph);
     tc_pack_table_destroy(h->pack);
     for (int seg = 0; seg < sv_handle::kSegs; ++seg) tc_pack_table_destroy(h->pack_seg[seg]);
-    if (h->ev_opt_fork2) cudaEventDestroy(h->ev_opt_fork2);
+    if (h->ev_seg_done) cudaEventDestroy(h->ev_seg_done);
     if (h->ev_opt_fork) cudaEventDestroy(h->ev_opt_fork);
     if (h->ev_opt_join) cudaEventDestroy(h->ev_opt_join);
     if (h->opt) cudaStreamDestroy(h->opt);
@@ -817,7 +843,12 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (const char* av = getenv("SV_AUX_PRIO")) if (*av) prio_aux = atoi(av);
   if (prio_aux > prio_least) prio_aux = prio_least;
   if (prio_aux < prio_greatest) prio_aux = prio_greatest;
-  const int prio_opt = prio_least;
+  // optimizer stream: level with the weight-gradient streams.  (At the lowest level the decoders' Adam starved behind every other
+  // kernel until the end of the step and the whole optimizer tail - 90 us - was exposed after the last weight gradient.)
+  int prio_opt = use_prio ? prio_aux : 0;
+  if (const char* ov = getenv("SV_OPT_PRIO")) if (*ov) prio_opt = atoi(ov);
+  if (prio_opt > prio_least) prio_opt = prio_least;
+  if (prio_opt < prio_greatest) prio_opt = prio_greatest;
   if (!h->side) {
     const char* one = getenv("SV_ONE_STREAM");
     h->two_streams = !(one && *one == '1');
@@ -832,7 +863,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
     if (!(off && *off == '0') &&
         (cudaStreamCreateWithPriority(&h->opt, cudaStreamNonBlocking, prio_opt) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_fork, cudaEventDisableTiming) != cudaSuccess ||
-         cudaEventCreateWithFlags(&h->ev_opt_fork2, cudaEventDisableTiming) != cudaSuccess ||
+         cudaEventCreateWithFlags(&h->ev_seg_done, cudaEventDisableTiming) != cudaSuccess ||
          cudaEventCreateWithFlags(&h->ev_opt_join, cudaEventDisableTiming) != cudaSuccess))
       return fail(h, SV_ERR_DEVICE, "optimizer stream / event creation failed");
   }
@@ -919,8 +950,7 @@ sv_status sv_segment_range(const sv_handle* h, int32_t seg, int32_t index, int64
   return SV_OK;
 }
 
-sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
-  REQUIRE_BOUND(h);
+static sv_status backward_segment_impl(sv_handle* h, int32_t seg, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const float* inputs = h->last_inputs;
   const bool loc = h->has_local;
@@ -954,6 +984,28 @@ sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
     return fail(h, SV_ERR_INVALID, "segment %d out of range", seg);
   }
   return check_launch(h, "sv_backward_segment");
+}
+
+sv_status sv_backward_segment(sv_handle* h, int32_t seg, void* stream) {
+  REQUIRE_BOUND(h);
+  h->defer_join = false;
+  const sv_status st = backward_segment_impl(h, seg, stream);
+  if (st == SV_OK) join_all_wgrad_streams(h, (cudaStream_t)stream);   // (streams a deferred call left unjoined)
+  return st;
+}
+
+sv_status sv_backward_segment_deferred(sv_handle* h, int32_t seg, void* stream, void* done_stream) {
+  REQUIRE_BOUND(h);
+  if (!done_stream || done_stream == stream || getenv_off("SV_DEFER_JOIN")) return sv_backward_segment(h, seg, stream);
+  h->defer_join = true;
+  const sv_status st = backward_segment_impl(h, seg, stream);
+  h->defer_join = false;
+  if (st != SV_OK) return st;
+  cudaStream_t s = (cudaStream_t)stream, d = (cudaStream_t)done_stream;
+  cudaEventRecord(h->ev_seg_done, s);               // the chain's own part: dgrads (readers of the packed weights), glue kernels
+  cudaStreamWaitEvent(d, h->ev_seg_done, 0);
+  join_all_wgrad_streams(h, d);
+  return check_launch(h, "sv_backward_segment_deferred");
 }
 
 sv_status sv_adam_segment(sv_handle* h, int32_t seg, void* stream) {
@@ -1016,14 +1068,16 @@ sv_status sv_train_step(sv_handle* h, const float* inputs, const float* eps_g, c
   // segment k's gradients are final after its backward: Adam + re-pack of segment k run on the optimizer stream while the
   // backward of segment k+1 runs; only the last (smallest) segment's update is exposed
   for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
-    if ((st = sv_backward_segment(h, seg, stream))) return st;
     if (h->opt && seg + 1 < sv_handle::kSegs) {
-      cudaEvent_t ev = seg == 0 ? h->ev_opt_fork : h->ev_opt_fork2;
-      cudaEventRecord(ev, s);
-      cudaStreamWaitEvent(h->opt, ev, 0);
+      if (seg == 0) {                                  // (brings the optimizer stream into a capture before it is a join target)
+        cudaEventRecord(h->ev_opt_fork, s);
+        cudaStreamWaitEvent(h->opt, h->ev_opt_fork, 0);
+      }
+      if ((st = sv_backward_segment_deferred(h, seg, stream, h->opt))) return st;
       if ((st = sv_adam_segment(h, seg, h->opt))) return st;
       if (seg + 2 == sv_handle::kSegs) cudaEventRecord(h->ev_opt_join, h->opt);
     } else {
+      if ((st = sv_backward_segment(h, seg, stream))) return st;
       if (h->opt) cudaStreamWaitEvent(s, h->ev_opt_join, 0);
       if ((st = sv_adam_segment(h, seg, stream))) return st;
     }

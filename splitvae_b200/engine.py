@@ -133,8 +133,15 @@ class Engine:
     def loss_fwd_bwd(self, inputs):
         check(self.lib.sv_loss_fwd_bwd(self.h, _ptr(inputs), _stream()), self.h, "sv_loss_fwd_bwd")
 
-    def backward_segment(self, seg):
-        check(self.lib.sv_backward_segment(self.h, seg, _stream()), self.h, "sv_backward_segment")
+    def backward_segment(self, seg, done_stream=None):
+        """Backward pass of one segment on the current stream.  done_stream (a torch stream already ordered behind the current one):
+        the segment's gradients are final THERE and the current stream only carries the activation-gradient chain
+        (sv_backward_segment_deferred); not for the last segment."""
+        if done_stream is None:
+            check(self.lib.sv_backward_segment(self.h, seg, _stream()), self.h, "sv_backward_segment")
+        else:
+            check(self.lib.sv_backward_segment_deferred(self.h, seg, _stream(), C.c_void_p(done_stream.cuda_stream)), self.h,
+                  "sv_backward_segment_deferred")
 
     def adam_step(self):
         check(self.lib.sv_adam_step(self.h, _stream()), self.h, "sv_adam_step")

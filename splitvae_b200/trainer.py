@@ -113,8 +113,10 @@ class StepRunner:
             nv = self.nvls
             mc_g, mc_p = nv.multicast_ptr(e.grads), nv.multicast_ptr(e.params)
             for s in range(nseg):
-                e.backward_segment(s)
                 opt.wait_stream(main)
+                e.backward_segment(s, done_stream=opt if s + 1 < nseg else None)
+                if s + 1 == nseg:
+                    opt.wait_stream(main)
                 with torch.cuda.stream(opt):
                     nv.barrier(2 * s)                       # every rank's gradients of segment s are written
                     e.nvls_adam_segment(s, mc_g, mc_p, nv.rank, nv.world, self.write_reduced_grads)
@@ -123,15 +125,17 @@ class StepRunner:
             main.wait_stream(opt)
             return
         for s in range(nseg):
-            e.backward_segment(s)
-            works = self.reducer.reduce(s)          # behind segment s on NCCL's stream
             if s + 1 < nseg:
                 opt.wait_stream(main)               # (joins the optimizer stream into the capture)
+                e.backward_segment(s, done_stream=opt)      # gradients final on opt; main goes on with segment s+1's chain
                 with torch.cuda.stream(opt):
+                    works = self.reducer.reduce(s)  # behind the optimizer stream on NCCL's stream
                     for w in works:
                         w.wait()                    # the optimizer stream waits for the reduction, the main stream does not
                     e.adam_segment(s)
             else:
+                e.backward_segment(s)
+                works = self.reducer.reduce(s)
                 for w in works:
                     w.wait()
                 main.wait_stream(opt)
