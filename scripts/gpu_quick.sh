@@ -10,7 +10,7 @@ i=0
 for SETTING in "$@"; do
   [ "$SETTING" = "-" ] && SETTING=""
   echo "== [$SETTING]"
-  env $SETTING timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-other-workloads --no-fast-mode > $OUT/bench_$i.json 2> $OUT/bench_$i.err
+  env $SETTING timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-other-workloads --no-fast-mode $BENCH_ARGS > $OUT/bench_$i.json 2> $OUT/bench_$i.err
   python -c "import sys,json; d=json.load(open('$OUT/bench_$i.json')); print('ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['ms_per_step'],4))" || tail -5 $OUT/bench_$i.err
   i=$((i+1))
 done

@@ -119,6 +119,12 @@ struct sv_handle {
 
 namespace {
 
+}  // namespace
+// Off by default: measured on the C2 step (two branches interleaving on two streams) PDL is a LOSS - 1.906 -> 1.930 ms - because the
+// next kernel's CTAs take their SM as soon as the previous kernel's CTA leaves it and then idle until that whole grid has drained,
+// where the other branch's kernel would have run; back-to-back launches of ONE chain gain ~3 us each (profiles/r02_pdl_*.txt).
+bool sv::pdl_enabled() { static const bool on = getenv("SV_PDL") && getenv("SV_PDL")[0] == '1'; return on; }
+namespace {
 bool getenv_off(const char* name) { const char* v = getenv(name); return v && *v == '0'; }
 
 sv_status fail(sv_handle* h, sv_status code, const char* fmt, ...) {
@@ -558,7 +564,7 @@ __global__ void pack_y_kernel(const float* __restrict__ y, void* yt, bf16* yt_lo
 // The Philox counter of the in-kernel noise (Sampling eps, gumbel u): its own device-side word, bumped once per forward pass, so
 // forward-only engines (evaluation, model(x), encode, get_y) draw fresh noise on every call like tf.random does - the optimizer's
 // iteration count, which only training advances, used to serve as the counter.
-__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
+__global__ void bump_counter_kernel(unsigned long long* ctr) { pdl_enter(); *ctr += 1ull; }
 __global__ void copy_cols_kernel(const float* __restrict__ src, int ld, int coff, float* __restrict__ dst, int B, int n) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * n) return;
@@ -906,7 +912,7 @@ static sv_status forward_impl(sv_handle* h, const float* inputs, const float* ep
   s2 = loc ? fork_side(h, s) : s;
   decoder_fwd(h, h->dec_x, s);
   if (loc) { decoder_fwd(h, h->dec_xh, s2); join_side(h, s); }
-  bump_counter_kernel<<<1, 1, 0, s>>>(noise_counter(h));
+  launch_pdl(bump_counter_kernel, dim3(1), dim3(1), 0, s, noise_counter(h));
   h->launches += 1;
   if (gm && prior_copies) {  // contiguous z_prior_mean / z_prior_sig for the reference's output tuple
     copy_cols_kernel<<<(h->B * 128 + 255) / 256, 256, 0, s>>>((const float*)bp(h, h->gm_enc.YHEADS), 768, 512, (float*)bp(h, h->ZPM_OUT), h->B, 128);

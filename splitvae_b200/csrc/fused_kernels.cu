@@ -41,6 +41,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) reparam_kernel(LatentBufs L, int B, const float* __restrict__ ueg, const float* __restrict__ uel,
                                                       unsigned long long seed, const unsigned long long* __restrict__ counter,
                                                       float* __restrict__ kl_partials) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   float kl_g = 0.f, kl_l = 0.f;
   if (idx < B * 128) {
@@ -101,13 +102,14 @@ int reparam_blocks(int B) { return (B * 128 + 255) / 256; }
 void reparam(const LatentBufs& L, int B, int act_dt, const float* ueg, const float* uel, unsigned long long seed,
              const unsigned long long* counter, float* kl_partials, cudaStream_t s) {
   const int nb = reparam_blocks(B);
-  if (act_dt == DT_F32) reparam_kernel<float><<<nb, 256, 0, s>>>(L, B, ueg, uel, seed, counter, kl_partials);
-  else reparam_kernel<bf16><<<nb, 256, 0, s>>>(L, B, ueg, uel, seed, counter, kl_partials);
+  if (act_dt == DT_F32) launch_pdl(reparam_kernel<float>, dim3(nb), dim3(256), 0, s, L, B, ueg, uel, seed, counter, kl_partials);
+  else launch_pdl(reparam_kernel<bf16>, dim3(nb), dim3(256), 0, s, L, B, ueg, uel, seed, counter, kl_partials);
 }
 
 // gradient w.r.t. the pre-activation encoder heads: reparam adjoint + KL gradient + softplus'
 template <typename T>
 __global__ void latent_bwd_kernel(LatentBufs L, int B, int gm, float beta, float inv_batch) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 128) return;
   const int b = idx >> 7, d = idx & 127;
@@ -138,8 +140,8 @@ __global__ void latent_bwd_kernel(LatentBufs L, int B, int gm, float beta, float
 
 void latent_bwd(const LatentBufs& L, int B, int act_dt, int gm, float beta, float inv_batch, cudaStream_t s) {
   const int n = B * 128;
-  if (act_dt == DT_F32) latent_bwd_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(L, B, gm, beta, inv_batch);
-  else latent_bwd_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>(L, B, gm, beta, inv_batch);
+  if (act_dt == DT_F32) launch_pdl(latent_bwd_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, L, B, gm, beta, inv_batch);
+  else launch_pdl(latent_bwd_kernel<bf16>, dim3((n + 255) / 256), dim3(256), 0, s, L, B, gm, beta, inv_batch);
 }
 
 // ------------------------------------------------------------------ gumbel softmax (one warp per row)
@@ -148,6 +150,7 @@ __global__ void gumbel_fwd_kernel(const float* __restrict__ logits, const float*
                                   float* __restrict__ u_saved, float* __restrict__ y, T* __restrict__ y_act, bf16* __restrict__ y_act_lo, int B,
                                   int K, float tau, unsigned long long seed,
                                   const unsigned long long* __restrict__ counter) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int k = threadIdx.x & 31;
   if (row >= B) return;
@@ -180,13 +183,14 @@ void gumbel_fwd(const float* logits, const float* user_u, float* u_saved, float*
                 int K, float tau, unsigned long long seed, const unsigned long long* counter, cudaStream_t s) {
   const int rows_per_block = 8;
   dim3 grid((B + rows_per_block - 1) / rows_per_block), block(32 * rows_per_block);
-  if (act_dt == DT_F32) gumbel_fwd_kernel<float><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (float*)y_act, nullptr, B, K, tau, seed, counter);
-  else gumbel_fwd_kernel<bf16><<<grid, block, 0, s>>>(logits, user_u, u_saved, y, (bf16*)y_act, (bf16*)y_act_lo, B, K, tau, seed, counter);
+  if (act_dt == DT_F32) launch_pdl(gumbel_fwd_kernel<float>, dim3(grid), dim3(block), 0, s, logits, user_u, u_saved, y, (float*)y_act, nullptr, B, K, tau, seed, counter);
+  else launch_pdl(gumbel_fwd_kernel<bf16>, dim3(grid), dim3(block), 0, s, logits, user_u, u_saved, y, (bf16*)y_act, (bf16*)y_act_lo, B, K, tau, seed, counter);
 }
 
 template <typename T>
 __global__ void gm_add_kernel(const T* __restrict__ yb0e1, const bf16* __restrict__ yb0e1_lo, const float* __restrict__ yheads,
                               T* __restrict__ hsum, bf16* __restrict__ hsum_lo, int B) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 512) return;
   const int b = idx >> 9, j = idx & 511;
@@ -198,14 +202,15 @@ __global__ void gm_add_kernel(const T* __restrict__ yb0e1, const bf16* __restric
 }
 void gm_add(const void* yb0e1_out, const void* yb0e1_lo, const float* yheads, void* hsum, void* hsum_lo, int act_dt, int B, cudaStream_t s) {
   const int n = B * 512;
-  if (act_dt == DT_F32) gm_add_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)yb0e1_out, nullptr, yheads, (float*)hsum, nullptr, B);
-  else gm_add_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)yb0e1_out, (const bf16*)yb0e1_lo, yheads, (bf16*)hsum, (bf16*)hsum_lo, B);
+  if (act_dt == DT_F32) launch_pdl(gm_add_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, (const float*)yb0e1_out, nullptr, yheads, (float*)hsum, nullptr, B);
+  else launch_pdl(gm_add_kernel<bf16>, dim3((n + 255) / 256), dim3(256), 0, s, (const bf16*)yb0e1_out, (const bf16*)yb0e1_lo, yheads, (bf16*)hsum, (bf16*)hsum_lo, B);
 }
 
 template <typename T>
 __global__ void gm_glue_a_kernel(const T* __restrict__ dhsum, const T* __restrict__ yb0e1, const float* __restrict__ yheads,
                                  const float* __restrict__ zm_g, const float* __restrict__ zs_g, T* __restrict__ d_yb0e1,
                                  T* __restrict__ d_yheads, int B, float beta, float inv_batch) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 640) return;
   const int b = idx / 640, j = idx % 640;
@@ -230,14 +235,15 @@ void gm_glue_a(const void* dhsum, const void* yb0e1_out, const float* yheads, co
                void* d_yb0e1, void* d_yheads, int act_dt, int B, float beta, float inv_batch, cudaStream_t s) {
   const int n = B * 640;
   if (act_dt == DT_F32)
-    gm_glue_a_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)dhsum, (const float*)yb0e1_out, yheads, zm_g, zs_g, (float*)d_yb0e1, (float*)d_yheads, B, beta, inv_batch);
+    launch_pdl(gm_glue_a_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, (const float*)dhsum, (const float*)yb0e1_out, yheads, zm_g, zs_g, (float*)d_yb0e1, (float*)d_yheads, B, beta, inv_batch);
   else
-    gm_glue_a_kernel<bf16><<<(n + 255) / 256, 256, 0, s>>>((const bf16*)dhsum, (const bf16*)yb0e1_out, yheads, zm_g, zs_g, (bf16*)d_yb0e1, (bf16*)d_yheads, B, beta, inv_batch);
+    launch_pdl(gm_glue_a_kernel<bf16>, dim3((n + 255) / 256), dim3(256), 0, s, (const bf16*)dhsum, (const bf16*)yb0e1_out, yheads, zm_g, zs_g, (bf16*)d_yb0e1, (bf16*)d_yheads, B, beta, inv_batch);
 }
 
 template <typename T>
 __global__ void gm_glue_b_kernel(const T* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ logits,
                                  T* __restrict__ dlogits, int B, int K, float tau, float alpha, float inv_batch) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int k = threadIdx.x & 31;
   if (row >= B) return;
@@ -268,8 +274,8 @@ __global__ void gm_glue_b_kernel(const T* __restrict__ dy, const float* __restri
 void gm_glue_b(const void* dy, const float* y, const float* logits, void* dlogits, int act_dt, int B, int K, float tau,
                float alpha, float inv_batch, cudaStream_t s) {
   dim3 grid((B + 7) / 8), block(256);
-  if (act_dt == DT_F32) gm_glue_b_kernel<float><<<grid, block, 0, s>>>((const float*)dy, y, logits, (float*)dlogits, B, K, tau, alpha, inv_batch);
-  else gm_glue_b_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dy, y, logits, (bf16*)dlogits, B, K, tau, alpha, inv_batch);
+  if (act_dt == DT_F32) launch_pdl(gm_glue_b_kernel<float>, dim3(grid), dim3(block), 0, s, (const float*)dy, y, logits, (float*)dlogits, B, K, tau, alpha, inv_batch);
+  else launch_pdl(gm_glue_b_kernel<bf16>, dim3(grid), dim3(block), 0, s, (const bf16*)dy, y, logits, (bf16*)dlogits, B, K, tau, alpha, inv_batch);
 }
 
 // ------------------------------------------------------------------ discretised logistic likelihood
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
                                                                   T* __restrict__ dout_x, T* __restrict__ dout_xh,
                                                                   long long npairs, float grad_scale,
                                                                   float* __restrict__ partials) {
+  pdl_enter();
   float sum_x = 0.f, sum_xh = 0.f;
   for (long long pr = blockIdx.x * (long long)kLossThreads + threadIdx.x; pr < npairs;
        pr += (long long)gridDim.x * kLossThreads) {
@@ -423,7 +430,7 @@ void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, vo
                 int dout_ld, long long npix, float grad_scale, float* partials, bool fast_math, cudaStream_t s) {
   const int blocks = pixel_loss_blocks(npix);
   const long long npairs = npix / 2;
-#define LAUNCH(T, LD, F) pixel_loss_kernel<T, LD, F><<<blocks, kLossThreads, 0, s>>>(inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials)
+#define LAUNCH(T, LD, F) launch_pdl(pixel_loss_kernel<T, LD, F>, dim3(blocks), dim3(kLossThreads), 0, s, inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials)
   if (dout_dt == DT_F32) {
     if (fast_math) LAUNCH(float, 6, true); else LAUNCH(float, 6, false);
   } else if (dout_ld == 8) {
@@ -441,6 +448,7 @@ __global__ void __launch_bounds__(1024) loss_scalars_kernel(const float* __restr
                                                             int gm, float beta, float alpha,
                                                             const float* __restrict__ partials, int nblocks,
                                                             float* __restrict__ scalars) {
+  pdl_enter();
   __shared__ double red[5][32];
   double acc[5] = {0, 0, 0, 0, 0};  // kl_x, kl_x_hat, y_kl, recon_x, recon_x_hat
   for (int i = threadIdx.x; i < kl_blocks; i += blockDim.x) { acc[0] += kl_partials[2 * i]; acc[1] += kl_partials[2 * i + 1]; }
@@ -493,11 +501,12 @@ __global__ void __launch_bounds__(1024) loss_scalars_kernel(const float* __restr
 
 void loss_scalars(const float* kl_partials, int kl_blocks, const float* y_logits, int B, int K, int gm, float beta, float alpha,
                   const float* partials, int nblocks, float* scalars, cudaStream_t s) {
-  loss_scalars_kernel<<<1, 1024, 0, s>>>(kl_partials, kl_blocks, y_logits, B, K, gm, beta, alpha, partials, nblocks, scalars);
+  launch_pdl(loss_scalars_kernel, dim3(1), dim3(1024), 0, s, kl_partials, kl_blocks, y_logits, B, K, gm, beta, alpha, partials, nblocks, scalars);
 }
 
 // ------------------------------------------------------------------ Keras Adam (ResourceApplyAdam)
 __global__ void adam_prepare_kernel(AdamState* st, float lr, int staircase) {
+  pdl_enter();
   const unsigned long long it = st->iterations;
   const double t = (double)(it + 1);
   double lr_t = (double)lr;
@@ -505,7 +514,7 @@ __global__ void adam_prepare_kernel(AdamState* st, float lr, int staircase) {
   st->alpha = (float)(lr_t * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
   st->iterations = it + 1;
 }
-void adam_prepare(AdamState* st, float lr, int staircase, cudaStream_t s) { adam_prepare_kernel<<<1, 1, 0, s>>>(st, lr, staircase); }
+void adam_prepare(AdamState* st, float lr, int staircase, cudaStream_t s) { launch_pdl(adam_prepare_kernel, dim3(1), dim3(1), 0, s, st, lr, staircase); }
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float alpha) {
   // exact op order of TF's ApplyAdam functor; explicit roundings forbid FMA contraction so the
@@ -519,6 +528,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, const AdamState* __restrict__ st,
                                                    float alpha_host) {
+  pdl_enter();
   const float alpha = st ? st->alpha : alpha_host;
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -541,7 +551,7 @@ void adam_apply(float* p, const float* g, float* m, float* v, long long n, const
   long long blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, n, st, alpha_host);
+  launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, s, p, g, m, v, n, st, alpha_host);
 }
 
 // ------------------------------------------------------------------ data parallel: reduce-scatter + Adam(shard) + all-gather in ONE kernel

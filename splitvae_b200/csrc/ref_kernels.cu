@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_vec_kernel(const bf16* __r
 // triples as the per-pixel kernel above, so results are bit-identical, with 4 loads per 4 outputs instead of 16.
 __global__ void __launch_bounds__(256) upsample2x_fwd_quad_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
                                                                   int B, int H, int W, int C8) {
+  pdl_enter();
   const int total = B * (H + 1) * (W + 1) * C8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c8 = idx % C8;
@@ -336,6 +337,7 @@ __device__ __forceinline__ F8 ld_pair8(const bf16* hi, const bf16* lo, size_t of
 }
 __global__ void __launch_bounds__(256) upsample2x_fwd_pair_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
                                                                   bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int B, int H, int W, int C8) {
+  pdl_enter();
   const int total = B * (H + 1) * (W + 1) * C8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c8 = idx % C8;
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_pair_kernel(const bf16* __
 __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
                                                                  const bf16* __restrict__ mask_src, int mask_act,
                                                                  int B, int H, int W, int C8) {
+  pdl_enter();
   const int total = B * H * W * C8;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c8 = idx % C8;
@@ -532,6 +535,7 @@ struct ColsumJob {
 };
 
 __global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJob* __restrict__ jobs, int njobs, float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float red[2048];
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
@@ -572,6 +576,7 @@ __global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJ
 
 __global__ void __launch_bounds__(256) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs, const float* __restrict__ partial,
                                                                  float* __restrict__ grads) {
+  pdl_enter();
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -677,8 +682,8 @@ void colsum_table_destroy(ColsumTable* t) {
 
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
-  colsum_multi_partial_kernel<<<t->nblocks, 256, 0, s>>>(t->dev, t->njobs, t->partial);
-  colsum_multi_final_kernel<<<t->nfblocks, 256, 0, s>>>(t->dev, t->njobs, t->partial, grads);
+  launch_pdl(colsum_multi_partial_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial);
+  launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial, grads);
   return 2;
 }
 
@@ -686,7 +691,7 @@ void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int 
   const long long total = (long long)B * 4 * H * W * C;
   if (dt == DT_BF16 && (C % 8) == 0 && total / 8 < (1ll << 31)) {
     const long long quads = (long long)B * (H + 1) * (W + 1) * (C / 8);
-    upsample2x_fwd_quad_kernel<<<grid_for(quads, 256, 148 * 32), 256, 0, s>>>((const bf16*)in, (bf16*)out, B, H, W, C / 8);
+    launch_pdl(upsample2x_fwd_quad_kernel, dim3(grid_for(quads, 256, 148 * 32)), dim3(256), 0, s, (const bf16*)in, (bf16*)out, B, H, W, C / 8);
     return;
   }
   if (dt == DT_F32)
@@ -697,15 +702,15 @@ void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int 
 
 void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C, cudaStream_t s) {
   const long long quads = (long long)B * (H + 1) * (W + 1) * (C / 8);     // (C % 8 == 0 for every decoder tensor: 128 / 64 / 32)
-  upsample2x_fwd_pair_kernel<<<grid_for(quads, 256, 148 * 32), 256, 0, s>>>((const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo,
-                                                                           B, H, W, C / 8);
+  launch_pdl(upsample2x_fwd_pair_kernel, dim3(grid_for(quads, 256, 148 * 32)), dim3(256), 0, s, (const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi,
+             (bf16*)out_lo, B, H, W, C / 8);
 }
 
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
                     int C, cudaStream_t s) {
   const long long total = (long long)B * H * W * C;
   if (dt == DT_BF16 && (C % 8) == 0 && total / 8 < (1ll << 29)) {
-    upsample2x_bwd_vec_kernel<<<grid_for(total / 8, 256, 148 * 32), 256, 0, s>>>((const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C / 8);
+    launch_pdl(upsample2x_bwd_vec_kernel, dim3(grid_for(total / 8, 256, 148 * 32)), dim3(256), 0, s, (const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C / 8);
     return;
   }
   if (dt == DT_F32)

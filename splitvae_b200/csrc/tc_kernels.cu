@@ -377,16 +377,17 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constant__ TcLaunch P) { igemm_body(P, blockIdx.z); }
+__global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); igemm_body(P, blockIdx.z); }
 
 // The s*s parity classes of a stride-s dgrad (each a small stride-1 convolution scattering into its own output parity)
 // as ONE launch: blockIdx.z selects the class.  4 x more CTAs in flight for layers whose single class does not fill the GPU.
 struct TcLaunch4 { TcLaunch l[4]; };
-__global__ void __launch_bounds__(kThreads, 3) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { igemm_body(P4.l[blockIdx.z], 0); }
+__global__ void __launch_bounds__(kThreads, 3) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); igemm_body(P4.l[blockIdx.z], 0); }
 
 // Split-K finish for dense layers (one output row per image): out[row][col] = epilogue(sum_z partial[z][row][col]).
 // Fixed summation order -> deterministic.  One thread per output element; consecutive threads = consecutive columns.
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ TcLaunch P) {
+  pdl_enter();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int col = (int)(idx % P.n_valid);
   const long long row = idx / P.n_valid;
@@ -677,9 +678,9 @@ __device__ __forceinline__ void halo_body(const TcLaunch& P) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) halo_conv_kernel(const __grid_constant__ TcLaunch P) { halo_body(P); }
+__global__ void __launch_bounds__(kThreads, 3) halo_conv_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); halo_body(P); }
 // the 4 parity classes of a stride-2 dgrad as one launch (blockIdx.z = class), as igemm4_kernel
-__global__ void __launch_bounds__(kThreads, 3) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { halo_body(P4.l[blockIdx.z]); }
+__global__ void __launch_bounds__(kThreads, 3) halo4_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); halo_body(P4.l[blockIdx.z]); }
 
 // ------------------------------------------------------------------------------------------------
 // Persistent, pipelined variant of the halo convolution (same operand addressing as halo_body).
@@ -909,7 +910,7 @@ __device__ __forceinline__ void pconv_body(const TcLaunch& P) {
     tc::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
-__global__ void __launch_bounds__(kPcThreads, 1) pconv_kernel(const __grid_constant__ TcLaunch4 P4) { pconv_body(P4.l[blockIdx.y]); }
+__global__ void __launch_bounds__(kPcThreads, 1) pconv_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); pconv_body(P4.l[blockIdx.y]); }
 
 // ------------------------------------------------------------------------------------------------
 // N-stacked persistent convolution (see TcNsConv in tc_kernels.h).
@@ -966,11 +967,19 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
     src[b] = (lane + d) & 31;
   }
   int xbuf = 0, i = 0;
+#ifdef SV_NS_TRACE
+  const bool etr = (P.debug & 4) != 0 && q == 0 && grp == 0 && cl == 0;
+#else
+  constexpr bool etr = false;
+#endif
+  long long t_ewait = 0, t_ework = 0, tq = 0;
   for (int t = cta; t < tiles; t += ncta, ++i) {
     if (i % groups != grp) continue;
     const int aph = (i / groups) & 1;
     const int n = t / tiles_per_img, y0 = (t - n * tiles_per_img) * R * mb;
+    if (etr) { const long long c = clock64(); if (i >= groups) t_ework += c - tq; tq = c; }
     tc::mbar_wait(&ctl->acc_full[grp], aph);
+    if (etr) { const long long c = clock64(); t_ewait += c - tq; tq = c; }
     tc::tc_fence_after();
     if (cl >= nchunk8) {                          // more chunk lanes than blocks: nothing to read, but the barrier counts every warp
       tc::tc_fence_before();
@@ -1089,6 +1098,11 @@ __device__ __forceinline__ void ns_epilogue_t(const TcNsConv& P, NsCtl* ctl, flo
     }
     }
   }
+  if (etr && lane == 0 && blockIdx.x < kTraceCtas) {
+    t_ework += clock64() - tq;
+    g_halo_trace[blockIdx.x * kTraceSlots + 6] = (unsigned long long)t_ewait;
+    g_halo_trace[blockIdx.x * kTraceSlots + 7] = (unsigned long long)t_ework;
+  }
 }
 
 #define SV_NS_EPI_ARGS P, ctl, xch, tmem_base, q, grp, cl, lane
@@ -1143,6 +1157,24 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
   NsCtl* ctl = reinterpret_cast<NsCtl*>(halo + (size_t)P.nstages * P.stage_bytes);
   float* xch = reinterpret_cast<float*>(halo + (size_t)P.nstages * P.stage_bytes + P.xch_off);
   const int split = blockIdx.x % P.co_splits, cta = blockIdx.x / P.co_splits, ncta = gridDim.x / P.co_splits;
+  // SV_NS_DEBUG bit 2: per-CTA cycle sums of where each role waits (read back through sv_debug_halo_trace, scripts/ns_trace.py):
+  //   [0] CTA lifetime  [1] MMA thread: weights landed  [2] MMA: sum of halo_full waits  [3] MMA: sum of acc_empty waits
+  //   [4] MMA: sum of issue + commit  [5] producer: sum of halo_empty waits  [6] epilogue warp 0: sum of acc_full waits  [7] its work
+  //   bit 3 (instead of bit 2): [0] CTA lifetime  [1] globaltimer at CTA start  [2] globaltimer at CTA end  [3] smid
+  // (compiled in only with -DSV_NS_TRACE - SV_BUILD_DEFINES=-DSV_NS_TRACE python splitvae_b200/build.py --force: the counters cost
+  //  registers in a kernel that already spills at its 96-register cap)
+#ifdef SV_NS_TRACE
+  const bool trc = (P.debug & 4) != 0, trg = (P.debug & 8) != 0;
+#else
+  constexpr bool trc = false, trg = false;
+#endif
+  const long long t_cta0 = (trc || trg) ? clock64() : 0;
+  if (trg && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+    unsigned smid; unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_halo_trace[blockIdx.x * kTraceSlots + 1] = gt; g_halo_trace[blockIdx.x * kTraceSlots + 3] = smid;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1158,6 +1190,7 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
   const int pair = P.pair, wrows = pair ? 2 * P.n_total : P.n_total;      // rows of one weight k-block
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(P.groups * acc_cols)) tmem_cols <<= 1;
+  tc::pdl_trigger();
   if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
@@ -1166,24 +1199,31 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
 
   if (warp == 0) {
     if (tc::elect_one()) {
+      // (the packed weights are written by the optimizer's re-pack, which every kernel of the step depends on in full: loading them
+      //  before pdl_wait() overlaps the previous kernel's tail)
       tc::mbar_expect_tx(&ctl->w_full, (uint32_t)(P.num_kb * P.wk_bytes));
       for (int j = 0; j < P.num_kb; ++j)
         for (int r0 = 0; r0 < wrows; r0 += P.n_box)
           tc::tma_load_2d(wsm + (size_t)j * P.wk_bytes + (size_t)r0 * P.pixB, &P.map_w, &ctl->w_full, j * P.ck, split * wrows + r0);
+      tc::pdl_wait();
       const uint32_t halo_tx = (uint32_t)(P.nchunks * P.halo_rows * P.W * P.pixB);
       const int passes = pair ? 2 : 1;            // pair: the hi plane and the lo plane of a tile are two consecutive ring stages
+      long long t_prod_wait = 0;
       int i = 0;
       for (int t = cta; t < P.tiles; t += ncta) {
         const int n = t / P.tiles_per_img, y0 = (t - n * P.tiles_per_img) * P.R * P.mb;
         for (int pl = 0; pl < passes; ++pl, ++i) {
           const int st = i % P.nstages, ph = (i / P.nstages) & 1;
+          const long long tw = trc ? clock64() : 0;
           tc::mbar_wait(&ctl->halo_empty[st], ph ^ 1);
+          if (trc) t_prod_wait += clock64() - tw;
           tc::mbar_expect_tx(&ctl->halo_full[st], halo_tx);
           for (int c = 0; c < P.nchunks; ++c)
             tc::tma_load_4d(halo + (size_t)st * P.stage_bytes + (size_t)c * P.chunk_bytes, pl ? &P.map_x_lo : &P.map_x, &ctl->halo_full[st],
                             c * P.ck, 0, y0 - P.pad_t, n);
         }
       }
+      if (trc && blockIdx.x < kTraceCtas) g_halo_trace[blockIdx.x * kTraceSlots + 5] = (unsigned long long)t_prod_wait;
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
@@ -1207,13 +1247,18 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
       const int passes = pair ? 2 : 1;
       const int pshape = !pair ? 0 : (kh == 6 && nchunks == 1 && ksteps == 4) ? 1 : (kh == 4 && nchunks == 2 && ksteps == 4) ? 2 : 0;
       tc::mbar_wait(&ctl->w_full, 0);
+      long long t_hw = 0, t_aw = 0, t_is = 0, tq = 0;
+      if (trc && blockIdx.x < kTraceCtas) g_halo_trace[blockIdx.x * kTraceSlots + 1] = (unsigned long long)(clock64() - t_cta0);
       int i = 0, it = 0;                        // i: ring stage counter, it: tile counter
       for (int t = cta; t < tiles; t += ncta, ++it) {
         const int ab = it % groups, aph = (it / groups) & 1;
         for (int pl = 0; pl < passes; ++pl, ++i) {
         const int st = i % nstages, ph = (i / nstages) & 1;
+        if (trc) tq = clock64();
         tc::mbar_wait(&ctl->halo_full[st], ph);
+        if (trc) { const long long c = clock64(); t_hw += c - tq; tq = c; }
         if (pl == 0) tc::mbar_wait(&ctl->acc_empty[ab], aph ^ 1);
+        if (trc) { const long long c = clock64(); t_aw += c - tq; tq = c; }
         tc::tc_fence_after();
         for (int mbi = 0; mbi < mb; ++mbi) {    // block mbi of the tile: rows mbi*R .. of the shared halo, its own accumulator
         const uint32_t h_addr = halo_addr + (uint32_t)st * stage_step + (uint32_t)mbi * blk_step;
@@ -1260,16 +1305,26 @@ __global__ void __launch_bounds__(kNsThreads, 1) nsconv_kernel(const __grid_cons
         }
         }
         tc::umma_commit(&ctl->halo_empty[st]);
+        if (trc) t_is += clock64() - tq;
         }
         tc::umma_commit(&ctl->acc_full[ab]);
       }
+      if (trc && blockIdx.x < kTraceCtas) {
+        unsigned long long* tr = g_halo_trace + blockIdx.x * kTraceSlots;
+        tr[2] = (unsigned long long)t_hw; tr[3] = (unsigned long long)t_aw; tr[4] = (unsigned long long)t_is;
+      }
     }
   } else {
+    tc::pdl_wait();                              // (stores, mask reads: only after the previous kernel of the stream has completed)
     const int e = (warp - 2) >> 2;               // epilogue warp set: (group, chunk lane); the TMEM quarter is warp % 4
     if (e < P.groups * P.lanes) ns_epilogue(P, ctl, xch, tmem_base, warp & 3, e / P.lanes, e % P.lanes, lane);
   }
   tc::tc_fence_before();
   __syncthreads();
+  if ((trc || trg) && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+    g_halo_trace[blockIdx.x * kTraceSlots + 0] = (unsigned long long)(clock64() - t_cta0);
+    if (trg) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_halo_trace[blockIdx.x * kTraceSlots + 2] = gt; }
+  }
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -1286,6 +1341,7 @@ struct WgCtl {
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ TcWgradLaunch P) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kPix = 64;
@@ -1447,6 +1503,7 @@ __device__ __forceinline__ void hw_issue_tile(uint64_t da0, uint64_t db0, const 
 }
 
 __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_constant__ TcHaloWgrad P) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   HwCtl* ctl = reinterpret_cast<HwCtl*>(smem + (size_t)P.stages * P.stage_bytes);
@@ -1599,6 +1656,7 @@ __device__ __forceinline__ int wg_col(const WgRowMap& R, int tap, int co) {
 // 8 partial sums are combined in a fixed order through shared memory -> deterministic, no atomics.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                            WgRowMap R, float* __restrict__ grads) {
+  pdl_enter();
   __shared__ float red[8][33];
   const int rows = g.kh * g.kw * g.Ci;
   const int cblocks = (g.Co + 31) / 32;
@@ -1632,6 +1690,7 @@ template <> struct VecF<1> { typedef float T; };
 template <int VEC>
 __global__ void __launch_bounds__(1024) wgrad_reduce_vec_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                                 WgRowMap R, float* __restrict__ grads) {
+  pdl_enter();
   typedef typename VecF<VEC>::T V;
   extern __shared__ float red_dyn[];   // [blockDim.y][32 * VEC]
   const int cov = g.Co / VEC;
@@ -1691,6 +1750,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_vec_kernel(ConvGeom g, cons
 // multiples of 4 and a row map with contiguous columns (mode < 4)
 __global__ void __launch_bounds__(256) wgrad_reduce_few4_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                                 WgRowMap R, float* __restrict__ grads) {
+  pdl_enter();
   const int co4 = g.Co >> 2;
   const long long total = (long long)g.kh * g.kw * g.Ci * co4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1713,6 +1773,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_few4_kernel(ConvGeom g, cons
 
 __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const float* __restrict__ partial, int k_splits, int m_pad, int n_pad,
                                                                WgRowMap R, float* __restrict__ grads) {
+  pdl_enter();
   const long long total = (long long)g.kh * g.kw * g.Ci * g.Co;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(idx % g.Co);
@@ -1763,6 +1824,7 @@ __device__ __forceinline__ float master_w(const PackJob& J, const float* params,
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* __restrict__ params) {
+  pdl_enter();
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {  // last job whose block_start <= blockIdx.x
     const int mid = (lo + hi + 1) >> 1;
@@ -2064,6 +2126,7 @@ const char* make_window_map(CUtensorMap* m, const void* xp, int N, int H, int W,
 
 __global__ void __launch_bounds__(256) stage_first_kernel(const float* __restrict__ inputs, bf16* __restrict__ xp, int coff, int B, int H, int W,
                                                           int split) {
+  pdl_enter();
   const long long total = (long long)B * H * W;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % W);
@@ -2492,7 +2555,7 @@ void tc_stage_first(const float* inputs, void* xp, int coff, int B, int H, int W
   const long long total = (long long)B * H * W;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stage_first_kernel<<<(int)blocks, 256, 0, s>>>(inputs, (bf16*)xp, coff, B, H, W, split ? 1 : 0);
+  launch_pdl(stage_first_kernel, dim3((int)blocks), dim3(256), 0, s, inputs, (bf16*)xp, coff, B, H, W, split ? 1 : 0);
 }
 
 // First conv of an encoder (6x6, stride 2, 3 input channels): the staged image is read as overlapping
@@ -3012,7 +3075,7 @@ void tc_pack_table_destroy(TcPackTable* t) {
 
 int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
-  pack_kernel<<<t->nblocks, 256, 0, s>>>(t->dev, t->njobs, params);
+  launch_pdl(pack_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, params);
   return 1;
 }
 
@@ -3020,25 +3083,25 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
   if (L.halo && L.persist) {
     TcLaunch4 P4;
     for (int j = 0; j < L.n_tiles; ++j) { P4.l[j] = L; P4.l[j].p_ntile = j; }   // (n_tiles > 1: one CTA class per column tile)
-    pconv_kernel<<<dim3(L.p_grid, L.n_tiles), kPcThreads, L.p_smem, s>>>(P4);
+    launch_pdl(pconv_kernel, dim3(L.p_grid, L.n_tiles), dim3(kPcThreads), L.p_smem, s, P4);
     return;
   }
   if (L.halo) {
     dim3 grid(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles);
-    halo_conv_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+    launch_pdl(halo_conv_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
     return;
   }
   const int tiles_per_img = L.grid_h / L.tile_h;
   const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
   dim3 grid(m_tiles, L.n_tiles, L.k_splits > 1 ? L.k_splits : 1);
-  igemm_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+  launch_pdl(igemm_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
   if (L.k_splits > 1) {
     const long long total = (long long)L.n_img * L.n_valid;
-    splitk_finish_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(L);
+    launch_pdl(splitk_finish_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, s, L);
   }
 }
 
-static void launch_ns(const TcNsConv& P, cudaStream_t s) { nsconv_kernel<<<P.grid, kNsThreads, P.smem_bytes, s>>>(P); }
+static void launch_ns(const TcNsConv& P, cudaStream_t s) { launch_pdl(nsconv_kernel, dim3(P.grid), dim3(kNsThreads), P.smem_bytes, s, P); }
 
 int tc_halo_trace_read(unsigned long long* out, int max_ctas) {
   const int n = max_ctas < kTraceCtas ? max_ctas : kTraceCtas;
@@ -3057,9 +3120,9 @@ void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
     const TcLaunch& L = t.dgrad[0];
     const int tiles_per_img = L.grid_h / L.tile_h;
     const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
-    if (L.halo && L.persist) pconv_kernel<<<dim3(L.p_grid, 4), kPcThreads, L.p_smem, s>>>(P4);
-    else if (L.halo) halo4_kernel<<<dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
-    else igemm4_kernel<<<dim3(m_tiles, L.n_tiles, 4), kThreads, L.smem_bytes, s>>>(P4);
+    if (L.halo && L.persist) launch_pdl(pconv_kernel, dim3(L.p_grid, 4), dim3(kPcThreads), L.p_smem, s, P4);
+    else if (L.halo) launch_pdl(halo4_kernel, dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), dim3(kThreads), L.smem_bytes, s, P4);
+    else launch_pdl(igemm4_kernel, dim3(m_tiles, L.n_tiles, 4), dim3(kThreads), L.smem_bytes, s, P4);
     return;
   }
   for (int c = 0; c < t.n_dgrad; ++c) launch(t.dgrad[c], s);
@@ -3072,8 +3135,8 @@ static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_s
     for (int j = 0; j < g.nparts; ++j) vec = vec && (g.part_n[j] % 4) == 0 && (g.part_w[j] % 4) == 0;
     long long blocks = ((vec ? total / 4 : total) + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (vec) wgrad_reduce_few4_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
-    else wgrad_reduce_few_kernel<<<(int)blocks, 256, 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    if (vec) launch_pdl(wgrad_reduce_few4_kernel, dim3((int)blocks), dim3(256), 0, s, g, partial, k_splits, m_pad, n_pad, R, grads);
+    else launch_pdl(wgrad_reduce_few_kernel, dim3((int)blocks), dim3(256), 0, s, g, partial, k_splits, m_pad, n_pad, R, grads);
   } else if (!env_int("SV_OLD_REDUCE", 0)) {
     int vec = 4;
     while (vec > 1) {
@@ -3088,12 +3151,12 @@ static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_s
     int lanes = 8;
     while (lanes < 32 && (k_splits > 8 * lanes || (long long)blocks * lanes < 148 * 16)) lanes <<= 1;
     const size_t smem = (size_t)lanes * 32 * vec * sizeof(float);
-    if (vec == 4) wgrad_reduce_vec_kernel<4><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
-    else if (vec == 2) wgrad_reduce_vec_kernel<2><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
-    else wgrad_reduce_vec_kernel<1><<<blocks, dim3(32, lanes), smem, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    if (vec == 4) launch_pdl(wgrad_reduce_vec_kernel<4>, dim3(blocks), dim3(32, lanes), smem, s, g, partial, k_splits, m_pad, n_pad, R, grads);
+    else if (vec == 2) launch_pdl(wgrad_reduce_vec_kernel<2>, dim3(blocks), dim3(32, lanes), smem, s, g, partial, k_splits, m_pad, n_pad, R, grads);
+    else launch_pdl(wgrad_reduce_vec_kernel<1>, dim3(blocks), dim3(32, lanes), smem, s, g, partial, k_splits, m_pad, n_pad, R, grads);
   } else {
     const int rblocks = g.kh * g.kw * g.Ci * ((g.Co + 31) / 32);
-    wgrad_reduce_kernel<<<rblocks, dim3(32, 8), 0, s>>>(g, partial, k_splits, m_pad, n_pad, R, grads);
+    launch_pdl(wgrad_reduce_kernel, dim3(rblocks), dim3(32, 8), 0, s, g, partial, k_splits, m_pad, n_pad, R, grads);
   }
 }
 
@@ -3101,7 +3164,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
   if (t.wg_halo) {
     const TcHaloWgrad& H = t.hw;
     dim3 grid(H.m_splits, 1, H.k_splits);
-    halo_wgrad_kernel<<<grid, kThreads, H.smem_bytes, s>>>(H);
+    launch_pdl(halo_wgrad_kernel, dim3(grid), dim3(kThreads), H.smem_bytes, s, H);
     const WgRowMap R{(H.nstack ? 4 : 2) + (H.mode ? 1 : 0), g.kw, 0, H.cb, H.nsub, H.gw, H.gpt, H.nb};
     launch_wgrad_reduce(g, H.partial, H.k_splits, H.m_pad, H.n_pad, R, grads, s);
     return;
@@ -3109,7 +3172,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
   const TcWgradLaunch& L = t.wg;
   const int m_splits = (L.groups + L.groups_per_cta - 1) / L.groups_per_cta;
   dim3 grid(m_splits, L.n_tiles, L.k_splits);
-  wgrad_kernel<<<grid, kThreads, L.smem_bytes, s>>>(L);
+  launch_pdl(wgrad_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
   const WgRowMap R{L.first ? 1 : 0, g.kw, L.ncb * L.cb, 0, 0, 0, 0, 0};
   launch_wgrad_reduce(g, L.partial, L.k_splits, L.m_pad, L.n_pad, R, grads, s);
 }
