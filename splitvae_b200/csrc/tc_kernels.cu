@@ -2464,6 +2464,8 @@ bool plan_nsconv(TcNsConv& P, int kh, int kw, int pad_t, int pad_l, int H, int W
     if (R + kh - 1 > 3 * R && can2) mb = 2;
     const int f = env_int("SV_NS_MB", 0);
     if (f == 1 || (f == 2 && can2)) mb = f;
+    // four blocks per tile (a 21-row halo for 16 rows of a 6x6 filter): 1.31x re-read; two accumulator buffers of 4 blocks in TMEM
+    if (f == 4 && nchunks == 1 && (H % (4 * R)) == 0 && 8 * kw * nb_all <= 512) mb = 4;
   }
   // split the output channels over CTAs when the resident weights would leave room for fewer than 4 halo stages
   const int chunk_bytes = round_up((mb * R + kh - 1) * W * pixB, 1024), stage_bytes = chunk_bytes * nchunks;

@@ -104,7 +104,9 @@ class StepRunner:
             return
         main = torch.cuda.current_stream()
         if self.opt_stream is None:
-            self.opt_stream = torch.cuda.Stream()
+            # level with the engine's weight-gradient streams, below the capture stream (-3): at the default (lowest) priority the
+            # first segment's reduction + update starved until the end of the step and the whole optimizer tail was exposed
+            self.opt_stream = torch.cuda.Stream(priority=-2)
         opt = self.opt_stream
         e.forward(self.inputs, self.eps_g, self.eps_l, self.u)
         e.loss_fwd_bwd(self.inputs)
