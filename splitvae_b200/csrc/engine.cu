@@ -112,6 +112,7 @@ struct sv_handle {
   // (encoders: part 0 = the layers of segment 1, part 1 = segment 2; decoders: part 0 only)
   int CSP[4][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
   ColsumTable* cs[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  float* cs_fold[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [decoder][d2..d5]: external partials
   cudaEvent_t ev_seg_done = nullptr;
   cudaGraph_t graph = nullptr;            // sv_capture_graph: one captured sv_train_step
   cudaGraphExec_t graph_exec = nullptr;
@@ -340,12 +341,26 @@ std::vector<int> segment_layers(const sv_handle* h, int seg) {
     for (int li : branch_layers(h, b, seg == 0 ? 0 : seg - 1)) v.push_back(li);
   return v;
 }
-std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, int part, bool with_ptrs) {
+// Decoder layers whose dY is produced by a CUDA-core kernel of the backward pass get their bias-gradient partials from that kernel
+// (d2-d4: upsample2x_bwd, d5: pixel_loss) instead of a second pass over dY; index into `fold` = 0..3 for d2..d5.
+std::vector<ColsumSpec> branch_specs(sv_handle* h, int which, int part, bool with_ptrs, int* fold_index = nullptr) {
   std::vector<ColsumSpec> v;
+  const bool fold = which < 2 && !getenv_off("SV_FOLD_COLSUM");
+  const Decoder* d = which == 0 ? &h->dec_x : which == 1 ? &h->dec_xh : nullptr;
+  if (fold_index) for (int k = 0; k < 4; ++k) fold_index[k] = -1;
   for (int li : branch_layers(h, which, part)) {
     ColsumSpec sp{};
     sp.g = h->layers[li].g;
     sp.dout = with_ptrs ? bp(h, h->layers[li].dout) : nullptr;
+    if (fold && d) {
+      const int B = h->B, H = h->H, W = h->W;
+      int k = -1;
+      if (li == d->d2) { k = 0; sp.ext_chunks = upsample2x_bwd_blocks(B, H / 8, W / 8, 128); }
+      else if (li == d->d3) { k = 1; sp.ext_chunks = upsample2x_bwd_blocks(B, H / 4, W / 4, 64); }
+      else if (li == d->d4) { k = 2; sp.ext_chunks = upsample2x_bwd_blocks(B, H / 2, W / 2, 32); }
+      else if (li == d->d5 && sp.g.dout_ld == 16) { k = 3; sp.ext_chunks = pixel_loss_blocks((long long)B * H * W); }
+      if (k >= 0 && fold_index) fold_index[k] = (int)v.size();
+    }
     v.push_back(sp);
   }
   return v;
@@ -530,12 +545,13 @@ void decoder_fwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
 
 void decoder_bwd(sv_handle* h, const Decoder& d, cudaStream_t s) {
   const int B = h->B, H = h->H, W = h->W, T = h->act_dt;
+  float* const* fold = h->cs_on ? h->cs_fold[&d == &h->dec_x ? 0 : 1] : nullptr;   // bias-gradient partials of d2..d4 ride along
   layer_bwd(h, d.d5, nullptr, s);
-  upsample2x_bwd(bp(h, d.dU3), bp(h, d.dD4), bp(h, d.D4), ACT_RELU, T, B, H / 2, W / 2, 32, s);
+  upsample2x_bwd(bp(h, d.dU3), bp(h, d.dD4), bp(h, d.D4), ACT_RELU, T, B, H / 2, W / 2, 32, s, fold ? fold[2] : nullptr);
   layer_bwd(h, d.d4, nullptr, s);
-  upsample2x_bwd(bp(h, d.dU2), bp(h, d.dD3), bp(h, d.D3), ACT_RELU, T, B, H / 4, W / 4, 64, s);
+  upsample2x_bwd(bp(h, d.dU2), bp(h, d.dD3), bp(h, d.D3), ACT_RELU, T, B, H / 4, W / 4, 64, s, fold ? fold[1] : nullptr);
   layer_bwd(h, d.d3, nullptr, s);
-  upsample2x_bwd(bp(h, d.dU1), bp(h, d.dD2), bp(h, d.D2), ACT_RELU, T, B, H / 8, W / 8, 128, s);
+  upsample2x_bwd(bp(h, d.dU1), bp(h, d.dD2), bp(h, d.D2), ACT_RELU, T, B, H / 8, W / 8, 128, s, fold ? fold[0] : nullptr);
   layer_bwd(h, d.d2, nullptr, s);
   layer_bwd(h, d.d1, nullptr, s);
   h->launches += 3;
@@ -827,12 +843,15 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (h->cs_on) {
     for (int b = 0; b < 4; ++b)
       for (int part = 0; part < 2; ++part) {
-        const std::vector<ColsumSpec> sp = branch_specs(h, b, part, true);
+        int fold_index[4];
+        const std::vector<ColsumSpec> sp = branch_specs(h, b, part, true, fold_index);
         if (sp.empty()) continue;
         const char* cerr = nullptr;
         colsum_table_destroy(h->cs[b][part]);
         h->cs[b][part] = colsum_table_create(sp.data(), (int)sp.size(), (float*)bp(h, h->CSP[b][part]), &cerr);
         if (!h->cs[b][part]) return fail(h, SV_ERR_DEVICE, "bias-gradient table: %s", cerr ? cerr : "?");
+        if (b < 2 && part == 0)
+          for (int k = 0; k < 4; ++k) h->cs_fold[b][k] = colsum_table_ext_partial(h->cs[b][part], fold_index[k]);
       }
   }
   // Stream priorities (only the order in which PENDING blocks are dispatched; nothing is pre-empted): the forward / dgrad chain
@@ -935,7 +954,8 @@ sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
   const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
   pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), loc ? (const float*)bp(h, h->dec_xh.OUT) : nullptr, bp(h, h->dec_x.dOUT),
              loc ? bp(h, h->dec_xh.dOUT) : nullptr, h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
-             (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s);
+             (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s, h->cs_on ? h->cs_fold[0][3] : nullptr,
+             h->cs_on && loc ? h->cs_fold[1][3] : nullptr);
   loss_scalars((const float*)bp(h, h->KLPART), reparam_blocks(h->B), gm ? (const float*)bp(h, h->gm_enc.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
                (const float*)bp(h, h->PARTIALS), pixel_loss_blocks(npix), (float*)bp(h, h->SCALARS), s);
   h->launches += 2;

@@ -368,9 +368,12 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
                                                                   const float* __restrict__ dec_xh,
                                                                   T* __restrict__ dout_x, T* __restrict__ dout_xh,
                                                                   long long npairs, float grad_scale,
-                                                                  float* __restrict__ partials) {
+                                                                  float* __restrict__ partials, float* __restrict__ cs_x,
+                                                                  float* __restrict__ cs_xh) {
   pdl_enter();
   float sum_x = 0.f, sum_xh = 0.f;
+  // cs_x / cs_xh (may be NULL): [gridDim.x][16] per-block column sums of the written gradients = d5's bias-gradient partials
+  float bsx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long pr = blockIdx.x * (long long)kLossThreads + threadIdx.x; pr < npairs;
        pr += (long long)gridDim.x * kLossThreads) {
     float in[12], ox[12], oh[12];
@@ -399,7 +402,36 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
       }
       store_dout<T, LD>(dout_x + (pr * 2 + px) * LD, gx);
       if (two) store_dout<T, LD>(dout_xh + (pr * 2 + px) * LD, gh);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { bsx[c] += gx[c]; if (two) bsh[c] += gh[c]; }
     }
+  }
+  if (cs_x) {
+    __shared__ float cred[2][kLossThreads / 32][6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        bsx[c] += __shfl_xor_sync(0xffffffffu, bsx[c], o);
+        bsh[c] += __shfl_xor_sync(0xffffffffu, bsh[c], o);
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { cred[0][threadIdx.x >> 5][c] = bsx[c]; cred[1][threadIdx.x >> 5][c] = bsh[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int which = threadIdx.x >> 4, c = threadIdx.x & 15;
+      float t = 0.f;
+      if (c < 6) {
+#pragma unroll
+        for (int w = 0; w < kLossThreads / 32; ++w) t += cred[which][w][c];
+      }
+      float* dst = which ? cs_xh : cs_x;
+      if (dst) dst[(size_t)blockIdx.x * 16 + c] = t;
+    }
+    __syncthreads();
   }
   // deterministic block reduction
   __shared__ float red[2][kLossThreads / 32];
@@ -427,10 +459,11 @@ int pixel_loss_blocks(long long npix) {
 }
 
 void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, void* dout_x, void* dout_xh, int dout_dt,
-                int dout_ld, long long npix, float grad_scale, float* partials, bool fast_math, cudaStream_t s) {
+                int dout_ld, long long npix, float grad_scale, float* partials, bool fast_math, cudaStream_t s, float* cs_x, float* cs_xh) {
+  if (dout_ld != 16 || dout_dt != DT_BF16) { cs_x = nullptr; cs_xh = nullptr; }     // (the external partial rows are 16 columns wide)
   const int blocks = pixel_loss_blocks(npix);
   const long long npairs = npix / 2;
-#define LAUNCH(T, LD, F) launch_pdl(pixel_loss_kernel<T, LD, F>, dim3(blocks), dim3(kLossThreads), 0, s, inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials)
+#define LAUNCH(T, LD, F) launch_pdl(pixel_loss_kernel<T, LD, F>, dim3(blocks), dim3(kLossThreads), 0, s, inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials, cs_x, cs_xh)
   if (dout_dt == DT_F32) {
     if (fast_math) LAUNCH(float, 6, true); else LAUNCH(float, 6, false);
   } else if (dout_ld == 8) {

@@ -17,18 +17,24 @@ void ref_conv_wgrad(const ConvGeom& g, const void* in, int in_dt, const void* do
 int colsum_chunks(long long rows);
 void bias_grad(const ConvGeom& g, const void* dout, int dt, float* partial_ws, float* grads, cudaStream_t s);
 // multi-tensor bias gradients (bf16 dY): all layers of one backward branch in two launches
-struct ColsumSpec { ConvGeom g; const void* dout; };
+// ext_chunks > 0: the per-chunk column partials [ext_chunks][ncols] of this layer are written by the kernel that PRODUCES dY
+// (upsample2x_bwd for the decoders' d2-d4, pixel_loss for d5: the values are still in registers there), the table only finishes them.
+struct ColsumSpec { ConvGeom g; const void* dout; int ext_chunks; };
 struct ColsumTable;
 bool colsum_multi_supported(const ColsumSpec* specs, int n);
 long long colsum_table_partial_floats(const ColsumSpec* specs, int n);
 ColsumTable* colsum_table_create(const ColsumSpec* specs, int n, float* partial_ws, const char** err);
 void colsum_table_destroy(ColsumTable* t);
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s);   // returns #launches
+float* colsum_table_ext_partial(ColsumTable* t, int spec_index);      // where the producer of spec i writes partial[chunk][colsum_ext_cols]
+int colsum_ext_cols(int dout_ld);                                      // columns of one external partial row (the padded pitch)
+int upsample2x_bwd_blocks(int B, int H, int W, int C);                 // grid of the bf16 upsample2x_bwd launch = its ext_chunks
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s);
 // bf16x3: input and output are bf16 pairs (value = hi + lo); out_lo may be NULL (the consumer reads single bf16: d5)
 void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C, cudaStream_t s);
+// colsum_partial (bf16 only, may be NULL): per-block column sums of din, [upsample2x_bwd_blocks][C] (the bias gradient of the producer)
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
-                    int C, cudaStream_t s);
+                    int C, cudaStream_t s, float* colsum_partial = nullptr);
 
 // ---- fused_kernels.cu -------------------------------------------------------------------------
 struct LatentBufs {
@@ -72,7 +78,8 @@ void gm_glue_b(const void* dy, const float* y, const float* logits, void* dlogit
 // fused reconstruction likelihood fwd+bwd for both decoders; partial sums -> loss_partials[2*nblocks]
 int pixel_loss_blocks(long long npix);
 void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, void* dout_x, void* dout_xh, int dout_dt,
-                int dout_ld, long long npix, float grad_scale, float* loss_partials, bool fast_math, cudaStream_t s);
+                int dout_ld, long long npix, float grad_scale, float* loss_partials, bool fast_math, cudaStream_t s,
+                float* colsum_x = nullptr, float* colsum_xh = nullptr);   // [pixel_loss_blocks][16] bias-gradient partials of the two d5 layers
 // final reduction of the KL partials (reparam) and pixel partials (pixel_loss) + categorical KL -> scalars[8]
 void loss_scalars(const float* kl_partials, int kl_blocks, const float* y_logits, int B, int K, int gm, float beta, float alpha,
                   const float* loss_partials, int nblocks, float* scalars, cudaStream_t s);

@@ -377,11 +377,14 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_pair_kernel(const bf16* __
   }
 }
 
+// colsum (may be NULL): [gridDim.x][8 * C8] per-block column sums of din (before its bf16 rounding) = the producer's bias-gradient
+// partials.  gridDim.x * 256 is a multiple of C8, so a thread keeps ONE channel group over its grid-stride items.
 __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
                                                                  const bf16* __restrict__ mask_src, int mask_act,
-                                                                 int B, int H, int W, int C8) {
+                                                                 int B, int H, int W, int C8, float* __restrict__ colsum) {
   pdl_enter();
   const int total = B * H * W * C8;
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c8 = idx % C8;
     int p = idx / C8;
@@ -416,6 +419,29 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __r
       for (int i = 0; i < 8; ++i) acc.v[i] *= act_grad_from_out(m.v[i], mask_act);
     }
     st_bf16x8(din + (size_t)idx * 8, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) csum[i] += acc.v[i];
+  }
+  if (colsum) {
+    // fixed-order block reduction: lanes of equal channel group (lane % C8) by xor-shuffles, then the 8 warps through shared memory
+    __shared__ float red[8][16][8];
+    for (int o = C8; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) csum[i] += __shfl_xor_sync(0xffffffffu, csum[i], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < C8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][lane][i] = csum[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C8 * 8) {
+      const int g = threadIdx.x >> 3, i = threadIdx.x & 7;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][g][i];
+      colsum[(size_t)blockIdx.x * (C8 * 8) + threadIdx.x] = t;
+    }
   }
 }
 
@@ -608,15 +634,35 @@ struct ColsumTable {
   ColsumJob* dev = nullptr;
   int njobs = 0, nblocks = 0, nfblocks = 0;
   float* partial = nullptr;
+  std::vector<long long> ext_off;     // per spec: float offset of its external partial block, or -1
 };
 
-static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>& jobs, long long& partial_floats, int& nblocks, int& nfblocks) {
+int colsum_ext_cols(int dout_ld) { return dout_ld; }
+static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>& jobs, long long& partial_floats, int& nblocks, int& nfblocks,
+                         std::vector<long long>* ext_off = nullptr) {
   jobs.clear();
   partial_floats = 0; nblocks = 0; nfblocks = 0;
   for (int i = 0; i < n; ++i) {
     const ConvGeom& g = specs[i].g;
     const long long rows = (long long)g.B * g.Ho * g.Wo;
     const int ld = g.dout_ld;
+    if (specs[i].ext_chunks > 0) {                  // partials come from the kernel that produces dY: only the final pass runs here
+      ColsumJob J{};
+      J.d = nullptr;
+      J.rows = rows; J.ld = ld; J.col0 = 0; J.c_valid = g.Co;
+      J.ncols = colsum_ext_cols(ld);
+      J.rows_per_chunk = 0; J.nchunks = specs[i].ext_chunks;
+      J.partial_off = partial_floats;
+      partial_floats += (long long)J.nchunks * J.ncols;
+      J.block_start = nblocks;                       // (no blocks in the partial kernel)
+      J.fblock_start = nfblocks; nfblocks += (J.ncols + 31) / 32;
+      J.nparts = g.nparts;
+      for (int k = 0; k < 3; ++k) { J.part_n[k] = g.part_n[k]; J.part_b[k] = g.part_b[k]; }
+      jobs.push_back(J);
+      if (ext_off) ext_off->push_back(J.partial_off);
+      continue;
+    }
+    if (ext_off) ext_off->push_back(-1);
     for (int col0 = 0; col0 < ld && col0 < ((g.Co + 7) & ~7); col0 += 256) {
       ColsumJob J{};
       J.d = (const bf16*)specs[i].dout;
@@ -662,8 +708,10 @@ long long colsum_table_partial_floats(const ColsumSpec* specs, int n) {
 ColsumTable* colsum_table_create(const ColsumSpec* specs, int n, float* partial_ws, const char** err) {
   std::vector<ColsumJob> jobs;
   long long pf; int nb, nf;
-  colsum_build(specs, n, jobs, pf, nb, nf);
+  std::vector<long long> ext;
+  colsum_build(specs, n, jobs, pf, nb, nf, &ext);
   ColsumTable* T = new ColsumTable();
+  T->ext_off = ext;
   T->njobs = (int)jobs.size(); T->nblocks = nb; T->nfblocks = nf; T->partial = partial_ws;
   if (T->njobs && (cudaMalloc(&T->dev, jobs.size() * sizeof(ColsumJob)) != cudaSuccess ||
                    cudaMemcpy(T->dev, jobs.data(), jobs.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -682,9 +730,12 @@ void colsum_table_destroy(ColsumTable* t) {
 
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
-  launch_pdl(colsum_multi_partial_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial);
+  if (t->nblocks) launch_pdl(colsum_multi_partial_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial);
   launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial, grads);
-  return 2;
+  return t->nblocks ? 2 : 1;
+}
+float* colsum_table_ext_partial(ColsumTable* t, int i) {
+  return (t && i >= 0 && i < (int)t->ext_off.size() && t->ext_off[i] >= 0) ? t->partial + t->ext_off[i] : nullptr;
 }
 
 void upsample2x_fwd(const void* in, void* out, int dt, int B, int H, int W, int C, cudaStream_t s) {
@@ -706,11 +757,17 @@ void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, voi
              (bf16*)out_lo, B, H, W, C / 8);
 }
 
+// grid of the bf16 launch: at most 8 blocks per SM (a multiple of every C / 8, so the grid-stride keeps a thread's channel group)
+int upsample2x_bwd_blocks(int B, int H, int W, int C) {
+  return grid_for((long long)B * H * W * (C / 8), 256, 148 * 8);
+}
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
-                    int C, cudaStream_t s) {
+                    int C, cudaStream_t s, float* colsum_partial) {
   const long long total = (long long)B * H * W * C;
   if (dt == DT_BF16 && (C % 8) == 0 && total / 8 < (1ll << 29)) {
-    launch_pdl(upsample2x_bwd_vec_kernel, dim3(grid_for(total / 8, 256, 148 * 32)), dim3(256), 0, s, (const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C / 8);
+    const bool fold = colsum_partial && C / 8 <= 16 && (256 % (C / 8)) == 0;
+    launch_pdl(upsample2x_bwd_vec_kernel, dim3(fold ? upsample2x_bwd_blocks(B, H, W, C) : grid_for(total / 8, 256, 148 * 32)), dim3(256), 0, s,
+               (const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C / 8, fold ? colsum_partial : (float*)nullptr);
     return;
   }
   if (dt == DT_F32)
