@@ -268,12 +268,15 @@ __device__ __forceinline__ void epilogue_dispatch(const EpiRegs& E, EpiSel e, ui
 }
 #undef SV_EPI_CALL
 
-__device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) {
+// (FAT is a template parameter: a run-time flag inside the producer / issue loops cost the plain path 30 % - d2 dgrad 20.5 -> 26.6 us)
+template <bool FAT>
+__device__ __forceinline__ void igemm_body_t(const TcLaunch& P, const int zsplit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = 128 * P.bk * 2;
   const int b_bytes = (P.tile_cols * P.bk * 2 + 1023) & ~1023;
-  const int stage_bytes = a_bytes + b_bytes;
+  constexpr bool fat = FAT;
+  const int stage_bytes = fat ? 2 * (a_bytes + b_bytes) : a_bytes + b_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)P.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,7 +284,8 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
   const int tiles_per_img = P.grid_h / P.tile_h;   // tile_w == grid_w
   const int n0 = (m_tile / tiles_per_img) * P.tile_n_img;
   const int y0 = (m_tile % tiles_per_img) * P.tile_h;
-  const int kb_total = P.taps_h * P.taps_w * P.kcl;                               // logical k-blocks (see TcLaunch::split)
+  const int units_per_tap = fat ? P.kc : P.kcl;
+  const int kb_total = P.taps_h * P.taps_w * units_per_tap;                       // logical k-blocks (see TcLaunch::split); fat: (tap, chunk) units
   const int kb_first = P.k_splits > 1 ? zsplit * P.kb_per_split : 0;              // split-K: this CTA's k-block range
   const int num_kb = P.k_splits > 1 ? min(P.kb_per_split, kb_total - kb_first) : kb_total;
 
@@ -307,6 +311,17 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
         const int stage = it % P.stages, phase = (it / P.stages) & 1;
         tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
         const int kb = kb_first + it;
+        if constexpr (FAT) {
+          const int tap = kb / P.kc, ch = kb - tap * P.kc;
+          const int ta = tap / P.taps_w, tb = tap - ta * P.taps_w;
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          const int wb = P.tile_cols * P.bk * 2;
+          tc::mbar_expect_tx(&ctl->full[stage], 2 * a_bytes + 2 * wb);
+          tc::tma_load_4d(sa, &P.map_a, &ctl->full[stage], ch * P.bk, tb - P.pad_l, y0 * P.a_stride + ta - P.pad_t, n0);
+          tc::tma_load_4d(sa + a_bytes, &P.map_a_lo, &ctl->full[stage], ch * P.bk, tb - P.pad_l, y0 * P.a_stride + ta - P.pad_t, n0);
+          tc::tma_load_2d(sa + 2 * a_bytes, &P.map_b, &ctl->full[stage], (tap * P.kcb + 2 * ch) * P.bk, n_tile * P.tile_cols);
+          tc::tma_load_2d(sa + 2 * a_bytes + b_bytes, &P.map_b, &ctl->full[stage], (tap * P.kcb + 2 * ch + 1) * P.bk, n_tile * P.tile_cols);
+        } else {
         const int tap = kb / P.kcl, chunk = kb - tap * P.kcl;                 // logical chunk -> physical A chunk / weight k-block
         int ap, bp;
         logical_chunk(P.split, P.kc, chunk, ap, bp);
@@ -317,6 +332,7 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
         tc::tma_load_4d(sa, a_is_lo ? &P.map_a_lo : &P.map_a, &ctl->full[stage], (a_is_lo ? ap - P.kc : ap) * P.bk, tb - P.pad_l,
                         y0 * P.a_stride + ta - P.pad_t, n0);
         tc::tma_load_2d(sa + a_bytes, &P.map_b, &ctl->full[stage], (tap * P.kcb + bp) * P.bk, n_tile * P.tile_cols);
+        }
       }
     }
   } else if (warp == 1) {
@@ -331,10 +347,20 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
         tc::mbar_wait(&ctl->full[stage], phase);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+        if constexpr (FAT) {      // hi*hi + lo*hi + hi*lo from one stage
+          const uint64_t dah = tmpl + (sa >> 4), dal = tmpl + ((sa + a_bytes) >> 4);
+          const uint64_t dbh = tmpl + ((sa + 2 * a_bytes) >> 4), dbl = tmpl + ((sa + 2 * a_bytes + b_bytes) >> 4);
+          for (int k = 0; k < ksteps; ++k) {
+            tc::umma_bf16(tmem_base, dah + 2u * k, dbh + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16(tmem_base, dal + 2u * k, dbh + 2u * k, idesc, 1u);
+            tc::umma_bf16(tmem_base, dah + 2u * k, dbl + 2u * k, idesc, 1u);
+          }
+        } else {
         const uint64_t da = tmpl + (sa >> 4), db = tmpl + ((sa + a_bytes) >> 4);
         tc::umma_bf16(tmem_base, da, db, idesc, kb != 0);
         if (ksteps > 1) tc::umma_bf16(tmem_base, da + 2, db + 2, idesc, 1u);
         if (ksteps > 2) { tc::umma_bf16(tmem_base, da + 4, db + 4, idesc, 1u); tc::umma_bf16(tmem_base, da + 6, db + 6, idesc, 1u); }
+        }
         tc::umma_commit(&ctl->empty[stage]);   // frees this smem stage once the MMAs above have read it
       }
       tc::umma_commit(&ctl->tmem_full);        // accumulator complete
@@ -377,7 +403,10 @@ __device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); igemm_body(P, blockIdx.z); }
+__device__ __forceinline__ void igemm_body(const TcLaunch& P, const int zsplit) { igemm_body_t<false>(P, zsplit); }
+__global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); igemm_body_t<false>(P, blockIdx.z); }
+// bf16x3 forward with fat ring stages (TcLaunch::fat)
+__global__ void __launch_bounds__(kThreads, 3) igemm_fat_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); igemm_body_t<true>(P, blockIdx.z); }
 
 // The s*s parity classes of a stride-s dgrad (each a small stride-1 convolution scattering into its own output parity)
 // as ONE launch: blockIdx.z selects the class.  4 x more CTAs in flight for layers whose single class does not fill the GPU.
@@ -2181,7 +2210,8 @@ void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concu
   set_chunks(L);
   L.tile_cols = n_cols_pad < 128 ? n_cols_pad : 128;
   L.n_tiles = n_cols_pad / L.tile_cols;
-  const int a_bytes = 128 * L.bk * 2, b_bytes = round_up(L.tile_cols * L.bk * 2, 1024);
+  L.fat = (L.split == 1 && env_int("SV_IGEMM_FAT", 1)) ? 1 : 0;
+  const int a_bytes = (L.fat ? 2 : 1) * 128 * L.bk * 2, b_bytes = (L.fat ? 2 : 1) * round_up(L.tile_cols * L.bk * 2, 1024);
   // ring budget: 100 KB keeps two CTAs per SM; a launch with at most one CTA per SM anyway (the 8x8-pixel layers: 128 CTAs)
   // takes the whole shared memory for a deeper ring instead
   const int tiles_per_img = L.tile_h > 0 ? L.grid_h / L.tile_h : 1;
@@ -2190,7 +2220,7 @@ void finish_launch(TcLaunch& L, int n_cols_pad, int concurrent = 1) {   // concu
   int stages = ((one_wave ? 192 : 100) * 1024) / (a_bytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  const int num_kb = L.taps_h * L.taps_w * L.kcl;
+  const int num_kb = L.taps_h * L.taps_w * (L.fat ? L.kc : L.kcl);
   if (stages > num_kb) stages = num_kb < 1 ? 1 : num_kb;
   L.stages = stages;
   L.smem_bytes = (size_t)stages * (a_bytes + b_bytes) + sizeof(SmemCtl) + 1024;
@@ -2208,7 +2238,7 @@ void plan_split_k(TcLaunch& L, int n_img, size_t& off) {
   L.k_splits = 1; L.kb_per_split = 0; L.partial = nullptr;
   if (env_int("SV_NO_SPLITK", 0)) return;
   if (L.halo || L.grid_h != 1 || L.grid_w != 1 || L.taps_h * L.taps_w != 1 || L.osy != 1 || L.osx != 1) return;
-  const int num_kb = L.kcl;
+  const int num_kb = L.fat ? L.kc : L.kcl;
   const int m_tiles = (n_img + 127) / 128, ctas = m_tiles * L.n_tiles;
   if (num_kb < 8 || ctas >= 74) return;
   int splits = (148 + ctas - 1) / ctas;
@@ -2890,6 +2920,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     L.mask_src = nullptr;
     L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_fwd_off) : nullptr;
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+    if (cudaFuncSetAttribute(igemm_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   if (t.fwd_ns || t.dgrad_ns) {
     if (cudaFuncSetAttribute(nsconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -2939,6 +2970,7 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
       L.partial = L.k_splits > 1 ? (float*)(ws + t.sk_dgrad_off) : nullptr;
     }
     if (cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
+    if (cudaFuncSetAttribute(igemm_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
     if (cudaFuncSetAttribute(igemm4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
   if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -3096,7 +3128,8 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
   const int tiles_per_img = L.grid_h / L.tile_h;
   const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
   dim3 grid(m_tiles, L.n_tiles, L.k_splits > 1 ? L.k_splits : 1);
-  launch_pdl(igemm_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
+  if (L.fat) launch_pdl(igemm_fat_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
+  else launch_pdl(igemm_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
   if (L.k_splits > 1) {
     const long long total = (long long)L.n_img * L.n_valid;
     launch_pdl(splitk_finish_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, s, L);

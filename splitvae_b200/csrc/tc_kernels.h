@@ -22,6 +22,10 @@ struct TcLaunch {
   //   split 0: plain, kcl = kca = kcb = kc;   split 1: kcl 3kc, kca 2kc, kcb 2kc;
   //   split 2 (first layer): the 8-channel staged pixel holds [hi(3) lo(3) 0 0]; k-block 0 = [Whi Whi 0 0], 1 = [Wlo 0 0 0]: kcl 2, kca 1, kcb 2
   int split, kcl, kca, kcb;
+  // per-tap kernel, split 1 ("fat" ring stages): one stage = [A_hi(ch) | A_lo(ch) | W_hi(ch) | W_lo(ch)] of one (tap, channel chunk) and
+  // feeds the three products, so every operand box is loaded ONCE per tap (the logical-chunk ring loaded A_hi and W_hi twice: the
+  // 8x8-pixel layers d2 / e3 and the dense layers are L2->SMEM bound).  k-block units (split-K ranges, stages) are then (tap, chunk).
+  int fat;
   int w_box3;                                   // halo kernel: map_b is the 3-D [bk][rows][blocks] view, one TMA box per ring stage
   int nstack2;                                  // halo kernel, split 1: A_hi x [W_hi ; W_lo] as ONE MMA of 2N columns (accumulator = [main | correction])
   void* out_lo;                                 // lo plane of a bf16 output (NULL: single bf16 / fp32 output)
