@@ -2304,7 +2304,7 @@ void try_halo(TcLaunch& L, int GH, int GW, int n_img, int sx = 1, int sy = 1, bo
       for (int stages = 3; stages >= 2; --stages) {
         const size_t smem = chunk * nch * sx + (size_t)stages * KB * kb_bytes + sizeof(HaloCtl) + 1024;
         if (smem > smem_cap) continue;
-        if (deep && chunk * nch * sx + 64 * 1024 > smem_cap) continue;         // leave >= 64 KB for the weight ring
+        if (deep && chunk * nch * sx + (size_t)env_int("SV_HALO_MIN_RING_KB", 64) * 1024 > smem_cap) continue;   // leave room for the weight ring
         int tmem_cols = 32;
         while (tmem_cols < MT * L.tile_cols) tmem_cols <<= 1;
         int per_sm = (int)((227 * 1024) / (smem + 1024));
