@@ -77,7 +77,7 @@ def check_layers(model, H, B, p=4, verbose=False):
     return e, batch, rows, worst
 
 
-@pytest.mark.parametrize("model,H,B", [("lgvae", 32, 4), ("lgvae", 64, 3), ("lggmvae", 32, 5), ("lggmvae", 64, 2), ("lgvae", 32, 130)])
+@pytest.mark.parametrize("model,H,B", [("lgvae", 32, 4), ("lgvae", 64, 3), ("lgvae", 64, 4), ("lggmvae", 32, 5), ("lggmvae", 64, 2), ("lgvae", 32, 130)])
 def test_split_forward_layers(model, H, B):
     e, batch, rows, worst = check_layers(model, H, B)
     print(f"{model} H={H} B={B}: {len(rows)} layers, worst rel-L2 {worst:.2e}")
