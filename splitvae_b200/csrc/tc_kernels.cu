@@ -408,144 +408,9 @@ __global__ void __launch_bounds__(kThreads, 3) igemm_kernel(const __grid_constan
 // bf16x3 forward with fat ring stages (TcLaunch::fat)
 __global__ void __launch_bounds__(kThreads, 3) igemm_fat_kernel(const __grid_constant__ TcLaunch P) { pdl_enter(); igemm_body_t<true>(P, blockIdx.z); }
 
-// Row mode (TcLaunch::rowmode): A ring stage = the row box(es) of one (filter row, channel chunk); B ring stage = the weight block(s)
-// of one (tap, chunk).  FAT: bf16 pairs - stages hold [hi | lo] and every (tap, chunk) issues hi*hi + lo*hi + hi*lo.
-struct TcLaunch4 { TcLaunch l[4]; };
-struct RowCtl {
-  uint64_t a_full[4], a_empty[4], b_full[kMaxStages], b_empty[kMaxStages], tmem_full;
-  uint32_t tmem_base;
-};
-template <bool FAT>
-__device__ __forceinline__ void igemm_row_body_t(const TcLaunch& P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_box = P.row_a_bytes;                                   // one row box (1024-aligned)
-  const int a_stage = FAT ? 2 * a_box : a_box;
-  const int b_box = (P.tile_cols * P.bk * 2 + 1023) & ~1023;
-  const int b_stage = FAT ? 2 * b_box : b_box;
-  const int a_stages = P.row_a_stages, b_stages = P.row_b_stages;
-  uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + (size_t)a_stages * a_stage;
-  RowCtl* ctl = reinterpret_cast<RowCtl*>(b_ring + (size_t)b_stages * b_stage);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-  const int n0 = m_tile * 2;                                         // two images per tile
-  const int taps_h = P.taps_h, taps_w = P.taps_w, kc = P.kc;
-
-  if (threadIdx.x == 0) {
-    tc::prefetch_tmap(&P.map_a);
-    tc::prefetch_tmap(&P.map_b);
-    if (FAT) tc::prefetch_tmap(&P.map_a_lo);
-    for (int i = 0; i < a_stages; ++i) { tc::mbar_init(&ctl->a_full[i], 1); tc::mbar_init(&ctl->a_empty[i], 1); }
-    for (int i = 0; i < b_stages; ++i) { tc::mbar_init(&ctl->b_full[i], 1); tc::mbar_init(&ctl->b_empty[i], 1); }
-    tc::mbar_init(&ctl->tmem_full, 1);
-    tc::fence_barrier_init();
-  }
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)P.tile_cols) tmem_cols <<= 1;
-  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, tmem_cols);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
-
-  if (warp == 0) {
-    if (tc::elect_one()) {
-      const int bk = P.bk, pad_t = P.pad_t, pad_l = P.pad_l, kcb = P.kcb, col0 = n_tile * P.tile_cols;
-      const uint32_t a_tx = (uint32_t)(2 * 8 * P.row_twp * bk * 2) * (FAT ? 2u : 1u);
-      const uint32_t b_tx = (uint32_t)(P.tile_cols * bk * 2) * (FAT ? 2u : 1u);
-      int ia = 0, ib = 0;
-      for (int ta = 0; ta < taps_h; ++ta)
-        for (int ch = 0; ch < kc; ++ch, ++ia) {
-          const int as = ia % a_stages, aph = (ia / a_stages) & 1;
-          tc::mbar_wait(&ctl->a_empty[as], aph ^ 1);
-          tc::mbar_expect_tx(&ctl->a_full[as], a_tx);
-          uint8_t* sa = a_ring + (size_t)as * a_stage;
-          tc::tma_load_4d(sa, &P.map_a, &ctl->a_full[as], ch * bk, -pad_l, ta - pad_t, n0);
-          if (FAT) tc::tma_load_4d(sa + a_box, &P.map_a_lo, &ctl->a_full[as], ch * bk, -pad_l, ta - pad_t, n0);
-          for (int tb = 0; tb < taps_w; ++tb, ++ib) {
-            const int bs = ib % b_stages, bph = (ib / b_stages) & 1;
-            tc::mbar_wait(&ctl->b_empty[bs], bph ^ 1);
-            tc::mbar_expect_tx(&ctl->b_full[bs], b_tx);
-            uint8_t* sb = b_ring + (size_t)bs * b_stage;
-            const int tap = ta * taps_w + tb;
-            if (FAT) {
-              tc::tma_load_2d(sb, &P.map_b, &ctl->b_full[bs], (tap * kcb + 2 * ch) * bk, col0);
-              tc::tma_load_2d(sb + b_box, &P.map_b, &ctl->b_full[bs], (tap * kcb + 2 * ch + 1) * bk, col0);
-            } else {
-              tc::tma_load_2d(sb, &P.map_b, &ctl->b_full[bs], (tap * kcb + ch) * bk, col0);
-            }
-          }
-        }
-    }
-  } else if (warp == 1) {
-    if (tc::elect_one()) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, P.tile_cols, 0, 0);
-      const uint32_t lt = tc::layout_type_for(P.swizzle);
-      const uint32_t pix = (uint32_t)P.bk * 2u;
-      const uint64_t a_tmpl = tc::make_smem_desc(0, 16, (uint32_t)P.row_twp * pix, lt);   // row group = one image row of the padded box
-      const uint64_t b_tmpl = tc::make_smem_desc(0, 16, 8u * pix, lt);
-      const int ksteps = P.bk / 16;
-      const uint32_t a_addr0 = tc::smem_u32(a_ring), b_addr0 = tc::smem_u32(b_ring);
-      int ia = 0, ib = 0;
-      uint32_t accum = 0u;
-      for (int ta = 0; ta < taps_h; ++ta)
-        for (int ch = 0; ch < kc; ++ch, ++ia) {
-          const int as = ia % a_stages, aph = (ia / a_stages) & 1;
-          tc::mbar_wait(&ctl->a_full[as], aph);
-          tc::tc_fence_after();
-          const uint32_t sa = a_addr0 + (uint32_t)as * (uint32_t)a_stage;
-          for (int tb = 0; tb < taps_w; ++tb, ++ib) {
-            const int bs = ib % b_stages, bph = (ib / b_stages) & 1;
-            tc::mbar_wait(&ctl->b_full[bs], bph);
-            tc::tc_fence_after();
-            const uint32_t sb = b_addr0 + (uint32_t)bs * (uint32_t)b_stage;
-            const uint64_t dah = a_tmpl + ((sa + (uint32_t)tb * pix) >> 4), dbh = b_tmpl + (sb >> 4);
-            if (FAT) {
-              const uint64_t dal = a_tmpl + ((sa + (uint32_t)a_box + (uint32_t)tb * pix) >> 4), dbl = b_tmpl + ((sb + (uint32_t)b_box) >> 4);
-              for (int k = 0; k < ksteps; ++k) {
-                tc::umma_bf16(tmem_base, dah + 2u * k, dbh + 2u * k, idesc, accum);
-                tc::umma_bf16(tmem_base, dal + 2u * k, dbh + 2u * k, idesc, 1u);
-                tc::umma_bf16(tmem_base, dah + 2u * k, dbl + 2u * k, idesc, 1u);
-                accum = 1u;
-              }
-            } else {
-              for (int k = 0; k < ksteps; ++k) {
-                tc::umma_bf16(tmem_base, dah + 2u * k, dbh + 2u * k, idesc, accum);
-                accum = 1u;
-              }
-            }
-            tc::umma_commit(&ctl->b_empty[bs]);
-          }
-          tc::umma_commit(&ctl->a_empty[as]);
-        }
-      tc::umma_commit(&ctl->tmem_full);
-    }
-  } else {
-    const EpiRegs E = load_epi_regs(P);
-    const EpiSel esel = epilogue_select(P, n_tile);
-    tc::mbar_wait(&ctl->tmem_full, 0);
-    tc::tc_fence_after();
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;                             // (image, y, x) = (row / 64, (row / 8) % 8, row % 8)
-    const int n = n0 + (row >> 6), y = (row >> 3) & 7, x = row & 7;
-    const bool valid = n < P.n_img;
-    const long long opix = ((long long)n * P.OH + (y * P.osy + P.ooy)) * P.OW + (x * P.osx + P.oox);
-    epilogue_dispatch(E, esel, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, 0, 1, opix, 0, 0, valid, n_tile * P.tile_cols);
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, tmem_cols);
-  }
-}
-__global__ void __launch_bounds__(kThreads, 1) igemm_row_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); igemm_row_body_t<false>(P4.l[blockIdx.z]); }
-__global__ void __launch_bounds__(kThreads, 1) igemm_row_fat_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); igemm_row_body_t<true>(P4.l[blockIdx.z]); }
-
 // The s*s parity classes of a stride-s dgrad (each a small stride-1 convolution scattering into its own output parity)
 // as ONE launch: blockIdx.z selects the class.  4 x more CTAs in flight for layers whose single class does not fill the GPU.
+struct TcLaunch4 { TcLaunch l[4]; };
 __global__ void __launch_bounds__(kThreads, 3) igemm4_kernel(const __grid_constant__ TcLaunch4 P4) { pdl_enter(); igemm_body(P4.l[blockIdx.z], 0); }
 
 // Split-K finish for dense layers (one output row per image): out[row][col] = epilogue(sum_z partial[z][row][col]).
@@ -2387,22 +2252,6 @@ void plan_split_k(TcLaunch& L, int n_img, size_t& off) {
   off = (off + 1023) / 1024 * 1024;
   // (the caller records `off` as the partial-buffer offset)
 }
-// Row mode of the per-tap kernel (TcLaunch::rowmode): 8x8-pixel grids at stride 1 that stayed on the per-tap kernel.
-void plan_rowmode(TcLaunch& L) {
-  L.rowmode = 0;
-  if (!env_int("SV_IGEMM_ROW", 1)) return;
-  if (L.halo || L.a_stride != 1 || L.k_splits > 1 || L.taps_w < 2) return;
-  if (L.tile_w != 8 || L.tile_h != 8 || L.tile_n_img != 2 || L.grid_h != 8 || L.grid_w != 8 || (L.n_img % 2)) return;
-  const int twp = 8 + L.taps_w - 1;
-  const int a_box = round_up(2 * 8 * twp * L.bk * 2, 1024), b_box = round_up(L.tile_cols * L.bk * 2, 1024);
-  const int a_stage = (L.fat ? 2 : 1) * a_box, b_stage = (L.fat ? 2 : 1) * b_box;
-  const int a_stages = 2;
-  int b_stages = (190 * 1024 - a_stages * a_stage) / b_stage;
-  if (b_stages > kMaxStages) b_stages = kMaxStages;
-  if (b_stages < 2) return;
-  L.rowmode = 1; L.row_twp = twp; L.row_a_bytes = a_box; L.row_a_stages = a_stages; L.row_b_stages = b_stages;
-  L.smem_bytes = (size_t)a_stages * a_stage + (size_t)b_stages * b_stage + sizeof(RowCtl) + 1024;
-}
 size_t split_k_bytes(const TcLaunch& L) {
   return L.k_splits > 1 ? ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024 : 0;
 }
@@ -2905,7 +2754,6 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         plan_split_k(L, g.B, off);
         t.sk_fwd_off = off;
         off += split_k_bytes(L);
-        if (!L.persist && cpad <= g.in_ld - g.in_coff) plan_rowmode(L);
         t.fwd_ok = true;
         t.fwd_launches = L.k_splits > 1 ? 2 : 1;
         t.w_fwd_off = off;
@@ -2948,7 +2796,6 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         t.sk_dgrad_off = off;
         off += split_k_bytes(L);
       }
-      if (!L.persist) plan_rowmode(L);
     }
     // (W = 64 dgrads - d5 - stay on the halo kernel: 4 shuffle blocks per tile with the cross-warp exchange make the
     // N-stacked epilogue the bottleneck there, 124 us vs 102 us)
@@ -2970,8 +2817,7 @@ void tc_plan_layer(TcLayer& t, const ConvGeom& g, int in_dt, int out_dt, bool ha
         same = same && C.halo == A.halo && C.k_splits <= 1 && C.smem_bytes == A.smem_bytes && C.n_tiles == A.n_tiles && C.tile_h == A.tile_h &&
                C.tile_n_img == A.tile_n_img && C.grid_h == A.grid_h && C.n_img == A.n_img &&
                (!C.halo || (C.TW == A.TW && C.TH == A.TH && C.tiles_x == A.tiles_x && C.tiles_y == A.tiles_y)) &&
-               C.persist == A.persist && (!C.persist || (C.p_smem == A.p_smem && C.p_grid == A.p_grid)) && C.rowmode == A.rowmode &&
-               (!C.rowmode || (C.row_twp == A.row_twp && C.row_b_stages == A.row_b_stages));
+               C.persist == A.persist && (!C.persist || (C.p_smem == A.p_smem && C.p_grid == A.p_grid));
       }
       t.dgrad_merged = same;
     }
@@ -3054,7 +2900,6 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
              : t.fwd_pair ? make_halo_map(m, base, g.B, g.Hi, g.Wi / 2, 2 * g.in_ld, 0, t.ci_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
              : t.first    ? make_window_map(m, base, g.B, g.Hi, g.Wi, g.Wo, L.tile_w, L.tile_h, L.tile_n_img)
              : L.halo     ? make_halo_map(m, base, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.TWp, L.THp, L.halo_sx, L.swizzle)
-             : L.rowmode  ? make_act_map(m, base, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad, L.bk, L.row_twp, 8, 2, 1, L.swizzle)
                           : make_act_map(m, base, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, t.ci_pad <= g.in_ld - g.in_coff ? t.ci_pad : g.Ci, L.bk,
                                          L.tile_w, L.tile_h, L.tile_n_img, g.stride, L.swizzle);
     };
@@ -3110,7 +2955,6 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     for (int cls = 0; cls < t.n_dgrad; ++cls) {
       TcLaunch& L = t.dgrad[cls];
       const char* e = L.halo ? make_halo_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.TWp, L.THp, 1, L.swizzle)
-                      : L.rowmode ? make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.row_twp, 8, 2, 1, L.swizzle)
                              : make_act_map(&L.map_a, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, t.co_pad, L.bk, L.tile_w, L.tile_h, L.tile_n_img, 1,
                                             L.swizzle);
       if (e) return e;
@@ -3129,8 +2973,6 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (cudaFuncSetAttribute(igemm_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
     if (cudaFuncSetAttribute(igemm4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   }
-  if (cudaFuncSetAttribute(igemm_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
-  if (cudaFuncSetAttribute(igemm_row_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(halo4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
   if (cudaFuncSetAttribute(pconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -3285,13 +3127,6 @@ static void launch(const TcLaunch& L, cudaStream_t s) {
   }
   const int tiles_per_img = L.grid_h / L.tile_h;
   const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
-  if (L.rowmode) {
-    TcLaunch4 P4{};
-    P4.l[0] = L;
-    if (L.fat) launch_pdl(igemm_row_fat_kernel, dim3(m_tiles, L.n_tiles, 1), dim3(kThreads), L.smem_bytes, s, P4);
-    else launch_pdl(igemm_row_kernel, dim3(m_tiles, L.n_tiles, 1), dim3(kThreads), L.smem_bytes, s, P4);
-    return;
-  }
   dim3 grid(m_tiles, L.n_tiles, L.k_splits > 1 ? L.k_splits : 1);
   if (L.fat) launch_pdl(igemm_fat_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
   else launch_pdl(igemm_kernel, dim3(grid), dim3(kThreads), L.smem_bytes, s, L);
@@ -3322,7 +3157,6 @@ void tc_conv_dgrad(TcLayer& t, cudaStream_t s) {
     const int m_tiles = L.tile_n_img > 1 ? (L.n_img + L.tile_n_img - 1) / L.tile_n_img : L.n_img * tiles_per_img;
     if (L.halo && L.persist) launch_pdl(pconv_kernel, dim3(L.p_grid, 4), dim3(kPcThreads), L.p_smem, s, P4);
     else if (L.halo) launch_pdl(halo4_kernel, dim3(L.tiles_x * L.tiles_y * L.n_img, L.n_tiles, 4), dim3(kThreads), L.smem_bytes, s, P4);
-    else if (L.rowmode) launch_pdl(igemm_row_kernel, dim3(m_tiles, L.n_tiles, 4), dim3(kThreads), L.smem_bytes, s, P4);
     else launch_pdl(igemm4_kernel, dim3(m_tiles, L.n_tiles, 4), dim3(kThreads), L.smem_bytes, s, P4);
     return;
   }

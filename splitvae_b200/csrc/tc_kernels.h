@@ -26,11 +26,6 @@ struct TcLaunch {
   // feeds the three products, so every operand box is loaded ONCE per tap (the logical-chunk ring loaded A_hi and W_hi twice: the
   // 8x8-pixel layers d2 / e3 and the dense layers are L2->SMEM bound).  k-block units (split-K ranges, stages) are then (tap, chunk).
   int fat;
-  // per-tap kernel, "row mode" (8x8-pixel grids, stride 1: d2 forward / dgrad, the parity classes of e3's dgrad): the M tile is two
-  // whole images, so ONE A box per filter ROW - [bk][8 + taps_w - 1][8 rows][2 images], x from -pad_l - serves every filter column
-  // through a descriptor shifted by tb pixels (row-group stride = the padded row, uniform across the two images).  The A traffic of
-  // these L2->SMEM-bound layers drops by taps_w * 8 / (8 + taps_w - 1); weights stream through their own ring.
-  int rowmode, row_twp, row_a_bytes, row_a_stages, row_b_stages;
   int w_box3;                                   // halo kernel: map_b is the 3-D [bk][rows][blocks] view, one TMA box per ring stage
   int nstack2;                                  // halo kernel, split 1: A_hi x [W_hi ; W_lo] as ONE MMA of 2N columns (accumulator = [main | correction])
   void* out_lo;                                 // lo plane of a bf16 output (NULL: single bf16 / fp32 output)

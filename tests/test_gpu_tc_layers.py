@@ -28,7 +28,6 @@ def _close(a, b, what):
     assert rel < 2e-3 and mx <= scale * 2 ** -6, f"{what}: rel-L2 {rel:.3e}, max abs diff {mx:.3e} (scale {scale:.3e})"
 
 
-# (B even at 64x64: the 8x8-pixel layers take the row mode of the per-tap kernel, two whole images per tile; odd B: the plain mode)
 @pytest.mark.parametrize("model,H,B", [("lgvae", 32, 4), ("lgvae", 64, 3), ("lgvae", 64, 4), ("lggmvae", 32, 5), ("lggmvae", 64, 2), ("lgvae", 32, 130)])
 def test_tc_layers_match_reference(model, H, B):
     torch.manual_seed(0)
@@ -96,11 +95,11 @@ def test_tc_layers_match_reference(model, H, B):
     {"SV_FIRST_PAIR": "0", "SV_S2_DGRAD_HALO": "0"},   # first layer through the window map, stride-2 dgrad per tap
     {"SV_NS_MB": "1", "SV_NS_SPLIT_WIDE": "0"},    # N-stacked conv: one block per tile, unsplit wide N (single accumulator set)
     {"SV_OLD_REDUCE": "1", "SV_HWG_SPLITS": "148", "SV_WGRAD_STREAMS": "1"},
-    {"SV_IGEMM_ROW": "0", "SV_FOLD_COLSUM": "0"},  # 8x8-pixel layers per tap (one A box per tap), bias gradients by the multi-tensor column sums only
+    {"SV_IGEMM_FAT": "0", "SV_FOLD_COLSUM": "0"},  # bf16x3 per-tap kernel with logical-chunk stages, bias gradients by the multi-tensor column sums only
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_tc_layers_planner_variants(env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     test_tc_layers_match_reference("lgvae", 64, 3)
-    if "SV_NS_MB" in env or "SV_PCONV" in env or "SV_IGEMM_ROW" in env:
+    if "SV_NS_MB" in env or "SV_PCONV" in env or "SV_FOLD_COLSUM" in env:
         test_tc_layers_match_reference("lggmvae", 64, 2)
