@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libsplitvae.so")
-SOURCES = ["engine.cu", "ref_kernels.cu", "fused_kernels.cu", "tc_kernels.cu"]
+SOURCES = ["engine.cu", "simt_kernels.cu", "fused_kernels.cu", "tc_kernels.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_kernels.h", "tc_device.cuh", os.path.join("..", "..", "include", "splitvae.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -7,7 +7,7 @@
 
 namespace sv {
 
-// ---- ref_kernels.cu --------------------------------------------------------------------------
+// ---- simt_kernels.cu --------------------------------------------------------------------------
 void ref_conv_fwd(const ConvGeom& g, const void* in, int in_dt, const float* params, void* out, int out_dt,
                   bool round_w, cudaStream_t s);
 void ref_conv_dgrad(const ConvGeom& g, const void* dout, int dt, const float* params, void* din,

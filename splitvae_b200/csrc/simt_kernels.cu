@@ -1,7 +1,8 @@
-// Reference (SIMT, fp32-accumulate) kernels: Conv2D/Dense forward, dgrad, wgrad, bias gradient,
-// bilinear 2x resize and its adjoint.  They define the arithmetic of every layer on the device
-// and are the production path for SV_PRECISION_FP32_REF and for the layers the tcgen05 path does
-// not cover yet; the tensor-core kernels in tc_kernels.cu are checked against them.
+// CUDA-core (SIMT) kernels, two roles:
+//  (1) production kernels of every precision mode: the bilinear 2x resize of the decoders and its adjoint (vectorised bf16 / bf16-pair
+//      variants; the adjoint also emits the producer layer's bias-gradient partials) and the multi-tensor bias-gradient column sums;
+//  (2) the fp32-accumulate reference of every layer - Conv2D/Dense forward, dgrad, wgrad, bias gradient - which is the whole device path
+//      of SV_PRECISION_FP32_REF and the checker the tensor-core kernels in tc_kernels.cu are tested against layer by layer.
 //
 // Reference semantics: Keras Conv2D(padding='same') / Dense (vae/model.py:36-42,49-76,152-156),
 // tf.image.resize bilinear half-pixel (vae/model.py:163-167), tape.gradient (vae/trainer.py:137).
