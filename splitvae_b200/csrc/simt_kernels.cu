@@ -7,6 +7,7 @@
 // Reference semantics: Keras Conv2D(padding='same') / Dense (vae/model.py:36-42,49-76,152-156),
 // tf.image.resize bilinear half-pixel (vae/model.py:163-167), tape.gradient (vae/trainer.py:137).
 #include "common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 #include "kernels.h"
@@ -446,6 +447,97 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_vec_kernel(const bf16* __r
   }
 }
 
+// Same adjoint, one thread = 8 channels of a 2x2 BLOCK of low-resolution pixels: the 6x6 high-resolution window of the block is
+// read once (36 loads for 4 outputs instead of 64) and streamed row by row - per input row the two horizontal 4-tap sums, then the
+// vertical accumulation into the block's two output rows - in exactly the operation order of upsample2x_bwd_vec_kernel, so the
+// results are bit-identical.  H and W even.  colsum as above.
+__global__ void __launch_bounds__(256) upsample2x_bwd_blk_kernel(const bf16* __restrict__ dout, bf16* __restrict__ din,
+                                                                 const bf16* __restrict__ mask_src, int mask_act,
+                                                                 int B, int H, int W, int C8, float* __restrict__ colsum) {
+  pdl_enter();
+  const int Hb = H >> 1, Wb = W >> 1;
+  const int total = B * Hb * Wb * C8;
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c8 = idx % C8;
+    int p = idx / C8;
+    const int bx = p % Wb;
+    p /= Wb;
+    const int by = p % Hb;
+    const int n = p / Hb;
+    const int y0 = 2 * by, x0 = 2 * bx;
+    // window rows / columns: [0] = tap 0 of the first output, [1..4] = 2*y0 .. 2*y0+3, [5] = tap 3 of the second output (edges clamp)
+    const int wr[6] = {y0 > 0 ? 2 * y0 - 1 : 0, 2 * y0, 2 * y0 + 1, 2 * y0 + 2, 2 * y0 + 3, y0 + 1 < H - 1 ? 2 * y0 + 4 : 2 * H - 1};
+    const int wc[6] = {x0 > 0 ? 2 * x0 - 1 : 0, 2 * x0, 2 * x0 + 1, 2 * x0 + 2, 2 * x0 + 3, x0 + 1 < W - 1 ? 2 * x0 + 4 : 2 * W - 1};
+    const bf16* b = dout + ((size_t)n * 4 * H * W) * C8 * 8 + c8 * 8;
+    F8 acc[2][2];                         // [output row][output column]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][j].v[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const bf16* rowp = b + (size_t)wr[r] * 2 * W * C8 * 8;
+      F8 t[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) t[q] = ld_bf16x8(rowp + (size_t)wc[q] * C8 * 8);
+      F8 h0, h1;                          // horizontal sums of output columns x0 (window columns 0..3) and x0 + 1 (2..5)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { h0.v[k] = 0.f; h1.v[k] = 0.f; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { h0.v[k] += wt[q] * t[q].v[k]; h1.v[k] += wt[q] * t[q + 2].v[k]; }
+      }
+      if (r < 4) {                        // window rows 0..3 are taps 0..3 of output row y0
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[0][0].v[k] += wt[r] * h0.v[k]; acc[0][1].v[k] += wt[r] * h1.v[k]; }
+      }
+      if (r >= 2) {                       // window rows 2..5 are taps 0..3 of output row y0 + 1
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[1][0].v[k] += wt[r - 2] * h0.v[k]; acc[1][1].v[k] += wt[r - 2] * h1.v[k]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const size_t o = ((((size_t)n * H + (y0 + i)) * W + (x0 + j)) * C8 + c8) * 8;
+        if (mask_act != ACT_NONE) {
+          const F8 m = ld_bf16x8(mask_src + o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[i][j].v[k] *= act_grad_from_out(m.v[k], mask_act);
+        }
+        st_bf16x8(din + o, acc[i][j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) csum[k] += acc[i][j].v[k];
+      }
+  }
+  if (colsum) {
+    __shared__ float red[8][16][8];
+    for (int o = C8; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) csum[i] += __shfl_xor_sync(0xffffffffu, csum[i], o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < C8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][lane][i] = csum[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C8 * 8) {
+      const int g = threadIdx.x >> 3, i = threadIdx.x & 7;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][g][i];
+      colsum[(size_t)blockIdx.x * (C8 * 8) + threadIdx.x] = t;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
   long long b = (total + block - 1) / block;
@@ -759,7 +851,12 @@ void upsample2x_fwd_pair(const void* in_hi, const void* in_lo, void* out_hi, voi
 }
 
 // grid of the bf16 launch: at most 8 blocks per SM (a multiple of every C / 8, so the grid-stride keeps a thread's channel group)
+static bool upsample2x_bwd_use_blk(int H, int W) {
+  const char* v = getenv("SV_UPS_BWD_BLK");          // (read per engine / per launch: the A/B test toggles it inside one process)
+  return !(v && v[0] == '0') && (H % 2) == 0 && (W % 2) == 0;
+}
 int upsample2x_bwd_blocks(int B, int H, int W, int C) {
+  if (upsample2x_bwd_use_blk(H, W)) return grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256, 148 * 8);
   return grid_for((long long)B * H * W * (C / 8), 256, 148 * 8);
 }
 void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_act, int dt, int B, int H, int W,
@@ -767,6 +864,12 @@ void upsample2x_bwd(const void* dout, void* din, const void* mask_src, int mask_
   const long long total = (long long)B * H * W * C;
   if (dt == DT_BF16 && (C % 8) == 0 && total / 8 < (1ll << 29)) {
     const bool fold = colsum_partial && C / 8 <= 16 && (256 % (C / 8)) == 0;
+    if (upsample2x_bwd_use_blk(H, W) && C / 8 <= 16 && (256 % (C / 8)) == 0) {
+      // (the grid is upsample2x_bwd_blocks() whether or not the partials are wanted: one launch shape per layer)
+      launch_pdl(upsample2x_bwd_blk_kernel, dim3(upsample2x_bwd_blocks(B, H, W, C)), dim3(256), 0, s, (const bf16*)dout, (bf16*)din,
+                 (const bf16*)mask_src, mask_act, B, H, W, C / 8, fold ? colsum_partial : (float*)nullptr);
+      return;
+    }
     launch_pdl(upsample2x_bwd_vec_kernel, dim3(fold ? upsample2x_bwd_blocks(B, H, W, C) : grid_for(total / 8, 256, 148 * 32)), dim3(256), 0, s,
                (const bf16*)dout, (bf16*)din, (const bf16*)mask_src, mask_act, B, H, W, C / 8, fold ? colsum_partial : (float*)nullptr);
     return;

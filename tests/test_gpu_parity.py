@@ -263,3 +263,24 @@ def test_deferred_backward_segments_equal_the_plain_ones(model):
         res.append(e.get_grads())
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_block_resize_adjoint_is_bit_identical_to_the_per_pixel_one(monkeypatch):
+    """upsample2x_bwd_blk_kernel (one thread = a 2x2 block of low-resolution pixels, 36 loads for 4 outputs) keeps the operation order of
+    upsample2x_bwd_vec_kernel: every activation gradient, hence every weight gradient of the step, is bit-equal; the bias gradients of
+    d2-d4 ride along as per-block partials, whose grouping differs between the two kernels (fp32 summation order: rel 1e-5)."""
+    model, H, B = "lgvae", 64, 4
+    params, batch = make_case(model, H, B, 8, seed_base=7)
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SV_UPS_BWD_BLK", flag)
+        e = make_engine(model, H, B, "bf16x3", 120.0)
+        e.load_params(params)
+        sc, grads = run_engine_step(e, batch, model, adam=False)
+        res.append(grads)
+    folded = {f"{d}.{l}.bias" for d in ("decoder_x", "decoder_x_hat") for l in ("d2", "d3", "d4")}
+    for k in res[0]:
+        if k in folded:
+            assert rel_l2(res[1][k], res[0][k]) < 1e-5, k
+        else:
+            assert np.array_equal(res[0][k], res[1][k]), k
