@@ -5,8 +5,9 @@
     python scripts/convert_checkpoint.py npz2h5 --model lgvae weights.npz weights.h5
     python scripts/convert_checkpoint.py h52npz --model lgvae weights.h5 weights.npz
 
-Needs h5py, which is NOT part of this build's image (no network to install it) - run it where TensorFlow / h5py live.  The variable
-layouts are identical on both sides (conv HWIO, dense [in,out], bias [out]); only the names differ.  The Keras-side names come
+The model classes read and write `.h5` themselves (`model.save_weights('run.h5')` / `load_weights`, through splitvae_b200.hdf5_lite);
+this converter is the stand-alone path and the cross-check: with h5py installed it goes through libhdf5 (so a file of either writer
+can be pushed through the other's reader), without h5py it falls back to hdf5_lite.  The variable layouts are identical on both sides (conv HWIO, dense [in,out], bias [out]); only the names differ.  The Keras-side names come
 from splitvae_b200.model.keras_weight_names (derived from Keras' naming rules, see its docstring): one HDF5 group per sub-model
 layer (`encoder`, `encoder_1`, `decoder`, `decoder_1`) with a `weight_names` attribute, datasets named `<model>/<layer>/.../kernel:0`."""
 import argparse
@@ -19,8 +20,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from splitvae_b200.model import keras_weight_names  # noqa: E402
 
 
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        return None
+
+
 def npz2h5(kind, src, dst):
-    import h5py
+    h5py = _h5py()
     names = keras_weight_names(kind)
     with np.load(src) as z:
         blob = {k: z[k] for k in z.files if k in names}
@@ -30,6 +39,10 @@ def npz2h5(kind, src, dst):
     groups = {}
     for ours, keras in names.items():
         groups.setdefault(keras.split("/")[1], []).append((keras, blob[ours]))
+    if h5py is None:
+        from splitvae_b200 import hdf5_lite
+        hdf5_lite.save_keras_weights(dst, list(groups.items()))
+        return
     with h5py.File(dst, "w") as f:
         f.attrs["layer_names"] = [g.encode() for g in groups]
         f.attrs["backend"] = b"tensorflow"
@@ -42,16 +55,20 @@ def npz2h5(kind, src, dst):
 
 
 def h52npz(kind, src, dst):
-    import h5py
+    h5py = _h5py()
     names = keras_weight_names(kind)
     out = {}
-    with h5py.File(src, "r") as f:
-        flat = {}
-        for g in f.keys():
-            grp = f[g]
-            for n in grp.attrs.get("weight_names", []):
-                n = n.decode() if isinstance(n, bytes) else n
-                flat[n] = np.asarray(grp[n])
+    if h5py is None:
+        from splitvae_b200 import hdf5_lite
+        flat, _ = hdf5_lite.load_keras_weights(src)
+    else:
+        with h5py.File(src, "r") as f:
+            flat = {}
+            for g in f.keys():
+                grp = f[g]
+                for n in grp.attrs.get("weight_names", []):
+                    n = n.decode() if isinstance(n, bytes) else n
+                    flat[n] = np.asarray(grp[n])
     for ours, keras in names.items():
         if keras not in flat:
             raise KeyError(f"{src} has no dataset {keras} (found e.g. {list(flat)[:3]})")
@@ -66,9 +83,5 @@ if __name__ == "__main__":
     ap.add_argument("src")
     ap.add_argument("dst")
     a = ap.parse_args()
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        raise SystemExit("h5py is not installed in this environment: run the converter where TensorFlow / h5py are available")
     (npz2h5 if a.direction == "npz2h5" else h52npz)(a.model, a.src, a.dst)
     print("wrote", a.dst)

@@ -35,7 +35,10 @@ def build_parser():
     parser.add_argument('--no_graph', action='store_true')
     parser.add_argument('--test_batches', type=int, default=4, help='synthetic test batches per evaluation pass (0: no evaluation)')
     parser.add_argument('--data_root', type=str, default='', help='directory with the SVHN .mat files (train/extra/test_32x32.mat); default: synthetic data')
-    parser.add_argument('--save_weights', type=str, default='', help='write the trained weights (.npz, Keras variable names) here')
+    parser.add_argument('--save_weights', type=str, default='',
+                        help="write the trained weights + Adam state here: '<run>.h5' = the reference's Keras HDF5 file (vae/trainer.py:421), anything else = .npz")
+    parser.add_argument('--load_weights', type=str, default='',
+                        help='start from this checkpoint (.h5 Keras weights file or .npz); Adam moments and the step count resume when the file holds them')
     return parser
 
 
@@ -77,6 +80,9 @@ def main(argv=None):
                       precision=config.precision)
     else:
         raise NotImplementedError("--model %s: expected lgvae | lggmvae | gmvae" % config.model)
+    if config.load_weights:
+        model.load_weights(config.load_weights)
+        print('loaded', config.load_weights)
     print('Training local-global autoencoder')
     history = trainer.train_local_global_autoencoder(model, optimizer, config.dataset, train_dataset, test_dataset, config=config)
     if config.save_weights:                       # vae/trainer.py:421

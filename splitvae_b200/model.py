@@ -162,33 +162,83 @@ class _SplitModel:
     _weights_version = 0
 
     # -- checkpoints (vae/trainer.py:421 model.save_weights; Keras variable names and layouts) ----
+    def _keras_layers(self, named):
+        """[(Keras layer name, [(Keras weight name, array), ...])] in Keras' order: model.layers = the sub-models in creation order,
+        layer.weights = kernel, bias per sub-layer in creation order (= the order of keras_weight_names)"""
+        layers = {}
+        for ours, keras in keras_weight_names(self._kind).items():
+            layers.setdefault(keras.split("/")[1], []).append((keras, named[ours]))
+        return list(layers.items())
+
     def save_weights(self, path, include_optimizer=False):
-        """The reference writes Keras HDF5 (`model.save_weights('models/<run>.h5')`); h5py is not part of this image, so the
-        same variables in Keras LAYOUTS (conv HWIO, dense [in,out], bias [out]) go into a NumPy `.npz` keyed by this build's
-        attribute-path names (`encoder_x.e1.kernel`, ...); the entry `keras_names` maps each key to the variable's name in a Keras
-        HDF5 file (see keras_weight_names), which scripts/convert_checkpoint.py uses to convert `.npz` <-> `.h5` where h5py exists.
-        With include_optimizer the Adam moments and the iteration counter are stored too (the reference cannot resume; this can)."""
+        """`model.save_weights('models/<run>.h5')` (vae/trainer.py:421).  A path ending in `.h5` / `.hdf5` / `.keras.h5` writes the
+        reference's format - a Keras HDF5 weights file (root attributes `layer_names` / `backend` / `keras_version`, one group per
+        sub-model with `weight_names`, datasets `<model>/<layer>/<sublayer>/kernel:0`; variables in Keras layouts: conv HWIO, dense
+        [in,out], bias [out]) - through splitvae_b200.hdf5_lite (h5py is not part of this image).  Any other path writes a NumPy `.npz`
+        keyed by this build's attribute-path names (`encoder_x.e1.kernel`, ...) plus the `keras_names` map.
+        With include_optimizer the Adam moments and the iteration counter are stored too (the reference cannot resume; this can): in the
+        HDF5 file they live in a top-level `optimizer_weights` group, which Keras' load_weights ignores."""
         import json
 
         import numpy as np
         e = self.engine
-        blob = {name: a for name, a in e.get_params().items()}
-        blob["keras_names"] = np.asarray(json.dumps(keras_weight_names(self._kind)))
+        params = {name: a for name, a in e.get_params().items()}
+        opt = None
         if include_optimizer:
-            for name, a in e._export(e.adam_m).items():
+            opt = (e._export(e.adam_m), e._export(e.adam_v), np.asarray(e.iterations, dtype=np.int64))
+        if str(path).endswith((".h5", ".hdf5")):
+            from . import hdf5_lite
+            extra = None
+            if opt is not None:
+                names = keras_weight_names(self._kind)
+                extra = {"optimizer_weights": {"Adam/iterations:0": opt[2]}}
+                for slot, blob in (("m", opt[0]), ("v", opt[1])):
+                    for ours, a in blob.items():
+                        extra["optimizer_weights"][f"Adam/{names[ours][:-2]}/{slot}:0"] = a
+            return hdf5_lite.save_keras_weights(str(path), self._keras_layers(params), extra_groups=extra)
+        blob = dict(params)
+        blob["keras_names"] = np.asarray(json.dumps(keras_weight_names(self._kind)))
+        if opt is not None:
+            for name, a in opt[0].items():
                 blob["adam_m/" + name] = a
-            for name, a in e._export(e.adam_v).items():
+            for name, a in opt[1].items():
                 blob["adam_v/" + name] = a
-            blob["optimizer/iterations"] = np.asarray(e.iterations, dtype=np.int64)
+            blob["optimizer/iterations"] = opt[2]
         if not str(path).endswith(".npz"):
             path = str(path) + ".npz"
         np.savez(path, **blob)
         return path
 
+    def _load_h5(self, path):
+        """Keras HDF5 weights file -> the `.npz`-style blob load_weights works on (by-name lookup, like load_weights(by_name=False) on an
+        identically built model: every variable of this architecture must be present with its shape)"""
+        import numpy as np
+
+        from . import hdf5_lite
+        flat, f = hdf5_lite.load_keras_weights(str(path))
+        names = keras_weight_names(self._kind)
+        missing = [k for k in names.values() if k not in flat]
+        if missing:
+            raise KeyError(f"{path}: no dataset {missing[0]} (+{len(missing) - 1} more); the file holds e.g. {sorted(flat)[:3]}")
+        blob = {ours: np.asarray(flat[keras], dtype=np.float32) for ours, keras in names.items()}
+        if "optimizer_weights" in f.keys():
+            g = f["optimizer_weights"]
+            blob["optimizer/iterations"] = np.asarray(g["Adam/iterations:0"].read())
+            for ours, keras in names.items():
+                for slot, pre in (("m", "adam_m/"), ("v", "adam_v/")):
+                    try:
+                        blob[pre + ours] = np.asarray(g[f"Adam/{keras[:-2]}/{slot}:0"].read(), dtype=np.float32)
+                    except KeyError:
+                        pass                      # reported as "optimizer state incomplete" below
+        return blob
+
     def load_weights(self, path):
         import numpy as np
-        with np.load(path) as z:
-            blob = {k: z[k] for k in z.files}
+        if str(path).endswith((".h5", ".hdf5")):
+            blob = self._load_h5(path)
+        else:
+            with np.load(path) as z:
+                blob = {k: z[k] for k in z.files}
         named = {k: v for k, v in blob.items() if "/" not in k and k != "keras_names"}
         self.set_weights_by_name(named)
         if "optimizer/iterations" in blob:       # resume: the Adam moments and the step count (LR schedule, bias correction) come back too

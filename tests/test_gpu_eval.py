@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _model(kind, H, precision="fp32"):
-    from splitvae_b200.model import LGGMVae, LGVae
+    from splitvae_b200.model import GMVae, LGGMVae, LGVae
     if kind == "lgvae":
         return LGVae(128, 128, image_shape=[-1, H, H, 3], precision=precision)
+    if kind == "gmvae":
+        return GMVae(128, [-1, H, H, 3], 30, 0.4, precision=precision)
     return LGGMVae(128, 128, [-1, H, H, 3], 30, 0.4, precision=precision)
 
 
@@ -99,6 +101,46 @@ def test_checkpoint_round_trip_resumes_bit_exactly(kind, tmp_path):
     assert torch.equal(a.engine.adam_v, b.engine.adam_v)
 
 
+@pytest.mark.parametrize("kind", ["lgvae", "lggmvae", "gmvae"])
+def test_keras_hdf5_checkpoint_round_trip(kind, tmp_path):
+    """vae/trainer.py:421 `model.save_weights('models/<run>.h5')`: a path ending in .h5 writes the Keras HDF5 layout (hdf5_lite); a fresh
+    model built from it resumes bit-exactly (weights, Adam moments, iteration count), and a weights-only file loads into a new model."""
+    from splitvae_b200 import hdf5_lite
+    from splitvae_b200.model import keras_weight_names
+    H, B = 32, 4
+    params, batch = make_case(kind, H, B, 4, seed_base=44)
+    x, eg = to_dev(batch["inputs"]), to_dev(batch["eps_g"])
+    el = to_dev(batch["eps_l"]) if kind != "gmvae" else None
+    u = to_dev(batch["u"]) if kind != "lgvae" else None
+    a = _model(kind, H)
+    a.set_weights_by_name(params)
+    a.build(B)
+    for _ in range(2):
+        a.engine.train_step(x, eg, el, u)
+    path = a.save_weights(str(tmp_path / "run.h5"), include_optimizer=True)
+    plain = a.save_weights(str(tmp_path / "weights_only.h5"))
+    flat, f = hdf5_lite.load_keras_weights(plain)
+    names = keras_weight_names(kind)
+    assert "optimizer_weights" not in f.keys() and len(flat) == len(names) == len(a.engine.table)
+    now = a.engine.get_params()
+    for name, shape, _, _ in a.engine.table:                        # Keras layouts (conv HWIO, dense [in,out], bias [out]) under Keras names
+        assert flat[names[name]].shape == tuple(shape) and np.array_equal(flat[names[name]], now[name])
+    a.engine.train_step(x, eg, el, u)
+    torch.cuda.synchronize()
+    b = _model(kind, H)
+    b.load_weights(path)                                            # no engine yet: applied by build()
+    b.build(B)
+    assert b.engine.iterations == 2
+    b.engine.train_step(x, eg, el, u)
+    torch.cuda.synchronize()
+    assert torch.equal(a.engine.params, b.engine.params)
+    assert torch.equal(a.engine.adam_m, b.engine.adam_m) and torch.equal(a.engine.adam_v, b.engine.adam_v)
+    c = _model(kind, H)
+    c.load_weights(plain)
+    c.build(B)
+    assert c.engine.iterations == 0 and all(np.array_equal(v, now[k]) for k, v in c.engine.get_params().items())
+
+
 def test_cli_trains_evaluates_and_saves(tmp_path, capsys):
     """`main.py --model lgvae --dataset svhn ...` with the reference's flags: train loop, evaluation report, weights file."""
     from splitvae_b200 import main as cli
@@ -112,6 +154,24 @@ def test_cli_trains_evaluates_and_saves(tmp_path, capsys):
     assert hist[-1][1]["total"] < hist[0][1]["total"]                # six Adam steps on a fixed synthetic pool reduce the loss
     with np.load(str(out) + ".npz") as z:
         assert "encoder_x.e1.kernel" in z.files or any(k.endswith("e1.kernel") for k in z.files)
+
+
+def test_cli_writes_the_reference_h5_and_resumes_from_it(tmp_path, capsys):
+    """--save_weights <run>.h5 = vae/trainer.py:421's file; --load_weights continues from it (step count and Adam state included)."""
+    from splitvae_b200 import hdf5_lite
+    from splitvae_b200 import main as cli
+    out = str(tmp_path / "run.h5")
+    common = ["--model", "lggmvae", "--dataset", "svhn", "--beta", "40", "--alpha", "40", "--patch_size", "4", "--batch_size", "8",
+              "--report_every", "2", "--test_batches", "0", "--precision", "fp32"]
+    cli.main(common + ["--training_steps", "4", "--save_weights", out])
+    flat, f = hdf5_lite.load_keras_weights(out)
+    assert [n.decode() for n in f.attrs["layer_names"]] == ["encoder", "encoder_1", "decoder", "decoder_1"]
+    assert "lggm_vae/encoder/y_dense/kernel:0" in flat and flat["lggm_vae/decoder_1/conv2d_13/kernel:0"].shape == (6, 6, 32, 6)
+    assert int(f["optimizer_weights/Adam/iterations:0"].read()) == 5      # steps 0..4: the loop stops AFTER step == training_steps (trainer.py:417)
+    capsys.readouterr()
+    cli.main(common + ["--training_steps", "2", "--load_weights", out, "--save_weights", str(tmp_path / "run2.h5")])
+    assert "loaded" in capsys.readouterr().out
+    assert int(hdf5_lite.File(str(tmp_path / "run2.h5"))["optimizer_weights/Adam/iterations:0"].read()) == 8
 
 
 def test_forward_calls_with_other_batch_sizes_keep_the_training_state():
