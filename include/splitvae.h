@@ -242,6 +242,8 @@ enum { SV_IMPL_REF = 0, SV_IMPL_TC = 1 };
 int32_t sv_debug_layer_count(const sv_handle* h);
 sv_status sv_debug_layer_info(const sv_handle* h, int32_t index, sv_layer_info* out);
 sv_status sv_debug_run_layer(sv_handle* h, int32_t index, int32_t pass, int32_t impl, const float* inputs_dev, void* stream);
+/* The pixel likelihood kernel of sv_loss_fwd_bwd ALONE (no scalar reduction behind it): what bench.py times for the kernel's HBM roofline. */
+sv_status sv_debug_pixel_loss(sv_handle* h, const float* inputs_dev, void* stream);
 /* With SV_HALO_TRACE=1 in the environment at sv_create, every CTA of the halo convolution kernel records the SM clock at its
  * phase boundaries; this copies 8 words per CTA of the LAST such launch to host memory (synchronises). Returns #CTAs or -1. */
 int32_t sv_debug_halo_trace(uint64_t* out_host, int32_t max_ctas);

@@ -25,7 +25,7 @@ SYMBOLS = ["sv_create", "sv_destroy", "sv_last_error", "sv_version", "sv_param_c
            "sv_num_segments", "sv_segment_num_ranges", "sv_segment_range", "sv_backward_segment", "sv_backward_segment_deferred", "sv_adam_step", "sv_adam_segment", "sv_nvls_adam_segment", "sv_repack_segment", "sv_train_step",
            "sv_capture_graph", "sv_replay", "sv_output_ptr", "sv_decode", "sv_encode_y", "sv_get_iterations", "sv_set_iterations", "sv_launch_count",
            "sv_discretised_logistic_loss", "sv_adam_flat", "sv_stage_scramble", "sv_stage_resize_scramble", "sv_draw_permutations", "sv_debug_layer_count",
-           "sv_debug_layer_info", "sv_debug_run_layer", "sv_debug_halo_trace"]
+           "sv_debug_layer_info", "sv_debug_run_layer", "sv_debug_pixel_loss", "sv_debug_halo_trace"]
 
 
 class SvConfig(C.Structure):
@@ -113,6 +113,7 @@ def load():
     lib.sv_debug_layer_count.argtypes = [vp]
     lib.sv_debug_layer_info.argtypes = [vp, i32, C.POINTER(SvLayerInfo)]
     lib.sv_debug_run_layer.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.sv_debug_pixel_loss.argtypes = [vp, vp, vp]
     lib.sv_debug_halo_trace.argtypes = [vp, i32]
     lib.sv_debug_halo_trace.restype = i32
     _lib = lib

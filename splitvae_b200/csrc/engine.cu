@@ -945,17 +945,30 @@ sv_status sv_forward(sv_handle* h, const float* inputs, const float* eps_g, cons
   return forward_impl(h, inputs, eps_g, eps_l, u, stream, true);
 }
 
-sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
-  REQUIRE_BOUND(h);
-  if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
-  cudaStream_t s = (cudaStream_t)stream;
-  const bool gm = h->gm, loc = h->has_local;
+static void run_pixel_loss(sv_handle* h, const float* inputs, cudaStream_t s) {
+  const bool loc = h->has_local;
   const long long npix = (long long)h->B * h->H * h->W;
   const float inv_batch = 1.f / ((float)h->B * (float)h->cfg.world_size);
   pixel_loss(inputs, (const float*)bp(h, h->dec_x.OUT), loc ? (const float*)bp(h, h->dec_xh.OUT) : nullptr, bp(h, h->dec_x.dOUT),
              loc ? bp(h, h->dec_xh.dOUT) : nullptr, h->act_dt, h->layers[h->dec_x.d5].g.dout_ld, npix, inv_batch,
              (float*)bp(h, h->PARTIALS), h->act_dt == DT_BF16, s, h->cs_on ? h->cs_fold[0][3] : nullptr,
              h->cs_on && loc ? h->cs_fold[1][3] : nullptr);
+}
+
+sv_status sv_debug_pixel_loss(sv_handle* h, const float* inputs, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
+  run_pixel_loss(h, inputs, (cudaStream_t)stream);
+  return check_launch(h, "sv_debug_pixel_loss");
+}
+
+sv_status sv_loss_fwd_bwd(sv_handle* h, const float* inputs, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!inputs) return fail(h, SV_ERR_INVALID, "inputs is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool gm = h->gm;
+  const long long npix = (long long)h->B * h->H * h->W;
+  run_pixel_loss(h, inputs, s);
   loss_scalars((const float*)bp(h, h->KLPART), reparam_blocks(h->B), gm ? (const float*)bp(h, h->gm_enc.LOGITS) : nullptr, h->B, h->K, gm, h->cfg.beta, h->cfg.alpha,
                (const float*)bp(h, h->PARTIALS), pixel_loss_blocks(npix), (float*)bp(h, h->SCALARS), s);
   h->launches += 2;

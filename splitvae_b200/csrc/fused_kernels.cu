@@ -358,53 +358,53 @@ __device__ __forceinline__ void store_dout(T* p, const float* g) {  // g[6] -> L
   }
 }
 
-// One thread = two consecutive pixels of both streams (x | x_hat): 3 x 16-byte loads per tensor.
+// One thread-iteration = ONE pixel of both streams (x | x_hat): three 8-byte loads per tensor (a pixel's 6 floats are 24 bytes; the
+// lanes of a warp cover 768 contiguous bytes per tensor, every sector is used).  The grid is ONE balanced wave: 148 x 4 blocks of 256
+// threads (<= 64 registers), so at CelebA64 x 256 every thread takes 6.92 -> 7 pixels; the two-pixel version ran 1184 blocks of 80
+// registers = 2.67 waves of blocks with 1 or 2 iterations each and left the HBM pipe 39 % busy.
 // Writes d(loss)/d(decoder output) (scaled by grad_scale = 1/(B*world)) and per-block partial
 // sums of the two reconstruction losses.
 constexpr int kLossThreads = 256;
 template <typename T, int LD, bool FAST>
-__global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* __restrict__ inputs,
-                                                                  const float* __restrict__ dec_x,
-                                                                  const float* __restrict__ dec_xh,
-                                                                  T* __restrict__ dout_x, T* __restrict__ dout_xh,
-                                                                  long long npairs, float grad_scale,
-                                                                  float* __restrict__ partials, float* __restrict__ cs_x,
-                                                                  float* __restrict__ cs_xh) {
+__global__ void __launch_bounds__(kLossThreads, 4) pixel_loss_kernel(const float* __restrict__ inputs,
+                                                                     const float* __restrict__ dec_x,
+                                                                     const float* __restrict__ dec_xh,
+                                                                     T* __restrict__ dout_x, T* __restrict__ dout_xh,
+                                                                     long long npix, float grad_scale,
+                                                                     float* __restrict__ partials, float* __restrict__ cs_x,
+                                                                     float* __restrict__ cs_xh) {
   pdl_enter();
   float sum_x = 0.f, sum_xh = 0.f;
   // cs_x / cs_xh (may be NULL): [gridDim.x][16] per-block column sums of the written gradients = d5's bias-gradient partials
   float bsx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long pr = blockIdx.x * (long long)kLossThreads + threadIdx.x; pr < npairs;
-       pr += (long long)gridDim.x * kLossThreads) {
-    float in[12], ox[12], oh[12];
-    const float4* ip = reinterpret_cast<const float4*>(inputs + pr * 12);
-    const float4* xp = reinterpret_cast<const float4*>(dec_x + pr * 12);
-    const bool two = dec_xh != nullptr;          // (plain GMVAE: one decoder, one likelihood term)
-    const float4* hp = reinterpret_cast<const float4*>(dec_xh + pr * 12);
+  const bool two = dec_xh != nullptr;            // (plain GMVAE: one decoder, one likelihood term)
+#pragma unroll 1
+  for (long long px = blockIdx.x * (long long)kLossThreads + threadIdx.x; px < npix; px += (long long)gridDim.x * kLossThreads) {
+    float in[6], ox[6], oh[6];
+    const float2* ip = reinterpret_cast<const float2*>(inputs + px * 6);
+    const float2* xp = reinterpret_cast<const float2*>(dec_x + px * 6);
+    const float2* hp = reinterpret_cast<const float2*>(dec_xh + px * 6);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      reinterpret_cast<float4*>(in)[i] = __ldg(ip + i);
-      reinterpret_cast<float4*>(ox)[i] = __ldg(xp + i);
-      reinterpret_cast<float4*>(oh)[i] = two ? __ldg(hp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float2*>(in)[i] = __ldg(ip + i);
+      reinterpret_cast<float2*>(ox)[i] = __ldg(xp + i);
+      reinterpret_cast<float2*>(oh)[i] = two ? __ldg(hp + i) : make_float2(0.f, 0.f);
     }
+    float gx[6], gh[6];
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      float gx[6], gh[6];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float gm_, gl_;
-        sum_x += dll_elem<FAST>(in[px * 6 + c], ox[px * 6 + c], ox[px * 6 + 3 + c], gm_, gl_);
-        gx[c] = gm_ * grad_scale; gx[3 + c] = gl_ * grad_scale;
-        if (two) {
-          sum_xh += dll_elem<FAST>(in[px * 6 + 3 + c], oh[px * 6 + c], oh[px * 6 + 3 + c], gm_, gl_);
-          gh[c] = gm_ * grad_scale; gh[3 + c] = gl_ * grad_scale;
-        }
+    for (int c = 0; c < 3; ++c) {
+      float gm_, gl_;
+      sum_x += dll_elem<FAST>(in[c], ox[c], ox[3 + c], gm_, gl_);
+      gx[c] = gm_ * grad_scale; gx[3 + c] = gl_ * grad_scale;
+      if (two) {
+        sum_xh += dll_elem<FAST>(in[3 + c], oh[c], oh[3 + c], gm_, gl_);
+        gh[c] = gm_ * grad_scale; gh[3 + c] = gl_ * grad_scale;
       }
-      store_dout<T, LD>(dout_x + (pr * 2 + px) * LD, gx);
-      if (two) store_dout<T, LD>(dout_xh + (pr * 2 + px) * LD, gh);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) { bsx[c] += gx[c]; if (two) bsh[c] += gh[c]; }
     }
+    store_dout<T, LD>(dout_x + px * LD, gx);
+    if (two) store_dout<T, LD>(dout_xh + px * LD, gh);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { bsx[c] += gx[c]; if (two) bsh[c] += gh[c]; }
   }
   if (cs_x) {
     __shared__ float cred[2][kLossThreads / 32][6];
@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(kLossThreads) pixel_loss_kernel(const float* _
 }
 
 int pixel_loss_blocks(long long npix) {
-  long long b = (npix / 2 + kLossThreads - 1) / kLossThreads;
-  if (b > 148 * 8) b = 148 * 8;
+  long long b = (npix + kLossThreads - 1) / kLossThreads;
+  if (b > 148 * 4) b = 148 * 4;                    // one wave: 4 resident blocks per SM (launch bounds)
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -462,8 +462,7 @@ void pixel_loss(const float* inputs, const float* dec_x, const float* dec_xh, vo
                 int dout_ld, long long npix, float grad_scale, float* partials, bool fast_math, cudaStream_t s, float* cs_x, float* cs_xh) {
   if (dout_ld != 16 || dout_dt != DT_BF16) { cs_x = nullptr; cs_xh = nullptr; }     // (the external partial rows are 16 columns wide)
   const int blocks = pixel_loss_blocks(npix);
-  const long long npairs = npix / 2;
-#define LAUNCH(T, LD, F) launch_pdl(pixel_loss_kernel<T, LD, F>, dim3(blocks), dim3(kLossThreads), 0, s, inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npairs, grad_scale, partials, cs_x, cs_xh)
+#define LAUNCH(T, LD, F) launch_pdl(pixel_loss_kernel<T, LD, F>, dim3(blocks), dim3(kLossThreads), 0, s, inputs, dec_x, dec_xh, (T*)dout_x, (T*)dout_xh, npix, grad_scale, partials, cs_x, cs_xh)
   if (dout_dt == DT_F32) {
     if (fast_math) LAUNCH(float, 6, true); else LAUNCH(float, 6, false);
   } else if (dout_ld == 8) {

@@ -692,30 +692,39 @@ __global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJ
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs, const float* __restrict__ partial,
-                                                                 float* __restrict__ grads) {
+constexpr int kColsumFinalLanes = 32;   // chunk lanes per column: the jobs fed by upsample2x_bwd / pixel_loss bring 592-1184 chunks for 16-128 columns,
+                                        // so a block is few columns x many lanes (8 lanes left each thread ~150 serial L2 loads: 16 us)
+__global__ void __launch_bounds__(32 * kColsumFinalLanes) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs,
+                                                                                    const float* __restrict__ partial, float* __restrict__ grads) {
   pdl_enter();
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (jobs[mid].fblock_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  // block = 32 columns x 8 chunk lanes (lane y sums chunks y, y+8, ...), fixed-order combine through shared memory
-  __shared__ float red[8][33];
+  // block = 32 columns x 32 chunk lanes (lane y sums chunks y, y+32, ... with four loads in flight), fixed-order combine through shared memory
+  __shared__ float red[kColsumFinalLanes][33];
   const ColsumJob& J = jobs[lo];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.x - J.fblock_start) * 32 + tx;
   float t = 0.f;
   if (c < J.ncols) {
     const float* p = partial + J.partial_off + c;
-    for (int k = ty; k < J.nchunks; k += 8) t += p[(long long)k * J.ncols];
+    const long long st = (long long)kColsumFinalLanes * J.ncols;
+    int k = ty;
+    for (; k + 3 * kColsumFinalLanes < J.nchunks; k += 4 * kColsumFinalLanes) {
+      const float* q = p + (long long)k * J.ncols;
+      const float a = q[0], b = q[st], d = q[2 * st], e = q[3 * st];
+      t += (a + b) + (d + e);
+    }
+    for (; k < J.nchunks; k += kColsumFinalLanes) t += p[(long long)k * J.ncols];
   }
   red[ty][tx] = t;
   __syncthreads();
   if (ty == 0 && c < J.ncols && J.col0 + c < J.c_valid) {
     float u = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u += red[i][tx];
+    for (int i = 0; i < kColsumFinalLanes; ++i) u += red[i][tx];
     int lc = J.col0 + c, j = 0;
     while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
     grads[J.part_b[j] + lc] = u;
@@ -823,7 +832,7 @@ void colsum_table_destroy(ColsumTable* t) {
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
   if (t->nblocks) launch_pdl(colsum_multi_partial_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial);
-  launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial, grads);
+  launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(32 * kColsumFinalLanes), 0, s, t->dev, t->njobs, t->partial, grads);
   return t->nblocks ? 2 : 1;
 }
 float* colsum_table_ext_partial(ColsumTable* t, int i) {

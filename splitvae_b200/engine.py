@@ -257,5 +257,8 @@ class Engine:
         nbytes = elems * (4 if dt == 0 else 2)
         return self._ws[off:off + nbytes].view(torch.float32 if dt == 0 else torch.bfloat16)
 
+    def debug_pixel_loss(self, inputs):
+        check(self.lib.sv_debug_pixel_loss(self.h, _ptr(inputs), _stream()), self.h, "sv_debug_pixel_loss")
+
     def debug_run_layer(self, index, pass_, impl, inputs=None):
         check(self.lib.sv_debug_run_layer(self.h, index, pass_, impl, _ptr(inputs), _stream()), self.h, "sv_debug_run_layer")
