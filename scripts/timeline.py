@@ -61,6 +61,6 @@ for t, d in pts:
 print("time with n kernels in flight:", {a: round(b, 1) for a, b in sorted(hist.items())})
 print("\nstart_us  dur_us  stream  grid  kernel")
 for v in k:
-    name = v["name"].split("(")[0].replace("sv::<unnamed>::", "").replace("sv::", "").replace("void ", "")[:38]
+    name = v["name"].replace("(anonymous namespace)::", "").split("(")[0].replace("sv::<unnamed>::", "").replace("sv::", "").replace("void ", "")[:38]
     g = v["args"].get("grid", "")
     print(f"{v['ts'] - t0:8.1f} {v['dur']:7.1f}  {streams.index(v['args']['stream'])}  {str(g):16s} {name}")

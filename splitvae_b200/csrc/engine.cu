@@ -101,10 +101,11 @@ struct sv_handle {
   // weight gradients run on one auxiliary stream per branch stream (dgrad chain = critical path, wgrad + reduce fill the gaps)
   // (SV_WGRAD_STREAMS = n streams per branch, used round-robin by consecutive layers; 0 = none.  Two per branch let wgrad(L-1) start
   // while wgrad(L) and its split-K reduce are still queued: on one in-order stream the encoders' last wgrads formed a serial tail)
-  cudaStream_t aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-  cudaEvent_t ev_aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, ev_aux_join[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  static constexpr int kMaxAux = 8;
+  cudaStream_t aux[2][kMaxAux] = {};
+  cudaEvent_t ev_aux[2][kMaxAux] = {}, ev_aux_join[2][kMaxAux] = {};
   int aux_n = 0, aux_rr[2] = {0, 0};
-  bool aux_dirty[2][2] = {{false, false}, {false, false}};   // forked since the last join
+  bool aux_dirty[2][kMaxAux] = {};                            // forked since the last join
   bool defer_join = false;                                    // inside sv_backward_segment_deferred
   bool wgrad_streams = false;
   // multi-tensor bias gradients, one table per backward branch: 0 decoder_x, 1 decoder_x_hat, 2 encoder_x, 3 encoder_x_hat
@@ -759,6 +760,16 @@ sv_status sv_create(const sv_config* cfg, sv_handle** out) {
     size_t tcws = 0;
     for (auto& L : h->layers) tcws += tc_workspace_bytes(L.tc, L.g);
     h->TCWS = new_buf(h, tcws + 1024);
+    if (plan_only && getenv("SV_PACK_DEBUG") && atoi(getenv("SV_PACK_DEBUG")) == 2) {      // job list of the per-segment operand re-pack, host only
+      for (int seg = 0; seg < sv_handle::kSegs; ++seg) {
+        std::vector<TcLayer*> sl;
+        std::vector<const ConvGeom*> sg;
+        for (int li : segment_layers(h, seg)) { sl.push_back(&h->layers[li].tc); sg.push_back(&h->layers[li].g); }
+        const char* perr = nullptr;
+        fprintf(stderr, "[pack] segment %d\n", seg);
+        tc_pack_table_destroy(tc_pack_table_create(sl.data(), sg.data(), (int)sl.size(), &perr));
+      }
+    }
   }
   *out = h;
   return SV_OK;
@@ -777,7 +788,7 @@ sv_status sv_destroy(sv_handle* h) {
     for (int b = 0; b < 4; ++b)
       for (int part = 0; part < 2; ++part) colsum_table_destroy(h->cs[b][part]);
     for (int k = 0; k < 2; ++k)
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < sv_handle::kMaxAux; ++j) {
         if (h->ev_aux[k][j]) cudaEventDestroy(h->ev_aux[k][j]);
         if (h->ev_aux_join[k][j]) cudaEventDestroy(h->ev_aux_join[k][j]);
         if (h->aux[k][j]) cudaStreamDestroy(h->aux[k][j]);
@@ -895,7 +906,7 @@ sv_status sv_bind(sv_handle* h, float* params, float* grads, float* adam_m, floa
   if (!h->aux[0][0]) {
     const char* off = getenv("SV_WGRAD_STREAMS");
     h->aux_n = off && *off ? atoi(off) : 2;
-    if (h->aux_n > 2) h->aux_n = 2;
+    if (h->aux_n > sv_handle::kMaxAux) h->aux_n = sv_handle::kMaxAux;
     h->wgrad_streams = h->aux_n > 0;
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < h->aux_n; ++j)

@@ -1827,6 +1827,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_few_kernel(ConvGeom g, const
 // weight packing: one multi-tensor kernel refreshes every bf16 operand copy from the fp32 masters
 // ------------------------------------------------------------------------------------------------
 constexpr int kPackKT = 4;
+constexpr int kPackDgIter = 4;      // kind 1 (dgrad copies): 8-element groups per thread
 struct PackJob {
   int kind;                 // 0: fwd weights, 1: dgrad weights (one parity class), 2: bias, 4 / 5: N-stacked fwd / dgrad weights
   int KH, KW, Ci, Co;       // layer geometry (logical)
@@ -1852,13 +1853,10 @@ __device__ __forceinline__ float master_w(const PackJob& J, const float* params,
   return params[J.part_w[j] + ((long long)(kh * J.KW + kw) * J.Ci + ci) * J.part_n[j] + lc];
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* __restrict__ params) {
+__global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ jobs, const uint16_t* __restrict__ block_job,
+                                                   const float* __restrict__ params) {
   pdl_enter();
-  int lo = 0, hi = njobs - 1;
-  while (lo < hi) {  // last job whose block_start <= blockIdx.x
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
+  const int lo = block_job[blockIdx.x];        // (one load: the binary search over block_start was six dependent L2 round trips per block)
   __shared__ PackJob Js;                       // the job descriptor is read hundreds of times: keep it on chip
   if (threadIdx.x < sizeof(PackJob) / 4) reinterpret_cast<uint32_t*>(&Js)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&jobs[lo])[threadIdx.x];
   __syncthreads();
@@ -1867,33 +1865,42 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
     // dgrad weights: dst[ci][tap'][co] = W[kh][kw][ci][co] (flipped sub-kernel) keeps co contiguous on both sides: one thread
     // converts 8 consecutive co (two 128-bit loads when the run lies inside one Keras variable, one 128-bit store)
     const int k8 = J.k_pad >> 3, ntap = J.taps_h * J.taps_w;
-    const int base8 = (blockIdx.x - J.block_start) * 256;      // 2048 elements per block
-    const int i8 = base8 + threadIdx.x;
-    if (i8 * 8 >= (int)J.count) return;
-    const int kk = (i8 % k8) * 8;
-    const int rt = i8 / k8;
-    const int tap = rt % ntap, r = rt / ntap;
-    const int a = tap / J.taps_w, b = tap - a * J.taps_w;
-    const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
-    float v[8];
+    const int base8 = (blockIdx.x - J.block_start) * (256 * kPackDgIter);      // 2048 * kPackDgIter elements per block
+    float v[kPackDgIter][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (r < J.Ci) {
-      int j = 0, lc = kk;
-      while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
-      const float* src = params + J.part_w[j] + ((long long)(kh * J.KW + kw) * J.Ci + r) * J.part_n[j] + lc;
-      if (lc + 8 <= J.part_n[j] && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const float4 p0 = __ldg(reinterpret_cast<const float4*>(src)), p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-      } else {
+    for (int it = 0; it < kPackDgIter; ++it) {                                 // all loads of the block's groups in flight before the first store
+      const int i8 = base8 + it * 256 + threadIdx.x;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (kk + i < J.Co) v[i] = master_w(J, params, kh, kw, r, kk + i);
+      for (int i = 0; i < 8; ++i) v[it][i] = 0.f;
+      if ((long long)i8 * 8 >= J.count) continue;
+      const int kk = (i8 % k8) * 8;
+      const int rt = i8 / k8;
+      const int tap = rt % ntap, r = rt / ntap;
+      const int a = tap / J.taps_w, b = tap - a * J.taps_w;
+      const int kh = J.stride * (J.taps_h - 1 - a) + J.rh, kw = J.stride * (J.taps_w - 1 - b) + J.rw;
+      if (r < J.Ci) {
+        int j = 0, lc = kk;
+        while (j + 1 < J.nparts && lc >= J.part_n[j]) { lc -= J.part_n[j]; ++j; }
+        const float* src = params + J.part_w[j] + ((long long)(kh * J.KW + kw) * J.Ci + r) * J.part_n[j] + lc;
+        if (lc + 8 <= J.part_n[j] && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(src)), p1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          v[it][0] = p0.x; v[it][1] = p0.y; v[it][2] = p0.z; v[it][3] = p0.w; v[it][4] = p1.x; v[it][5] = p1.y; v[it][6] = p1.z; v[it][7] = p1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (kk + i < J.Co) v[it][i] = master_w(J, params, kh, kw, r, kk + i);
+        }
       }
     }
-    uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(J.dst)[i8] = pk;
+#pragma unroll
+    for (int it = 0; it < kPackDgIter; ++it) {
+      const int i8 = base8 + it * 256 + threadIdx.x;
+      if ((long long)i8 * 8 >= J.count) continue;
+      uint4 pk;
+      pk.x = pack_bf16x2(v[it][0], v[it][1]); pk.y = pack_bf16x2(v[it][2], v[it][3]);
+      pk.z = pack_bf16x2(v[it][4], v[it][5]); pk.w = pack_bf16x2(v[it][6], v[it][7]);
+      reinterpret_cast<uint4*>(J.dst)[i8] = pk;
+    }
     return;
   }
   if (J.kind == 0 && J.fast) {
@@ -1926,15 +1933,22 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackJob* __restrict__ j
         tile[ty + 8 * i][tx] = (co < J.Co && ci < J.Ci) ? src[(long long)ci * pn] : 0.f;
       }
       __syncthreads();
+      {
+        // thread = (section, output row, group of 8 consecutive channels): one 128-bit store each (2-byte stores were 8x the
+        // store instructions); tile[ci][co] column reads: bank = (8 g + i + r) mod 32, distinct over the warp's (g, r)
+        const int sec = threadIdx.x >> 7, rr = (threadIdx.x & 127) >> 2, g8 = threadIdx.x & 3;
+        const int r = tr * 32 + rr;
+        if (sec < J.nsec && r < J.rows_pad) {
+          float v[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = tr * 32 + ty + 8 * i;
-        if (r < J.rows_pad) {
-          const float v = tile[tx][ty + 8 * i];
-          const float hi = round_bf16(v);
-          bf16* d = (bf16*)J.dst + ((long long)r * ntap + tap) * J.k_pad + (long long)chunk * J.nsec * J.cpp + w0 + tx;
-          d[0] = __float2bfloat16_rn(hi);
-          if (J.nsec == 2) d[J.cpp] = __float2bfloat16_rn(v - hi);
+          for (int i = 0; i < 8; ++i) {
+            const float w = tile[g8 * 8 + i][rr];
+            v[i] = sec ? w - round_bf16(w) : w;
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+          bf16* d = (bf16*)J.dst + ((long long)r * ntap + tap) * J.k_pad + (long long)chunk * J.nsec * J.cpp + (long long)sec * J.cpp + w0 + g8 * 8;
+          *reinterpret_cast<uint4*>(d) = pk;
         }
       }
     }
@@ -3022,8 +3036,10 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
 
 struct TcPackTable {
   PackJob* dev = nullptr;
+  uint16_t* block_job = nullptr;      // block index -> job
   int njobs = 0, nblocks = 0;
 };
+void tc_pack_table_destroy(TcPackTable* t);
 
 TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const* geoms, int n, const char** err) {
   std::vector<PackJob> jobs;
@@ -3032,7 +3048,11 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     J.block_start = blocks;
     if (J.kind == 0 && J.fast) blocks += J.taps_h * J.taps_w * ((J.rows_pad + 31) / 32) * ((J.k_pad / J.nsec / 32 + kPackKT - 1) / kPackKT);
     else if (J.kind == 0) blocks += J.taps_h * J.taps_w * ((J.rows_pad + 31) / 32) * ((J.k_pad + 31) / 32);   // 32x32 transpose tiles
+    else if (J.kind == 1) blocks += (int)((J.count + 2048 * kPackDgIter - 1) / (2048 * kPackDgIter));
     else blocks += (int)((J.count + 2047) / 2048);
+    if (env_int("SV_PACK_DEBUG", 0))
+      fprintf(stderr, "[pack] job %zu kind %d fast %d %dx%d Ci %d Co %d rows_pad %d taps %dx%d k_pad %d nsec %d ppx %d count %lld blocks %d\n", jobs.size(), J.kind,
+              J.fast, J.KH, J.KW, J.Ci, J.Co, J.rows_pad, J.taps_h, J.taps_w, J.k_pad, J.nsec, J.ppx, J.count, blocks - J.block_start);
     jobs.push_back(J);
   };
   for (int i = 0; i < n; ++i) {
@@ -3059,7 +3079,8 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
     if (t.fwd_ok) {
       PackJob J = B;
       const TcLaunch& L = t.fwd;
-      J.kind = 0; J.rows_pad = t.n_pad_fwd; J.taps_h = L.taps_h; J.taps_w = L.taps_w;
+      J.kind = t.fwd_ns ? -1 : 0;                   // (the N-stacked kernel serves this layer's forward: the plain copy would never be read)
+      J.rows_pad = t.n_pad_fwd; J.taps_h = L.taps_h; J.taps_w = L.taps_w;
       // pixels per k-block: 8 for the first layer's window view (one k-block per filter row), 2 for the pixel-pair views
       J.ppx = (t.first && !t.first_pair) ? 8 : (t.first_pair || t.fwd_pair) ? 2 : 1;
       J.cpp = L.bk / J.ppx;                           // channels per pixel slot of one k-block
@@ -3069,12 +3090,12 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
       J.fast = (J.ppx == 1 && !J.first_cat && (J.cpp % 32) == 0 && (J.nsec == 1 || J.nsec == 2) && !env_int("SV_PACK_SLOW", 0)) ? 1 : 0;
       J.dst = t.ws + t.w_fwd_off;
       J.count = (long long)t.n_pad_fwd * J.taps_h * J.taps_w * J.k_pad;
-      push(J);
+      if (J.kind == 0) push(J);
       PackJob Jb = B;
       Jb.kind = 2; Jb.dst = t.ws + t.bias_off; Jb.count = t.n_pad_fwd;
       push(Jb);
     }
-    if (t.dgrad_ok) {
+    if (t.dgrad_ok && !t.dgrad_ns) {              // (dgrad_ns: the N-stacked copy above is the one tc_conv_dgrad uses)
       const int s = g.stride;
       const size_t per_class = round_up((int)((size_t)t.n_pad_dg * t.dg_taps_h * t.dg_taps_w * t.co_pad * 2), 1024);
       for (int cls = 0; cls < t.n_dgrad; ++cls) {
@@ -3090,11 +3111,18 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
   TcPackTable* T = new TcPackTable();
   T->njobs = (int)jobs.size();
   T->nblocks = blocks;
-  if (T->njobs) {
+  if (T->njobs && env_int("SV_PACK_DEBUG", 0) != 2) {       // (2: dry run on a plan-only handle, job list on stderr only)
+    std::vector<uint16_t> bj((size_t)blocks);
+    for (size_t j = 0; j < jobs.size(); ++j) {
+      const int end = j + 1 < jobs.size() ? jobs[j + 1].block_start : blocks;
+      for (int b = jobs[j].block_start; b < end; ++b) bj[b] = (uint16_t)j;
+    }
     if (cudaMalloc(&T->dev, jobs.size() * sizeof(PackJob)) != cudaSuccess ||
-        cudaMemcpy(T->dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(T->dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&T->block_job, bj.size() * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMemcpy(T->block_job, bj.data(), bj.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
       *err = "pack table upload failed";
-      delete T;
+      tc_pack_table_destroy(T);
       return nullptr;
     }
   }
@@ -3104,12 +3132,13 @@ TcPackTable* tc_pack_table_create(TcLayer* const* layers, const ConvGeom* const*
 void tc_pack_table_destroy(TcPackTable* t) {
   if (!t) return;
   if (t->dev) cudaFree(t->dev);
+  if (t->block_job) cudaFree(t->block_job);
   delete t;
 }
 
 int tc_repack_all(TcPackTable* t, const float* params, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
-  launch_pdl(pack_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, params);
+  launch_pdl(pack_kernel, dim3(t->nblocks), dim3(256), 0, s, (const PackJob*)t->dev, (const uint16_t*)t->block_job, params);
   return 1;
 }
 
