@@ -1572,7 +1572,7 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
         tc::mbar_wait(&ctl->empty[st], ph ^ 1);
         tc::mbar_expect_tx(&ctl->full[st], tx_bytes);
         for (int c = 0; c < P.nchunks; ++c)
-          tc::tma_load_4d(sx + (size_t)c * P.x_chunk_bytes, &P.map_x, &ctl->full[st], c * P.cb, x0 + P.x_dx, y0 + P.x_dy, n);
+          tc::tma_load_4d(sx + (size_t)c * P.x_chunk_bytes, &P.map_x, &ctl->full[st], c * P.cb, x0 + P.x_dx, y0 * P.sy + P.x_dy, n);
         for (int c = 0; c < P.nbchunks; ++c)
           tc::tma_load_4d(sx + x_bytes + (size_t)c * P.dy_chunk_bytes, &P.map_dy, &ctl->full[st], c * P.cbn, x0 + P.dy_dx, y0, n);
       }
@@ -1588,7 +1588,7 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
       const uint32_t n_pad = (uint32_t)P.n_pad;
       const int ksx = P.TW / 16;
       const uint32_t a_xs = (16u * pix) >> 4, b_xs = (16u * pixb) >> 4;
-      const uint32_t a_row = ((uint32_t)P.x_tw * pix) >> 4, b_row = ((uint32_t)P.dy_tw * pixb) >> 4;
+      const uint32_t a_row = ((uint32_t)(P.sy * P.x_tw) * pix) >> 4, b_row = ((uint32_t)P.dy_tw * pixb) >> 4;   // (sy = 2: every other X row)
       const volatile uint32_t* goff = ctl->goff;
       for (int t = t_begin; t < t_end; ++t) {
         const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
@@ -1662,11 +1662,19 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
 }
 
 // row of (tap, ci) inside the split-K partial buffer for each wgrad flavour
-struct WgRowMap { int mode, kw, ci_pad, cb, nsub, gw, gpt, nb; };
+struct WgRowMap { int mode, kw, ci_pad, cb, nsub, gw, gpt, nb; int pair_c = 0, pair_sh = 0, kwp = 0; };
 // mode 0: tap*ci_pad+ci; 1: first layer; 2: halo, taps stacked along the filter row; 3: halo, chunks of one tap;
 // 4/5: N-stacked halo (rows enumerate (filter row a, ci); columns (kw-1-b)*nb + co): 4 = vertical taps stacked, 5 = chunks stacked
-__device__ __forceinline__ size_t wg_row(const WgRowMap& R, int tap, int ci) {
-  const int a = tap / R.kw, b = tap - a * R.kw;
+// pair_c > 0 (stride-2 layer on the halo kernel through the pixel-PAIR view [W/2][2 * pair_c]): filter column b of the layer is
+// pair tap u >> 1 and parity u & 1 with u = b + pair_sh; the parity selects the half of the pair's 2 * pair_c channels
+__device__ __forceinline__ void wg_tap(const WgRowMap& R, int tap, int& a, int& b, int& ci, int& kw) {
+  a = tap / R.kw; b = tap - a * R.kw; kw = R.kw;
+  if (R.pair_c) { const int u = b + R.pair_sh; b = u >> 1; ci += (u & 1) * R.pair_c; kw = R.kwp; }
+}
+__device__ __forceinline__ size_t wg_row(const WgRowMap& R, int tap0, int ci) {
+  int a, b, kw;
+  wg_tap(R, tap0, a, b, ci, kw);
+  const int tap = a * kw + b;
   switch (R.mode) {
     case 1: return (size_t)a * 64 + b * 8 + ci;
     case 2: return (size_t)(a * R.gw + b / R.nsub) * 128 + (b % R.nsub) * R.cb + ci;
@@ -1677,7 +1685,10 @@ __device__ __forceinline__ size_t wg_row(const WgRowMap& R, int tap, int ci) {
   }
 }
 __device__ __forceinline__ int wg_col(const WgRowMap& R, int tap, int co) {
-  return R.mode >= 4 ? (R.kw - 1 - tap % R.kw) * R.nb + co : co;
+  if (R.mode < 4) return co;
+  int a, b, kw, ci = 0;
+  wg_tap(R, tap, a, b, ci, kw);
+  return (kw - 1 - b) * R.nb + co;
 }
 
 // sums the split-K partials in a fixed order and scatters into the Keras-layout gradient arena.
@@ -2167,6 +2178,24 @@ const char* make_window_map(CUtensorMap* m, const void* xp, int N, int H, int W,
   return nullptr;
 }
 
+// natural pixel pairs of the staged first-layer image [N][H][W + 8][8] (pixel x in column x + 2): [N][H][W / 2][16], 32-byte swizzle
+const char* make_first_pair_map(CUtensorMap* m, const void* xp, int N, int H, int W, int tw, int th) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  const cuuint64_t row_pitch = (cuuint64_t)(W + 8) * 16;
+  cuuint64_t dims[4] = {16, (cuuint64_t)(W / 2), (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {32, row_pitch, row_pitch * H};
+  cuuint32_t box[4] = {16, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)((const bf16*)xp + 16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_error, sizeof(g_tc_error), "cuTensorMapEncodeTiled(first pair) failed: %d (H %d W %d box %u,%u)", (int)r, H, W, box[1], box[2]);
+    return g_tc_error;
+  }
+  return nullptr;
+}
+
 __global__ void __launch_bounds__(256) stage_first_kernel(const float* __restrict__ inputs, bf16* __restrict__ xp, int coff, int B, int H, int W,
                                                           int split) {
   pdl_enter();
@@ -2404,8 +2433,29 @@ void plan_persist(TcLaunch& L, int n_classes) {
 }
 
 // Plans the halo-resident wgrad for a stride-1 convolution; returns false when the layer is not eligible.
-bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int cbn, int copad) {
+bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g0, int cb, int cipad, int cbn, int copad) {
   if (env_int("SV_NO_HALO_WGRAD", 0)) return false;
+  ConvGeom g = g0;
+  H.sy = 1; H.pair_c = 0; H.pair_sh = 0;
+  if (g0.stride == 2) {
+    // Stride 2 through the pixel-PAIR view of X: [H][W/2][2 * ld] - consecutive output pixels are consecutive pairs, the filter column
+    // b = 2 q + r (relative to the padding) becomes pair tap q and selects the parity-r half of the pair's channels, so horizontally
+    // this is a stride-1 layer with 2 * Ci channels and ceil-ish(kw / 2) + 1 taps; vertically the MMA loop steps two X rows per
+    // output row.  (The per-tap kernel re-read the input once per tap: e2's 8 MB input became ~290 MB of L2 -> SMEM traffic.)
+    if (env_int("SV_NO_PAIR_WGRAD", 0)) return false;
+    if (g0.in_coff || g0.in_ld != g0.Ci || (g0.Ci % 8) || (g0.Wi & 1) || g0.Wo * 2 != g0.Wi || g0.Ho * 2 != g0.Hi) return false;
+    const int plp = (g0.pl + 1) / 2;
+    H.pair_c = g0.Ci;
+    H.pair_sh = 2 * plp - g0.pl;                                  // u = b - pl + 2 plp >= 0
+    g.kw = (g0.kw - 1 + H.pair_sh) / 2 + 1;
+    g.pl = plp;
+    g.Ci = 2 * g0.Ci; g.in_ld = 2 * g0.in_ld;
+    g.Wi = g0.Wi / 2; g.Hi = g.Ho;                                // (checked below as a same-size layer)
+    g.stride = 1;
+    choose_bk(g.Ci, cb, cipad);
+    H.sy = 2;
+  }
+  const int sy = H.sy;
   if (g.stride != 1 || (g.Wo % 16) || g.Wo != g.Wi || g.Ho != g.Hi || copad > 256 || g.kh * g.kw < 2) return false;
   H.taps_h = g.kh; H.taps_w = g.kw; H.pad_t = g.pt; H.pad_l = g.pl;
   H.cb = cb; H.nchunks = cipad / cb; H.x_swizzle = cb * 2;
@@ -2447,14 +2497,14 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   for (int th = 1; th <= g.Ho && th <= 32; ++th) {
     if (g.Ho % th) continue;
     if (force_th && th != force_th) continue;
-    const int thp = th + g.kh - 1;
+    const int thp = (th - 1) * sy + g.kh;
     const size_t xc = ((size_t)thp * x_tw * cb * 2 + 1023) / 1024 * 1024, dc = ((size_t)th * dy_tw * cbn * 2 + 1023) / 1024 * 1024;
     const size_t smem = (size_t)H.stages * (xc * H.nchunks + dc * H.nbchunks) + slack + sizeof(HwCtl) + 1024;
     if (smem <= 190 * 1024) best_th = th;
   }
   if (!best_th) return false;
   H.TH = best_th;
-  H.x_tw = x_tw; H.x_th = H.TH + g.kh - 1; H.dy_tw = dy_tw; H.dy_th = H.TH;
+  H.x_tw = x_tw; H.x_th = (H.TH - 1) * sy + g.kh; H.dy_tw = dy_tw; H.dy_th = H.TH;
   H.x_dx = H.nstack ? 0 : -g.pl; H.x_dy = -g.pt; H.dy_dx = H.nstack ? -(g.kw - 1) + g.pl : 0;
   H.x_chunk_bytes = (int)(((size_t)H.x_th * H.x_tw * cb * 2 + 1023) / 1024 * 1024);
   H.dy_chunk_bytes = (int)(((size_t)H.dy_th * H.dy_tw * cbn * 2 + 1023) / 1024 * 1024);
@@ -2476,7 +2526,7 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g, int cb, int cipad, int c
   }
   H.tiles_x = g.Wo / H.TW; H.tiles_y = g.Ho / H.TH; H.n_img = g.B;
   H.tiles = H.tiles_x * H.tiles_y * g.B;
-  int ks = env_int("SV_HWG_SPLITS", 37) / H.m_splits;   // measured (B200, C2 step): 148 -> 1.78 ms, 74 -> 1.71, 37 -> 1.68, 26 -> 1.71, 18 -> 1.83 (the wgrads share the GPU with the dgrad chain)
+  int ks = (H.pair_c ? env_int("SV_HWG_SPLITS_S2", 74) : env_int("SV_HWG_SPLITS", 37)) / H.m_splits;   // measured (B200, C2 step): 148 -> 1.78 ms, 74 -> 1.71, 37 -> 1.68, 26 -> 1.71, 18 -> 1.83 (the wgrads share the GPU with the dgrad chain)
   if (ks < 1) ks = 1;
   if (ks > H.tiles) ks = H.tiles;
   H.tiles_per_split = (H.tiles + ks - 1) / ks;
@@ -2679,8 +2729,22 @@ static void plan_first_layer(TcLayer& t, const ConvGeom& g, int out_dt, size_t& 
     L.smem_bytes = (size_t)L.a_stages * 128 * 64 * 2 + (size_t)L.b_stages * L.tile_cols * 64 * 2 + sizeof(WgCtl) + 1024;
     t.wgrad_ok = true;
     t.wgrad_launches = 2;
+    size_t partial_bytes = (size_t)L.k_splits * L.m_pad * L.n_pad * 4;
+    // Halo kernel through the pixel-pair view of the staged image (natural pairs: pixel x sits in column x + 2 of the [W + 8][8] row,
+    // so the map starts two pixels in and the zero borders become TMA out-of-bounds fill): M rows = (filter row, parity, 8-channel
+    // pixel slot), one 96-column MMA per 16 pixels instead of 6 x 2 per-tap box loads of the whole input.
+    {
+      ConvGeom g1 = g;
+      g1.Ci = 8; g1.in_ld = 8; g1.in_coff = 0;
+      int cb1 = 0, cipad1 = 0;
+      if (env_int("SV_FIRST_PAIR_WGRAD", 1) && plan_halo_wgrad(t.hw, g1, cb1, cipad1, cbn, copad)) {
+        t.wg_halo = true;
+        const size_t hb = (size_t)t.hw.k_splits * t.hw.m_pad * t.hw.n_pad * 4;
+        if (hb > partial_bytes) partial_bytes = hb;
+      }
+    }
     t.wg_partial_off = off;
-    off += ((size_t)L.k_splits * L.m_pad * L.n_pad * 4 + 1023) / 1024 * 1024;
+    off += (partial_bytes + 1023) / 1024 * 1024;
   }
 }
 
@@ -3019,15 +3083,17 @@ const char* tc_bind_layer(TcLayer& t, const ConvGeom& g, const void* in, void* o
     if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
     if (t.wg_halo) {
       TcHaloWgrad& H = t.hw;
-      e = make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, H.nchunks * H.cb, H.cb, H.x_tw, H.x_th, 1, 1, H.x_swizzle);
+      e = t.first  ? make_first_pair_map(&H.map_x, in, g.B, g.Hi, g.Wi, H.x_tw, H.x_th)
+          : H.pair_c ? make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi / 2, 2 * g.in_ld, 0, H.nchunks * H.cb, H.cb, H.x_tw, H.x_th, 1, 1, H.x_swizzle)
+                   : make_act_map(&H.map_x, in, g.B, g.Hi, g.Wi, g.in_ld, g.in_coff, H.nchunks * H.cb, H.cb, H.x_tw, H.x_th, 1, 1, H.x_swizzle);
       if (e) return e;
       e = make_act_map(&H.map_dy, dout, g.B, g.Ho, g.Wo, g.dout_ld, 0, H.nbchunks * H.cbn, H.cbn, H.dy_tw, H.dy_th, 1, 1, H.dy_swizzle);
       if (e) return e;
       H.partial = (float*)(ws + t.wg_partial_off);
       if (cudaFuncSetAttribute(halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return "cudaFuncSetAttribute failed";
       if (env_int("SV_TC_VERBOSE", 0))
-        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d wgrad: HALO mode %d nstack %d tile %dx%d groups %d (%d/CTA, m_splits %d) N %d tiles %d k_splits %d smem %zu\n",
-                g.kh, g.kw, g.stride, g.Ci, g.Co, H.mode, H.nstack, H.TW, H.TH, H.groups, H.groups_per_cta, H.m_splits, H.n_pad, H.tiles, H.k_splits,
+        fprintf(stderr, "[tc] %dx%d s%d Ci%d Co%d wgrad: HALO mode %d nstack %d pair %d tile %dx%d groups %d (%d/CTA, m_splits %d) N %d tiles %d k_splits %d smem %zu\n",
+                g.kh, g.kw, g.stride, g.Ci, g.Co, H.mode, H.nstack, H.pair_c, H.TW, H.TH, H.groups, H.groups_per_cta, H.m_splits, H.n_pad, H.tiles, H.k_splits,
                 H.smem_bytes);
     }
   }
@@ -3229,7 +3295,7 @@ void tc_conv_wgrad(TcLayer& t, const ConvGeom& g, float* grads, cudaStream_t s) 
     const TcHaloWgrad& H = t.hw;
     dim3 grid(H.m_splits, 1, H.k_splits);
     launch_pdl(halo_wgrad_kernel, dim3(grid), dim3(kThreads), H.smem_bytes, s, H);
-    const WgRowMap R{(H.nstack ? 4 : 2) + (H.mode ? 1 : 0), g.kw, 0, H.cb, H.nsub, H.gw, H.gpt, H.nb};
+    const WgRowMap R{(H.nstack ? 4 : 2) + (H.mode ? 1 : 0), g.kw, 0, H.cb, H.nsub, H.gw, H.gpt, H.nb, H.pair_c, H.pair_sh, H.taps_w};
     launch_wgrad_reduce(g, H.partial, H.k_splits, H.m_pad, H.n_pad, R, grads, s);
     return;
   }

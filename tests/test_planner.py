@@ -17,8 +17,9 @@ def _plan(model, H, B, precision="bf16"):
 def test_c2_layer_to_kernel_map():
     e, plan = _plan("lgvae", 64, 256)
     for enc in ("encoder_x", "encoder_x_hat"):
-        assert plan[f"{enc}.e1"] == ("pconv_kernel", "reference", "wgrad_kernel")        # first conv: no input gradient
-        assert plan[f"{enc}.e2"] == ("pconv_kernel", "pconv_kernel", "wgrad_kernel")
+        # the stride-2 weight gradients with >= 16 output columns run on the halo kernel through the pixel-pair view
+        assert plan[f"{enc}.e1"] == ("pconv_kernel", "reference", "halo_wgrad_kernel")   # first conv: no input gradient
+        assert plan[f"{enc}.e2"] == ("pconv_kernel", "pconv_kernel", "halo_wgrad_kernel")
         assert plan[f"{enc}.e3"] == ("igemm_kernel", "igemm_kernel", "wgrad_kernel")
     for dec in ("decoder_x", "decoder_x_hat"):
         assert plan[f"{dec}.d3"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
@@ -42,9 +43,12 @@ def test_every_pass_of_the_hot_path_has_a_tensor_core_kernel(model, H, B, precis
 def test_planner_knobs_are_read_at_plan_time(monkeypatch):
     monkeypatch.setenv("SV_PCONV", "0")
     monkeypatch.setenv("SV_NO_NSCONV", "1")
+    monkeypatch.setenv("SV_NO_PAIR_WGRAD", "1")
     _, plan = _plan("lgvae", 64, 256)
     assert plan["decoder_x.d5"][1] == "halo_conv_kernel"
     assert plan["decoder_x.d4"][0] == "igemm_kernel"
+    assert plan["encoder_x.e1"][2] == plan["encoder_x.e2"][2] == "wgrad_kernel"      # per-tap fallback of the stride-2 weight gradients
+    assert plan["decoder_x.d4"][2] == "halo_wgrad_kernel"
 
 
 def test_c2_layer_to_kernel_map_bf16x3():
