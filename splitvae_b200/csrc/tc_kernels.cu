@@ -1583,12 +1583,16 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
     __syncwarp();
     if (tc::elect_one()) {
       const uint32_t idesc = tc::make_idesc_bf16(128, P.n_pad, 1, 1);
-      const uint64_t a_tmpl = tc::make_smem_desc(0, (uint32_t)P.a_lbo, 8u * pix, tc::layout_type_for(P.x_swizzle));
-      const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)P.b_lbo, 8u * pixb, tc::layout_type_for(P.dy_swizzle));
+      // A K step is 16 pixels = two groups of 8 (the descriptors' stride-dimension offset): 16 horizontally adjacent pixels of one
+      // output row, or - 8-pixel-wide images (krows = 2) - the same 8 columns of two consecutive output rows, one tile-row pitch apart.
+      const int kr = P.krows;
+      const uint32_t a_sbo = kr == 2 ? (uint32_t)(P.sy * P.x_tw) * pix : 8u * pix, b_sbo = kr == 2 ? (uint32_t)P.dy_tw * pixb : 8u * pixb;
+      const uint64_t a_tmpl = tc::make_smem_desc(0, (uint32_t)P.a_lbo, a_sbo, tc::layout_type_for(P.x_swizzle));
+      const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)P.b_lbo, b_sbo, tc::layout_type_for(P.dy_swizzle));
       const uint32_t n_pad = (uint32_t)P.n_pad;
-      const int ksx = P.TW / 16;
+      const int ksx = kr == 2 ? 1 : P.TW / 16, ny = P.TH / kr;
       const uint32_t a_xs = (16u * pix) >> 4, b_xs = (16u * pixb) >> 4;
-      const uint32_t a_row = ((uint32_t)(P.sy * P.x_tw) * pix) >> 4, b_row = ((uint32_t)P.dy_tw * pixb) >> 4;   // (sy = 2: every other X row)
+      const uint32_t a_row = ((uint32_t)(kr * P.sy * P.x_tw) * pix) >> 4, b_row = ((uint32_t)(kr * P.dy_tw) * pixb) >> 4;   // (sy = 2: every other X row)
       const volatile uint32_t* goff = ctl->goff;
       for (int t = t_begin; t < t_end; ++t) {
         const int i = t - t_begin, st = i % P.stages, ph = (i / P.stages) & 1;
@@ -1602,15 +1606,15 @@ __global__ void __launch_bounds__(kThreads) halo_wgrad_kernel(const __grid_const
 #pragma unroll
           for (int g = 0; g < 4; ++g) go[g] = goff[g < ng ? g : 0];
           switch (ng) {
-            case 1: hw_issue_tile<1>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
-            case 2: hw_issue_tile<2>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
-            case 3: hw_issue_tile<3>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
-            default: hw_issue_tile<4>(da0, db0, go, tmem_base, n_pad, idesc, P.TH, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            case 1: hw_issue_tile<1>(da0, db0, go, tmem_base, n_pad, idesc, ny, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            case 2: hw_issue_tile<2>(da0, db0, go, tmem_base, n_pad, idesc, ny, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            case 3: hw_issue_tile<3>(da0, db0, go, tmem_base, n_pad, idesc, ny, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
+            default: hw_issue_tile<4>(da0, db0, go, tmem_base, n_pad, idesc, ny, ksx, a_row, b_row, a_xs, b_xs, accum0); break;
           }
         } else {
           uint64_t da_y = da0, db_y = db0;
           uint32_t accum = accum0;
-          for (int yy = 0; yy < P.TH; ++yy, da_y += a_row, db_y += b_row) {
+          for (int yy = 0; yy < ny; ++yy, da_y += a_row, db_y += b_row) {
             uint64_t da = da_y, db = db_y;
             for (int xs = 0; xs < ksx; ++xs, da += a_xs, db += b_xs) {
               uint32_t acc = tmem_base;
@@ -2456,7 +2460,9 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g0, int cb, int cipad, int 
     H.sy = 2;
   }
   const int sy = H.sy;
-  if (g.stride != 1 || (g.Wo % 16) || g.Wo != g.Wi || g.Ho != g.Hi || copad > 256 || g.kh * g.kw < 2) return false;
+  const bool narrow = g.Wo == 8 && (g.Ho % 2) == 0 && !env_int("SV_NO_NARROW_WGRAD", 0);     // 8-pixel-wide images: a K step = 8 columns x 2 rows
+  if (g.stride != 1 || ((g.Wo % 16) && !narrow) || g.Wo != g.Wi || g.Ho != g.Hi || copad > 256 || g.kh * g.kw < 2) return false;
+  H.krows = narrow ? 2 : 1;
   H.taps_h = g.kh; H.taps_w = g.kw; H.pad_t = g.pt; H.pad_l = g.pl;
   H.cb = cb; H.nchunks = cipad / cb; H.x_swizzle = cb * 2;
   H.cbn = cbn; H.nbchunks = copad / cbn; H.dy_swizzle = cbn * 2;
@@ -2485,7 +2491,7 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g0, int cb, int cipad, int 
   H.groups_per_cta = (H.groups + H.m_splits - 1) / H.m_splits;   // balanced
   // tile: TW = 32 when it divides the width (16 otherwise); TH = largest divisor of the height whose two stages fit
   const int force_th = env_int("SV_HWG_TH", 0), force_tw = env_int("SV_HWG_TW", 0);
-  H.TW = force_tw ? force_tw : ((g.Wo % 32) == 0 ? 32 : 16);
+  H.TW = narrow ? 8 : force_tw ? force_tw : ((g.Wo % 32) == 0 ? 32 : 16);
   if (g.Wo % H.TW) return false;
   H.stages = env_int("SV_HWG_STAGES", 2);
   if (H.stages < 2) H.stages = 2;
@@ -2495,7 +2501,7 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g0, int cb, int cipad, int 
   const size_t slack = H.nstack ? (size_t)(H.nsub - 1) * x_tw * cb * 2 : (size_t)H.nsub * cb * 2;
   int best_th = 0;
   for (int th = 1; th <= g.Ho && th <= 32; ++th) {
-    if (g.Ho % th) continue;
+    if (g.Ho % th || th % H.krows) continue;
     if (force_th && th != force_th) continue;
     const int thp = (th - 1) * sy + g.kh;
     const size_t xc = ((size_t)thp * x_tw * cb * 2 + 1023) / 1024 * 1024, dc = ((size_t)th * dy_tw * cbn * 2 + 1023) / 1024 * 1024;

@@ -107,6 +107,7 @@ struct TcHaloWgrad {
   int x_tw, x_th, dy_tw, dy_th;     // shared-memory tile extents (pixels) of X and dY
   int x_dx, x_dy, dy_dx;            // TMA start = tile origin + these offsets
   int sy;                           // X rows per output row (2: stride-2 layer through the pixel-pair view)
+  int krows;                        // output rows per K step: 1 (16 adjacent pixels of a row) or 2 (8-pixel-wide images: 8 columns x 2 rows)
   int pair_c, pair_sh;              // pair view: channels per pixel of the layer, u = b + pair_sh -> (pair tap u >> 1, parity u & 1)
   int a_lbo, b_lbo;                 // byte distance between the stacked sub-blocks of A (M) / B (N)
   uint32_t goff[32];                // per 128-row group: (byte offset of its first sub-block inside the X tile) >> 4

@@ -95,6 +95,7 @@ def test_tc_layers_match_reference(model, H, B):
     {"SV_FIRST_PAIR": "0", "SV_S2_DGRAD_HALO": "0"},   # first layer through the window map, stride-2 dgrad per tap
     {"SV_NS_MB": "1", "SV_NS_SPLIT_WIDE": "0"},    # N-stacked conv: one block per tile, unsplit wide N (single accumulator set)
     {"SV_OLD_REDUCE": "1", "SV_HWG_SPLITS": "148", "SV_WGRAD_STREAMS": "1"},
+    {"SV_NO_NARROW_WGRAD": "1"},                   # 8-pixel-wide layers' weight gradients on the per-tap kernel
     {"SV_NO_PAIR_WGRAD": "1"},                     # stride-2 weight gradients on the per-tap kernel (default: halo kernel through the pixel-pair view)
     {"SV_IGEMM_FAT": "0", "SV_FOLD_COLSUM": "0"},  # bf16x3 per-tap kernel with logical-chunk stages, bias gradients by the multi-tensor column sums only
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
@@ -102,5 +103,5 @@ def test_tc_layers_planner_variants(env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     test_tc_layers_match_reference("lgvae", 64, 3)
-    if "SV_NS_MB" in env or "SV_PCONV" in env or "SV_FOLD_COLSUM" in env or "SV_NO_PAIR_WGRAD" in env:
+    if "SV_NS_MB" in env or "SV_PCONV" in env or "SV_FOLD_COLSUM" in env or "SV_NO_PAIR_WGRAD" in env or "SV_NO_NARROW_WGRAD" in env:
         test_tc_layers_match_reference("lggmvae", 64, 2)

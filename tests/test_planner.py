@@ -20,7 +20,7 @@ def test_c2_layer_to_kernel_map():
         # the stride-2 weight gradients with >= 16 output columns run on the halo kernel through the pixel-pair view
         assert plan[f"{enc}.e1"] == ("pconv_kernel", "reference", "halo_wgrad_kernel")   # first conv: no input gradient
         assert plan[f"{enc}.e2"] == ("pconv_kernel", "pconv_kernel", "halo_wgrad_kernel")
-        assert plan[f"{enc}.e3"] == ("igemm_kernel", "igemm_kernel", "wgrad_kernel")
+        assert plan[f"{enc}.e3"] == ("igemm_kernel", "igemm_kernel", "halo_wgrad_kernel")   # 8-pixel-wide output: K step = 8 columns x 2 rows
     for dec in ("decoder_x", "decoder_x_hat"):
         assert plan[f"{dec}.d3"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
         assert plan[f"{dec}.d4"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
@@ -49,6 +49,9 @@ def test_planner_knobs_are_read_at_plan_time(monkeypatch):
     assert plan["decoder_x.d4"][0] == "igemm_kernel"
     assert plan["encoder_x.e1"][2] == plan["encoder_x.e2"][2] == "wgrad_kernel"      # per-tap fallback of the stride-2 weight gradients
     assert plan["decoder_x.d4"][2] == "halo_wgrad_kernel"
+    monkeypatch.setenv("SV_NO_NARROW_WGRAD", "1")
+    _, plan = _plan("lgvae", 64, 256)
+    assert plan["decoder_x.d2"][2] == plan["encoder_x.e3"][2] == "wgrad_kernel"
 
 
 def test_c2_layer_to_kernel_map_bf16x3():
