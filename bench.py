@@ -400,19 +400,24 @@ def main():
                 if not kern:
                     continue
                 t = timed(lambda: e.debug_run_layer(i, p, 1, runner.inputs))
-                k = by_kernel.setdefault(KERNEL_NAMES[kern], {"launch_groups": 0, "us": 0.0, "gflop": 0.0})
+                k = by_kernel.setdefault(KERNEL_NAMES[kern], {"launch_groups": 0, "us": 0.0, "gflop": 0.0, "sm_us": 0.0})
                 k["launch_groups"] += 1
                 k["us"] += t * 1e6
                 k["gflop"] += flops / 1e9
+                # the halo weight-gradient launches occupy a fixed number of CTAs, one per SM (planner defaults, tc_kernels.cu:plan_halo_wgrad)
+                ctas = 148
+                if KERNEL_NAMES[kern] == "halo_wgrad_kernel":
+                    ctas = int(os.environ.get("SV_HWG_SPLITS_S2", 37)) if L.stride == 2 else int(os.environ.get("SV_HWG_SPLITS", 28))
+                k["sm_us"] += t * 1e6 * min(ctas, 148) / 148.0
         for k in by_kernel.values():
             k["tflops"] = k["gflop"] / k["us"] * 1e3 if k["us"] else 0.0   # GFLOP/us = PFLOP/s
         # Dominant kernel = largest share of the step's SM-TIME (isolated time x the fraction of the 148 SMs its launches occupy).  The
-        # halo weight-gradient kernel is launched on 36-37 CTAs (one per SM) on purpose - it runs on auxiliary streams beside the dgrad
-        # chain, SV_HWG_SPLITS sweep in DESIGN.md - so its isolated time is ~4x its share of the step; every other tensor-core kernel
+        # halo weight-gradient kernel is launched on 28-37 CTAs (one per SM) on purpose - it runs on auxiliary streams beside the dgrad
+        # chain, SV_HWG_SPLITS sweep in DESIGN.md - so its isolated time is 4-5x its share of the step; every other tensor-core kernel
         # fills the GPU.  Both orderings are reported (by_kernel[*].us and .sm_us).
         for n, k in by_kernel.items():
-            k["sm_frac"] = 0.25 if n == "halo_wgrad_kernel" else 1.0
-            k["sm_us"] = k["us"] * k["sm_frac"]
+            k.setdefault("sm_us", k["us"])
+            k["sm_frac"] = k["sm_us"] / k["us"] if k["us"] else 1.0
         dom = max(by_kernel, key=lambda n: by_kernel[n]["sm_us"])
         d = by_kernel[dom]
         traffic = None
@@ -435,9 +440,9 @@ def main():
         if dom == "halo_wgrad_kernel":
             # the halo wgrads are launched on ~37 of the 148 SMs on purpose: they run on auxiliary streams beside the dgrad chain
             # (148-CTA launches starved the chain: 1.78 vs 1.68 ms/step), so their isolated time overstates their share of the step
-            roof["sms_used"] = 37
-            roof["frac_of_sms_used"] = roof["frac"] * 148.0 / 37.0
-            roof["note"] += "; this kernel is launched on 37 of 148 SMs by design (it overlaps the dgrad chain), frac_of_sms_used = frac * 148/37"
+            roof["sms_used"] = round(148.0 * d["sm_frac"], 1)
+            roof["frac_of_sms_used"] = roof["frac"] / d["sm_frac"]
+            roof["note"] += "; this kernel is launched on 28-37 of 148 SMs by design (it overlaps the dgrad chain), frac_of_sms_used = frac / (share of the SMs)"
         t_loss = timed(lambda: e.debug_pixel_loss(runner.inputs), reps=10)      # the likelihood kernel alone (no scalar reduction behind it)
         loss_bytes = B * LOSS_BYTES_PER_IMAGE[H]
         ach = loss_bytes / t_loss / 1e9

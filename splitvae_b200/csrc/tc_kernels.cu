@@ -2532,7 +2532,10 @@ bool plan_halo_wgrad(TcHaloWgrad& H, const ConvGeom& g0, int cb, int cipad, int 
   }
   H.tiles_x = g.Wo / H.TW; H.tiles_y = g.Ho / H.TH; H.n_img = g.B;
   H.tiles = H.tiles_x * H.tiles_y * g.B;
-  int ks = (H.pair_c ? env_int("SV_HWG_SPLITS_S2", 74) : env_int("SV_HWG_SPLITS", 37)) / H.m_splits;   // measured (B200, C2 step): 148 -> 1.78 ms, 74 -> 1.71, 37 -> 1.68, 26 -> 1.71, 18 -> 1.83 (the wgrads share the GPU with the dgrad chain)
+  // CTAs per launch (the weight gradients share the GPU with the dgrad chain and with each other).  Measured on the C2 step once every
+  // convolution's weight gradient ran on this kernel: stride-1 layers 74 -> 1.731 ms, 56 -> 1.711, 37 -> 1.695, 28 -> 1.681, 20 -> 1.679
+  // (with 28 on the pair-view layers); pair-view layers 111 -> 1.718, 74 -> 1.695, 37 -> 1.681, 28 -> 1.667 = 37 within noise.
+  int ks = (H.pair_c ? env_int("SV_HWG_SPLITS_S2", 37) : env_int("SV_HWG_SPLITS", 28)) / H.m_splits;
   if (ks < 1) ks = 1;
   if (ks > H.tiles) ks = H.tiles;
   H.tiles_per_split = (H.tiles + ks - 1) / ks;
