@@ -692,21 +692,23 @@ __global__ void __launch_bounds__(256) colsum_multi_partial_kernel(const ColsumJ
   }
 }
 
-constexpr int kColsumFinalLanes = 32;   // chunk lanes per column: the jobs fed by upsample2x_bwd / pixel_loss bring 592-1184 chunks for 16-128 columns,
-                                        // so a block is few columns x many lanes (8 lanes left each thread ~150 serial L2 loads: 16 us)
-__global__ void __launch_bounds__(32 * kColsumFinalLanes) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs,
-                                                                                    const float* __restrict__ partial, float* __restrict__ grads) {
+constexpr int kColsumFinalLanes = 32;   // chunk lanes per column: the jobs fed by upsample2x_bwd / pixel_loss bring 592-1184 chunks for 16-128 columns
+constexpr int kColsumFinalCols = 8;     // columns per block (one 32-byte sector per partial row); 256-thread blocks fit beside the persistent
+                                        // chain kernels' registers, 1024-thread ones waited 70 us for a drained SM
+__global__ void __launch_bounds__(kColsumFinalCols * kColsumFinalLanes) colsum_multi_final_kernel(const ColsumJob* __restrict__ jobs, int njobs,
+                                                                                                  const float* __restrict__ partial,
+                                                                                                  float* __restrict__ grads) {
   pdl_enter();
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (jobs[mid].fblock_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  // block = 32 columns x 32 chunk lanes (lane y sums chunks y, y+32, ... with four loads in flight), fixed-order combine through shared memory
-  __shared__ float red[kColsumFinalLanes][33];
+  // block = 8 columns x 32 chunk lanes (lane y sums chunks y, y+32, ... with four loads in flight), fixed-order combine through shared memory
+  __shared__ float red[kColsumFinalLanes][kColsumFinalCols + 1];
   const ColsumJob& J = jobs[lo];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = (blockIdx.x - J.fblock_start) * 32 + tx;
+  const int tx = threadIdx.x % kColsumFinalCols, ty = threadIdx.x / kColsumFinalCols;
+  const int c = (blockIdx.x - J.fblock_start) * kColsumFinalCols + tx;
   float t = 0.f;
   if (c < J.ncols) {
     const float* p = partial + J.partial_off + c;
@@ -756,7 +758,7 @@ static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>&
       J.partial_off = partial_floats;
       partial_floats += (long long)J.nchunks * J.ncols;
       J.block_start = nblocks;                       // (no blocks in the partial kernel)
-      J.fblock_start = nfblocks; nfblocks += (J.ncols + 31) / 32;
+      J.fblock_start = nfblocks; nfblocks += (J.ncols + kColsumFinalCols - 1) / kColsumFinalCols;
       J.nparts = g.nparts;
       for (int k = 0; k < 3; ++k) { J.part_n[k] = g.part_n[k]; J.part_b[k] = g.part_b[k]; }
       jobs.push_back(J);
@@ -782,7 +784,7 @@ static void colsum_build(const ColsumSpec* specs, int n, std::vector<ColsumJob>&
       J.partial_off = partial_floats;
       partial_floats += (long long)J.nchunks * J.ncols;
       J.block_start = nblocks; nblocks += J.nchunks;
-      J.fblock_start = nfblocks; nfblocks += (J.ncols + 31) / 32;
+      J.fblock_start = nfblocks; nfblocks += (J.ncols + kColsumFinalCols - 1) / kColsumFinalCols;
       J.nparts = g.nparts;
       for (int k = 0; k < 3; ++k) { J.part_n[k] = g.part_n[k]; J.part_b[k] = g.part_b[k]; }
       jobs.push_back(J);
@@ -832,7 +834,7 @@ void colsum_table_destroy(ColsumTable* t) {
 int colsum_table_run(ColsumTable* t, float* grads, cudaStream_t s) {
   if (!t || !t->njobs) return 0;
   if (t->nblocks) launch_pdl(colsum_multi_partial_kernel, dim3(t->nblocks), dim3(256), 0, s, t->dev, t->njobs, t->partial);
-  launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(32 * kColsumFinalLanes), 0, s, t->dev, t->njobs, t->partial, grads);
+  launch_pdl(colsum_multi_final_kernel, dim3(t->nfblocks), dim3(kColsumFinalCols * kColsumFinalLanes), 0, s, t->dev, t->njobs, t->partial, grads);
   return t->nblocks ? 2 : 1;
 }
 float* colsum_table_ext_partial(ColsumTable* t, int i) {

@@ -3287,8 +3287,12 @@ static void launch_wgrad_reduce(const ConvGeom& g, const float* partial, int k_s
     const long long items = (long long)g.kh * g.kw * g.Ci * (g.Co / vec);
     const int blocks = (int)((items + 31) / 32);
     // split lanes: enough that every lane has <= ~8 loads, more when the grid alone would not fill the GPU
+    // 256-thread blocks: the reduce runs on a low-priority stream beside the persistent chain kernels (nsconv: 576 threads x 96 registers per
+    // SM), where a 1024-thread block finds no SM with enough free registers until that kernel has drained - in the step's timeline the
+    // 9 us reduce of d3 took 50-80 us and held up every weight gradient queued behind it on its stream
+    const int max_lanes = env_int("SV_REDUCE_LANES", 8);
     int lanes = 8;
-    while (lanes < 32 && (k_splits > 8 * lanes || (long long)blocks * lanes < 148 * 16)) lanes <<= 1;
+    while (lanes < max_lanes && (k_splits > 8 * lanes || (long long)blocks * lanes < 148 * 16)) lanes <<= 1;
     const size_t smem = (size_t)lanes * 32 * vec * sizeof(float);
     if (vec == 4) launch_pdl(wgrad_reduce_vec_kernel<4>, dim3(blocks), dim3(32, lanes), smem, s, g, partial, k_splits, m_pad, n_pad, R, grads);
     else if (vec == 2) launch_pdl(wgrad_reduce_vec_kernel<2>, dim3(blocks), dim3(32, lanes), smem, s, g, partial, k_splits, m_pad, n_pad, R, grads);
