@@ -2,7 +2,7 @@
  *
  * The reference (51616/split-vae) has no FFI: its boundary is the Python surface of
  * vae/model.py + vae/trainer.py.  Each entry point below states which reference lines it
- * replaces.  The Python host (splitvae_b200/*.py) binds these with ctypes and re-exposes the
+ * replaces.  The Python host (the modules under splitvae_b200/) binds these with ctypes and re-exposes the
  * reference's classes/functions (LGVae, LGGMVae, kl_divergence, ...) on top.
  *
  * Conventions

@@ -117,6 +117,7 @@ struct sv_handle {
   cudaEvent_t ev_seg_done = nullptr;
   cudaGraph_t graph = nullptr;            // sv_capture_graph: one captured sv_train_step
   cudaGraphExec_t graph_exec = nullptr;
+  long long graph_kernels = 0;
 };
 
 namespace {
@@ -1147,6 +1148,7 @@ sv_status sv_capture_graph(sv_handle* h, const float* inputs, const float* eps_g
   }
   const long long before = h->launches;
   const sv_status st = sv_train_step(h, inputs, eps_g, eps_l, u, stream);
+  h->graph_kernels = h->launches - before;                 // kernels of one captured step (counted by sv_replay)
   h->launches = before;                                    // (capture records, nothing ran)
   cudaGraph_t g = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(s, &g);
@@ -1169,6 +1171,7 @@ sv_status sv_replay(sv_handle* h, int32_t n_steps, void* stream) {
       cudaGetLastError();
       return fail(h, SV_ERR_DEVICE, "cudaGraphLaunch failed");
     }
+  h->launches += (long long)n_steps * h->graph_kernels;
   return SV_OK;
 }
 

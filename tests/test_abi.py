@@ -84,3 +84,32 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle", src, flags=re.M), fn
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: include/splitvae.h compiles as C99 (-pedantic, no warnings) and examples/c_host.c - a non-Python host that
+    binds caller-owned buffers, captures the train step as a CUDA graph and replays it - links against the library; its plan-only mode
+    runs without a GPU and prints the same variable inventory the Python host sees."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    cudart = "/usr/local/cuda/lib64"
+    if not os.path.exists(os.path.join(cudart, "libcudart.so")):
+        pytest.skip("no CUDA runtime to link the example's --run mode against")
+    exe = str(tmp_path / "c_host")
+    lib_dir = os.path.join(ROOT, "splitvae_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_host.c"), "-o", exe, "-L" + lib_dir, "-lsplitvae", "-Wl,-rpath," + lib_dir,
+                        "-L" + cudart, "-lcudart"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    e = Engine(model="lgvae", height=64, width=64, batch=256, plan_only=True)
+    lines = out.stdout.splitlines()
+    assert "sm_100a" in lines[0]
+    assert lines[1].split()[:6] == ["variables", str(len(e.table)), "arena_floats", str(e.arena_floats), "workspace_bytes", str(e.workspace_bytes)]
+    for line, (name, shape, off, cnt) in zip(lines[2:], e.table):
+        f = line.split()
+        assert f[0] == name and f[1] == "[" + ",".join(str(d) for d in shape) + "]" and int(f[3]) == off and int(f[5]) == cnt
