@@ -18,10 +18,15 @@ reference itself: its own source, executed here against a stand-in for the few `
     model_forward / step_losses agree to 1e-10 on every output tensor and scalar;
   * the patch scramble: augmentation.py imported UNMODIFIED, Augmentator.scramble driven by an injected patch
     permutation (scripts/make_reference_scramble_golden.py) - oracle.scramble agrees bit for bit.
+Pinned by a THIRD-PARTY implementation of TensorFlow's semantics (not the reference, not this repository):
+  * Conv2D padding='SAME' (strides 1 and 2, even and odd kernels / image sizes) and tf.image.resize (bilinear,
+    half-pixel centres; the decoder's x2 and the CelebA 178 -> 64 down-scale): OpenCV's TensorFlow-graph importer
+    executing a hand-encoded TF GraphDef (scripts/make_opencv_primitive_golden.py ->
+    tests/golden/opencv_tf_primitives.npz, tests/test_oracle_tf_primitives.py) - conv2d_same / resize2x agree to
+    fp32 rounding (3e-5 / 1e-6) on the fixture and on a live random sweep where cv2 is importable.
 What stays UNPINNED (restated from the published TF/Keras semantics listed below, checked only by
-analytic known-answer tests and fp64 finite differences): the library primitives themselves -
-Conv2D 'same' padding, bilinear resize, activations, Keras Adam / ExponentialDecay - and autodiff,
-for which a second, independent numpy backward of the loss block exists (tests/test_oracle.py).
+analytic known-answer tests and fp64 finite differences): activations, Keras Adam / ExponentialDecay - and
+autodiff, for which a second, independent numpy backward of the loss block exists (tests/test_oracle.py).
 
 What is restated (reference file:line):
   * Sampling                      vae/model.py:9-13
