@@ -291,3 +291,24 @@ def test_celeba_preprocess_known_answers():
         assert abs(out[o, 5, 0] - ((cy + src) / 255.0 * 2 - 1)) < 1e-5            # row ramp (crop offset 20)
         assert abs(out[5, o, 1] - (src / 255.0 * 2 - 1)) < 1e-5                   # column ramp (crop offset 0)
     assert np.allclose(out[..., 2], 77 / 255.0 * 2 - 1, atol=1e-6)
+
+
+def test_keras_adam_is_standard_adam_with_epsilon_hat():
+    """tf.keras.optimizers.Adam applies epsilon to sqrt(v) BEFORE the bias correction ("epsilon hat" of Kingma & Ba, the note just before
+    section 2.1 - the TF docstring says so); torch.optim.Adam applies it after.  The two coincide when torch's eps is
+    eps_hat / sqrt(1 - beta2^t).  Running torch's optimizer (an independent implementation of the m / v / bias-correction arithmetic)
+    with that per-step eps must reproduce the oracle's Keras update over a trajectory."""
+    rng = np.random.default_rng(7)
+    p0 = rng.normal(size=257) * 1e-2                              # small weights: the fp32 ulp of p stays far below the displacement
+    grads = [rng.normal(size=257) * (0.1 + i % 3) for i in range(25)]
+    lr, b1, b2, eps_hat = 1e-4, 0.9, 0.999, 1e-7
+    tp = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([tp], lr=lr, betas=(b1, b2), eps=eps_hat)
+    p, m, v = p0.astype(np.float32), np.zeros(257, np.float32), np.zeros(257, np.float32)
+    for t, g in enumerate(grads, start=1):
+        opt.param_groups[0]["eps"] = eps_hat / math.sqrt(1.0 - b2 ** t)
+        tp.grad = torch.tensor(g, dtype=torch.float64)
+        opt.step()
+        p, m, v = O.keras_adam_update(p, g.astype(np.float32), m, v, O.adam_alpha(lr, t))
+    disp = np.abs(p0 - tp.detach().numpy()).max()                  # ~25 * lr
+    assert disp > 1e-3 and np.abs(p - tp.detach().numpy()).max() < 1e-4 * disp               # fp32 oracle vs fp64 torch
