@@ -235,6 +235,8 @@ typedef struct sv_layer_info {
   int32_t kern_fwd, kern_dgrad, kern_wgrad;
   int32_t split_fwd;                      /* 1: the forward product multiplies bf16 pairs (SV_PRECISION_BF16X3) */
   void *in_lo, *out_lo;                   /* lo planes of in / out (value = hi + lo) in the bf16x3 mode, else NULL */
+  int32_t wgrad_ctas;                     /* CTAs of the weight-gradient launch (the halo kernel runs on a fixed few, one per SM, beside the dgrad chain) */
+  int32_t reserved;
 } sv_layer_info;
 enum { SV_KERN_NONE = 0, SV_KERN_IGEMM = 1, SV_KERN_HALO_CONV = 2, SV_KERN_NSCONV = 3, SV_KERN_WGRAD = 4, SV_KERN_HALO_WGRAD = 5, SV_KERN_PCONV = 6 };
 enum { SV_PASS_FWD = 0, SV_PASS_DGRAD = 1, SV_PASS_WGRAD = 2 };

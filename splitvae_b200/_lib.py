@@ -47,7 +47,8 @@ class SvLayerInfo(C.Structure):
                [(n, C.c_void_p) for n in ("in_", "out", "dout", "din")] + \
                [(n, C.c_int64) for n in ("in_elems", "out_elems", "dout_elems", "din_elems")] + \
                [(n, C.c_int32) for n in ("kern_fwd", "kern_dgrad", "kern_wgrad", "split_fwd")] + \
-               [(n, C.c_void_p) for n in ("in_lo", "out_lo")]
+               [(n, C.c_void_p) for n in ("in_lo", "out_lo")] + \
+               [(n, C.c_int32) for n in ("wgrad_ctas", "reserved_")]
 
 
 KERNEL_NAMES = {0: "reference", 1: "igemm_kernel", 2: "halo_conv_kernel", 3: "nsconv_kernel", 4: "wgrad_kernel", 5: "halo_wgrad_kernel", 6: "pconv_kernel"}

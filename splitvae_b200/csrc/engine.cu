@@ -1290,6 +1290,11 @@ sv_status sv_debug_layer_info(const sv_handle* hc, int32_t i, sv_layer_info* o) 
     o->kern_fwd = !L.tc.fwd_ok ? SV_KERN_NONE : L.tc.fwd_ns ? SV_KERN_NSCONV : L.tc.fwd.halo ? (L.tc.fwd.persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;
     o->kern_dgrad = !L.tc.dgrad_ok ? SV_KERN_NONE : L.tc.dgrad_ns ? SV_KERN_NSCONV : L.tc.dgrad[0].halo ? (L.tc.dgrad[0].persist ? SV_KERN_PCONV : SV_KERN_HALO_CONV) : SV_KERN_IGEMM;
     o->kern_wgrad = !L.tc.wgrad_ok ? SV_KERN_NONE : L.tc.wg_halo ? SV_KERN_HALO_WGRAD : SV_KERN_WGRAD;
+    if (L.tc.wgrad_ok) {
+      const TcWgradLaunch& W = L.tc.wg;
+      o->wgrad_ctas = L.tc.wg_halo ? L.tc.hw.m_splits * L.tc.hw.k_splits
+                                   : ((W.groups + W.groups_per_cta - 1) / W.groups_per_cta) * W.n_tiles * W.k_splits;
+    }
   }
   o->in_elems = (int64_t)g.B * g.Hi * g.Wi * g.in_ld; o->out_elems = (int64_t)g.B * g.Ho * g.Wo * g.out_ld;
   o->dout_elems = (int64_t)g.B * g.Ho * g.Wo * g.dout_ld; o->din_elems = (int64_t)g.B * g.Hi * g.Wi * g.din_ld;

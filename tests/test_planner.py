@@ -26,6 +26,9 @@ def test_c2_layer_to_kernel_map():
         assert plan[f"{dec}.d4"] == ("nsconv_kernel", "nsconv_kernel", "halo_wgrad_kernel")
         assert plan[f"{dec}.d5"] == ("nsconv_kernel", "pconv_kernel", "halo_wgrad_kernel")
     assert e.workspace_bytes < 4 << 30
+    # the halo weight-gradient launches run on a fixed few CTAs (one per SM) beside the dgrad chain: 28 for stride-1 layers, <= 37 through the pair view
+    ctas = {L.name.decode(): L.wgrad_ctas for L in e.debug_layers()}
+    assert ctas["decoder_x.d4"] == ctas["decoder_x.d5"] == ctas["decoder_x.d2"] == 28 and ctas["encoder_x.e1"] == 37 and 30 <= ctas["encoder_x.e2"] <= 37
 
 
 @pytest.mark.parametrize("model,H,B", [("lgvae", 32, 64), ("lgvae", 64, 256), ("lggmvae", 32, 256), ("lggmvae", 64, 256), ("lgvae", 16, 3)])
