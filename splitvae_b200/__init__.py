@@ -4,11 +4,11 @@ Python is host plumbing only; the arithmetic lives in libsplitvae.so (include/sp
 Importing the package does not load the library; the first use of the product path does, and fails
 loudly if it has not been built or if no sm_100 GPU is present (there is no CPU fallback)."""
 
-__all__ = ["LGVae", "LGGMVae", "Engine", "Augmentator"]
+__all__ = ["LGVae", "LGGMVae", "GMVae", "Engine", "Augmentator"]
 
 
 def __getattr__(name):
-    if name in ("LGVae", "LGGMVae"):
+    if name in ("LGVae", "LGGMVae", "GMVae"):
         from . import model
         return getattr(model, name)
     if name == "Engine":
